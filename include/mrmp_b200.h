@@ -1,0 +1,190 @@
+/*
+ * mrmp_b200.h -- C ABI of the B200-native connect / collide / roadmap hot path.
+ *
+ * Drop-in boundary for Kei18/sssp (MRMP.jl).  The reference has no FFI: its seam is
+ * the closure API  gen_connect / gen_collide / gen_check_goal  (src/MRMP.jl:98).  Each
+ * entry point below names the reference closure method (file:line under
+ * /root/reference) it replaces; julia/MRMPB200.jl and INTEGRATION.md show the `ccall`
+ * glue that rebuilds the closures on top of this library.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; every pointer is a HOST pointer to caller-owned,
+ *    caller-sized memory unless the function name ends in _dev (then: device pointers
+ *    on the ctx's device plus a cudaStream_t passed as void*).
+ *  - states are the reference's isbits layout: StatePoint2D = double[2] (point2d.jl:3-6),
+ *    StatePoint3D = double[3] (point3d.jl:3-7), StateArm22 = double[2] (arm22.jl:3-6);
+ *    obstacles are CircleObstacle2D/3D = double[3]/double[4] (obstacle.jl:7-19);
+ *    verdicts are Julia Bool = uint8_t 0/1.
+ *  - agent indices and vertex ids are 0-BASED here (the Julia glue subtracts 1).
+ *  - every function returns MRMP_OK (0) or a negative error; the message is available
+ *    from mrmp_last_error() (thread-local).  Nothing throws or aborts.
+ *  - a ctx is confined to one host thread at a time (one CUDA stream set); distinct
+ *    ctxs may be used concurrently (scripts/eval.jl:152 creates closures per thread).
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    MRMP_ERR_CUDA.
+ */
+#ifndef MRMP_B200_H
+#define MRMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRMP_OK 0
+#define MRMP_ERR_INVALID (-1)     /* bad argument */
+#define MRMP_ERR_CUDA (-2)        /* CUDA runtime / no device */
+#define MRMP_ERR_CAPACITY (-3)    /* caller-provided output too small (see *_out sizes) */
+#define MRMP_ERR_NOMEM (-4)
+#define MRMP_ERR_UNSUPPORTED (-5)
+
+#define MRMP_MODEL_POINT2D 0 /* src/models/point2d.jl */
+#define MRMP_MODEL_POINT3D 1 /* src/models/point3d.jl */
+#define MRMP_MODEL_ARM22 2   /* src/models/arm22.jl   */
+
+typedef struct mrmp_ctx mrmp_ctx;           /* one problem instance (obstacles, radii) */
+typedef struct mrmp_roadmaps mrmp_roadmaps; /* device-resident per-agent roadmaps */
+
+/* ---- library ----------------------------------------------------------------- */
+const char *mrmp_last_error(void);
+const char *mrmp_version(void);
+/* number of kernels this library has launched in the calling process (diagnostics,
+ * bench.py's gpu_launches) */
+int64_t mrmp_kernel_launch_count(void);
+int mrmp_device_count(int *n_out);
+
+/* pinned host memory for the batch entry points (plain pageable pointers also work) */
+int mrmp_host_alloc(void **ptr_out, int64_t bytes);
+int mrmp_host_free(void *ptr);
+
+/* ---- context: replaces the closure constructors ------------------------------- */
+/* gen_connect(q, obstacles, ins_params...; step_dist, max_dist, safety_dist) and
+ * gen_collide(q, ins_params...; step_dist, safety_dist):
+ *   point2d.jl:42-69, point3d.jl:47-80, point.jl:5-36, arm22.jl:29-37, arm22.jl:90-96.
+ * rads[n_agents]; base_pos[n_agents*2] only for ARM22 (positions, arm22.jl:32) else NULL;
+ * aux reserved (NULL); obstacles_aos[n_obs*(d+1)] = x,y,(z),r; step_dist / safety_dist
+ * only used by ARM22 (src/MRMP.jl:65-66); max_dist NaN == nothing; device = CUDA ordinal. */
+int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const double *rads,
+                    const double *base_pos, const double *aux, int n_obs,
+                    const double *obstacles_aos, double step_dist, double safety_dist,
+                    double max_dist, int device);
+void mrmp_ctx_destroy(mrmp_ctx *ctx);
+int mrmp_ctx_state_dim(const mrmp_ctx *ctx);
+int mrmp_ctx_sync(mrmp_ctx *ctx);
+
+/* ---- connect -------------------------------------------------------------------- */
+/* connect(q, i): point2d.jl:49-57, point3d.jl:54-64, arm22.jl:40-54 */
+int mrmp_connect_point(mrmp_ctx *ctx, int agent, const double *q, uint8_t *out);
+int mrmp_connect_points(mrmp_ctx *ctx, int64_t n, const int32_t *agent, const double *q,
+                        uint8_t *out);
+/* connect(q_from, q_to, i): point2d.jl:59-66, point3d.jl:66-77, arm22.jl:56-86 */
+int mrmp_connect_edge(mrmp_ctx *ctx, int agent, const double *q_from, const double *q_to,
+                      uint8_t *out);
+int mrmp_connect_edges(mrmp_ctx *ctx, int64_t n, const int32_t *agent, const double *q_from,
+                       const double *q_to, uint8_t *out);
+
+/* ---- collide -------------------------------------------------------------------- */
+/* collide(qi_from, qi_to, qj_from, qj_to, i, j): point.jl:9-12, arm22.jl:100-146 */
+int mrmp_collide_pair(mrmp_ctx *ctx, int i, int j, const double *qi_from, const double *qi_to,
+                      const double *qj_from, const double *qj_to, uint8_t *out);
+int mrmp_collide_pairs(mrmp_ctx *ctx, int64_t n, const int32_t *i, const int32_t *j,
+                       const double *qi_from, const double *qi_to, const double *qj_from,
+                       const double *qj_to, uint8_t *out);
+/* collide(q_i, q_j, i, j): point.jl:14-16, arm22.jl:148-162 */
+int mrmp_collide_static_pairs(mrmp_ctx *ctx, int64_t n, const int32_t *i, const int32_t *j,
+                              const double *qi, const double *qj, uint8_t *out);
+/* collide(Q_from, Q_to) for n_cfg configuration pairs (each N states): point.jl:18-25,
+ * arm22.jl:164-171; callers utils.jl:360 (validate), sssp.jl:207.  first_pair_out (may be
+ * NULL) receives i*N+j of the first colliding pair in the reference's (i asc, j asc)
+ * loop order, or -1. */
+int mrmp_collide_configs(mrmp_ctx *ctx, int64_t n_cfg, const double *Q_from, const double *Q_to,
+                         uint8_t *out, int64_t *first_pair_out);
+/* collide(Q, q_to, i) for n_cand candidate targets of agent i against the static other
+ * agents of Q (N states): point.jl:27-33, arm22.jl:173-209; caller sssp.jl:206. */
+int mrmp_collide_config_moves(mrmp_ctx *ctx, int agent_i, const double *Q, int64_t n_cand,
+                              const double *q_to, uint8_t *out);
+
+/* device-pointer forms (inputs already resident in HBM; asynchronous on `stream`) */
+int mrmp_connect_points_dev(mrmp_ctx *ctx, int64_t n, const int32_t *agent, const double *q,
+                            uint8_t *out, void *stream);
+int mrmp_connect_edges_dev(mrmp_ctx *ctx, int64_t n, const int32_t *agent, const double *q_from,
+                           const double *q_to, uint8_t *out, void *stream);
+int mrmp_collide_pairs_dev(mrmp_ctx *ctx, int64_t n, const int32_t *i, const int32_t *j,
+                           const double *qi_from, const double *qi_to, const double *qj_from,
+                           const double *qj_to, uint8_t *out, void *stream);
+int mrmp_collide_static_pairs_dev(mrmp_ctx *ctx, int64_t n, const int32_t *i, const int32_t *j,
+                                  const double *qi, const double *qj, uint8_t *out,
+                                  void *stream);
+int mrmp_collide_configs_dev(mrmp_ctx *ctx, int64_t n_cfg, const double *Q_from,
+                             const double *Q_to, uint8_t *out, int64_t *first_pair_out,
+                             void *stream);
+int mrmp_collide_config_moves_dev(mrmp_ctx *ctx, int agent_i, const double *Q, int64_t n_cand,
+                                  const double *q_to, uint8_t *out, void *stream);
+
+/* ---- roadmaps (new batched API; the reference builds them one check at a time) --- */
+/* A roadmap set holds, on the device, the node tables and CSR adjacency of `n_agents`
+ * consecutive agents starting at `agent0` (the shard of one GPU), nv_cap vertices each. */
+int mrmp_roadmaps_create(mrmp_ctx *ctx, int agent0, int n_agents, int nv_cap,
+                         mrmp_roadmaps **out);
+void mrmp_roadmaps_destroy(mrmp_roadmaps *rm);
+/* upload node tables: nodes[n_agents][nv][d] (Vector{Node}.q gathered flat by the glue) */
+int mrmp_roadmaps_set_nodes(mrmp_roadmaps *rm, int nv, const double *nodes);
+/* PRM! sampling loop (prm.jl:193-199) on the device: vertex 0 = q_init, 1 = q_goal
+ * (prm.jl:232), then the first nv-2 free samples of the counter-based sampler
+ * (Philox4x32-10, stream (seed, agent)) in try order.  tries_out[n_agents] may be NULL. */
+int mrmp_roadmaps_sample(mrmp_roadmaps *rm, int nv, uint64_t seed, const double *q_init,
+                         const double *q_goal, int64_t *tries_out);
+/* PRM! neighbour pass (prm.jl:202-210) for every agent of the set: directed edges j->k,
+ * j != k, (rad is NaN || dist(q_j,q_k) <= rad) && connect(q_j,q_k,i); rows ascending in k.
+ * rad[n_agents].  Also covers the all-pairs pass of sssp.jl:388-395 (rad = epsilon). */
+int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad);
+int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out);
+int mrmp_roadmaps_get_nodes(mrmp_roadmaps *rm, double *nodes_out);
+/* packed CSR over all rows of all agents: row_ptr[n_agents*nv+1] (offsets into col_idx),
+ * col_idx[nnz] = target vertex id within the same agent.  MRMP_ERR_CAPACITY if
+ * col_cap < nnz (nnz_out is still written so the caller can retry). */
+int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_t *col_idx,
+                          int64_t col_cap, int64_t *nnz_out);
+/* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
+int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
+                              int32_t **row_ptr_dev, int32_t **col_idx_dev, int64_t *nnz_out);
+/* adopt externally filled device arrays (after an all-gather): copies device->device */
+int mrmp_roadmaps_set_nodes_dev(mrmp_roadmaps *rm, int nv, const double *nodes_dev,
+                                void *stream);
+
+/* one-shot host-buffer forms */
+/* PRM! neighbour pass on caller-provided nodes[n_agents][nv][d] (prm.jl:202-210) */
+int mrmp_prm_build(mrmp_ctx *ctx, int agent0, int n_agents, int nv, const double *rad,
+                   const double *nodes, int32_t *row_ptr, int32_t *col_idx, int64_t col_cap,
+                   int64_t *nnz_out);
+/* PRMs(config_init, config_goal, connect, nv; rads) (prm.jl:251-276): sampling + neighbour
+ * pass for agents agent0..agent0+n_agents-1; q_init/q_goal [n_agents][d] */
+int mrmp_prms(mrmp_ctx *ctx, int agent0, int n_agents, int nv, const double *rad, uint64_t seed,
+              const double *q_init, const double *q_goal, double *nodes_out, int32_t *row_ptr,
+              int32_t *col_idx, int64_t col_cap, int64_t *nnz_out);
+
+/* collide(6-arity) over roadmap edges by id: check k tests agent i[k]'s edge
+ * (vi_from[k] -> vi_to[k]) against agent j[k]'s edge (vj_from[k] -> vj_to[k]); agent ids are
+ * global, vertices are looked up in `rm` (which must hold both agents).  Callers:
+ * pp.jl:179-189, cbs.jl:336-347,384-409, smoother.jl:86-103. */
+int mrmp_collide_edges_indexed(mrmp_roadmaps *rm, int64_t n, const int32_t *i, const int32_t *j,
+                               const int32_t *vi_from, const int32_t *vi_to,
+                               const int32_t *vj_from, const int32_t *vj_to, uint8_t *out);
+int mrmp_collide_edges_indexed_dev(mrmp_roadmaps *rm, int64_t n, const int32_t *i,
+                                   const int32_t *j, const int32_t *vi_from,
+                                   const int32_t *vi_to, const int32_t *vj_from,
+                                   const int32_t *vj_to, uint8_t *out, void *stream);
+
+/* sampler: gen_uniform_sampling (point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218)
+ * restated on a counter-based generator; writes try t0..t0+n-1 of (seed, agent) */
+int mrmp_sample_states(mrmp_ctx *ctx, int agent, uint64_t seed, uint64_t t0, int64_t n,
+                       double *q_out);
+/* first n_wanted free samples in try order; *n_tried_out = tries consumed */
+int mrmp_sample_free(mrmp_ctx *ctx, int agent, uint64_t seed, int64_t n_wanted, double *q_out,
+                     int64_t *n_tried_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRMP_B200_H */

@@ -1,0 +1,17 @@
+"""sssp_b200 -- B200-native connect / collide / roadmap hot path of Kei18/sssp (MRMP.jl).
+
+Host-side mirror of the reference's closure API (gen_connect / gen_collide /
+gen_check_goal, src/MRMP.jl:98) on top of the C-ABI CUDA library
+(include/mrmp_b200.h).  There is no CPU fallback.
+"""
+from .lib import MRMPError, MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22  # noqa: F401
+from .closures import (  # noqa: F401
+    StatePoint2D, StatePoint3D, StateArm22, CircleObstacle2D, CircleObstacle3D, Node,
+    Context, Roadmaps, gen_connect, gen_collide, gen_check_goal, PRMs,
+)
+
+__all__ = [
+    "MRMPError", "MODEL_POINT2D", "MODEL_POINT3D", "MODEL_ARM22",
+    "StatePoint2D", "StatePoint3D", "StateArm22", "CircleObstacle2D", "CircleObstacle3D", "Node",
+    "Context", "Roadmaps", "gen_connect", "gen_collide", "gen_check_goal", "PRMs",
+]

@@ -1,0 +1,402 @@
+"""Host-side mirror of the reference's closure API on top of the C ABI.
+
+Reference surface (Kei18/sssp, paths under /root/reference):
+  gen_connect(q, obstacles, ins_params...; step_dist, max_dist, safety_dist) -> f
+      f(q, i), f(q_from, q_to, i)                 point2d.jl:42-69, point3d.jl:47-80, arm22.jl:29-88
+  gen_collide(q, ins_params...; step_dist, safety_dist) -> f
+      f(qi_from, qi_to, qj_from, qj_to, i, j), f(q_i, q_j, i, j),
+      f(Q_from, Q_to), f(Q, q_to, i)              point.jl:5-36, arm22.jl:90-212
+  gen_check_goal(config_goal; goal_rad, goal_rads) -> f     utils.jl:117-138
+  PRMs(config_init, config_goal, connect, num_vertices; rad, rads)   prm.jl:251-276
+
+Differences from Julia, all mechanical: agent indices and vertex ids are 0-based here;
+methods that Julia selects by arity/type are selected the same way (argument count and
+whether the first argument is a configuration); every closure additionally exposes
+batched entry points (`.points`, `.edges`, `.pairs`, ...) which are the new API surface
+the GPU path adds.  All verdicts come from the CUDA library -- no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, NamedTuple, Optional, Sequence
+
+import numpy as np
+
+from . import lib as L
+
+STEP_DIST = 0.01         # src/MRMP.jl:65
+SAFETY_DIST_LINE = 0.01  # src/MRMP.jl:66
+
+
+class StatePoint2D(NamedTuple):  # src/models/point2d.jl:3-6
+    x: float
+    y: float
+
+
+class StatePoint3D(NamedTuple):  # src/models/point3d.jl:3-7
+    x: float
+    y: float
+    z: float
+
+
+class StateArm22(NamedTuple):  # src/models/arm22.jl:3-6
+    theta1: float
+    theta2: float
+
+
+class CircleObstacle2D(NamedTuple):  # src/obstacle.jl:7-11
+    x: float
+    y: float
+    r: float
+
+
+class CircleObstacle3D(NamedTuple):  # src/obstacle.jl:14-19
+    x: float
+    y: float
+    z: float
+    r: float
+
+
+@dataclass
+class Node:  # src/MRMP.jl:73-77
+    q: tuple
+    id: int
+    neighbors: List[int] = field(default_factory=list)
+
+
+_MODEL_OF = {StatePoint2D: L.MODEL_POINT2D, StatePoint3D: L.MODEL_POINT3D,
+             StateArm22: L.MODEL_ARM22}
+_STATE_OF = {L.MODEL_POINT2D: StatePoint2D, L.MODEL_POINT3D: StatePoint3D,
+             L.MODEL_ARM22: StateArm22}
+
+
+def _model_of(q) -> int:
+    for t, m in _MODEL_OF.items():
+        if isinstance(q, t) or q is t:
+            return m
+    raise TypeError(f"unsupported state type {type(q).__name__}")
+
+
+def _states(qs, d: int) -> np.ndarray:
+    """Vector{State} / Vector{Node} / ndarray -> contiguous float64 [n][d]."""
+    if isinstance(qs, np.ndarray):
+        return L.f64(qs).reshape(-1, d)
+    rows = [(q.q if isinstance(q, Node) else q) for q in qs]
+    return L.f64(rows).reshape(-1, d)
+
+
+class Context:
+    """One problem instance on one GPU (wraps mrmp_ctx)."""
+
+    def __init__(self, model: int, rads, obstacles=(), base_pos=None, step_dist=STEP_DIST,
+                 safety_dist=SAFETY_DIST_LINE, max_dist: Optional[float] = None, device: int = 0):
+        self.model = int(model)
+        self.d = L.STATE_DIM[self.model]
+        self.rads = L.f64(rads).ravel()
+        self.N = int(self.rads.size)
+        obs = L.f64([tuple(o) for o in obstacles] if not isinstance(obstacles, np.ndarray)
+                    else obstacles).reshape(-1, self.d + 1)
+        self.obstacles = obs
+        base = None if base_pos is None else L.f64(base_pos).reshape(self.N, 2)
+        self.base_pos = base
+        self.device = int(device)
+        self._lib = L.load()
+        h = C.c_void_p()
+        L.check(self._lib.mrmp_ctx_create(
+            C.byref(h), self.model, self.N, L.ptr(self.rads, L._dp),
+            L.ptr(base, L._dp) if base is not None else None, None, obs.shape[0],
+            L.ptr(obs, L._dp) if obs.size else None, float(step_dist), float(safety_dist),
+            math.nan if max_dist is None else float(max_dist), self.device))
+        self._h = h
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mrmp_ctx_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- batched host-buffer entry points (numpy in / numpy out) ---------------------
+    def connect_points(self, agent, q) -> np.ndarray:
+        agent, q = L.i32(agent).ravel(), _states(q, self.d)
+        out = np.empty(agent.size, np.uint8)
+        L.check(self._lib.mrmp_connect_points(self._h, agent.size, L.ptr(agent, L._ip),
+                                              L.ptr(q, L._dp), L.ptr(out, L._bp)))
+        return out
+
+    def connect_edges(self, agent, q_from, q_to) -> np.ndarray:
+        agent = L.i32(agent).ravel()
+        qf, qt = _states(q_from, self.d), _states(q_to, self.d)
+        out = np.empty(agent.size, np.uint8)
+        L.check(self._lib.mrmp_connect_edges(self._h, agent.size, L.ptr(agent, L._ip),
+                                             L.ptr(qf, L._dp), L.ptr(qt, L._dp),
+                                             L.ptr(out, L._bp)))
+        return out
+
+    def collide_pairs(self, i, j, qi_from, qi_to, qj_from, qj_to) -> np.ndarray:
+        i, j = L.i32(i).ravel(), L.i32(j).ravel()
+        a, b, c, d = (_states(x, self.d) for x in (qi_from, qi_to, qj_from, qj_to))
+        out = np.empty(i.size, np.uint8)
+        L.check(self._lib.mrmp_collide_pairs(self._h, i.size, L.ptr(i, L._ip), L.ptr(j, L._ip),
+                                             L.ptr(a, L._dp), L.ptr(b, L._dp), L.ptr(c, L._dp),
+                                             L.ptr(d, L._dp), L.ptr(out, L._bp)))
+        return out
+
+    def collide_static_pairs(self, i, j, qi, qj) -> np.ndarray:
+        i, j = L.i32(i).ravel(), L.i32(j).ravel()
+        a, b = _states(qi, self.d), _states(qj, self.d)
+        out = np.empty(i.size, np.uint8)
+        L.check(self._lib.mrmp_collide_static_pairs(self._h, i.size, L.ptr(i, L._ip),
+                                                    L.ptr(j, L._ip), L.ptr(a, L._dp),
+                                                    L.ptr(b, L._dp), L.ptr(out, L._bp)))
+        return out
+
+    def collide_configs(self, Q_from, Q_to):
+        """n_cfg x N states each -> (verdict[n_cfg], first_pair[n_cfg] = i*N+j or -1)"""
+        a, b = L.f64(Q_from).reshape(-1, self.N, self.d), L.f64(Q_to).reshape(-1, self.N, self.d)
+        n = a.shape[0]
+        out = np.empty(n, np.uint8)
+        fp = np.empty(n, np.int64)
+        L.check(self._lib.mrmp_collide_configs(self._h, n, L.ptr(a, L._dp), L.ptr(b, L._dp),
+                                               L.ptr(out, L._bp), L.ptr(fp, L._lp)))
+        return out, fp
+
+    def collide_config_moves(self, agent_i: int, Q, q_to) -> np.ndarray:
+        Q, q_to = _states(Q, self.d), _states(q_to, self.d)
+        out = np.empty(q_to.shape[0], np.uint8)
+        L.check(self._lib.mrmp_collide_config_moves(self._h, int(agent_i), L.ptr(Q, L._dp),
+                                                    q_to.shape[0], L.ptr(q_to, L._dp),
+                                                    L.ptr(out, L._bp)))
+        return out
+
+    def sample_states(self, agent: int, seed: int, t0: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.d))
+        L.check(self._lib.mrmp_sample_states(self._h, int(agent), int(seed), int(t0), int(n),
+                                             L.ptr(out, L._dp)))
+        return out
+
+    def sample_free(self, agent: int, seed: int, n_wanted: int):
+        out = np.empty((n_wanted, self.d))
+        tried = C.c_int64(-1)
+        L.check(self._lib.mrmp_sample_free(self._h, int(agent), int(seed), int(n_wanted),
+                                           L.ptr(out, L._dp), C.byref(tried)))
+        return out, int(tried.value)
+
+    def prm_build(self, nodes, rad, agent0: int = 0):
+        """nodes [n][nv][d], rad scalar/array/None -> (row_ptr [n*nv+1], col_idx [nnz])"""
+        nodes = L.f64(nodes)
+        n, nv = nodes.shape[0], nodes.shape[1]
+        radv = np.broadcast_to(L.f64(math.nan if rad is None else rad), (n,)).copy()
+        row_ptr = np.empty(n * nv + 1, np.int32)
+        cap = max(1, n * nv * 64)
+        nnz = C.c_int64(0)
+        while True:
+            col = np.empty(cap, np.int32)
+            rc = self._lib.mrmp_prm_build(self._h, int(agent0), n, nv, L.ptr(radv, L._dp),
+                                          L.ptr(nodes, L._dp), L.ptr(row_ptr, L._ip),
+                                          L.ptr(col, L._ip), cap, C.byref(nnz))
+            if rc == L.ERR_CAPACITY and nnz.value > cap:
+                cap = int(nnz.value)
+                continue
+            L.check(rc)
+            return row_ptr, col[: nnz.value].copy()
+
+
+class Roadmaps:
+    """Device-resident roadmaps of agents [agent0, agent0+n) (wraps mrmp_roadmaps)."""
+
+    def __init__(self, ctx: Context, agent0: int, n_agents: int, nv_cap: int):
+        self.ctx, self.agent0, self.n, self.nv_cap = ctx, int(agent0), int(n_agents), int(nv_cap)
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        L.check(self._lib.mrmp_roadmaps_create(ctx._h, self.agent0, self.n, self.nv_cap,
+                                               C.byref(h)))
+        self._h = h
+        self.nv = 0
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mrmp_roadmaps_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_nodes(self, nodes) -> None:
+        nodes = L.f64(nodes).reshape(self.n, -1, self.ctx.d)
+        self.nv = nodes.shape[1]
+        L.check(self._lib.mrmp_roadmaps_set_nodes(self._h, self.nv, L.ptr(nodes, L._dp)))
+
+    def sample(self, nv: int, seed: int, q_init, q_goal) -> np.ndarray:
+        qi, qg = _states(q_init, self.ctx.d), _states(q_goal, self.ctx.d)
+        tries = np.empty(self.n, np.int64)
+        L.check(self._lib.mrmp_roadmaps_sample(self._h, int(nv), int(seed), L.ptr(qi, L._dp),
+                                               L.ptr(qg, L._dp), L.ptr(tries, L._lp)))
+        self.nv = int(nv)
+        return tries
+
+    def build(self, rad) -> int:
+        radv = np.broadcast_to(L.f64(math.nan if rad is None else rad), (self.n,)).copy()
+        L.check(self._lib.mrmp_roadmaps_build(self._h, L.ptr(radv, L._dp)))
+        nnz = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_nnz(self._h, C.byref(nnz)))
+        return int(nnz.value)
+
+    def nodes(self) -> np.ndarray:
+        out = np.empty((self.n, self.nv, self.ctx.d))
+        L.check(self._lib.mrmp_roadmaps_get_nodes(self._h, L.ptr(out, L._dp)))
+        return out
+
+    def csr(self):
+        nnz = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_nnz(self._h, C.byref(nnz)))
+        row_ptr = np.empty(self.n * self.nv + 1, np.int32)
+        col = np.empty(max(1, nnz.value), np.int32)
+        L.check(self._lib.mrmp_roadmaps_get_csr(self._h, L.ptr(row_ptr, L._ip), L.ptr(col, L._ip),
+                                                col.size, C.byref(nnz)))
+        return row_ptr, col[: nnz.value]
+
+    def device_ptrs(self):
+        nv = C.c_int(0)
+        nodes, rp, ci = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_device_ptrs(self._h, C.byref(nv), C.byref(nodes),
+                                                    C.byref(rp), C.byref(ci), C.byref(nnz)))
+        return dict(nv=nv.value, nodes=nodes.value, row_ptr=rp.value, col_idx=ci.value,
+                    nnz=nnz.value)
+
+    def collide_edges_indexed(self, i, j, vi_from, vi_to, vj_from, vj_to) -> np.ndarray:
+        a = [L.i32(x).ravel() for x in (i, j, vi_from, vi_to, vj_from, vj_to)]
+        out = np.empty(a[0].size, np.uint8)
+        L.check(self._lib.mrmp_collide_edges_indexed(self._h, a[0].size,
+                                                     *[L.ptr(x, L._ip) for x in a],
+                                                     L.ptr(out, L._bp)))
+        return out
+
+    def to_nodes(self) -> List[List[Node]]:
+        """Vector{Vector{Node}} as the reference's PRMs returns it (0-based ids)."""
+        tabs = self.nodes()
+        row_ptr, col = self.csr()
+        State = _STATE_OF[self.ctx.model]
+        res = []
+        for a in range(self.n):
+            rm = []
+            for v in range(self.nv):
+                r = a * self.nv + v
+                rm.append(Node(State(*tabs[a, v]), v, col[row_ptr[r]: row_ptr[r + 1]].tolist()))
+            res.append(rm)
+        return res
+
+
+# ---------------------------------------------------------------------------------------
+# closure constructors
+# ---------------------------------------------------------------------------------------
+def _split_ins_params(model: int, ins_params):
+    if model == L.MODEL_ARM22:  # (positions, rads)  arm22.jl:29-37
+        positions, rads = ins_params
+        return L.f64(rads).ravel(), L.f64(positions).reshape(-1, 2)
+    (rads,) = ins_params        # (rads,)  point2d.jl:42-46
+    return L.f64(rads).ravel(), None
+
+
+def gen_connect(q, obstacles, *ins_params, step_dist: float = STEP_DIST,
+                max_dist: Optional[float] = None, safety_dist: float = SAFETY_DIST_LINE,
+                device: int = 0):
+    """gen_connect(q, obstacles, ins_params...) -> f;  f(q, i) / f(q_from, q_to, i)."""
+    model = _model_of(q)
+    rads, base = _split_ins_params(model, ins_params)
+    ctx = Context(model, rads, obstacles, base, step_dist, safety_dist, max_dist, device)
+
+    def f(*args) -> bool:
+        if len(args) == 2:    # f(q, i)
+            return bool(ctx.connect_points([args[1]], [args[0]])[0])
+        if len(args) == 3:    # f(q_from, q_to, i)
+            return bool(ctx.connect_edges([args[2]], [args[0]], [args[1]])[0])
+        raise TypeError("connect takes (q, i) or (q_from, q_to, i)")
+
+    f.ctx = ctx
+    f.points = ctx.connect_points   # batched f(q, i)
+    f.edges = ctx.connect_edges     # batched f(q_from, q_to, i)
+    return f
+
+
+def gen_collide(q, *ins_params, step_dist: float = STEP_DIST,
+                safety_dist: float = SAFETY_DIST_LINE, device: int = 0):
+    """gen_collide(q, ins_params...) -> f with the reference's four methods."""
+    model = _model_of(q)
+    rads, base = _split_ins_params(model, ins_params)
+    ctx = Context(model, rads, (), base, step_dist, safety_dist, None, device)
+    State = _STATE_OF[model]
+
+    def _is_config(x) -> bool:
+        return (isinstance(x, (list, tuple, np.ndarray)) and not isinstance(x, State)
+                and len(x) > 0 and isinstance(x[0], (Node, State, tuple, list, np.ndarray)))
+
+    def f(*args) -> bool:
+        if len(args) == 6:    # f(qi_from, qi_to, qj_from, qj_to, i, j)
+            a, b, c, d, i, j = args
+            return bool(ctx.collide_pairs([i], [j], [a], [b], [c], [d])[0])
+        if len(args) == 4:    # f(q_i, q_j, i, j)
+            a, b, i, j = args
+            return bool(ctx.collide_static_pairs([i], [j], [a], [b])[0])
+        if len(args) == 2 and _is_config(args[0]):   # f(Q_from, Q_to)
+            v, _ = ctx.collide_configs(_states(args[0], ctx.d), _states(args[1], ctx.d))
+            return bool(v[0])
+        if len(args) == 3 and _is_config(args[0]):   # f(Q, q_to, i)
+            return bool(ctx.collide_config_moves(args[2], args[0], [args[1]])[0])
+        raise TypeError("no collide method matches the arguments")
+
+    f.ctx = ctx
+    f.pairs = ctx.collide_pairs
+    f.static_pairs = ctx.collide_static_pairs
+    f.configs = ctx.collide_configs
+    f.config_moves = ctx.collide_config_moves
+    return f
+
+
+def gen_check_goal(config_goal: Sequence, goal_rad: float = 0.0,
+                   goal_rads: Optional[Sequence[float]] = None, dist=None):
+    """utils.jl:117-138.  O(N) host logic (stays on the host in the reference design too:
+    SURVEY 8(b)); `dist` is the model's state distance (defaults to Euclidean, exact for the
+    default goal_rad = 0 equality test of every model)."""
+    N = len(config_goal)
+    rads = list(goal_rads) if goal_rads is not None else [goal_rad] * N
+
+    def _d(a, b):
+        if dist is not None:
+            return dist(a, b)
+        return math.sqrt(sum((x - y) * (x - y) for x, y in zip(a, b)))
+
+    def _q(v):
+        return v.q if isinstance(v, Node) else v
+
+    def f(*args) -> bool:
+        if len(args) == 1:   # f(C) / f(Q)
+            return all(_d(_q(args[0][i]), config_goal[i]) <= rads[i] for i in range(N))
+        v, i = args          # f(v, i)
+        return _d(_q(v), config_goal[i]) <= rads[i]
+
+    return f
+
+
+def PRMs(config_init, config_goal, connect, num_vertices: int = 100, *, rad=None, rads=None,
+         seed: int = 0) -> List[List[Node]]:
+    """prm.jl:251-276 on the GPU: sampling (counter-based stream `seed`) + neighbour pass for
+    every agent in one batched call.  `connect` must come from gen_connect()."""
+    ctx: Context = connect.ctx
+    N = len(config_init)
+    rm = Roadmaps(ctx, 0, N, max(2, num_vertices))
+    rm.sample(num_vertices, seed, config_init, config_goal)
+    rm.build(rads if rads is not None else rad)
+    out = rm.to_nodes()
+    rm.close()
+    return out

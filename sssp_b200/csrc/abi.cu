@@ -1,0 +1,987 @@
+// abi.cu -- the C ABI (include/mrmp_b200.h): contexts, host<->device plumbing, roadmaps.
+// Host-side C++ only orchestrates; all arithmetic of the hot path runs in the kernels.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/mrmp_b200.h"
+#include "mrmp_internal.cuh"
+
+using namespace mrmp;
+
+// ------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+namespace mrmp {
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace mrmp
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(expr)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(MRMP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+extern "C" const char *mrmp_last_error(void) { return g_err; }
+extern "C" const char *mrmp_version(void) { return "mrmp_b200 0.1 (sm_100a, fp64)"; }
+extern "C" int64_t mrmp_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int mrmp_device_count(int *n_out) {
+    if (!n_out) return fail(MRMP_ERR_INVALID, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *n_out = 0;
+        return fail(MRMP_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n_out = n;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_host_alloc(void **ptr_out, int64_t bytes) {
+    if (!ptr_out || bytes < 0) return fail(MRMP_ERR_INVALID, "bad arguments");
+    CU(cudaHostAlloc(ptr_out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return MRMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact squared-threshold helpers (see geom.cuh header comment)
+// ------------------------------------------------------------------------------------------
+// min{ s : RN(sqrt(s)) >= thr }: then  sqrt(s) < thr  <=>  s < T2  for every double s >= 0.
+static double sq_lt_threshold(double thr) {
+    if (!(thr > 0.0)) return 0.0;  // dist < thr never holds for thr <= 0 or NaN
+    if (isinf(thr)) return INFINITY;
+    double s = thr * thr;
+    while (s > 0.0 && sqrt(s) >= thr) s = nextafter(s, -INFINITY);
+    while (sqrt(s) < thr) s = nextafter(s, INFINITY);
+    return s;
+}
+// max{ s : RN(sqrt(s)) <= rad }: then  sqrt(s) <= rad  <=>  s <= R2.
+static double sq_le_threshold(double rad) {
+    if (isnan(rad)) return NAN;
+    if (rad < 0.0) return -1.0;
+    if (isinf(rad)) return INFINITY;
+    double s = rad * rad;
+    while (sqrt(s) <= rad) s = nextafter(s, INFINITY);
+    while (s > 0.0 && sqrt(s) > rad) s = nextafter(s, -INFINITY);
+    return s;
+}
+// min{ s : RN(sqrt(s)) > thr }: then  sqrt(s) > thr  <=>  s >= G2.  (unused helper kept tiny)
+
+static const double kFilterPad = 9.5367431640625e-07;  // 2^-20, absolute slack of the broad phase
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static const int kSlots = 3;
+static const int64_t kChunk = 1 << 20;     // checks per pipeline chunk
+static const int64_t kSmallBatch = 1 << 16;  // single-stream fast path below this
+
+struct mrmp_ctx {
+    int device = 0;
+    int model = 0, d = 2, n_agents = 0, n_obs = 0;
+    int sm_count = 148;
+    CtxView cv{};
+    double *blob = nullptr;
+    std::vector<double> h_rads;
+    cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[kSlots]{}, ev_k[kSlots]{}, ev_out[kSlots]{};
+    // chunk slots (device) and small-batch staging (pinned host + device)
+    unsigned char *slot_buf[kSlots]{};
+    size_t slot_bytes = 0;
+    unsigned char *small_h = nullptr, *small_d = nullptr;
+    size_t small_bytes = 0;
+};
+
+static inline int pad2(int n) { return (n + 1) & ~1; }
+
+static int ensure_small(mrmp_ctx *c, size_t bytes) {
+    if (bytes <= c->small_bytes) return MRMP_OK;
+    size_t nb = c->small_bytes ? c->small_bytes : (1 << 16);
+    while (nb < bytes) nb *= 2;
+    if (c->small_h) CU(cudaFreeHost(c->small_h));
+    if (c->small_d) CU(cudaFree(c->small_d));
+    c->small_h = c->small_d = nullptr;
+    c->small_bytes = 0;
+    CU(cudaHostAlloc((void **)&c->small_h, nb, cudaHostAllocDefault));
+    CU(cudaMalloc((void **)&c->small_d, nb));
+    c->small_bytes = nb;
+    return MRMP_OK;
+}
+
+static int ensure_slots(mrmp_ctx *c, size_t bytes) {
+    if (bytes <= c->slot_bytes) return MRMP_OK;
+    for (int s = 0; s < kSlots; ++s) {
+        if (c->slot_buf[s]) CU(cudaFree(c->slot_buf[s]));
+        c->slot_buf[s] = nullptr;
+    }
+    c->slot_bytes = 0;
+    for (int s = 0; s < kSlots; ++s) CU(cudaMalloc((void **)&c->slot_buf[s], bytes));
+    c->slot_bytes = bytes;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const double *rads,
+                               const double *base_pos, const double *aux, int n_obs,
+                               const double *obstacles_aos, double step_dist,
+                               double safety_dist, double max_dist, int device) {
+    (void)aux;
+    if (!out) return fail(MRMP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (model < 0 || model > 2) return fail(MRMP_ERR_INVALID, "unknown model %d", model);
+    if (n_agents <= 0 || !rads) return fail(MRMP_ERR_INVALID, "need n_agents > 0 and rads");
+    if (n_obs < 0 || (n_obs > 0 && !obstacles_aos))
+        return fail(MRMP_ERR_INVALID, "need obstacles_aos for n_obs > 0");
+    if (model == MRMP_MODEL_ARM22 && !base_pos)
+        return fail(MRMP_ERR_INVALID, "arm22 needs base_pos (positions)");
+    if ((int64_t)n_agents * (n_obs > 0 ? n_obs : 1) > (int64_t)1 << 24)
+        return fail(MRMP_ERR_UNSUPPORTED, "n_agents * n_obs too large");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0)
+        return fail(MRMP_ERR_CUDA, "no CUDA device (%s); mrmp_b200 has no CPU fallback",
+                    e0 != cudaSuccess ? cudaGetErrorString(e0) : "0 devices");
+    if (device < 0 || device >= ndev)
+        return fail(MRMP_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    mrmp_ctx *c = new (std::nothrow) mrmp_ctx();
+    if (!c) return fail(MRMP_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->model = model;
+    c->d = model == MRMP_MODEL_POINT3D ? 3 : 2;
+    const int wd = c->d;  // workspace dimension of obstacle centres (2 for arm22 as well)
+    c->n_agents = n_agents;
+    c->n_obs = n_obs;
+    c->h_rads.assign(rads, rads + n_agents);
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+
+    const int N = n_agents, M = n_obs;
+    const int mp = pad2(M > 0 ? M : 1), np = pad2(N);
+    const bool arm = model == MRMP_MODEL_ARM22;
+    const int n_thr_rows = arm ? 1 : N;  // arm22 compares with o.r alone (arm22.jl:46,77)
+    const bool pair_tab = !arm && N <= 1024;
+
+    std::vector<double> h;
+    auto section = [&](size_t len) {
+        size_t off = h.size();
+        h.resize(off + ((len + 1) & ~(size_t)1), 0.0);
+        return (int)off;
+    };
+    CtxView &cv = c->cv;
+    cv.model = model;
+    cv.d = c->d;
+    cv.n_agents = N;
+    cv.n_obs = M;
+    cv.mp = mp;
+    cv.np = np;
+    // ---- connect segment
+    cv.con_off = 0;
+    cv.obs_off = section((size_t)(wd + 1) * mp);
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k <= wd; ++k) h[cv.obs_off + k * mp + m] = obstacles_aos[(wd + 1) * m + k];
+    for (int m = M; m < mp; ++m) {  // padding obstacles: far away, zero radius
+        for (int k = 0; k < wd; ++k) h[cv.obs_off + k * mp + m] = 1.0e300;
+        h[cv.obs_off + wd * mp + m] = 0.0;
+    }
+    cv.rads_off = section(np);
+    for (int i = 0; i < N; ++i) h[cv.rads_off + i] = rads[i];
+    cv.base_off = section(arm ? 2 * np : 0);
+    if (arm)
+        for (int i = 0; i < 2 * N; ++i) h[cv.base_off + i] = base_pos[i];
+    cv.t2_obs_off = section((size_t)n_thr_rows * mp);
+    cv.g_obs_off = section((size_t)n_thr_rows * mp);
+    for (int i = 0; i < n_thr_rows; ++i)
+        for (int m = 0; m < mp; ++m) {
+            const double orad = h[cv.obs_off + wd * mp + m];
+            const double thr = arm ? orad : orad + rads[i];  // o.r + rads[i]  point2d.jl:54,63
+            h[cv.t2_obs_off + i * mp + m] = m < M ? sq_lt_threshold(thr) : 0.0;
+            const double tp = (thr > 0 ? thr : 0.0) + kFilterPad;
+            h[cv.g_obs_off + i * mp + m] = 2.0 * tp * tp * (1.0 + 1e-9);
+        }
+    cv.con_len = (int)h.size() - cv.con_off;
+    // ---- collide segment
+    cv.col_off = (int)h.size();
+    cv.crads_off = section(np);
+    for (int i = 0; i < N; ++i) h[cv.crads_off + i] = rads[i];
+    cv.cbase_off = section(arm ? 2 * np : 0);
+    if (arm)
+        for (int i = 0; i < 2 * N; ++i) h[cv.cbase_off + i] = base_pos[i];
+    cv.has_pair_tab = pair_tab ? 1 : 0;
+    cv.t2_pair_off = section(pair_tab ? (size_t)N * N : 0);
+    cv.g_pair_off = section(pair_tab ? (size_t)N * N : 0);
+    if (pair_tab)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                const double thr = rads[i] + rads[j];  // point.jl:11,15,30
+                h[cv.t2_pair_off + i * N + j] = sq_lt_threshold(thr);
+                const double tp = (thr > 0 ? thr : 0.0) + kFilterPad;
+                h[cv.g_pair_off + i * N + j] = 3.0 * tp * tp * (1.0 + 1e-9);
+            }
+    cv.col_len = (int)h.size() - cv.col_off;
+    cv.step_dist = step_dist;
+    cv.safety_dist = safety_dist;
+    cv.max_dist = max_dist;
+    cv.safety_t2 = sq_lt_threshold(safety_dist);
+
+    cudaError_t e = cudaMalloc((void **)&c->blob, h.size() * sizeof(double));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(c->blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
+        e = cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_k[s], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[s], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        mrmp_ctx_destroy(c);
+        return fail(MRMP_ERR_CUDA, "ctx setup: %s", cudaGetErrorString(e));
+    }
+    cv.blob = c->blob;
+    *out = c;
+    return MRMP_OK;
+}
+
+extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_k) cudaStreamSynchronize(c->s_k);
+    for (int s = 0; s < kSlots; ++s) {
+        if (c->ev_in[s]) cudaEventDestroy(c->ev_in[s]);
+        if (c->ev_k[s]) cudaEventDestroy(c->ev_k[s]);
+        if (c->ev_out[s]) cudaEventDestroy(c->ev_out[s]);
+        if (c->slot_buf[s]) cudaFree(c->slot_buf[s]);
+    }
+    if (c->small_h) cudaFreeHost(c->small_h);
+    if (c->small_d) cudaFree(c->small_d);
+    if (c->s_k) cudaStreamDestroy(c->s_k);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->blob) cudaFree(c->blob);
+    delete c;
+}
+
+extern "C" int mrmp_ctx_state_dim(const mrmp_ctx *c) { return c ? c->d : 0; }
+
+extern "C" int mrmp_ctx_sync(mrmp_ctx *c) {
+    if (!c) return fail(MRMP_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_in));
+    CU(cudaStreamSynchronize(c->s_k));
+    CU(cudaStreamSynchronize(c->s_out));
+    return MRMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer batches: small single-stream path, chunked 3-stream pipeline for large n
+// ------------------------------------------------------------------------------------------
+struct Arr {
+    const void *in;  // host source (inputs) or NULL
+    void *out;       // host destination (outputs) or NULL
+    size_t stride;   // bytes per check
+};
+
+static inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// launch(dev_ptrs[], n_chunk, stream) -> cudaError_t
+template <class F>
+static int run_batch(mrmp_ctx *c, int64_t n, std::vector<Arr> &arrs, F launch) {
+    CU(cudaSetDevice(c->device));
+    const size_t na = arrs.size();
+    std::vector<void *> dptr(na);
+    if (n <= kSmallBatch) {
+        // pack everything into one pinned buffer: one H2D, one kernel, one D2H
+        std::vector<size_t> off(na);
+        size_t in_bytes = 0, tot = 0;
+        for (size_t a = 0; a < na; ++a)
+            if (arrs[a].in) {
+                off[a] = tot;
+                tot += align16(arrs[a].stride * (size_t)n);
+            }
+        in_bytes = tot;
+        for (size_t a = 0; a < na; ++a)
+            if (arrs[a].out) {
+                off[a] = tot;
+                tot += align16(arrs[a].stride * (size_t)n);
+            }
+        int rc = ensure_small(c, tot);
+        if (rc) return rc;
+        for (size_t a = 0; a < na; ++a) {
+            dptr[a] = c->small_d + off[a];
+            if (arrs[a].in) memcpy(c->small_h + off[a], arrs[a].in, arrs[a].stride * (size_t)n);
+        }
+        if (in_bytes)
+            CU(cudaMemcpyAsync(c->small_d, c->small_h, in_bytes, cudaMemcpyHostToDevice, c->s_k));
+        CU(launch(dptr.data(), n, c->s_k));
+        if (tot > in_bytes)
+            CU(cudaMemcpyAsync(c->small_h + in_bytes, c->small_d + in_bytes, tot - in_bytes,
+                               cudaMemcpyDeviceToHost, c->s_k));
+        CU(cudaStreamSynchronize(c->s_k));
+        for (size_t a = 0; a < na; ++a)
+            if (arrs[a].out) memcpy(arrs[a].out, c->small_h + off[a], arrs[a].stride * (size_t)n);
+        return MRMP_OK;
+    }
+    // chunked pipeline
+    std::vector<size_t> off(na);
+    size_t tot = 0;
+    for (size_t a = 0; a < na; ++a) {
+        off[a] = tot;
+        tot += align16(arrs[a].stride * (size_t)kChunk);
+    }
+    int rc = ensure_slots(c, tot);
+    if (rc) return rc;
+    int64_t done = 0;
+    for (int64_t ch = 0; done < n; ++ch) {
+        const int s = (int)(ch % kSlots);
+        const int64_t len = n - done < kChunk ? n - done : kChunk;
+        if (ch >= kSlots) {
+            CU(cudaStreamWaitEvent(c->s_in, c->ev_k[s], 0));   // inputs of this slot consumed
+            CU(cudaStreamWaitEvent(c->s_k, c->ev_out[s], 0));  // outputs of this slot drained
+        }
+        for (size_t a = 0; a < na; ++a) {
+            dptr[a] = c->slot_buf[s] + off[a];
+            if (arrs[a].in)
+                CU(cudaMemcpyAsync(dptr[a], (const char *)arrs[a].in + arrs[a].stride * (size_t)done,
+                                   arrs[a].stride * (size_t)len, cudaMemcpyHostToDevice, c->s_in));
+        }
+        CU(cudaEventRecord(c->ev_in[s], c->s_in));
+        CU(cudaStreamWaitEvent(c->s_k, c->ev_in[s], 0));
+        CU(launch(dptr.data(), len, c->s_k));
+        CU(cudaEventRecord(c->ev_k[s], c->s_k));
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_k[s], 0));
+        for (size_t a = 0; a < na; ++a)
+            if (arrs[a].out)
+                CU(cudaMemcpyAsync((char *)arrs[a].out + arrs[a].stride * (size_t)done, dptr[a],
+                                   arrs[a].stride * (size_t)len, cudaMemcpyDeviceToHost, c->s_out));
+        CU(cudaEventRecord(c->ev_out[s], c->s_out));
+        done += len;
+    }
+    CU(cudaStreamSynchronize(c->s_out));
+    CU(cudaStreamSynchronize(c->s_k));
+    return MRMP_OK;
+}
+
+static inline LaunchCfg lcfg(const mrmp_ctx *c, cudaStream_t s) { return LaunchCfg{c->sm_count, s}; }
+
+#define NEED(cond, msg) \
+    if (!(cond)) return fail(MRMP_ERR_INVALID, msg)
+
+static int check_agents_host(const mrmp_ctx *c, int64_t n, const int32_t *a) {
+    for (int64_t k = 0; k < n; ++k)
+        if ((unsigned)a[k] >= (unsigned)c->n_agents)
+            return fail(MRMP_ERR_INVALID, "agent index %d out of range at %lld", a[k], (long long)k);
+    return MRMP_OK;
+}
+
+static inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// ---- connect ---------------------------------------------------------------------------------
+extern "C" int mrmp_connect_points(mrmp_ctx *c, int64_t n, const int32_t *agent, const double *q,
+                                   uint8_t *out) {
+    NEED(c && n >= 0, "bad ctx / n");
+    if (n == 0) return MRMP_OK;
+    NEED(agent && q && out, "NULL buffer");
+    int rc = check_agents_host(c, n, agent);
+    if (rc) return rc;
+    const size_t sb = sizeof(double) * c->d;
+    std::vector<Arr> arrs = {{agent, nullptr, 4}, {q, nullptr, sb}, {nullptr, out, 1}};
+    return run_batch(c, n, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_connect_points(c->cv, lcfg(c, s), len, (const int32_t *)d[0],
+                                     (const double *)d[1], (uint8_t *)d[2]);
+    });
+}
+
+extern "C" int mrmp_connect_point(mrmp_ctx *c, int agent, const double *q, uint8_t *out) {
+    int32_t a = agent;
+    return mrmp_connect_points(c, 1, &a, q, out);
+}
+
+extern "C" int mrmp_connect_edges(mrmp_ctx *c, int64_t n, const int32_t *agent,
+                                  const double *q_from, const double *q_to, uint8_t *out) {
+    NEED(c && n >= 0, "bad ctx / n");
+    if (n == 0) return MRMP_OK;
+    NEED(agent && q_from && q_to && out, "NULL buffer");
+    int rc = check_agents_host(c, n, agent);
+    if (rc) return rc;
+    const size_t sb = sizeof(double) * c->d;
+    std::vector<Arr> arrs = {{agent, nullptr, 4}, {q_from, nullptr, sb}, {q_to, nullptr, sb},
+                             {nullptr, out, 1}};
+    return run_batch(c, n, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_connect_edges(c->cv, lcfg(c, s), len, (const int32_t *)d[0],
+                                    (const double *)d[1], (const double *)d[2], (uint8_t *)d[3]);
+    });
+}
+
+extern "C" int mrmp_connect_edge(mrmp_ctx *c, int agent, const double *q_from, const double *q_to,
+                                 uint8_t *out) {
+    int32_t a = agent;
+    return mrmp_connect_edges(c, 1, &a, q_from, q_to, out);
+}
+
+// ---- collide ---------------------------------------------------------------------------------
+extern "C" int mrmp_collide_pairs(mrmp_ctx *c, int64_t n, const int32_t *i, const int32_t *j,
+                                  const double *qi_from, const double *qi_to,
+                                  const double *qj_from, const double *qj_to, uint8_t *out) {
+    NEED(c && n >= 0, "bad ctx / n");
+    if (n == 0) return MRMP_OK;
+    NEED(i && j && qi_from && qi_to && qj_from && qj_to && out, "NULL buffer");
+    int rc = check_agents_host(c, n, i);
+    if (!rc) rc = check_agents_host(c, n, j);
+    if (rc) return rc;
+    const size_t sb = sizeof(double) * c->d;
+    std::vector<Arr> arrs = {{i, nullptr, 4},        {j, nullptr, 4},        {qi_from, nullptr, sb},
+                             {qi_to, nullptr, sb},   {qj_from, nullptr, sb}, {qj_to, nullptr, sb},
+                             {nullptr, out, 1}};
+    return run_batch(c, n, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_collide_pairs(c->cv, lcfg(c, s), len, (const int32_t *)d[0],
+                                    (const int32_t *)d[1], (const double *)d[2],
+                                    (const double *)d[3], (const double *)d[4],
+                                    (const double *)d[5], (uint8_t *)d[6]);
+    });
+}
+
+extern "C" int mrmp_collide_pair(mrmp_ctx *c, int i, int j, const double *qi_from,
+                                 const double *qi_to, const double *qj_from, const double *qj_to,
+                                 uint8_t *out) {
+    int32_t a = i, b = j;
+    return mrmp_collide_pairs(c, 1, &a, &b, qi_from, qi_to, qj_from, qj_to, out);
+}
+
+extern "C" int mrmp_collide_static_pairs(mrmp_ctx *c, int64_t n, const int32_t *i, const int32_t *j,
+                                         const double *qi, const double *qj, uint8_t *out) {
+    NEED(c && n >= 0, "bad ctx / n");
+    if (n == 0) return MRMP_OK;
+    NEED(i && j && qi && qj && out, "NULL buffer");
+    int rc = check_agents_host(c, n, i);
+    if (!rc) rc = check_agents_host(c, n, j);
+    if (rc) return rc;
+    const size_t sb = sizeof(double) * c->d;
+    std::vector<Arr> arrs = {{i, nullptr, 4}, {j, nullptr, 4}, {qi, nullptr, sb}, {qj, nullptr, sb},
+                             {nullptr, out, 1}};
+    return run_batch(c, n, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_collide_static_pairs(c->cv, lcfg(c, s), len, (const int32_t *)d[0],
+                                           (const int32_t *)d[1], (const double *)d[2],
+                                           (const double *)d[3], (uint8_t *)d[4]);
+    });
+}
+
+extern "C" int mrmp_collide_configs(mrmp_ctx *c, int64_t n_cfg, const double *Q_from,
+                                    const double *Q_to, uint8_t *out, int64_t *first_pair_out) {
+    NEED(c && n_cfg >= 0, "bad ctx / n_cfg");
+    if (n_cfg == 0) return MRMP_OK;
+    NEED(Q_from && Q_to && out, "NULL buffer");
+    const size_t sb = sizeof(double) * c->d * c->n_agents;
+    std::vector<int64_t> fp_tmp;
+    int64_t *fp = first_pair_out;
+    if (!fp) {
+        fp_tmp.resize((size_t)n_cfg);
+        fp = fp_tmp.data();
+    }
+    std::vector<Arr> arrs = {{Q_from, nullptr, sb}, {Q_to, nullptr, sb}, {nullptr, out, 1},
+                             {nullptr, fp, 8}};
+    return run_batch(c, n_cfg, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_collide_configs(c->cv, lcfg(c, s), len, (const double *)d[0],
+                                      (const double *)d[1], (uint8_t *)d[2], (int64_t *)d[3]);
+    });
+}
+
+extern "C" int mrmp_collide_config_moves(mrmp_ctx *c, int agent_i, const double *Q, int64_t n_cand,
+                                         const double *q_to, uint8_t *out) {
+    NEED(c && n_cand >= 0, "bad ctx / n_cand");
+    NEED((unsigned)agent_i < (unsigned)c->n_agents, "agent_i out of range");
+    if (n_cand == 0) return MRMP_OK;
+    NEED(Q && q_to && out, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    // Q (N states) rides in front of the candidate list of the first chunk; it is tiny, so it
+    // is uploaded once into the small staging buffer and shared by every chunk.
+    const size_t qb = align16(sizeof(double) * c->d * c->n_agents);
+    int rc = ensure_small(c, qb + 64);
+    if (rc) return rc;
+    if (n_cand <= kSmallBatch) {
+        const size_t sb = sizeof(double) * c->d;
+        const size_t in_b = align16(sb * (size_t)n_cand), out_b = align16((size_t)n_cand);
+        rc = ensure_small(c, qb + in_b + out_b);
+        if (rc) return rc;
+        memcpy(c->small_h, Q, sizeof(double) * c->d * c->n_agents);
+        memcpy(c->small_h + qb, q_to, sb * (size_t)n_cand);
+        CU(cudaMemcpyAsync(c->small_d, c->small_h, qb + in_b, cudaMemcpyHostToDevice, c->s_k));
+        CU(launch_collide_config_moves(c->cv, lcfg(c, c->s_k), agent_i, (const double *)c->small_d,
+                                       n_cand, (const double *)(c->small_d + qb),
+                                       c->small_d + qb + in_b));
+        CU(cudaMemcpyAsync(c->small_h + qb + in_b, c->small_d + qb + in_b, (size_t)n_cand,
+                           cudaMemcpyDeviceToHost, c->s_k));
+        CU(cudaStreamSynchronize(c->s_k));
+        memcpy(out, c->small_h + qb + in_b, (size_t)n_cand);
+        return MRMP_OK;
+    }
+    memcpy(c->small_h, Q, sizeof(double) * c->d * c->n_agents);
+    CU(cudaMemcpyAsync(c->small_d, c->small_h, qb, cudaMemcpyHostToDevice, c->s_k));
+    CU(cudaStreamSynchronize(c->s_k));
+    const double *Qd = (const double *)c->small_d;
+    const size_t sb = sizeof(double) * c->d;
+    std::vector<Arr> arrs = {{q_to, nullptr, sb}, {nullptr, out, 1}};
+    return run_batch(c, n_cand, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_collide_config_moves(c->cv, lcfg(c, s), agent_i, Qd, len,
+                                           (const double *)d[0], (uint8_t *)d[1]);
+    });
+}
+
+// ---- device-pointer forms --------------------------------------------------------------------
+#define DEV_PROLOGUE(c, n)                          \
+    NEED(c && n >= 0, "bad ctx / n");               \
+    if (n == 0) return MRMP_OK;                     \
+    CU(cudaSetDevice(c->device))
+
+static int need_aligned(const mrmp_ctx *c, const void *p) {
+    if (c->d == 2 && !aligned16(p))
+        return fail(MRMP_ERR_INVALID, "device state arrays must be 16-byte aligned");
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_connect_points_dev(mrmp_ctx *c, int64_t n, const int32_t *agent,
+                                       const double *q, uint8_t *out, void *stream) {
+    DEV_PROLOGUE(c, n);
+    if (need_aligned(c, q)) return MRMP_ERR_INVALID;
+    CU(launch_connect_points(c->cv, lcfg(c, (cudaStream_t)stream), n, agent, q, out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_connect_edges_dev(mrmp_ctx *c, int64_t n, const int32_t *agent,
+                                      const double *q_from, const double *q_to, uint8_t *out,
+                                      void *stream) {
+    DEV_PROLOGUE(c, n);
+    if (need_aligned(c, q_from) || need_aligned(c, q_to)) return MRMP_ERR_INVALID;
+    CU(launch_connect_edges(c->cv, lcfg(c, (cudaStream_t)stream), n, agent, q_from, q_to, out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_pairs_dev(mrmp_ctx *c, int64_t n, const int32_t *i, const int32_t *j,
+                                      const double *qi_from, const double *qi_to,
+                                      const double *qj_from, const double *qj_to, uint8_t *out,
+                                      void *stream) {
+    DEV_PROLOGUE(c, n);
+    if (need_aligned(c, qi_from) || need_aligned(c, qi_to) || need_aligned(c, qj_from) ||
+        need_aligned(c, qj_to))
+        return MRMP_ERR_INVALID;
+    CU(launch_collide_pairs(c->cv, lcfg(c, (cudaStream_t)stream), n, i, j, qi_from, qi_to,
+                            qj_from, qj_to, out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_static_pairs_dev(mrmp_ctx *c, int64_t n, const int32_t *i,
+                                             const int32_t *j, const double *qi, const double *qj,
+                                             uint8_t *out, void *stream) {
+    DEV_PROLOGUE(c, n);
+    if (need_aligned(c, qi) || need_aligned(c, qj)) return MRMP_ERR_INVALID;
+    CU(launch_collide_static_pairs(c->cv, lcfg(c, (cudaStream_t)stream), n, i, j, qi, qj, out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_configs_dev(mrmp_ctx *c, int64_t n_cfg, const double *Q_from,
+                                        const double *Q_to, uint8_t *out, int64_t *first_pair_out,
+                                        void *stream) {
+    DEV_PROLOGUE(c, n_cfg);
+    if (need_aligned(c, Q_from) || need_aligned(c, Q_to)) return MRMP_ERR_INVALID;
+    CU(launch_collide_configs(c->cv, lcfg(c, (cudaStream_t)stream), n_cfg, Q_from, Q_to, out,
+                              first_pair_out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_config_moves_dev(mrmp_ctx *c, int agent_i, const double *Q,
+                                             int64_t n_cand, const double *q_to, uint8_t *out,
+                                             void *stream) {
+    DEV_PROLOGUE(c, n_cand);
+    NEED((unsigned)agent_i < (unsigned)c->n_agents, "agent_i out of range");
+    if (need_aligned(c, Q) || need_aligned(c, q_to)) return MRMP_ERR_INVALID;
+    CU(launch_collide_config_moves(c->cv, lcfg(c, (cudaStream_t)stream), agent_i, Q, n_cand, q_to,
+                                   out));
+    return MRMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sampler
+// ------------------------------------------------------------------------------------------
+extern "C" int mrmp_sample_states(mrmp_ctx *c, int agent, uint64_t seed, uint64_t t0, int64_t n,
+                                  double *q_out) {
+    NEED(c && n >= 0, "bad ctx / n");
+    NEED((unsigned)agent < (unsigned)c->n_agents, "agent out of range");
+    if (n == 0) return MRMP_OK;
+    NEED(q_out, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    double *d = nullptr;
+    const size_t bytes = sizeof(double) * c->d * (size_t)n;
+    CU(cudaMalloc((void **)&d, bytes));
+    cudaError_t e = launch_sample_states(c->cv, lcfg(c, c->s_k), agent, seed, t0, n, d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_out, d, bytes, cudaMemcpyDeviceToHost, c->s_k);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_k);
+    cudaFree(d);
+    CU(e);
+    return MRMP_OK;
+}
+
+static const int64_t kMaxTriesFactor = 1 << 14;  // give up after 16384 * n_wanted tries
+
+extern "C" int mrmp_sample_free(mrmp_ctx *c, int agent, uint64_t seed, int64_t n_wanted,
+                                double *q_out, int64_t *n_tried_out) {
+    NEED(c && n_wanted >= 0 && n_wanted < (1 << 30), "bad ctx / n_wanted");
+    NEED((unsigned)agent < (unsigned)c->n_agents, "agent out of range");
+    if (n_wanted == 0) {
+        if (n_tried_out) *n_tried_out = 0;
+        return MRMP_OK;
+    }
+    NEED(q_out, "NULL buffer");
+    CU(cudaSetDevice(c->device));
+    double *d = nullptr;
+    const size_t bytes = sizeof(double) * c->d * (size_t)n_wanted;
+    CU(cudaMalloc((void **)&d, align16(bytes) + 16));
+    int64_t *dt = (int64_t *)((char *)d + align16(bytes));
+    int64_t tried = -1;
+    cudaError_t e = launch_sample_free(c->cv, lcfg(c, c->s_k), agent, 1, 0, (int)n_wanted,
+                                       (int)n_wanted, seed, d, dt, kMaxTriesFactor * n_wanted);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_out, d, bytes, cudaMemcpyDeviceToHost, c->s_k);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&tried, dt, 8, cudaMemcpyDeviceToHost, c->s_k);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_k);
+    cudaFree(d);
+    CU(e);
+    if (n_tried_out) *n_tried_out = tried;
+    if (tried < 0) return fail(MRMP_ERR_CAPACITY, "free-space sampling gave up (space too cluttered?)");
+    return MRMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// roadmaps
+// ------------------------------------------------------------------------------------------
+struct mrmp_roadmaps {
+    mrmp_ctx *ctx = nullptr;
+    int agent0 = 0, n_agents = 0, nv_cap = 0, nv = 0;
+    int words = 0;
+    double *nodes = nullptr;     // [n_agents][nv][d] (stride nv, repacked on set)
+    uint32_t *bitmap = nullptr;  // [n_agents*nv][words]
+    int32_t *row_cnt = nullptr, *row_ptr = nullptr, *col_idx = nullptr;
+    int64_t col_cap = 0;
+    int64_t *nnz_d = nullptr;    // device scalar
+    int64_t *tries_d = nullptr;  // [n_agents]
+    double *rad_d = nullptr;     // [2][n_agents]: rad, r2
+    int64_t nnz = -1;            // host copy after build
+    bool built = false;
+};
+
+extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int nv_cap,
+                                    mrmp_roadmaps **out) {
+    NEED(c && out, "bad ctx / out");
+    *out = nullptr;
+    NEED(agent0 >= 0 && n_agents > 0 && agent0 + n_agents <= c->n_agents, "agent range");
+    NEED(nv_cap >= 2 && nv_cap <= (1 << 20), "nv_cap out of range");
+    CU(cudaSetDevice(c->device));
+    mrmp_roadmaps *rm = new (std::nothrow) mrmp_roadmaps();
+    if (!rm) return fail(MRMP_ERR_NOMEM, "out of host memory");
+    rm->ctx = c;
+    rm->agent0 = agent0;
+    rm->n_agents = n_agents;
+    rm->nv_cap = nv_cap;
+    const int words_cap = (nv_cap + 31) / 32;
+    const int64_t rows = (int64_t)n_agents * nv_cap;
+    cudaError_t e = cudaMalloc((void **)&rm->nodes, sizeof(double) * c->d * rows);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->bitmap, sizeof(uint32_t) * rows * words_cap);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_cnt, sizeof(int32_t) * (rows + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_ptr, sizeof(int32_t) * (rows + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->nnz_d, 16);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->tries_d, sizeof(int64_t) * n_agents);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->rad_d, sizeof(double) * 2 * n_agents);
+    if (e != cudaSuccess) {
+        mrmp_roadmaps_destroy(rm);
+        return fail(MRMP_ERR_CUDA, "roadmaps alloc: %s", cudaGetErrorString(e));
+    }
+    *out = rm;
+    return MRMP_OK;
+}
+
+extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
+    if (!rm) return;
+    cudaSetDevice(rm->ctx->device);
+    cudaStreamSynchronize(rm->ctx->s_k);
+    cudaFree(rm->nodes);
+    cudaFree(rm->bitmap);
+    cudaFree(rm->row_cnt);
+    cudaFree(rm->row_ptr);
+    cudaFree(rm->col_idx);
+    cudaFree(rm->nnz_d);
+    cudaFree(rm->tries_d);
+    cudaFree(rm->rad_d);
+    delete rm;
+}
+
+extern "C" int mrmp_roadmaps_set_nodes(mrmp_roadmaps *rm, int nv, const double *nodes) {
+    NEED(rm && nodes, "bad roadmaps / nodes");
+    NEED(nv >= 1 && nv <= rm->nv_cap, "nv out of range");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    rm->nv = nv;
+    rm->built = false;
+    CU(cudaMemcpyAsync(rm->nodes, nodes, sizeof(double) * c->d * (size_t)nv * rm->n_agents,
+                       cudaMemcpyHostToDevice, c->s_k));
+    CU(cudaStreamSynchronize(c->s_k));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_set_nodes_dev(mrmp_roadmaps *rm, int nv, const double *nodes_dev,
+                                           void *stream) {
+    NEED(rm && nodes_dev, "bad roadmaps / nodes");
+    NEED(nv >= 1 && nv <= rm->nv_cap, "nv out of range");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    rm->nv = nv;
+    rm->built = false;
+    CU(cudaMemcpyAsync(rm->nodes, nodes_dev, sizeof(double) * c->d * (size_t)nv * rm->n_agents,
+                       cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_sample(mrmp_roadmaps *rm, int nv, uint64_t seed, const double *q_init,
+                                    const double *q_goal, int64_t *tries_out) {
+    NEED(rm && q_init && q_goal, "bad roadmaps / init / goal");
+    NEED(nv >= 2 && nv <= rm->nv_cap, "nv out of range");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    rm->nv = nv;
+    rm->built = false;
+    const int d = c->d, n = rm->n_agents;
+    // vertices 0 / 1 = init / goal (prm.jl:232)
+    const size_t sb = sizeof(double) * d;
+    int rc = ensure_small(c, 2 * sb * n);
+    if (rc) return rc;
+    for (int a = 0; a < n; ++a) {
+        memcpy(c->small_h + (2 * a) * sb, q_init + (size_t)a * d, sb);
+        memcpy(c->small_h + (2 * a + 1) * sb, q_goal + (size_t)a * d, sb);
+    }
+    CU(cudaMemcpy2DAsync(rm->nodes, sb * nv, c->small_h, 2 * sb, 2 * sb, n, cudaMemcpyHostToDevice,
+                         c->s_k));
+    CU(launch_sample_free(c->cv, lcfg(c, c->s_k), rm->agent0, n, 2, nv, nv, seed, rm->nodes,
+                          rm->tries_d, kMaxTriesFactor * (int64_t)nv));
+    std::vector<int64_t> tries(n);
+    CU(cudaMemcpyAsync(tries.data(), rm->tries_d, sizeof(int64_t) * n, cudaMemcpyDeviceToHost,
+                       c->s_k));
+    CU(cudaStreamSynchronize(c->s_k));
+    for (int a = 0; a < n; ++a) {
+        if (tries_out) tries_out[a] = tries[a];
+        if (tries[a] < 0)
+            return fail(MRMP_ERR_CAPACITY, "free-space sampling gave up for agent %d",
+                        rm->agent0 + a);
+    }
+    return MRMP_OK;
+}
+
+static int roadmaps_emit(mrmp_roadmaps *rm, cudaStream_t s) {
+    mrmp_ctx *c = rm->ctx;
+    const int64_t rows = (int64_t)rm->n_agents * rm->nv;
+    if (rm->col_cap == 0) {
+        rm->col_cap = rows * 32;
+        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+    }
+    CU(launch_prm_emit(lcfg(c, s), rows, rm->nv, rm->bitmap, rm->words, rm->row_ptr, rm->col_idx,
+                       rm->col_cap));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
+    NEED(rm && rad, "bad roadmaps / rad");
+    NEED(rm->nv >= 1, "no nodes set");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    const int n = rm->n_agents, nv = rm->nv;
+    const int64_t rows = (int64_t)n * nv;
+    rm->words = (nv + 31) / 32;
+    int rc = ensure_small(c, sizeof(double) * 2 * n + 64);
+    if (rc) return rc;
+    double *hr = (double *)c->small_h;
+    for (int a = 0; a < n; ++a) {
+        hr[a] = rad[a];
+        hr[n + a] = sq_le_threshold(rad[a]);
+    }
+    CU(cudaMemcpyAsync(rm->rad_d, hr, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->s_k));
+    CU(launch_prm_adjacency(c->cv, lcfg(c, c->s_k), rm->agent0, n, nv, rm->rad_d + n, rm->rad_d,
+                            rm->nodes, rm->bitmap, rm->words, rm->row_cnt));
+    CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
+    int64_t *h_nnz = (int64_t *)(c->small_h + align16(sizeof(double) * 2 * n));
+    CU(cudaMemcpyAsync(h_nnz, rm->nnz_d, 8, cudaMemcpyDeviceToHost, c->s_k));
+    rc = roadmaps_emit(rm, c->s_k);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->s_k));
+    rm->nnz = *h_nnz;
+    if (rm->nnz >= ((int64_t)1 << 31)) return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
+    if (rm->nnz > rm->col_cap) {  // rare: grow and re-emit
+        CU(cudaFree(rm->col_idx));
+        rm->col_idx = nullptr;
+        rm->col_cap = rm->nnz + rm->nnz / 4;
+        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+        rc = roadmaps_emit(rm, c->s_k);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->s_k));
+    }
+    rm->built = true;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out) {
+    NEED(rm && nnz_total_out, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    *nnz_total_out = rm->nnz;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_get_nodes(mrmp_roadmaps *rm, double *nodes_out) {
+    NEED(rm && nodes_out, "bad arguments");
+    NEED(rm->nv >= 1, "no nodes set");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(nodes_out, rm->nodes, sizeof(double) * c->d * (size_t)rm->nv * rm->n_agents,
+                       cudaMemcpyDeviceToHost, c->s_k));
+    CU(cudaStreamSynchronize(c->s_k));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_t *col_idx,
+                                     int64_t col_cap, int64_t *nnz_out) {
+    NEED(rm && row_ptr && nnz_out, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    *nnz_out = rm->nnz;
+    const int64_t rows = (int64_t)rm->n_agents * rm->nv;
+    CU(cudaMemcpyAsync(row_ptr, rm->row_ptr, sizeof(int32_t) * (rows + 1), cudaMemcpyDeviceToHost,
+                       c->s_k));
+    if (col_cap < rm->nnz) {
+        CU(cudaStreamSynchronize(c->s_k));
+        return fail(MRMP_ERR_CAPACITY, "col_cap %lld < nnz %lld", (long long)col_cap,
+                    (long long)rm->nnz);
+    }
+    NEED(col_idx || rm->nnz == 0, "col_idx is NULL");
+    if (rm->nnz > 0)
+        CU(cudaMemcpyAsync(col_idx, rm->col_idx, sizeof(int32_t) * rm->nnz, cudaMemcpyDeviceToHost,
+                           c->s_out));
+    CU(cudaStreamSynchronize(c->s_k));
+    CU(cudaStreamSynchronize(c->s_out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
+                                         int32_t **row_ptr_dev, int32_t **col_idx_dev,
+                                         int64_t *nnz_out) {
+    NEED(rm, "bad roadmaps");
+    if (nv_out) *nv_out = rm->nv;
+    if (nodes_dev) *nodes_dev = rm->nodes;
+    if (row_ptr_dev) *row_ptr_dev = rm->row_ptr;
+    if (col_idx_dev) *col_idx_dev = rm->col_idx;
+    if (nnz_out) *nnz_out = rm->built ? rm->nnz : -1;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_prm_build(mrmp_ctx *c, int agent0, int n_agents, int nv, const double *rad,
+                              const double *nodes, int32_t *row_ptr, int32_t *col_idx,
+                              int64_t col_cap, int64_t *nnz_out) {
+    NEED(c && rad && nodes && row_ptr && nnz_out, "bad arguments");
+    mrmp_roadmaps *rm = nullptr;
+    int rc = mrmp_roadmaps_create(c, agent0, n_agents, nv < 2 ? 2 : nv, &rm);
+    if (rc) return rc;
+    rc = mrmp_roadmaps_set_nodes(rm, nv, nodes);
+    if (!rc) rc = mrmp_roadmaps_build(rm, rad);
+    if (!rc) rc = mrmp_roadmaps_get_csr(rm, row_ptr, col_idx, col_cap, nnz_out);
+    mrmp_roadmaps_destroy(rm);
+    return rc;
+}
+
+extern "C" int mrmp_prms(mrmp_ctx *c, int agent0, int n_agents, int nv, const double *rad,
+                         uint64_t seed, const double *q_init, const double *q_goal,
+                         double *nodes_out, int32_t *row_ptr, int32_t *col_idx, int64_t col_cap,
+                         int64_t *nnz_out) {
+    NEED(c && rad && q_init && q_goal && nodes_out && row_ptr && nnz_out, "bad arguments");
+    mrmp_roadmaps *rm = nullptr;
+    int rc = mrmp_roadmaps_create(c, agent0, n_agents, nv, &rm);
+    if (rc) return rc;
+    rc = mrmp_roadmaps_sample(rm, nv, seed, q_init, q_goal, nullptr);
+    if (!rc) rc = mrmp_roadmaps_build(rm, rad);
+    if (!rc) rc = mrmp_roadmaps_get_nodes(rm, nodes_out);
+    if (!rc) rc = mrmp_roadmaps_get_csr(rm, row_ptr, col_idx, col_cap, nnz_out);
+    mrmp_roadmaps_destroy(rm);
+    return rc;
+}
+
+// ---- collide over roadmap edges by id ----------------------------------------------------------
+static int check_rm_agents(const mrmp_roadmaps *rm, int64_t n, const int32_t *a) {
+    for (int64_t k = 0; k < n; ++k)
+        if (a[k] < rm->agent0 || a[k] >= rm->agent0 + rm->n_agents)
+            return fail(MRMP_ERR_INVALID, "agent %d not held by this roadmap set", a[k]);
+    return MRMP_OK;
+}
+static int check_vertices(const mrmp_roadmaps *rm, int64_t n, const int32_t *v) {
+    for (int64_t k = 0; k < n; ++k)
+        if ((unsigned)v[k] >= (unsigned)rm->nv)
+            return fail(MRMP_ERR_INVALID, "vertex id %d out of range at %lld", v[k], (long long)k);
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_edges_indexed(mrmp_roadmaps *rm, int64_t n, const int32_t *i,
+                                          const int32_t *j, const int32_t *vi_from,
+                                          const int32_t *vi_to, const int32_t *vj_from,
+                                          const int32_t *vj_to, uint8_t *out) {
+    NEED(rm && n >= 0, "bad roadmaps / n");
+    if (n == 0) return MRMP_OK;
+    NEED(i && j && vi_from && vi_to && vj_from && vj_to && out, "NULL buffer");
+    NEED(rm->nv >= 1, "no nodes set");
+    int rc = check_rm_agents(rm, n, i);
+    if (!rc) rc = check_rm_agents(rm, n, j);
+    if (!rc) rc = check_vertices(rm, n, vi_from);
+    if (!rc) rc = check_vertices(rm, n, vi_to);
+    if (!rc) rc = check_vertices(rm, n, vj_from);
+    if (!rc) rc = check_vertices(rm, n, vj_to);
+    if (rc) return rc;
+    mrmp_ctx *c = rm->ctx;
+    std::vector<Arr> arrs = {{i, nullptr, 4},       {j, nullptr, 4},     {vi_from, nullptr, 4},
+                             {vi_to, nullptr, 4},   {vj_from, nullptr, 4}, {vj_to, nullptr, 4},
+                             {nullptr, out, 1}};
+    return run_batch(c, n, arrs, [&](void **d, int64_t len, cudaStream_t s) {
+        return launch_collide_edges_indexed(
+            c->cv, lcfg(c, s), len, (const int32_t *)d[0], (const int32_t *)d[1],
+            (const int32_t *)d[2], (const int32_t *)d[3], (const int32_t *)d[4],
+            (const int32_t *)d[5], rm->nodes, rm->agent0, rm->n_agents, rm->nv, (uint8_t *)d[6]);
+    });
+}
+
+extern "C" int mrmp_collide_edges_indexed_dev(mrmp_roadmaps *rm, int64_t n, const int32_t *i,
+                                              const int32_t *j, const int32_t *vi_from,
+                                              const int32_t *vi_to, const int32_t *vj_from,
+                                              const int32_t *vj_to, uint8_t *out, void *stream) {
+    NEED(rm && n >= 0, "bad roadmaps / n");
+    if (n == 0) return MRMP_OK;
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(launch_collide_edges_indexed(c->cv, lcfg(c, (cudaStream_t)stream), n, i, j, vi_from, vi_to,
+                                    vj_from, vj_to, rm->nodes, rm->agent0, rm->n_agents, rm->nv,
+                                    out));
+    return MRMP_OK;
+}

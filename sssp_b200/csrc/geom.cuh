@@ -1,0 +1,175 @@
+// geom.cuh -- FP64 geometry primitives of the connect/collide hot path (device side).
+//
+// Restates src/utils.jl:17-94 of the reference for sm_100a.  Every arithmetic step uses
+// the round-to-nearest intrinsics (__dadd_rn, __dmul_rn, ...), which nvcc never contracts
+// into FMA, so results are bit-identical to the reference's un-fused Julia arithmetic
+// independent of -fmad.
+//
+// Two exact (verdict-preserving) transformations are used throughout:
+//  (1) sqrt elimination.  The reference compares  norm(p) = sqrt(sum p_k^2)  with a
+//      threshold.  RN(sqrt(.)) is monotone, so  sqrt(s) < thr  <=>  s < T2  where
+//      T2 = min{ s : RN(sqrt(s)) >= thr } is precomputed once per threshold on the host
+//      (abi.cu: sq_lt_threshold).  Julia's generic_norm2 only leaves the plain
+//      sum-of-squares path when the sum under/overflows; s == 0 catches the underflow
+//      case and takes norm_slow().
+//  (2) endpoint short-cut of the segment-point distance: for e == 1 / e == 0 the
+//      reference evaluates (e*a + (1-e)*b) - c, which is exactly a-c / b-c.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace mrmp {
+
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+
+// LinearAlgebra.dot on 2-3 element vectors: x1*y1 + x2*y2 (+ x3*y3), left to right
+template <int D>
+__device__ __forceinline__ double dotd(const double *a, const double *b) {
+    double s = dmul(a[0], b[0]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) s = dadd(s, dmul(a[k], b[k]));
+    return s;
+}
+
+// sum of squares, left to right (fast path of LinearAlgebra.generic_norm2)
+template <int D>
+__device__ __forceinline__ double sumsq(const double *v) {
+    double s = dmul(v[0], v[0]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) s = dadd(s, dmul(v[k], v[k]));
+    return s;
+}
+
+// generic_norm2 when the plain sum of squares is 0: either all-zero or underflow
+template <int D>
+__device__ __noinline__ double norm_slow(const double *v) {
+    double maxabs = fabs(v[0]);
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+        double a = fabs(v[k]);
+        maxabs = (isnan(maxabs) || isnan(a)) ? CUDART_NAN : (a > maxabs ? a : maxabs);
+    }
+    if (maxabs == 0.0 || isinf(maxabs)) return maxabs;
+    double t = ddiv(fabs(v[0]), maxabs);
+    double s = dmul(t, t);
+#pragma unroll
+    for (int k = 1; k < D; ++k) {
+        t = ddiv(fabs(v[k]), maxabs);
+        s = dadd(s, dmul(t, t));
+    }
+    return dmul(maxabs, dsqrt(s));
+}
+
+// full norm value (used where the distance itself is returned to the host)
+template <int D>
+__device__ __forceinline__ double norm_val(const double *v) {
+    double s = sumsq<D>(v);
+    if (s == 0.0) return norm_slow<D>(v);
+    return dsqrt(s);
+}
+
+// norm(v) < thr.  TAB: T2 = sq_lt_threshold(thr) is available (sqrt-free exact compare);
+// otherwise the square root is taken like the reference does.
+template <int D, bool TAB = true>
+__device__ __forceinline__ bool norm_lt(const double *v, double s, double thr, double T2) {
+    if (s == 0.0) return norm_slow<D>(v) < thr;
+    if constexpr (TAB) return s < T2;
+    return dsqrt(s) < thr;
+}
+
+// src/utils.jl:44-57: segment [a,b] to point c.  u = a-b and uu = dot(u,u) are passed in
+// (shared between several c).  Writes the difference vector p and returns sum p_k^2.
+template <int D>
+__device__ __forceinline__ double segpt_ss(const double *a, const double *b, const double *u,
+                                           double uu, const double *c, double *p) {
+    double bc[D], ac[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        bc[k] = dsub(b[k], c[k]);
+        ac[k] = dsub(a[k], c[k]);
+    }
+    const double df0 = dotd<D>(u, bc);  // :46
+    const double df1 = dotd<D>(u, ac);  // :47
+    if (dmul(df0, df1) < 0.0) {         // :50
+        const double e = ddiv(-df0, uu);  // :51
+        const double f = dsub(1.0, e);
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+            p[k] = dsub(dadd(dmul(e, a[k]), dmul(f, b[k])), c[k]);  // :56
+    } else if (df0 >= 0.0) {  // :52  e = 0  ->  p = b - c
+#pragma unroll
+        for (int k = 0; k < D; ++k) p[k] = bc[k];
+    } else {  // e = 1  ->  p = a - c
+#pragma unroll
+        for (int k = 0; k < D; ++k) p[k] = ac[k];
+    }
+    return sumsq<D>(p);
+}
+
+// verdict  dist(a,b,c) < thr
+template <int D, bool TAB = true>
+__device__ __forceinline__ bool segpt_lt(const double *a, const double *b, const double *u,
+                                         double uu, const double *c, double thr, double T2) {
+    double p[D];
+    const double s = segpt_ss<D>(a, b, u, uu, c, p);
+    return norm_lt<D, TAB>(p, s, thr, T2);
+}
+
+// src/utils.jl:59-94: verdict  dist(p11,p12,p21,p22) < thr
+template <int D, bool TAB = true>
+__device__ __forceinline__ bool segseg_lt(const double *p11, const double *p12, const double *p21,
+                                          const double *p22, double thr, double T2) {
+    double v1[D], v2[D], w[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        v1[k] = dsub(p12[k], p11[k]);  // :68
+        v2[k] = dsub(p22[k], p21[k]);  // :69
+        w[k] = dsub(p21[k], p11[k]);
+    }
+    const double D1 = dotd<D>(w, v1);   // :70
+    const double D2 = dotd<D>(w, v2);   // :71
+    const double Dv = dotd<D>(v1, v2);  // :72
+    const double V1 = dotd<D>(v1, v1);  // :73
+    const double V2 = dotd<D>(v2, v2);  // :74
+    const double Dd = dsub(dmul(V1, V2), dmul(Dv, Dv));  // :75
+    if (Dd > 0.0) {
+        const double t1 = ddiv(dsub(dmul(D1, V2), dmul(D2, Dv)), Dd);  // :77
+        const double t2 = ddiv(dsub(dmul(D1, Dv), dmul(D2, V1)), Dd);  // :78
+        if (0.0 <= t1 && t1 <= 1.0 && 0.0 <= t2 && t2 <= 1.0) {
+            double q[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                q[k] = dsub(dadd(p11[k], dmul(t1, v1[k])), dadd(p21[k], dmul(t2, v2[k])));  // :80-82
+            return norm_lt<D, TAB>(q, sumsq<D>(q), thr, T2);
+        }
+    }
+    // :86-93  minimum of the four endpoint-to-segment distances (NaN-propagating)
+    double u1[D], u2[D], p[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        u1[k] = dsub(p11[k], p12[k]);  // a - b of dist(p11,p12,.); dot(u1,u1) == V1 bitwise
+        u2[k] = dsub(p21[k], p22[k]);
+    }
+    double s;
+    bool hit;
+    double nan_probe;
+    s = segpt_ss<D>(p11, p12, u1, V1, p21, p);
+    hit = norm_lt<D, TAB>(p, s, thr, T2);
+    nan_probe = s;
+    s = segpt_ss<D>(p11, p12, u1, V1, p22, p);
+    hit |= norm_lt<D, TAB>(p, s, thr, T2);
+    nan_probe = dadd(nan_probe, s);
+    s = segpt_ss<D>(p21, p22, u2, V2, p11, p);
+    hit |= norm_lt<D, TAB>(p, s, thr, T2);
+    nan_probe = dadd(nan_probe, s);
+    s = segpt_ss<D>(p21, p22, u2, V2, p12, p);
+    hit |= norm_lt<D, TAB>(p, s, thr, T2);
+    nan_probe = dadd(nan_probe, s);
+    return hit && !isnan(nan_probe);
+}
+
+}  // namespace mrmp

@@ -1,0 +1,140 @@
+// mrmp_internal.cuh -- shared between the kernel translation units and abi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "geom.cuh"
+
+namespace mrmp {
+
+// Device-side view of one problem instance.  `blob` is one contiguous array of doubles in
+// HBM; offsets are in doubles.  Layout (each section padded to a multiple of 2 doubles so
+// that every section start is 16-byte aligned for the 1-D TMA bulk copy):
+//   [CONNECT SEGMENT]  obs SoA: x[mp] y[mp] (z[mp]) r[mp] | rads[np] | base[2*np] |
+//                      t2_obs[N][mp] | g_obs[N][mp]
+//   [COLLIDE SEGMENT]  rads[np] | base[2*np] | t2_pair[N][N] | g_pair[N][N] (when has_pair_tab)
+// t2_* = sq_lt_threshold(thr) (sqrt-free exact compare), g_* = broad-phase bound; the
+// thresholds themselves (o.r + rads[i], rads[i] + rads[j]) are recomputed on the fly where
+// the rare slow path needs them.
+struct CtxView {
+    const double *blob;
+    int model, d, n_agents, n_obs;
+    int mp, np;          // padded obstacle / agent counts
+    // connect segment
+    int con_off, con_len;  // segment [con_off, con_off+con_len) is staged to smem
+    int obs_off;           // SoA base: coordinate k of obstacle m at obs_off + k*mp + m; radius at k = wd
+    int rads_off, base_off;
+    int t2_obs_off, g_obs_off;  // [agent*mp + m]
+    // collide segment
+    int col_off, col_len;
+    int crads_off, cbase_off;
+    int has_pair_tab;
+    int t2_pair_off, g_pair_off;  // [i*N + j]
+    double step_dist, safety_dist, max_dist;
+    double safety_t2;  // sq_lt_threshold(safety_dist)
+};
+
+constexpr int kMaxStageBytes = 96 * 1024;  // larger segments are read from global (L1/L2)
+
+// ---- 1-D TMA bulk copy global -> shared with mbarrier completion (UBLKCP in SASS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Stage `n_doubles` (multiple of 2) from gsrc (16-byte aligned) into smem_dst.  All threads
+// of the CTA must call it; returns after the data is visible to every thread.
+__device__ __forceinline__ void tma_stage(double *smem_dst, const double *gsrc, int n_doubles,
+                                          uint64_t *bar) {
+    const uint32_t bytes = static_cast<uint32_t>(n_doubles) * 8u;
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                     "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(smem_u32(smem_dst)),
+            "l"(gsrc), "r"(bytes), "r"(bar_a)
+            : "memory");
+    }
+    // every thread waits on phase 0 of the barrier
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar_a)
+        : "memory");
+}
+
+// Returns a pointer through which segment-relative offsets can be read: the staged smem copy
+// when dyn_smem_bytes > 0, else the blob in global memory.  smem layout: [bar(16B) | data].
+__device__ __forceinline__ const double *stage_segment(const CtxView &cv, int seg_off, int seg_len,
+                                                       unsigned char *smem_raw, bool staged) {
+    if (!staged) return cv.blob + seg_off;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *dst = reinterpret_cast<double *>(smem_raw + 16);
+    tma_stage(dst, cv.blob + seg_off, seg_len, bar);
+    return dst;
+}
+
+// ---- launch bookkeeping ------------------------------------------------------------
+struct LaunchCfg {
+    int sm_count;
+    cudaStream_t stream;
+};
+
+void count_launch(int n = 1);
+
+// kernels_point.cu
+cudaError_t launch_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                  const int32_t *agent, const double *q, uint8_t *out);
+cudaError_t launch_connect_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                 const int32_t *agent, const double *qf, const double *qt,
+                                 uint8_t *out);
+cudaError_t launch_collide_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                 const int32_t *ai, const int32_t *aj, const double *qif,
+                                 const double *qit, const double *qjf, const double *qjt,
+                                 uint8_t *out);
+cudaError_t launch_collide_static_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                        const int32_t *ai, const int32_t *aj, const double *qi,
+                                        const double *qj, uint8_t *out);
+cudaError_t launch_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64_t n_cfg,
+                                   const double *Qf, const double *Qt, uint8_t *out,
+                                   int64_t *first_pair);
+cudaError_t launch_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, int agent_i,
+                                        const double *Q, int64_t n_cand, const double *q_to,
+                                        uint8_t *out);
+cudaError_t launch_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                         const int32_t *ai, const int32_t *aj,
+                                         const int32_t *vif, const int32_t *vit,
+                                         const int32_t *vjf, const int32_t *vjt,
+                                         const double *nodes, int agent0, int n_local,
+                                         int nv_stride, uint8_t *out);
+
+// kernels_prm.cu
+// adjacency bitmap [n_agents*nv rows][words] + row counts, exclusive scan, CSR emit
+cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
+                                 int nv, const double *rad_le /*[n] R2 or NaN*/,
+                                 const double *rad /*[n]*/, const double *nodes,
+                                 uint32_t *bitmap, int words, int32_t *row_cnt);
+cudaError_t launch_row_scan(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_cnt,
+                            int32_t *row_ptr, int64_t *nnz_total);
+cudaError_t launch_prm_emit(const LaunchCfg &lc, int64_t n_rows, int nv, const uint32_t *bitmap,
+                            int words, const int32_t *row_ptr, int32_t *col_idx, int64_t col_cap);
+cudaError_t launch_sample_states(const CtxView &cv, const LaunchCfg &lc, int agent, uint64_t seed,
+                                 uint64_t t0, int64_t n, double *q_out);
+// per agent: nodes[a][0]=init, [1]=goal, then the first nv-2 free samples in try order
+cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
+                               int n_fixed, int nv, int nv_stride, uint64_t seed, double *nodes,
+                               int64_t *tries_out, int64_t max_tries);
+
+}  // namespace mrmp

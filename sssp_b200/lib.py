@@ -1,0 +1,130 @@
+"""ctypes binding of the C ABI (include/mrmp_b200.h).
+
+The product path has no CPU fallback: if the CUDA shared library is missing or no
+device is present, calls raise MRMPError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22 = 0, 1, 2
+STATE_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+_lp = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+
+class MRMPError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mrmp_b200 error {code}: {msg}")
+        self.code = code
+
+
+_SIGS = {
+    "mrmp_last_error": (C.c_char_p, []),
+    "mrmp_version": (C.c_char_p, []),
+    "mrmp_kernel_launch_count": (C.c_int64, []),
+    "mrmp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "mrmp_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_int64]),
+    "mrmp_host_free": (C.c_int, [_vp]),
+    "mrmp_ctx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp,
+                                  C.c_double, C.c_double, C.c_double, C.c_int]),
+    "mrmp_ctx_destroy": (None, [_vp]),
+    "mrmp_ctx_state_dim": (C.c_int, [_vp]),
+    "mrmp_ctx_sync": (C.c_int, [_vp]),
+    "mrmp_connect_point": (C.c_int, [_vp, C.c_int, _dp, _bp]),
+    "mrmp_connect_points": (C.c_int, [_vp, C.c_int64, _ip, _dp, _bp]),
+    "mrmp_connect_edge": (C.c_int, [_vp, C.c_int, _dp, _dp, _bp]),
+    "mrmp_connect_edges": (C.c_int, [_vp, C.c_int64, _ip, _dp, _dp, _bp]),
+    "mrmp_collide_pair": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _bp]),
+    "mrmp_collide_pairs": (C.c_int, [_vp, C.c_int64, _ip, _ip, _dp, _dp, _dp, _dp, _bp]),
+    "mrmp_collide_static_pairs": (C.c_int, [_vp, C.c_int64, _ip, _ip, _dp, _dp, _bp]),
+    "mrmp_collide_configs": (C.c_int, [_vp, C.c_int64, _dp, _dp, _bp, _lp]),
+    "mrmp_collide_config_moves": (C.c_int, [_vp, C.c_int, _dp, C.c_int64, _dp, _bp]),
+    "mrmp_connect_points_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "mrmp_connect_edges_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "mrmp_collide_pairs_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mrmp_collide_static_pairs_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mrmp_collide_configs_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "mrmp_collide_config_moves_dev": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, _vp, _vp]),
+    "mrmp_roadmaps_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "mrmp_roadmaps_destroy": (None, [_vp]),
+    "mrmp_roadmaps_set_nodes": (C.c_int, [_vp, C.c_int, _dp]),
+    "mrmp_roadmaps_sample": (C.c_int, [_vp, C.c_int, C.c_uint64, _dp, _dp, _lp]),
+    "mrmp_roadmaps_build": (C.c_int, [_vp, _dp]),
+    "mrmp_roadmaps_nnz": (C.c_int, [_vp, _lp]),
+    "mrmp_roadmaps_get_nodes": (C.c_int, [_vp, _dp]),
+    "mrmp_roadmaps_get_csr": (C.c_int, [_vp, _ip, _ip, C.c_int64, _lp]),
+    "mrmp_roadmaps_device_ptrs": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp),
+                                            C.POINTER(_vp), C.POINTER(_vp), _lp]),
+    "mrmp_roadmaps_set_nodes_dev": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "mrmp_prm_build": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _ip, C.c_int64,
+                                 _lp]),
+    "mrmp_prms": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_uint64, _dp, _dp, _dp, _ip,
+                            _ip, C.c_int64, _lp]),
+    "mrmp_collide_edges_indexed": (C.c_int, [_vp, C.c_int64, _ip, _ip, _ip, _ip, _ip, _ip, _bp]),
+    "mrmp_collide_edges_indexed_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp]),
+    "mrmp_sample_states": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _dp]),
+    "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),
+}
+
+_LIB = None
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """Load libmrmp_b200.so (building it in-tree if the sources are newer)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or os.environ.get("MRMP_B200_LIB") or _build.LIB_PATH
+    if path is None and "MRMP_B200_LIB" not in os.environ:
+        try:
+            p = _build.build()
+        except Exception as e:  # nvcc missing on the GPU box: use the shipped .so
+            if not os.path.exists(p):
+                raise MRMPError(ERR_CUDA, f"libmrmp_b200.so missing and cannot be built: {e}")
+    lib = C.CDLL(p)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise MRMPError(rc, load().mrmp_last_error().decode("utf-8", "replace"))
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def kernel_launch_count() -> int:
+    return int(load().mrmp_kernel_launch_count())
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    rc = load().mrmp_device_count(C.byref(n))
+    return int(n.value) if rc == OK else 0

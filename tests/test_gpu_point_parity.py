@@ -1,0 +1,142 @@
+"""GPU parity for the point models: every C-ABI entry point against the CPU oracle on the
+same seeded inputs -- verdicts must be BIT-EXACT (integer/boolean work: zero mismatches)."""
+import math
+
+import numpy as np
+import pytest
+
+import sssp_b200 as S
+from sssp_b200 import lib as L
+from oracle import oracle as O
+from helpers import make_point_instance, near_threshold_connect, near_threshold_pairs, random_edges
+
+pytestmark = pytest.mark.gpu
+
+MODELS = [(O.POINT2D, 2), (O.POINT3D, 3)]
+
+
+def _pair(model, N, M, seed, **kw):
+    rads, obs = make_point_instance(model, N, M, seed, **kw)
+    return S.Context(model, rads, obs), O.Oracle(model, rads, obs), rads, obs
+
+
+def test_kats_through_the_abi():
+    # derived KATs through gen_connect / gen_collide closures
+    connect = S.gen_connect(S.StatePoint2D(0, 0), [S.CircleObstacle2D(0.5, 0.5, 0.1)], [0.1])
+    P = S.StatePoint2D
+    assert connect(P(0.2, 0.5), P(0.8, 0.5), 0) is False
+    assert connect(P(0.2, 0.2), P(0.8, 0.2), 0) is True
+    assert connect(P(0.2, 0.2), P(0.95, 0.2), 0) is False
+    assert connect(P(0.95, 0.2), P(0.8, 0.2), 0) is True      # q_from not bounds-checked
+    assert connect(P(0.5, 0.2), 0) is True and connect(P(0.05, 0.5), 0) is False
+    collide = S.gen_collide(P(0, 0), [0.25, 0.25])
+    assert collide(P(0, 0), P(0.5, 0), 0, 1) is False           # == threshold: strict <
+    assert collide(P(0, 0), P(math.nextafter(0.5, 0), 0), 0, 1) is True
+    # test/dist.jl vector: distance exactly 0 -> collides for any positive radius
+    assert collide(P(-1, -2), P(1, 2), P(1, -2), P(-1, 2), 0, 1) is True
+    Q = [S.Node(P(0.1, 0.1), 0), S.Node(P(0.5, 0.5), 1)]
+    assert collide(Q, Q) is False
+    assert collide(Q, P(0.5, 0.45), 0) is True and collide(Q, P(0.1, 0.2), 0) is False
+
+
+@pytest.mark.parametrize("model,d", MODELS)
+def test_connect_parity(model, d):
+    N, M = 50, 10
+    ctx, orc, rads, obs = _pair(model, N, M, seed=100 + d)
+    rng = np.random.default_rng(1)
+    n = 300_000
+    ag = rng.integers(0, N, n).astype(np.int32)
+    qf, qt = random_edges(rng, n, d, 0.1)
+    assert np.array_equal(ctx.connect_points(ag, qf), orc.connect_points(ag, qf, nthreads=0))
+    g, o = ctx.connect_edges(ag, qf, qt), orc.connect_edges(ag, qf, qt, nthreads=0)
+    assert np.array_equal(g, o) and 0 < o.sum() < n
+    nf, nt = near_threshold_connect(rng, n, rads, obs, ag)
+    g, o = ctx.connect_edges(ag, nf, nt), orc.connect_edges(ag, nf, nt, nthreads=0)
+    assert np.array_equal(g, o) and 0.1 * n < o.sum() < 0.9 * n
+    # field-boundary cases: coordinates exactly at rads[i] and 1 - rads[i]
+    qb = np.stack([rads[ag], 1 - rads[ag]] + [np.full(n, 0.5)] * (d - 2), axis=1)
+    assert np.array_equal(ctx.connect_points(ag, qb), orc.connect_points(ag, qb, nthreads=0))
+
+
+@pytest.mark.parametrize("model,d", MODELS)
+def test_collide_parity(model, d):
+    N = 50
+    ctx, orc, rads, obs = _pair(model, N, 0, seed=200 + d)
+    rng = np.random.default_rng(2)
+    n = 300_000
+    ai = rng.integers(0, N, n).astype(np.int32)
+    aj = ((ai + 1 + rng.integers(0, N - 1, n)) % N).astype(np.int32)
+    a, b = random_edges(rng, n, d, 0.1)
+    c, e = random_edges(rng, n, d, 0.1)
+    c = a + (c - 0.5) * 0.2          # keep the second edge nearby so that hits occur
+    e = c + (e - c)
+    g, o = ctx.collide_pairs(ai, aj, a, b, c, e), orc.collide_pairs(ai, aj, a, b, c, e, nthreads=0)
+    assert np.array_equal(g, o) and 0 < o.sum() < n
+    p = near_threshold_pairs(rng, n, rads, ai, aj, d)
+    g, o = ctx.collide_pairs(ai, aj, *p), orc.collide_pairs(ai, aj, *p, nthreads=0)
+    assert np.array_equal(g, o) and 0.1 * n < o.sum() < 0.9 * n
+    # degenerate edges (stay actions) and parallel edges take the endpoint fallback
+    g = ctx.collide_pairs(ai, aj, a, a, c, c)
+    assert np.array_equal(g, orc.collide_pairs(ai, aj, a, a, c, c, nthreads=0))
+    g = ctx.collide_pairs(ai, aj, a, b, a + 0.01, b + 0.01)
+    assert np.array_equal(g, orc.collide_pairs(ai, aj, a, b, a + 0.01, b + 0.01, nthreads=0))
+    g, o = ctx.collide_static_pairs(ai, aj, a, c), orc.collide_static_pairs(ai, aj, a, c, nthreads=0)
+    assert np.array_equal(g, o) and 0 < o.sum() < n
+
+
+@pytest.mark.parametrize("model,d", MODELS)
+@pytest.mark.parametrize("N", [2, 5, 50])
+def test_collide_configs_and_moves(model, d, N):
+    ctx, orc, rads, obs = _pair(model, N, 0, seed=300 + d + N, rad=(0.02, 0.05))
+    rng = np.random.default_rng(3 + N)
+    n_cfg = 3000
+    Qf = rng.random((n_cfg, N, d))
+    Qt = Qf + rng.normal(scale=0.03, size=Qf.shape)
+    gv, gfp = ctx.collide_configs(Qf, Qt)
+    ov, ofp = orc.collide_configs_batch(Qf, Qt, nthreads=0)
+    assert np.array_equal(gv, ov) and np.array_equal(gfp, ofp)
+    assert 0 < ov.sum() or N == 2
+    for i in (0, N - 1):
+        Q = rng.random((N, d))
+        cand = Q[i] + rng.normal(scale=0.2, size=(5000, d))
+        assert np.array_equal(ctx.collide_config_moves(i, Q, cand),
+                              orc.collide_config_moves(i, Q, cand, nthreads=0))
+
+
+def test_edge_cases_empty_single_and_chunked():
+    ctx, orc, rads, obs = _pair(O.POINT2D, 7, 3, seed=9)
+    z = np.zeros((0, 2))
+    assert ctx.connect_edges(np.zeros(0, np.int32), z, z).size == 0
+    assert ctx.collide_pairs([], [], z, z, z, z).size == 0
+    assert ctx.connect_edges([3], [[0.2, 0.2]], [[0.25, 0.22]]).tolist() == \
+        orc.connect_edges([3], [[0.2, 0.2]], [[0.25, 0.22]]).tolist()
+    # > 1<<20 checks: exercises the chunked three-stream pipeline incl. a ragged last chunk
+    rng = np.random.default_rng(4)
+    n = (1 << 21) + 12345
+    ag = rng.integers(0, 7, n).astype(np.int32)
+    qf, qt = random_edges(rng, n, 2, 0.1)
+    assert np.array_equal(ctx.connect_edges(ag, qf, qt), orc.connect_edges(ag, qf, qt, nthreads=0))
+    aj = ((ag + 1) % 7).astype(np.int32)
+    c, e = random_edges(rng, n, 2, 0.1)
+    assert np.array_equal(ctx.collide_pairs(ag, aj, qf, qt, c, e),
+                          orc.collide_pairs(ag, aj, qf, qt, c, e, nthreads=0))
+    with pytest.raises(L.MRMPError):
+        ctx.connect_edges([7], [[0.2, 0.2]], [[0.3, 0.3]])       # agent out of range
+
+
+def test_no_obstacles_and_single_agent():
+    ctx, orc, rads, obs = _pair(O.POINT3D, 1, 0, seed=11)
+    rng = np.random.default_rng(5)
+    q = rng.random((1000, 3)) * 1.1 - 0.05
+    ag = np.zeros(1000, np.int32)
+    assert np.array_equal(ctx.connect_points(ag, q), orc.connect_points(ag, q))
+    v, fp = ctx.collide_configs(q[:1].reshape(1, 1, 3), q[:1].reshape(1, 1, 3))
+    assert v.tolist() == [0] and fp.tolist() == [-1]
+
+
+def test_launches_are_counted_and_lib_is_in_tree():
+    before = L.kernel_launch_count()
+    ctx, _, _, _ = _pair(O.POINT2D, 3, 2, seed=1)
+    ctx.connect_points([0], [[0.5, 0.5]])
+    assert L.kernel_launch_count() == before + 1
+    assert "/sssp_b200/_lib/libmrmp_b200.so" in L.load()._name

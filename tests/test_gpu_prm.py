@@ -1,0 +1,94 @@
+"""GPU parity for roadmap construction: sampler stream, free-space sampling order, and
+bit-exact CSR edge sets (rows ascending) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import sssp_b200 as S
+from oracle import oracle as O
+from helpers import make_point_instance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("model,d", [(O.POINT2D, 2), (O.POINT3D, 3)])
+def test_sampler_stream_matches_oracle(model, d):
+    rads, obs = make_point_instance(model, 4, 5, seed=1, rad_obs=(0.05, 0.1))
+    ctx, orc = S.Context(model, rads, obs), O.Oracle(model, rads, obs)
+    g = ctx.sample_states(agent=2, seed=46, t0=5, n=4096)
+    o = np.stack([orc.sample_state(46, 2, 5 + t) for t in range(4096)])
+    assert np.array_equal(g, o)
+    assert 0.45 < g.mean() < 0.55 and g.min() >= 0 and g.max() < 1
+    gq, gt = ctx.sample_free(agent=1, seed=7, n_wanted=700)
+    oq, ot = orc.sample_free(1, 7, 700)
+    assert gt == ot and np.array_equal(gq, oq)
+
+
+@pytest.mark.parametrize("model,d,nv,rad", [(O.POINT2D, 2, 500, 0.1), (O.POINT3D, 3, 200, 0.3),
+                                            (O.POINT2D, 2, 97, None), (O.POINT2D, 2, 2, 0.1)])
+def test_prm_csr_bit_exact(model, d, nv, rad):
+    N = 6
+    rads, obs = make_point_instance(model, N, 10, seed=5 + nv)
+    ctx, orc = S.Context(model, rads, obs), O.Oracle(model, rads, obs)
+    rng = np.random.default_rng(nv)
+    nodes = rng.random((N, nv, d)) * 0.9 + 0.05
+    row_ptr, col = ctx.prm_build(nodes, rad)
+    orp, ocol, onnz = orc.prm_build(0, nodes, rad, nthreads=0)
+    assert row_ptr[-1] == onnz.sum() == col.size
+    for a in range(N):
+        for v in range(nv):
+            r = a * nv + v
+            assert np.array_equal(col[row_ptr[r]:row_ptr[r + 1]],
+                                  ocol[a, orp[a, v]:orp[a, v + 1]]), (a, v)
+    if nv > 2:
+        assert col.size > 0
+
+
+def test_prms_end_to_end_matches_sequential_reference_loop():
+    """PRMs(config_init, config_goal, connect, 300; rad=0.1) (prm.jl:251-276): vertices 0/1
+    are init/goal, the rest the first free samples in try order, then the neighbour pass."""
+    N, nv, rad = 5, 300, 0.1
+    rads, obs = make_point_instance(O.POINT2D, N, 10, seed=46)
+    orc = O.Oracle(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(46)
+    init, goal = rng.random((N, 2)) * 0.8 + 0.1, rng.random((N, 2)) * 0.8 + 0.1
+    connect = S.gen_connect(S.StatePoint2D(0, 0), obs, rads)
+    roadmaps = S.PRMs(init, goal, connect, nv, rad=rad, seed=1234)
+    nodes = np.empty((N, nv, 2))
+    for a in range(N):
+        nodes[a, 0], nodes[a, 1] = init[a], goal[a]
+        nodes[a, 2:], _ = orc.sample_free(a, 1234, nv - 2)
+    orp, ocol, _ = orc.prm_build(0, nodes, rad, nthreads=0)
+    for a in range(N):
+        assert len(roadmaps[a]) == nv
+        for v in range(nv):
+            assert tuple(roadmaps[a][v].q) == tuple(nodes[a, v])
+            assert roadmaps[a][v].id == v
+            assert roadmaps[a][v].neighbors == ocol[a, orp[a, v]:orp[a, v + 1]].tolist()
+
+
+def test_roadmaps_indexed_collide_and_shards():
+    N, nv = 8, 120
+    rads, obs = make_point_instance(O.POINT2D, N, 4, seed=3, rad=(0.02, 0.04))
+    ctx, orc = S.Context(O.POINT2D, rads, obs), O.Oracle(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(8)
+    nodes = rng.random((N, nv, 2))
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    assert np.array_equal(rm.nodes(), nodes)
+    n = 200_000
+    ai = rng.integers(0, N, n)
+    aj = (ai + 1 + rng.integers(0, N - 1, n)) % N
+    v = rng.integers(0, nv, (4, n))
+    g = rm.collide_edges_indexed(ai, aj, *v)
+    o = orc.collide_edges_indexed(ai, aj, *v, nodes, nv, nthreads=0)
+    assert np.array_equal(g, o) and 0 < o.sum() < n
+    # an agent shard [3, 6) builds the same rows as the full set (multi-GPU partitioning)
+    nnz_full = rm.build(0.2)
+    rp, col = rm.csr()
+    sh = S.Roadmaps(ctx, 3, 3, nv)
+    sh.set_nodes(nodes[3:6])
+    sh.build(0.2)
+    srp, scol = sh.csr()
+    lo, hi = rp[3 * nv], rp[6 * nv]
+    assert np.array_equal(scol, col[lo:hi]) and np.array_equal(srp, rp[3 * nv:6 * nv + 1] - lo)
+    assert nnz_full == col.size
