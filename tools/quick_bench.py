@@ -10,7 +10,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sssp_b200 as S
 from sssp_b200 import lib as L
-from tests.helpers import make_point_instance, random_edges
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from helpers import make_point_instance, random_edges
 
 dev = torch.device("cuda:0")
 lib = L.load()
