@@ -72,6 +72,9 @@ int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const double *rads,
 void mrmp_ctx_destroy(mrmp_ctx *ctx);
 int mrmp_ctx_state_dim(const mrmp_ctx *ctx);
 int mrmp_ctx_sync(mrmp_ctx *ctx);
+/* run the ctx's kernels and small copies on a caller-owned cudaStream_t (NULL restores the
+ * ctx's own stream); lets a host framework order and time the work on its stream */
+int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
 
 /* ---- connect -------------------------------------------------------------------- */
 /* connect(q, i): point2d.jl:49-57, point3d.jl:54-64, arm22.jl:40-54 */
@@ -152,6 +155,11 @@ int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev
 /* adopt externally filled device arrays (after an all-gather): copies device->device */
 int mrmp_roadmaps_set_nodes_dev(mrmp_roadmaps *rm, int nv, const double *nodes_dev,
                                 void *stream);
+
+/* use caller-owned device storage nodes_dev[n_agents][nv][d] as the node table (e.g. a slice
+ * of an NCCL all-gather buffer, so sampling writes straight into the send buffer and the
+ * gathered buffer is consumed in place); NULL switches back to the set's own storage */
+int mrmp_roadmaps_bind_nodes(mrmp_roadmaps *rm, int nv, double *nodes_dev);
 
 /* one-shot host-buffer forms */
 /* PRM! neighbour pass on caller-provided nodes[n_agents][nv][d] (prm.jl:202-210) */

@@ -122,6 +122,10 @@ class Context:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream: int | None) -> None:
+        """Run this ctx's kernels on a caller-owned CUDA stream (e.g. torch's current)."""
+        L.check(self._lib.mrmp_ctx_set_stream(self._h, cuda_stream))
+
     # ---- batched host-buffer entry points (numpy in / numpy out) ---------------------
     def connect_points(self, agent, q) -> np.ndarray:
         agent, q = L.i32(agent).ravel(), _states(q, self.d)
@@ -235,6 +239,11 @@ class Roadmaps:
         nodes = L.f64(nodes).reshape(self.n, -1, self.ctx.d)
         self.nv = nodes.shape[1]
         L.check(self._lib.mrmp_roadmaps_set_nodes(self._h, self.nv, L.ptr(nodes, L._dp)))
+
+    def bind_nodes(self, nv: int, nodes_dev_ptr: int | None) -> None:
+        """Use caller-owned device memory [n][nv][d] as the node table (NCCL buffer slice)."""
+        L.check(self._lib.mrmp_roadmaps_bind_nodes(self._h, int(nv), nodes_dev_ptr))
+        self.nv = int(nv)
 
     def sample(self, nv: int, seed: int, q_init, q_goal) -> np.ndarray:
         qi, qg = _states(q_init, self.ctx.d), _states(q_goal, self.ctx.d)

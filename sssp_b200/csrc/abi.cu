@@ -108,6 +108,7 @@ struct mrmp_ctx {
     double *blob = nullptr;
     std::vector<double> h_rads;
     cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_k_owned = nullptr;  // s_k unless the caller installed its own stream
     cudaEvent_t ev_in[kSlots]{}, ev_k[kSlots]{}, ev_out[kSlots]{};
     // chunk slots (device) and small-batch staging (pinned host + device)
     unsigned char *slot_buf[kSlots]{};
@@ -251,6 +252,7 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     if (e == cudaSuccess)
         e = cudaMemcpy(c->blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
+    c->s_k_owned = c->s_k;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
@@ -279,7 +281,7 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
     }
     if (c->small_h) cudaFreeHost(c->small_h);
     if (c->small_d) cudaFree(c->small_d);
-    if (c->s_k) cudaStreamDestroy(c->s_k);
+    if (c->s_k_owned) cudaStreamDestroy(c->s_k_owned);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->blob) cudaFree(c->blob);
@@ -287,6 +289,14 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
 }
 
 extern "C" int mrmp_ctx_state_dim(const mrmp_ctx *c) { return c ? c->d : 0; }
+
+extern "C" int mrmp_ctx_set_stream(mrmp_ctx *c, void *stream) {
+    if (!c) return fail(MRMP_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_k));
+    c->s_k = stream ? (cudaStream_t)stream : c->s_k_owned;
+    return MRMP_OK;
+}
 
 extern "C" int mrmp_ctx_sync(mrmp_ctx *c) {
     if (!c) return fail(MRMP_ERR_INVALID, "ctx is NULL");
@@ -681,6 +691,7 @@ struct mrmp_roadmaps {
     int agent0 = 0, n_agents = 0, nv_cap = 0, nv = 0;
     int words = 0;
     double *nodes = nullptr;     // [n_agents][nv][d] (stride nv, repacked on set)
+    double *nodes_owned = nullptr;  // == nodes unless bound to caller storage
     uint32_t *bitmap = nullptr;  // [n_agents*nv][words]
     int32_t *row_cnt = nullptr, *row_ptr = nullptr, *col_idx = nullptr;
     int64_t col_cap = 0;
@@ -706,7 +717,8 @@ extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int n
     rm->nv_cap = nv_cap;
     const int words_cap = (nv_cap + 31) / 32;
     const int64_t rows = (int64_t)n_agents * nv_cap;
-    cudaError_t e = cudaMalloc((void **)&rm->nodes, sizeof(double) * c->d * rows);
+    cudaError_t e = cudaMalloc((void **)&rm->nodes_owned, sizeof(double) * c->d * rows);
+    rm->nodes = rm->nodes_owned;
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->bitmap, sizeof(uint32_t) * rows * words_cap);
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_cnt, sizeof(int32_t) * (rows + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_ptr, sizeof(int32_t) * (rows + 1));
@@ -725,7 +737,7 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     if (!rm) return;
     cudaSetDevice(rm->ctx->device);
     cudaStreamSynchronize(rm->ctx->s_k);
-    cudaFree(rm->nodes);
+    cudaFree(rm->nodes_owned);
     cudaFree(rm->bitmap);
     cudaFree(rm->row_cnt);
     cudaFree(rm->row_ptr);
@@ -759,6 +771,21 @@ extern "C" int mrmp_roadmaps_set_nodes_dev(mrmp_roadmaps *rm, int nv, const doub
     rm->built = false;
     CU(cudaMemcpyAsync(rm->nodes, nodes_dev, sizeof(double) * c->d * (size_t)nv * rm->n_agents,
                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_bind_nodes(mrmp_roadmaps *rm, int nv, double *nodes_dev) {
+    NEED(rm, "bad roadmaps");
+    if (!nodes_dev) {  // back to the set's own storage
+        rm->nodes = rm->nodes_owned;
+        rm->built = false;
+        return MRMP_OK;
+    }
+    NEED(nv >= 1 && nv <= rm->nv_cap, "nv out of range");
+    NEED(aligned16(nodes_dev), "nodes_dev must be 16-byte aligned");
+    rm->nodes = nodes_dev;
+    rm->nv = nv;
+    rm->built = false;
     return MRMP_OK;
 }
 

@@ -16,11 +16,10 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2,
 MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22 = 0, 1, 2
 STATE_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2}
 
-_dp = C.POINTER(C.c_double)
-_ip = C.POINTER(C.c_int32)
-_bp = C.POINTER(C.c_uint8)
-_lp = C.POINTER(C.c_int64)
+# every buffer argument is declared void* so that numpy arrays (ndarray.ctypes.data_as),
+# torch pinned tensors (data_ptr()) and raw device pointers can all be passed
 _vp = C.c_void_p
+_dp = _ip = _bp = _lp = C.c_void_p
 
 
 class MRMPError(RuntimeError):
@@ -41,6 +40,7 @@ _SIGS = {
     "mrmp_ctx_destroy": (None, [_vp]),
     "mrmp_ctx_state_dim": (C.c_int, [_vp]),
     "mrmp_ctx_sync": (C.c_int, [_vp]),
+    "mrmp_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "mrmp_connect_point": (C.c_int, [_vp, C.c_int, _dp, _bp]),
     "mrmp_connect_points": (C.c_int, [_vp, C.c_int64, _ip, _dp, _bp]),
     "mrmp_connect_edge": (C.c_int, [_vp, C.c_int, _dp, _dp, _bp]),
@@ -67,6 +67,7 @@ _SIGS = {
     "mrmp_roadmaps_device_ptrs": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp),
                                             C.POINTER(_vp), C.POINTER(_vp), _lp]),
     "mrmp_roadmaps_set_nodes_dev": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "mrmp_roadmaps_bind_nodes": (C.c_int, [_vp, C.c_int, _vp]),
     "mrmp_prm_build": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _ip, C.c_int64,
                                  _lp]),
     "mrmp_prms": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_uint64, _dp, _dp, _dp, _ip,
