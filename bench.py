@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- connect+collide edge checks/sec and roadmap build ms (BASELINE.json metric).
 
-Workload (configs[1]: StatePoint2D point2d_many, N=50, M=10): one STEP =
-  (A) PRMs(num_vertices=500, rad=0.1): free-space sampling + neighbour pass for the N agents
-      (sharded by agent across ranks, node tables + CSR all-gathered over NCCL);
-  (B) a batch of explicit connect(q_from,q_to,i) edge checks (PRM-like edges);
-  (C) a batch of collide(6-arity) checks between random roadmap edges of random agent
-      pairs, referenced by (agent, vertex) ids into the device-resident roadmaps.
-`value`  = (B)+(C) checks / step time, inputs resident in HBM (weak scaling: the per-GPU
-           batch is fixed, the N=50 roadmap build is split across ranks);
-`e2e`    = the same through the host-buffer C ABI: pinned host inputs, H2D/D2H inside the
-           timed region, roadmaps (nodes + CSR) and verdicts read back every step;
-`--impl reference` = the CPU oracle (C restatement of the reference, OpenMP, all host
-           cores) on the identical workload.  The reference itself is pure Julia and cannot
-           run in this image (no Julia runtime), see DESIGN.md.
+Workload = configs[1] of BASELINE.json: StatePoint2D point2d_many at N=50 agents, M=10
+obstacles (scripts/config/eval/point2d_many.yaml).  One STEP is one pass of the hot path:
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference] [--log2-checks 24]
+  (A) roadmap build  PRMs(num_vertices=500, rad=0.1)  (prm.jl:251-276): free-space sampling
+      + all-pairs radius gate + connect(q_j,q_k,i) for the N agents -> CSR adjacency.
+      connect checks counted: the pairs that pass the radius gate (= connect() calls the
+      reference issues, prm.jl:207).
+  (B) inter-agent collide batch in the shape PP's invalid() issues it (pp.jl:179-189): EVERY
+      roadmap edge of every agent against the path edges of all OTHER agents over T=64 time
+      steps (max_makespan of point2d_many.yaml), OR-reduced per time step -> the conflict
+      table the search consults.  collide checks counted: nnz * T * (N-1).
+
+Multi-GPU (weak scaling): the roadmap build is sharded by agent, node tables and CSR are
+all-gathered over NCCL, then every rank evaluates the full table against its OWN path
+scenario (e.g. PP's random-priority restarts, pp.jl:104-128): per-GPU work is fixed.
+
+`value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream.
+`e2e`    = same through the host-buffer C ABI: host init/goal and path ids in, roadmaps
+           (nodes + CSR) and the conflict table bits out, every step.
+`--impl reference` = the CPU oracle (C restatement of the reference, OpenMP on all host
+           cores).  The reference is pure Julia and cannot run in this image;
+           each step builds all N roadmaps and evaluates a bounded 1/64 row sample of (B).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -34,11 +44,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "connect+collide edge checks/sec"
 UNIT = "checks/s"
-N_AGENTS, NV, RAD = 50, 500, 0.1
+N_AGENTS, NV, RAD, T_STEPS = 50, 500, 0.1, 64
+CPU_ROW_STRIDE = 64            # reference arm: every 64th roadmap edge as a row of (B)
 
-# algorithmic figures (DESIGN.md "Kernels"): bytes per check of the explicit-list forms
-BYTES_CONNECT = 2 * 16 + 4 + 1      # q_from, q_to (2 x double2), agent id, verdict byte
-BYTES_COLLIDE_IDX = 6 * 4 + 4 * 16 + 1  # ids (6 x int32) + 4 gathered states + verdict
+# algorithmic work per unit (DESIGN.md "Kernels"), FP64 flops with add/mul/cmp = 1 each
+FLOPS_BROAD = 7                # midpoint bound per pair: 2 sub, 2 mul, 2 add, 1 cmp
+FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
+FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
+BYTES_CONNECT = 2 * 16 + 4 + 1
+BYTES_COLLIDE = 4 * 16 + 8 + 1
 
 
 def parse():
@@ -47,8 +61,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2-checks", type=int, default=24, help="checks per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     return ap.parse_args()
 
 
@@ -60,72 +74,93 @@ def peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def config_dict(world):
+    return {"workload": "point2d_many N=50 M=10: PRMs(500, rad=0.1) + conflict table (all "
+                        "roadmap edges x other agents' path edges, T=64) per GPU",
+            "n_agents": N_AGENTS, "num_vertices": NV, "rad": RAD, "path_steps": T_STEPS,
+            "n_obstacles": 10, "path_scenarios": world,
+            "l2": "L2 flushed between timed steps (256 MB memset); per-step inputs are KB-sized"}
+
+
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the CPU oracle on the same workload
 # ------------------------------------------------------------------------------------------
-def cpu_reference_step(orc, inst, con, col, threads):
-    """One full step on the host: roadmap build for all N agents + both check batches."""
-    N, nv = inst.rads.size, inst.nv
-    nodes = np.empty((N, nv, 2))
-    nodes[:, 0], nodes[:, 1] = inst.q_init, inst.q_goal
-    t0 = time.perf_counter()
-    for a in range(N):  # prm.jl:193-199 per agent (sequential sampler loop, cheap)
-        nodes[a, 2:], _ = orc.sample_free(a, inst.seed, nv - 2)
-    row_ptr, colidx, nnz = orc.prm_build(0, nodes, inst.rad, nthreads=threads)
-    t1 = time.perf_counter()
-    v1 = orc.connect_edges(*con, nthreads=threads)
-    v2 = orc.collide_edges_indexed(*col, nodes, nv, nthreads=threads)
-    t2 = time.perf_counter()
-    return t2 - t0, t1 - t0, int(v1.sum()) + int(v2.sum())
+class CpuArm:
+    def __init__(self, inst):
+        from oracle import oracle as O
+        O.build()
+        self.O = O
+        self.threads = O.max_threads()
+        self.inst = inst
+        self.orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
+
+    def build(self):
+        """(A) on the host: sampling loop per agent (prm.jl:193-199), neighbour pass with
+        OpenMP over agents (the reference's `map` over agents, prm.jl:265-275)."""
+        inst, N, nv = self.inst, self.inst.rads.size, self.inst.nv
+        nodes = np.empty((N, nv, 2))
+        nodes[:, 0], nodes[:, 1] = inst.q_init, inst.q_goal
+        for a in range(N):
+            nodes[a, 2:], _ = self.orc.sample_free(a, inst.seed, nv - 2)
+        rp, colidx, nnz = self.orc.prm_build(0, nodes, inst.rad, nthreads=self.threads)
+        row_ptr = np.zeros(N * nv + 1, np.int64)
+        cols = []
+        for a in range(N):
+            row_ptr[a * nv + 1:(a + 1) * nv + 1] = row_ptr[a * nv] + rp[a, 1:]
+            cols.append(colidx[a, :nnz[a]])
+        return nodes, row_ptr, np.concatenate(cols)
+
+    def table_sample(self, nodes, row_ptr, col, ca, vf, vt, stride):
+        """(B) on a bounded row sample: every `stride`-th roadmap edge against all columns."""
+        nv = self.inst.nv
+        rows = np.repeat(np.arange(row_ptr.size - 1), np.diff(row_ptr))[::stride]
+        ra = (rows // nv).astype(np.int32)
+        rf = nodes[ra, rows % nv]
+        rt = nodes[ra, col[::stride]]
+        cf, ct = nodes[ca, vf], nodes[ca, vt]
+        bits = self.orc.collide_cross(ra, rf, rt, ca, cf, ct, self.inst.rads.size,
+                                      nthreads=self.threads)
+        return rows.size, bits
+
+    def step(self, ca, vf, vt, stride):
+        t0 = time.perf_counter()
+        nodes, row_ptr, col = self.build()
+        t1 = time.perf_counter()
+        n_rows, _ = self.table_sample(nodes, row_ptr, col, ca, vf, vt, stride)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, n_rows, nodes, row_ptr, col
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the host arm
-    from oracle import oracle as O
     from sssp_b200 import workload as W
-    O.build()
-    threads = O.max_threads()
     inst = W.point2d_many(N_AGENTS, seed=0, nv=NV, rad=RAD)
-    orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
-    n = 1 << args.log2_checks
-    n_con, n_col = n // 2, n - n // 2
-    nodes = np.empty((N_AGENTS, NV, 2))
-    nodes[:, 0], nodes[:, 1] = inst.q_init, inst.q_goal
-    for a in range(N_AGENTS):
-        nodes[a, 2:], _ = orc.sample_free(a, inst.seed, NV - 2)
-    rp, colidx, nnz = orc.prm_build(0, nodes, inst.rad, nthreads=threads)
-    row_ptr = np.zeros(N_AGENTS * NV + 1, np.int64)
-    cols = []
-    for a in range(N_AGENTS):
-        row_ptr[a * NV + 1:(a + 1) * NV + 1] = row_ptr[a * NV] + rp[a, 1:]
-        cols.append(colidx[a, :nnz[a]])
-    cols = np.concatenate(cols)
-    con = W.connect_list(inst, n_con)
-    col = W.collide_list(inst, row_ptr, cols, n_col)
-    times, builds = [], []
+    cpu = CpuArm(inst)
+    nodes, row_ptr, col = cpu.build()
+    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr, col, T_STEPS, seed=4321)
+    gate = W.gate_pass_count(nodes, RAD)
+    tb, tt, checks = [], [], 0
     for it in range(args.warmup + args.steps):
-        t, tb, _ = cpu_reference_step(orc, inst, con, col, threads)
+        b, t, n_rows, *_ = cpu.step(ca, vf, vt, CPU_ROW_STRIDE)
         if it >= args.warmup:
-            times.append(t)
-            builds.append(tb)
-    T = float(np.sum(times))
-    value = n * args.steps / T
+            tb.append(b)
+            tt.append(t)
+            checks += gate + n_rows * T_STEPS * (N_AGENTS - 1)
+    T = float(np.sum(tb) + np.sum(tt))
+    value = checks / T
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "point2d_many N=50 M=10: PRMs(500, rad=0.1) + 2^%d checks "
-                               "(half connect edges, half indexed collide)" % args.log2_checks,
-                   "n_agents": N_AGENTS, "num_vertices": NV, "rad": RAD,
-                   "checks_per_step": n},
-        "roadmap_build_ms": 1e3 * float(np.mean(builds)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "full step (N=50 roadmap build + 2^%d checks), C oracle, "
-                                   "OpenMP %d threads; reference is pure Julia and cannot run "
-                                   "here" % (args.log2_checks, threads)},
+        "data": "synthetic", "config": config_dict(1),
+        "roadmap_build_ms": 1e3 * float(np.mean(tb)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
+                         "sample": "per step: full N=50 roadmap build + conflict table on every "
+                                   "%dth roadmap edge (%d rows x %d columns); C oracle, OpenMP %d "
+                                   "threads; the reference is pure Julia and cannot run here"
+                                   % (CPU_ROW_STRIDE, n_rows, ca.size, cpu.threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -146,24 +181,27 @@ class Clocks:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.3)   # let the sampler come up before the timed region
         except Exception:
             self.p = None
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.p.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and not (t_begin - 0.06 <= ts <= t_end + 0.06):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -203,107 +241,92 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
+    warmup = max(args.warmup, 3)
 
     inst = W.point2d_many(N_AGENTS, seed=0, nv=NV, rad=RAD)
     N, nv, d = N_AGENTS, NV, 2
     ctx = S.Context(inst.model, inst.rads, inst.obstacles, device=local)
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    st = stream.cuda_stream
+    ctx.set_stream(st)
     a0, n_local, cap = SH.agent_block(N, world, rank)
 
-    # device-resident roadmaps: the gathered node table is the NCCL buffer; this rank's shard
-    # is a slice of it (kernels write straight into the send buffer), rm_all consumes it in place
+    # The gathered node table IS the NCCL buffer: this rank's shard is a slice of it (the
+    # sampling kernel writes straight into the send buffer) and rm_all consumes it in place.
     gathered = torch.zeros((world * cap, nv, d), dtype=torch.float64, device=dev)
     rm_all = S.Roadmaps(ctx, 0, N, nv)
     rm_all.bind_nodes(nv, gathered.data_ptr())
-    rm_sh = S.Roadmaps(ctx, a0, max(n_local, 1), nv) if n_local > 0 else None
-    if rm_sh is not None:
+    if world > 1:
+        rm_sh = S.Roadmaps(ctx, a0, max(n_local, 1), nv)
         rm_sh.bind_nodes(nv, gathered[a0].data_ptr())
+    else:
+        rm_sh = rm_all
     radv = np.full(max(n_local, 1), inst.rad)
     init_sh = np.ascontiguousarray(inst.q_init[a0:a0 + n_local])
     goal_sh = np.ascontiguousarray(inst.q_goal[a0:a0 + n_local])
 
-    def build_roadmaps(gather_csr=True):
-        """(A): sample + all-gather nodes + neighbour pass + all-gather CSR."""
-        if rm_sh is not None:
-            rm_sh.sample(nv, inst.seed, init_sh, goal_sh)
+    def build_roadmaps():
+        """(A): sample + [all-gather nodes] + neighbour pass + [all-gather CSR]."""
+        rm_sh.sample(nv, inst.seed, init_sh, goal_sh)
         if world > 1:
             SH.allgather_nodes_inplace(gathered, cap, nv, d)
-        nnz = rm_sh.build(radv) if rm_sh is not None else 0
-        if gather_csr and world > 1:
-            if rm_sh is not None:
-                p = rm_sh.device_ptrs()
-                rp_t = torch.as_tensor(CudaArray(p["row_ptr"], (n_local * nv + 1,), "<i4"), device=dev)
-                ci_t = torch.as_tensor(CudaArray(p["col_idx"], (max(nnz, 1),), "<i4"), device=dev)[:nnz]
-            else:
-                rp_t = torch.zeros(1, dtype=torch.int32, device=dev)
-                ci_t = torch.zeros(0, dtype=torch.int32, device=dev)
-            return SH.allgather_csr(rp_t, ci_t, N, nv, world, rank)
+        nnz = rm_sh.build(radv)
+        if world > 1:
+            p = rm_sh.device_ptrs()
+            rp_t = torch.as_tensor(CudaArray(p["row_ptr"], (n_local * nv + 1,), "<i4"), device=dev)
+            ci_t = torch.as_tensor(CudaArray(p["col_idx"], (max(nnz, 1),), "<i4"), device=dev)[:nnz]
+            rp_g, ci_g = SH.allgather_csr(rp_t, ci_t, N, nv, world, rank)
+            rp32 = rp_g.to(torch.int32)
+            L.check(lib.mrmp_roadmaps_set_csr_dev(rm_all._h, rp32.data_ptr(), ci_g.data_ptr(),
+                                                  int(ci_g.numel()), st))
+            torch.cuda.current_stream().synchronize()  # rp32 / ci_g are consumed by now
+            return int(ci_g.numel())
         return nnz
 
-    # ---- setup: one build to obtain the CSR the collide list draws its edges from
-    build_roadmaps(gather_csr=False)
+    # ---- setup: one build gives the CSR the synthetic paths walk on
+    nnz_total = build_roadmaps()
     torch.cuda.synchronize()
-    full = S.Roadmaps(ctx, 0, N, nv)
-    full.sample(nv, inst.seed, inst.q_init, inst.q_goal)
-    full.build(np.full(N, inst.rad))
-    row_ptr_h, col_h = full.csr()
-    nnz_total = int(col_h.size)
-    full.close()
+    nodes_h = rm_all.nodes()
+    row_ptr_h, col_h = rm_all.csr()
+    gate = W.gate_pass_count(nodes_h, RAD)
+    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr_h, col_h, T_STEPS, seed=4321 + rank)
+    n_cols = int(ca.size)
+    pair_checks = nnz_total * T_STEPS * (N - 1)
+    wpr = (T_STEPS + 31) // 32
 
-    n = 1 << args.log2_checks
-    n_con, n_col = n // 2, n - n // 2
-    con = W.connect_list(inst, n_con, seed=1234 + rank)
-    col = W.collide_list(inst, row_ptr_h, col_h, n_col, seed=4321 + rank)
-
-    # pinned host copies (e2e inputs / outputs) and device-resident copies (value)
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
-    con_h = [pin(x) for x in con]
-    col_hh = [pin(x) for x in col]
-    con_d = [t.to(dev) for t in con_h]
-    col_d = [t.to(dev) for t in col_hh]
-    out_con_d = torch.empty(n_con, dtype=torch.uint8, device=dev)
-    out_col_d = torch.empty(n_col, dtype=torch.uint8, device=dev)
-    out_con_h = torch.empty(n_con, dtype=torch.uint8).pin_memory()
-    out_col_h = torch.empty(n_col, dtype=torch.uint8).pin_memory()
+    cols_h = [pin(x) for x in (ca, vf, vt)]
+    cols_d = [t.to(dev) for t in cols_h]
+    bits_d = torch.zeros((nnz_total, wpr), dtype=torch.int32, device=dev)
+    bits_h = torch.zeros((nnz_total, wpr), dtype=torch.int32).pin_memory()
     rows_sh = max(n_local, 1) * nv
     nodes_out_h = torch.empty((max(n_local, 1), nv, d), dtype=torch.float64).pin_memory()
     rowptr_out_h = torch.empty(rows_sh + 1, dtype=torch.int32).pin_memory()
     colidx_out_h = torch.empty(max(nnz_total, 1), dtype=torch.int32).pin_memory()
-    st = stream.cuda_stream
-    import ctypes as C
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def k_connect():
-        L.check(lib.mrmp_connect_edges_dev(ctx._h, n_con, con_d[0].data_ptr(), con_d[1].data_ptr(),
-                                           con_d[2].data_ptr(), out_con_d.data_ptr(), st))
-
-    def k_collide():
-        L.check(lib.mrmp_collide_edges_indexed_dev(
-            rm_all._h, n_col, *[t.data_ptr() for t in col_d], out_col_d.data_ptr(), st))
+    def k_table():
+        L.check(lib.mrmp_roadmaps_edge_conflicts_dev(rm_all._h, None, n_cols,
+                                                     cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                                     cols_d[2].data_ptr(), N, bits_d.data_ptr(), st))
 
     def step_value():
-        build_roadmaps(gather_csr=True)
-        k_connect()
-        k_collide()
+        build_roadmaps()
+        k_table()
 
     def step_e2e():
-        build_roadmaps(gather_csr=True)
-        if rm_sh is not None:  # roadmaps back to the host (what PRMs() returns)
-            L.check(lib.mrmp_roadmaps_get_nodes(rm_sh._h, C.c_void_p(nodes_out_h.data_ptr())))
-            nnz = C.c_int64(0)
-            L.check(lib.mrmp_roadmaps_get_csr(rm_sh._h, C.c_void_p(rowptr_out_h.data_ptr()),
-                                              C.c_void_p(colidx_out_h.data_ptr()),
-                                              colidx_out_h.numel(), C.byref(nnz)))
-        L.check(lib.mrmp_connect_edges(ctx._h, n_con, C.c_void_p(con_h[0].data_ptr()),
-                                       C.c_void_p(con_h[1].data_ptr()),
-                                       C.c_void_p(con_h[2].data_ptr()),
-                                       C.c_void_p(out_con_h.data_ptr())))
-        L.check(lib.mrmp_collide_edges_indexed(rm_all._h, n_col,
-                                               *[C.c_void_p(t.data_ptr()) for t in col_hh],
-                                               C.c_void_p(out_col_h.data_ptr())))
+        build_roadmaps()
+        # roadmaps back to the host (what PRMs() returns to the solver)
+        L.check(lib.mrmp_roadmaps_get_nodes(rm_sh._h, nodes_out_h.data_ptr()))
+        nnz = C.c_int64(0)
+        L.check(lib.mrmp_roadmaps_get_csr(rm_sh._h, rowptr_out_h.data_ptr(),
+                                          colidx_out_h.data_ptr(), colidx_out_h.numel(),
+                                          C.byref(nnz)))
+        L.check(lib.mrmp_roadmaps_edge_conflicts(rm_all._h, None, n_cols, cols_h[0].data_ptr(),
+                                                 cols_h[1].data_ptr(), cols_h[2].data_ptr(), N,
+                                                 bits_h.data_ptr(), bits_h.numel()))
 
     def barrier():
         if world > 1:
@@ -317,26 +340,31 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: device-resident, CUDA events on the launching stream
-    for _ in range(max(args.warmup, 3)):
+    # ---- value: device-resident, CUDA events per step on the launching stream, L2 flushed
+    for _ in range(warmup):
         step_value()
     barrier()
     clocks = Clocks(local)
     clocks.start()
     launches0 = L.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
+    t_begin = time.perf_counter()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()                      # evict L2 (outside the per-step event pair)
+        ev[k][0].record(stream)
         step_value()
-    e1.record(stream)
+        ev[k][1].record(stream)
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    t_end = time.perf_counter()
     launches = L.kernel_launch_count() - launches0
-    clk = clocks.stop()
+    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    clk = clocks.stop(t_begin, t_end)
     ms_step = ms_total / args.steps
-    value = n * world / (ms_step * 1e-3)
+    checks_step = gate + world * pair_checks
+    value = checks_step / (ms_step * 1e-3)
 
-    # ---- per-kernel durations (same stream, same inputs) for the roofline
+    # ---- per-kernel durations for the roofline (same stream, same inputs)
     def timed(fn, reps=10):
         fn()
         torch.cuda.synchronize()
@@ -348,65 +376,92 @@ def run_b200(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    ms_con, ms_col = timed(k_connect), timed(k_collide)
-    ms_build = timed(lambda: build_roadmaps(gather_csr=False), reps=5)
+    ms_build = timed(build_roadmaps, reps=5)
+    ctx.stats(reset=True)
+    ms_table = timed(k_table, reps=10)
+    survivors = int(ctx.stats()[0]) / 11.0
+    n_pairs = nnz_total * n_cols
+    flops = n_pairs * FLOPS_BROAD + survivors * FLOPS_EXACT
+    achieved = flops / (ms_table * 1e-3) / 1e12
     pk, pk_kind = peaks()
-    if ms_con >= ms_col:
-        dom, dom_ms, dom_bytes = "k_connect_edges<2>", ms_con, n_con * BYTES_CONNECT
-    else:
-        dom, dom_ms, dom_bytes = "k_collide_edges_indexed<2>", ms_col, n_col * BYTES_COLLIDE_IDX
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
-                "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel_ms": {"connect_edges": ms_con, "collide_edges_indexed": ms_col,
-                              "roadmap_build": ms_build},
-                "fp64_unfused_peak_tflops": 18.58}
+    roofline = {
+        "bound": "fp64", "kernel": "k_cross_collide<2,true> (+ column prep)",
+        "achieved": achieved, "peak": FP64_UNFUSED_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved / FP64_UNFUSED_PEAK_TFLOPS, "traffic": None,
+        "peak_source": "un-fused DADD/DMUL issue peak measured with tools/fp64_peak.cu on this "
+                       "pool (profiles/r1_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure "
+                       "and bit parity forbids FMA",
+        "algorithmic_flops": {"pairs": n_pairs, "per_pair_broad_phase": FLOPS_BROAD,
+                              "survivors": survivors, "per_survivor_exact": FLOPS_EXACT},
+        "pair_checks_per_s": n_pairs / (ms_table * 1e-3),
+        "kernel_ms": {"conflict_table": ms_table, "roadmap_build": ms_build},
+    }
 
     # ---- e2e: host buffers through the C ABI
     for _ in range(2):
         step_e2e()
     barrier()
-    t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    h2d = n_con * (4 + 32) + n_col * 24 + 2 * n_local * d * 8
-    d2h = n + n_local * nv * d * 8 + (rows_sh + 1) * 4 + nnz_total * 4 // world
-    e2e = {"value": n * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+    h2d = 2 * n_local * d * 8 + 3 * n_cols * 4
+    d2h = n_local * nv * d * 8 + (rows_sh + 1) * 4 + (nnz_total // world) * 4 + nnz_total * wpr * 4
+    e2e = {"value": checks_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
+
+    # ---- extras: explicit-list kernels (HBM-side of the path), inputs resident in HBM
+    extras = None
+    if rank == 0 and not args.no_extras:
+        n = 1 << 24
+        con = W.connect_list(inst, n, seed=1234)
+        con_d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in con]
+        cl = W.collide_list(inst, row_ptr_h, col_h, n, seed=99)
+        cl_d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in cl]
+        out = torch.empty(n, dtype=torch.uint8, device=dev)
+        ms_con = timed(lambda: L.check(lib.mrmp_connect_edges_dev(
+            ctx._h, n, con_d[0].data_ptr(), con_d[1].data_ptr(), con_d[2].data_ptr(),
+            out.data_ptr(), st)))
+        ms_idx = timed(lambda: L.check(lib.mrmp_collide_edges_indexed_dev(
+            rm_all._h, n, *[t.data_ptr() for t in cl_d], out.data_ptr(), st)))
+        extras = {"explicit_list_n": n,
+                  "connect_edges": {"ms": ms_con, "checks_per_s": n / ms_con * 1e3,
+                                    "hbm_gbs": n * BYTES_CONNECT / ms_con / 1e6,
+                                    "hbm_frac": n * BYTES_CONNECT / ms_con / 1e6 / pk["hbm_gbs"]},
+                  "collide_edges_indexed": {"ms": ms_idx, "checks_per_s": n / ms_idx * 1e3}}
+        del con_d, cl_d, out
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        O.build()
-        threads = O.max_threads()
-        orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
-        t, tb, _ = cpu_reference_step(orc, inst, con, col, threads)   # warm-up
-        ts = [cpu_reference_step(orc, inst, con, col, threads) for _ in range(3)]
-        tbest = min(x[0] for x in ts)
-        cpu = {"value": n / tbest, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "full step (N=50 roadmap build + 2^%d checks) x3, best; C oracle with "
-                         "OpenMP on %d threads" % (args.log2_checks, threads),
-               "roadmap_build_ms": 1e3 * min(x[1] for x in ts)}
+        arm = CpuArm(inst)
+        arm.step(ca, vf, vt, CPU_ROW_STRIDE)      # warm-up
+        best = None
+        for _ in range(3):
+            b, t, n_rows, *_ = arm.step(ca, vf, vt, CPU_ROW_STRIDE)
+            if best is None or b + t < best[0] + best[1]:
+                best = (b, t, n_rows)
+        cchecks = gate + best[2] * T_STEPS * (N - 1)
+        cpu = {"value": cchecks / (best[0] + best[1]), "unit": UNIT, "cores": arm.threads,
+               "kind": "port",
+               "sample": "full N=50 roadmap build + conflict table on every %dth roadmap edge "
+                         "(%d rows x %d columns), best of 3; C oracle, OpenMP %d threads"
+                         % (CPU_ROW_STRIDE, best[2], n_cols, arm.threads),
+               "roadmap_build_ms": 1e3 * best[0],
+               "collide_pair_checks_per_s": best[2] * T_STEPS * (N - 1) / best[1]}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "point2d_many N=50 M=10: PRMs(500, rad=0.1) + 2^%d checks per "
-                                   "GPU (half connect edges, half indexed collide)"
-                                   % args.log2_checks,
-                       "n_agents": N, "num_vertices": nv, "rad": RAD, "checks_per_step": n * world,
-                       "l2": "inputs larger than L2 (%.0f MB per step per GPU)"
-                             % ((n_con * 36 + n_col * 24) / 1e6)},
+            "config": config_dict(world),
+            "checks_per_step": {"connect": gate, "collide": world * pair_checks},
             "roadmap_build_ms": ms_build, "roadmap_nnz": nnz_total,
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

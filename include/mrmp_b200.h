@@ -75,6 +75,9 @@ int mrmp_ctx_sync(mrmp_ctx *ctx);
 /* run the ctx's kernels and small copies on a caller-owned cudaStream_t (NULL restores the
  * ctx's own stream); lets a host framework order and time the work on its stream */
 int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
+/* diagnostics: out4[0] = pairs that survived the cross kernels' broad phase (ran the exact
+ * reference arithmetic) since the last reset; out4[1..3] reserved */
+int mrmp_ctx_stats(mrmp_ctx *ctx, int64_t *out4, int reset);
 
 /* ---- connect -------------------------------------------------------------------- */
 /* connect(q, i): point2d.jl:49-57, point3d.jl:54-64, arm22.jl:40-54 */
@@ -149,6 +152,9 @@ int mrmp_roadmaps_get_nodes(mrmp_roadmaps *rm, double *nodes_out);
  * col_cap < nnz (nnz_out is still written so the caller can retry). */
 int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_t *col_idx,
                           int64_t col_cap, int64_t *nnz_out);
+/* adopt an adjacency assembled elsewhere (all-gathered shards): device arrays, packed CSR */
+int mrmp_roadmaps_set_csr_dev(mrmp_roadmaps *rm, const int32_t *row_ptr_dev,
+                              const int32_t *col_idx_dev, int64_t nnz, void *stream);
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
                               int32_t **row_ptr_dev, int32_t **col_idx_dev, int64_t *nnz_out);
@@ -183,6 +189,39 @@ int mrmp_collide_edges_indexed_dev(mrmp_roadmaps *rm, int64_t n, const int32_t *
                                    const int32_t *j, const int32_t *vi_from,
                                    const int32_t *vi_to, const int32_t *vj_from,
                                    const int32_t *vj_to, uint8_t *out, void *stream);
+
+/* ---- cross-product collide (new batched API): every row edge x every column edge --------- */
+/* verdict(r, c) = row_agent[r] != col_agent[c] &&
+ *                 collide(row_from[r], row_to[r], col_from[c], col_to[c], row_agent[r], col_agent[c])
+ * (point.jl:9-12; row edge is the FIRST segment).  Batched form of PP's invalid()
+ * (pp.jl:179-189), CBS's soft conflict count (cbs.jl:336-347), the TPG dependency scan
+ * (smoother.jl:86-103) and SSSP's successor filter (sssp.jl:196-223).
+ * group_size == 0: out_bits is the full bit matrix, words_per_row = ceil(n_cols/32), bit c%32
+ *   of word c/32 of row r.
+ * group_size  > 0: columns form consecutive groups of group_size (e.g. all agents' path edges
+ *   of one time step); bit g of row r = OR over group g; words_per_row =
+ *   ceil(ceil(n_cols/group_size)/32). */
+int mrmp_collide_cross(mrmp_ctx *ctx, int64_t n_rows, const int32_t *row_agent,
+                       const double *row_from, const double *row_to, int64_t n_cols,
+                       const int32_t *col_agent, const double *col_from, const double *col_to,
+                       int group_size, uint32_t *out_bits);
+int mrmp_collide_cross_dev(mrmp_ctx *ctx, int64_t n_rows, const int32_t *row_agent,
+                           const double *row_from, const double *row_to, int64_t n_cols,
+                           const int32_t *col_agent, const double *col_from,
+                           const double *col_to, int group_size, uint32_t *out_bits,
+                           void *stream);
+/* rows = every edge of the (built) roadmap set in packed CSR order (row e <-> col_idx[e]);
+ * columns = roadmap edges given by ids (col_agent, col_vfrom -> col_vto) into rm_cols (NULL:
+ * the same set; a shard passes the all-gathered full set here).  out_bits
+ * [nnz][words_per_row]; out_cap_words = capacity of out_bits in 32-bit words. */
+int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_t n_cols,
+                                 const int32_t *col_agent,
+                                 const int32_t *col_vfrom, const int32_t *col_vto,
+                                 int group_size, uint32_t *out_bits, int64_t out_cap_words);
+int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_t n_cols,
+                                     const int32_t *col_agent, const int32_t *col_vfrom,
+                                     const int32_t *col_vto, int group_size, uint32_t *out_bits,
+                                     void *stream);
 
 /* sampler: gen_uniform_sampling (point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218)
  * restated on a counter-based generator; writes try t0..t0+n-1 of (seed, agent) */

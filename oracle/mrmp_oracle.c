@@ -573,6 +573,30 @@ void orc_collide_edges_indexed_batch(const orc_ctx *c, int64_t n, const int32_t 
     }
 }
 
+/* Cross product of the 6-arity collide (point.jl:9-12 / arm22.jl:100-146): every row edge
+ * against every column edge, same-agent pairs excluded; the loop shape of PP's invalid()
+ * (pp.jl:179-189) and CBS's conflict count (cbs.jl:336-347).  group_size == 0: full bit
+ * matrix [n_rows][ceil(n_cols/32)]; > 0: OR over consecutive column groups. */
+void orc_collide_cross(const orc_ctx *c, int64_t n_rows, const int32_t *ra, const double *rf,
+                       const double *rt, int64_t n_cols, const int32_t *ca, const double *cf,
+                       const double *ct, int group_size, uint32_t *out, int nthreads) {
+    int d = c->d, nt = pick_threads(nthreads);
+    int64_t bits = group_size > 0 ? (n_cols + group_size - 1) / group_size : n_cols;
+    int64_t wpr = (bits + 31) / 32;
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 8)
+    for (int64_t r = 0; r < n_rows; ++r) {
+        uint32_t *o = out + r * wpr;
+        for (int64_t w = 0; w < wpr; ++w) o[w] = 0;
+        for (int64_t k = 0; k < n_cols; ++k) {
+            if (ra[r] == ca[k]) continue;
+            if (orc_collide_pair(c, rf + d * r, rt + d * r, cf + d * k, ct + d * k, ra[r], ca[k])) {
+                int64_t b = group_size > 0 ? k / group_size : k;
+                o[b >> 5] |= 1u << (b & 31);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* sampler: counter-based Philox4x32-10 (Salmon et al., SC'11)               */
 /* ------------------------------------------------------------------------ */

@@ -106,6 +106,10 @@ void orc_collide_edges_indexed_batch(const orc_ctx *c, int64_t n, const int32_t 
                                      const double *nodes, int64_t nv_stride, uint8_t *out,
                                      int nthreads);
 
+void orc_collide_cross(const orc_ctx *c, int64_t n_rows, const int32_t *ra, const double *rf,
+                       const double *rt, int64_t n_cols, const int32_t *ca, const double *cf,
+                       const double *ct, int group_size, uint32_t *out, int nthreads);
+
 /* counter-based sampler (Philox4x32-10), replaces Julia's task-local RNG:
  * gen_uniform_sampling, point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218 */
 void orc_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,

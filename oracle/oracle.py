@@ -72,6 +72,8 @@ def _load(name: str) -> C.CDLL:
                                                    _bp, C.c_int]
     lib.orc_collide_edges_indexed_batch.argtypes = [C.c_void_p, C.c_int64, _ip, _ip, _ip, _ip,
                                                     _ip, _ip, _dp, C.c_int64, _bp, C.c_int]
+    lib.orc_collide_cross.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, C.c_int64, _ip, _dp, _dp,
+                                      C.c_int, C.c_void_p, C.c_int]
     lib.orc_philox4x32.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     lib.orc_sample_state.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, _dp]
     lib.orc_sample_free.restype = C.c_int64
@@ -274,6 +276,16 @@ class Oracle:
         self._lib.orc_collide_edges_indexed_batch(
             self._h, ai.size, _p(ai, _ip), _p(aj, _ip), _p(vif, _ip), _p(vit, _ip), _p(vjf, _ip),
             _p(vjt, _ip), _p(nodes, _dp), int(nv_stride), _p(out, _bp), nthreads)
+        return out
+
+    def collide_cross(self, ra, rf, rt, ca, cf, ct, group_size=0, nthreads=1) -> np.ndarray:
+        ra, ca = _i32(ra), _i32(ca)
+        rf, rt, cf, ct = _f64(rf), _f64(rt), _f64(cf), _f64(ct)
+        bits = -(-ca.size // group_size) if group_size > 0 else ca.size
+        out = np.zeros((ra.size, (bits + 31) // 32), np.uint32)
+        self._lib.orc_collide_cross(self._h, ra.size, _p(ra, _ip), _p(rf, _dp), _p(rt, _dp),
+                                    ca.size, _p(ca, _ip), _p(cf, _dp), _p(ct, _dp),
+                                    int(group_size), out.ctypes.data_as(C.c_void_p), nthreads)
         return out
 
     # sampler / roadmap

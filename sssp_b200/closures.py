@@ -122,6 +122,11 @@ class Context:
         except Exception:
             pass
 
+    def stats(self, reset: bool = False) -> np.ndarray:
+        out = np.zeros(4, np.int64)
+        L.check(self._lib.mrmp_ctx_stats(self._h, L.ptr(out, L._vp), int(reset)))
+        return out
+
     def set_stream(self, cuda_stream: int | None) -> None:
         """Run this ctx's kernels on a caller-owned CUDA stream (e.g. torch's current)."""
         L.check(self._lib.mrmp_ctx_set_stream(self._h, cuda_stream))
@@ -177,6 +182,22 @@ class Context:
         L.check(self._lib.mrmp_collide_config_moves(self._h, int(agent_i), L.ptr(Q, L._dp),
                                                     q_to.shape[0], L.ptr(q_to, L._dp),
                                                     L.ptr(out, L._bp)))
+        return out
+
+    def collide_cross(self, row_agent, row_from, row_to, col_agent, col_from, col_to,
+                      group_size: int = 0) -> np.ndarray:
+        """Every row edge x every column edge -> bit matrix uint32 [n_rows][words_per_row]
+        (group_size > 0: OR-reduced over consecutive column groups).  Same-agent pairs are 0."""
+        ra, ca = L.i32(row_agent).ravel(), L.i32(col_agent).ravel()
+        rf, rt = _states(row_from, self.d), _states(row_to, self.d)
+        cf, ct = _states(col_from, self.d), _states(col_to, self.d)
+        bits = -(-ca.size // group_size) if group_size > 0 else ca.size
+        wpr = (bits + 31) // 32
+        out = np.zeros((ra.size, max(wpr, 0)), np.uint32)
+        L.check(self._lib.mrmp_collide_cross(self._h, ra.size, L.ptr(ra, L._ip), L.ptr(rf, L._dp),
+                                             L.ptr(rt, L._dp), ca.size, L.ptr(ca, L._ip),
+                                             L.ptr(cf, L._dp), L.ptr(ct, L._dp), int(group_size),
+                                             L.ptr(out, L._vp)))
         return out
 
     def sample_states(self, agent: int, seed: int, t0: int, n: int) -> np.ndarray:
@@ -289,6 +310,23 @@ class Roadmaps:
         L.check(self._lib.mrmp_collide_edges_indexed(self._h, a[0].size,
                                                      *[L.ptr(x, L._ip) for x in a],
                                                      L.ptr(out, L._bp)))
+        return out
+
+    def edge_conflicts(self, col_agent, col_vfrom, col_vto, group_size: int = 0,
+                       cols: "Roadmaps | None" = None) -> np.ndarray:
+        """All roadmap edges (packed CSR order) x the given roadmap edges (by ids) -> bits
+        uint32 [nnz][words_per_row]; the conflict table PP / CBS consult (pp.jl:179-189)."""
+        ca, vf, vt = (L.i32(x).ravel() for x in (col_agent, col_vfrom, col_vto))
+        nnz = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_nnz(self._h, C.byref(nnz)))
+        bits = -(-ca.size // group_size) if group_size > 0 else ca.size
+        wpr = (bits + 31) // 32
+        out = np.zeros((nnz.value, wpr), np.uint32)
+        L.check(self._lib.mrmp_roadmaps_edge_conflicts(self._h, cols._h if cols else None,
+                                                       ca.size, L.ptr(ca, L._ip),
+                                                       L.ptr(vf, L._ip), L.ptr(vt, L._ip),
+                                                       int(group_size), L.ptr(out, L._vp),
+                                                       out.size))
         return out
 
     def to_nodes(self) -> List[List[Node]]:

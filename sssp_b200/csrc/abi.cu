@@ -115,6 +115,12 @@ struct mrmp_ctx {
     size_t slot_bytes = 0;
     unsigned char *small_h = nullptr, *small_d = nullptr;
     size_t small_bytes = 0;
+    // named device scratch buffers (column tiles, staged rows/cols, output bits)
+    static const int kScratch = 6;
+    unsigned char *scratch[kScratch]{};
+    size_t scratch_bytes[kScratch]{};
+    double max_rad = 0.0;
+    unsigned long long *stats_d = nullptr;  // [4]: cross-kernel survivors, reserved
 };
 
 static inline int pad2(int n) { return (n + 1) & ~1; }
@@ -130,6 +136,20 @@ static int ensure_small(mrmp_ctx *c, size_t bytes) {
     CU(cudaHostAlloc((void **)&c->small_h, nb, cudaHostAllocDefault));
     CU(cudaMalloc((void **)&c->small_d, nb));
     c->small_bytes = nb;
+    return MRMP_OK;
+}
+
+static int ensure_scratch(mrmp_ctx *c, int k, size_t bytes) {
+    if (bytes <= c->scratch_bytes[k]) return MRMP_OK;
+    if (c->scratch[k]) {
+        CU(cudaStreamSynchronize(c->s_k));
+        CU(cudaFree(c->scratch[k]));
+    }
+    c->scratch[k] = nullptr;
+    c->scratch_bytes[k] = 0;
+    size_t nb = bytes + bytes / 4 + 256;
+    CU(cudaMalloc((void **)&c->scratch[k], nb));
+    c->scratch_bytes[k] = nb;
     return MRMP_OK;
 }
 
@@ -178,6 +198,8 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     c->n_agents = n_agents;
     c->n_obs = n_obs;
     c->h_rads.assign(rads, rads + n_agents);
+    for (int i = 0; i < n_agents; ++i)
+        if (rads[i] > c->max_rad) c->max_rad = rads[i];
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
 
     const int N = n_agents, M = n_obs;
@@ -251,6 +273,8 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cudaError_t e = cudaMalloc((void **)&c->blob, h.size() * sizeof(double));
     if (e == cudaSuccess)
         e = cudaMemcpy(c->blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->stats_d, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->stats_d, 0, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
     c->s_k_owned = c->s_k;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
@@ -281,14 +305,28 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
     }
     if (c->small_h) cudaFreeHost(c->small_h);
     if (c->small_d) cudaFree(c->small_d);
+    for (int k = 0; k < mrmp_ctx::kScratch; ++k)
+        if (c->scratch[k]) cudaFree(c->scratch[k]);
     if (c->s_k_owned) cudaStreamDestroy(c->s_k_owned);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->blob) cudaFree(c->blob);
+    if (c->stats_d) cudaFree(c->stats_d);
     delete c;
 }
 
 extern "C" int mrmp_ctx_state_dim(const mrmp_ctx *c) { return c ? c->d : 0; }
+
+extern "C" int mrmp_ctx_stats(mrmp_ctx *c, int64_t *out4, int reset) {
+    if (!c || !out4) return fail(MRMP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_k));
+    unsigned long long h[4];
+    CU(cudaMemcpy(h, c->stats_d, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; ++k) out4[k] = (int64_t)h[k];
+    if (reset) CU(cudaMemset(c->stats_d, 0, sizeof(h)));
+    return MRMP_OK;
+}
 
 extern "C" int mrmp_ctx_set_stream(mrmp_ctx *c, void *stream) {
     if (!c) return fail(MRMP_ERR_INVALID, "ctx is NULL");
@@ -700,6 +738,11 @@ struct mrmp_roadmaps {
     double *rad_d = nullptr;     // [2][n_agents]: rad, r2
     int64_t nnz = -1;            // host copy after build
     bool built = false;
+    // CSR edges expanded to explicit (agent, from, to) rows for the cross kernels
+    int32_t *e_agent = nullptr;
+    double *e_from = nullptr, *e_to = nullptr;
+    int64_t e_cap = 0;
+    bool e_valid = false;
 };
 
 extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int nv_cap,
@@ -745,6 +788,9 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     cudaFree(rm->nnz_d);
     cudaFree(rm->tries_d);
     cudaFree(rm->rad_d);
+    cudaFree(rm->e_agent);
+    cudaFree(rm->e_from);
+    cudaFree(rm->e_to);
     delete rm;
 }
 
@@ -871,6 +917,35 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
         CU(cudaStreamSynchronize(c->s_k));
     }
     rm->built = true;
+    rm->e_valid = false;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_set_csr_dev(mrmp_roadmaps *rm, const int32_t *row_ptr_dev,
+                                         const int32_t *col_idx_dev, int64_t nnz, void *stream) {
+    NEED(rm && row_ptr_dev && nnz >= 0 && nnz < ((int64_t)1 << 31), "bad arguments");
+    NEED(rm->nv >= 1, "no nodes set");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rows = (int64_t)rm->n_agents * rm->nv;
+    if (nnz > rm->col_cap) {
+        CU(cudaStreamSynchronize(s));
+        if (rm->col_idx) CU(cudaFree(rm->col_idx));
+        rm->col_idx = nullptr;
+        rm->col_cap = nnz + nnz / 4 + 64;
+        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+    }
+    CU(cudaMemcpyAsync(rm->row_ptr, row_ptr_dev, sizeof(int32_t) * (rows + 1),
+                       cudaMemcpyDeviceToDevice, s));
+    if (nnz > 0) {
+        NEED(col_idx_dev, "col_idx_dev is NULL");
+        CU(cudaMemcpyAsync(rm->col_idx, col_idx_dev, sizeof(int32_t) * nnz,
+                           cudaMemcpyDeviceToDevice, s));
+    }
+    rm->nnz = nnz;
+    rm->built = true;
+    rm->e_valid = false;
     return MRMP_OK;
 }
 
@@ -1010,5 +1085,193 @@ extern "C" int mrmp_collide_edges_indexed_dev(mrmp_roadmaps *rm, int64_t n, cons
     CU(launch_collide_edges_indexed(c->cv, lcfg(c, (cudaStream_t)stream), n, i, j, vi_from, vi_to,
                                     vj_from, vj_to, rm->nodes, rm->agent0, rm->n_agents, rm->nv,
                                     out));
+    return MRMP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// cross-product collide (rows x columns -> bits)
+// ------------------------------------------------------------------------------------------
+static int cross_words(int64_t n_cols, int group_size) {
+    const int64_t bits = group_size > 0 ? (n_cols + group_size - 1) / group_size : n_cols;
+    return (int)((bits + 31) / 32);
+}
+
+// rows / cols / out are device pointers; column tiles live in ctx scratch slot 0
+static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
+                         const double *row_from, const double *row_to, int64_t n_cols,
+                         const int32_t *col_agent, const double *col_from, const double *col_to,
+                         const int32_t *col_vf, const int32_t *col_vt, const double *nodes,
+                         int agent0, int nv_stride, int group_size, uint32_t *out,
+                         cudaStream_t s) {
+    const int64_t n_tiles = (n_cols + kCrossCols - 1) / kCrossCols;
+    const size_t tb = cross_tile_bytes(c->d);
+    int rc = ensure_scratch(c, 0, (size_t)n_tiles * tb);
+    if (rc) return rc;
+    LaunchCfg lc = lcfg(c, s);
+    CU(launch_cross_prep_cols(c->cv, lc, n_cols, col_agent, col_from, col_to, col_vf, col_vt,
+                              nodes, agent0, nv_stride, c->scratch[0]));
+    const int wpr = cross_words(n_cols, group_size);
+    if (group_size <= 0) {
+        CU(launch_cross_collide(c->cv, lc, n_rows, row_agent, row_from, row_to, n_cols,
+                                c->scratch[0], 0, wpr, wpr, out, c->max_rad, c->stats_d));
+        return MRMP_OK;
+    }
+    // reduced mode: at most kCrossMaxGroups groups per launch
+    const int64_t n_groups = (n_cols + group_size - 1) / group_size;
+    for (int64_t g0 = 0; g0 < n_groups; g0 += kCrossMaxGroups) {
+        const int64_t c0 = g0 * group_size;
+        if (c0 % kCrossCols != 0)
+            return fail(MRMP_ERR_UNSUPPORTED, "group_size * %d must be a multiple of %d",
+                        kCrossMaxGroups, kCrossCols);
+        const int64_t c1 = (g0 + kCrossMaxGroups) * (int64_t)group_size < n_cols
+                               ? (g0 + kCrossMaxGroups) * (int64_t)group_size
+                               : n_cols;
+        const int w = cross_words(c1 - c0, group_size);
+        CU(launch_cross_collide(c->cv, lc, n_rows, row_agent, row_from, row_to, c1 - c0,
+                                c->scratch[0] + (size_t)(c0 / kCrossCols) * tb, group_size, w, wpr,
+                                out + g0 / 32, c->max_rad, c->stats_d));
+    }
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_cross_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
+                                      const double *row_from, const double *row_to,
+                                      int64_t n_cols, const int32_t *col_agent,
+                                      const double *col_from, const double *col_to,
+                                      int group_size, uint32_t *out_bits, void *stream) {
+    NEED(c && n_rows >= 0 && n_cols >= 0 && group_size >= 0, "bad arguments");
+    if (n_rows == 0 || n_cols == 0) return MRMP_OK;
+    CU(cudaSetDevice(c->device));
+    if (need_aligned(c, row_from) || need_aligned(c, row_to) || need_aligned(c, col_from) ||
+        need_aligned(c, col_to))
+        return MRMP_ERR_INVALID;
+    return cross_run_dev(c, n_rows, row_agent, row_from, row_to, n_cols, col_agent, col_from,
+                         col_to, nullptr, nullptr, nullptr, 0, 0, group_size, out_bits,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int mrmp_collide_cross(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
+                                  const double *row_from, const double *row_to, int64_t n_cols,
+                                  const int32_t *col_agent, const double *col_from,
+                                  const double *col_to, int group_size, uint32_t *out_bits) {
+    NEED(c && n_rows >= 0 && n_cols >= 0 && group_size >= 0, "bad arguments");
+    if (n_rows == 0 || n_cols == 0) return MRMP_OK;
+    NEED(row_agent && row_from && row_to && col_agent && col_from && col_to && out_bits,
+         "NULL buffer");
+    int rc = check_agents_host(c, n_rows, row_agent);
+    if (!rc) rc = check_agents_host(c, n_cols, col_agent);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const size_t sb = sizeof(double) * c->d;
+    const int wpr = cross_words(n_cols, group_size);
+    // scratch slots: 1 rows+cols staging, 2 output bits
+    const size_t o_ra = 0, o_rf = align16(o_ra + 4 * (size_t)n_rows),
+                 o_rt = align16(o_rf + sb * (size_t)n_rows),
+                 o_ca = align16(o_rt + sb * (size_t)n_rows),
+                 o_cf = align16(o_ca + 4 * (size_t)n_cols),
+                 o_ct = align16(o_cf + sb * (size_t)n_cols),
+                 tot = align16(o_ct + sb * (size_t)n_cols);
+    rc = ensure_scratch(c, 1, tot);
+    if (!rc) rc = ensure_scratch(c, 2, sizeof(uint32_t) * (size_t)n_rows * wpr);
+    if (rc) return rc;
+    unsigned char *b = c->scratch[1];
+    cudaStream_t s = c->s_k;
+    CU(cudaMemcpyAsync(b + o_ra, row_agent, 4 * (size_t)n_rows, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_rf, row_from, sb * (size_t)n_rows, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_rt, row_to, sb * (size_t)n_rows, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_ca, col_agent, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_cf, col_from, sb * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_ct, col_to, sb * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    rc = cross_run_dev(c, n_rows, (const int32_t *)(b + o_ra), (const double *)(b + o_rf),
+                       (const double *)(b + o_rt), n_cols, (const int32_t *)(b + o_ca),
+                       (const double *)(b + o_cf), (const double *)(b + o_ct), nullptr, nullptr,
+                       nullptr, 0, 0, group_size, (uint32_t *)c->scratch[2], s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_bits, c->scratch[2], sizeof(uint32_t) * (size_t)n_rows * wpr,
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MRMP_OK;
+}
+
+// rows = every CSR edge of the roadmap set (packed CSR order); columns = edges of roadmap
+// agents given by (agent, v_from, v_to) ids
+static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
+    if (rm->e_valid) return MRMP_OK;
+    mrmp_ctx *c = rm->ctx;
+    if (rm->nnz > rm->e_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(rm->e_agent);
+        cudaFree(rm->e_from);
+        cudaFree(rm->e_to);
+        rm->e_agent = nullptr;
+        rm->e_from = rm->e_to = nullptr;
+        rm->e_cap = rm->nnz + rm->nnz / 8 + 64;
+        CU(cudaMalloc((void **)&rm->e_agent, sizeof(int32_t) * rm->e_cap));
+        CU(cudaMalloc((void **)&rm->e_from, sizeof(double) * c->d * rm->e_cap));
+        CU(cudaMalloc((void **)&rm->e_to, sizeof(double) * c->d * rm->e_cap));
+    }
+    CU(launch_csr_expand_edges(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
+                               rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes, rm->e_agent,
+                               rm->e_from, rm->e_to));
+    rm->e_valid = true;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,
+                                                int64_t n_cols, const int32_t *col_agent,
+                                                const int32_t *col_vfrom, const int32_t *col_vto,
+                                                int group_size, uint32_t *out_bits,
+                                                void *stream) {
+    NEED(rm && n_cols >= 0 && group_size >= 0, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    if (!rm_cols) rm_cols = rm;
+    NEED(rm_cols->ctx == rm->ctx && rm_cols->nv >= 1, "rm_cols must belong to the same ctx");
+    if (n_cols == 0 || rm->nnz == 0) return MRMP_OK;
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = roadmaps_expand_edges(rm, s);
+    if (rc) return rc;
+    return cross_run_dev(c, rm->nnz, rm->e_agent, rm->e_from, rm->e_to, n_cols, col_agent,
+                         nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes, rm_cols->agent0,
+                         rm_cols->nv, group_size, out_bits, s);
+}
+
+extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,
+                                            int64_t n_cols, const int32_t *col_agent,
+                                            const int32_t *col_vfrom,
+                                            const int32_t *col_vto, int group_size,
+                                            uint32_t *out_bits, int64_t out_cap_words) {
+    NEED(rm && n_cols >= 0 && group_size >= 0, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    if (n_cols == 0 || rm->nnz == 0) return MRMP_OK;
+    NEED(col_agent && col_vfrom && col_vto && out_bits, "NULL buffer");
+    if (!rm_cols) rm_cols = rm;
+    int rc = check_rm_agents(rm_cols, n_cols, col_agent);
+    if (!rc) rc = check_vertices(rm_cols, n_cols, col_vfrom);
+    if (!rc) rc = check_vertices(rm_cols, n_cols, col_vto);
+    if (rc) return rc;
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    const int wpr = cross_words(n_cols, group_size);
+    if (out_cap_words < rm->nnz * wpr)
+        return fail(MRMP_ERR_CAPACITY, "out_bits needs %lld words", (long long)(rm->nnz * wpr));
+    const size_t ib = align16(4 * (size_t)n_cols);
+    rc = ensure_scratch(c, 1, 3 * ib);
+    if (!rc) rc = ensure_scratch(c, 2, sizeof(uint32_t) * (size_t)rm->nnz * wpr);
+    if (rc) return rc;
+    unsigned char *b = c->scratch[1];
+    cudaStream_t s = c->s_k;
+    CU(cudaMemcpyAsync(b, col_agent, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + ib, col_vfrom, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + 2 * ib, col_vto, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    rc = mrmp_roadmaps_edge_conflicts_dev(rm, rm_cols, n_cols, (const int32_t *)b,
+                                          (const int32_t *)(b + ib),
+                                          (const int32_t *)(b + 2 * ib), group_size,
+                                          (uint32_t *)c->scratch[2], s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_bits, c->scratch[2], sizeof(uint32_t) * (size_t)rm->nnz * wpr,
+                       cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return MRMP_OK;
 }

@@ -137,4 +137,23 @@ cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent
                                int n_fixed, int nv, int nv_stride, uint64_t seed, double *nodes,
                                int64_t *tries_out, int64_t max_tries);
 
+
+// kernels_cross.cu
+constexpr int kCrossCols = 64;        // columns per staged tile
+constexpr int kCrossMaxGroups = 256;  // reduced mode: groups per launch
+size_t cross_tile_bytes(int d);
+cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64_t n_cols,
+                                   const int32_t *agent, const double *qf, const double *qt,
+                                   const int32_t *vf, const int32_t *vt, const double *nodes,
+                                   int agent0, int nv_stride, void *tiles);
+cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
+                                    int nv, int agent0, const int32_t *row_ptr,
+                                    const int32_t *col_idx, const double *nodes, int32_t *e_agent,
+                                    double *e_from, double *e_to);
+cudaError_t launch_cross_collide(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
+                                 const int32_t *row_agent, const double *row_from,
+                                 const double *row_to, int64_t n_cols, const void *tiles,
+                                 int group_size, int words_per_row, int64_t out_stride, uint32_t *out,
+                                 double max_rad, unsigned long long *stats);
+
 }  // namespace mrmp

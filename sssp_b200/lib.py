@@ -75,6 +75,16 @@ _SIGS = {
     "mrmp_collide_edges_indexed": (C.c_int, [_vp, C.c_int64, _ip, _ip, _ip, _ip, _ip, _ip, _bp]),
     "mrmp_collide_edges_indexed_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
                                                  _vp, _vp]),
+    "mrmp_collide_cross": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
+                                     _vp]),
+    "mrmp_collide_cross_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp,
+                                         C.c_int, _vp, _vp]),
+    "mrmp_roadmaps_edge_conflicts": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
+                                               C.c_int64]),
+    "mrmp_roadmaps_edge_conflicts_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
+                                                   _vp, _vp]),
+    "mrmp_roadmaps_set_csr_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "mrmp_ctx_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "mrmp_sample_states": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _dp]),
     "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),
 }

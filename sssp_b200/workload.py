@@ -74,3 +74,37 @@ def collide_list(inst: Instance, row_ptr: np.ndarray, col: np.ndarray, n: int, s
     vif, vit = edges(ai)
     vjf, vjt = edges(aj)
     return ai, aj, vif, vit, vjf, vjt
+
+
+def random_walk_paths(inst: Instance, row_ptr: np.ndarray, col: np.ndarray, T: int, seed: int):
+    """Synthetic planned paths: for every agent a T-step random walk on its own roadmap from
+    vertex 0 (its start, prm.jl:232); an agent without out-edges waits.  Returns the vertex
+    table [N][T+1] and the path-edge columns in t-major order (column t*N + j is agent j's
+    move at step t), i.e. what PP's invalid() iterates over (pp.jl:179-189)."""
+    rng = np.random.default_rng(seed)
+    N, nv = inst.rads.size, inst.nv
+    row_ptr = row_ptr.astype(np.int64)
+    paths = np.zeros((N, T + 1), np.int32)
+    v = np.zeros(N, np.int64)
+    base = np.arange(N, dtype=np.int64) * nv
+    for t in range(T):
+        r = base + v
+        deg = row_ptr[r + 1] - row_ptr[r]
+        pick = (rng.random(N) * np.maximum(deg, 1)).astype(np.int64)
+        nxt = np.where(deg > 0, col[np.minimum(row_ptr[r] + pick, col.size - 1)], v)
+        v = nxt.astype(np.int64)
+        paths[:, t + 1] = v
+    col_agent = np.tile(np.arange(N, dtype=np.int32), T)
+    col_vfrom = np.ascontiguousarray(paths[:, :-1].T).reshape(-1).astype(np.int32)
+    col_vto = np.ascontiguousarray(paths[:, 1:].T).reshape(-1).astype(np.int32)
+    return paths, col_agent, col_vfrom, col_vto
+
+
+def gate_pass_count(nodes: np.ndarray, rad: float) -> int:
+    """Number of ordered vertex pairs (j != k) within `rad`: the connect(q_j, q_k) calls the
+    reference's PRM! loop actually issues (prm.jl:207)."""
+    tot = 0
+    for a in range(nodes.shape[0]):
+        d = nodes[a][:, None, :] - nodes[a][None, :, :]
+        tot += int((np.sqrt((d * d).sum(-1)) <= rad).sum()) - nodes.shape[1]
+    return tot

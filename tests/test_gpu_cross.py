@@ -1,0 +1,87 @@
+"""GPU parity of the cross-product collide kernels (broad phase + compaction + exact path):
+bit matrices must equal the exhaustive CPU oracle -- the broad phase may never change a
+verdict."""
+import numpy as np
+import pytest
+
+import sssp_b200 as S
+from oracle import oracle as O
+from helpers import make_point_instance, random_edges
+
+pytestmark = pytest.mark.gpu
+
+
+def _edges(rng, n, d, N, spread=1.0, max_len=0.1):
+    a = rng.integers(0, N, n).astype(np.int32)
+    qf, qt = random_edges(rng, n, d, max_len)
+    return a, qf * spread + (1 - spread) * 0.5, qt * spread + (1 - spread) * 0.5
+
+
+@pytest.mark.parametrize("model,d", [(O.POINT2D, 2), (O.POINT3D, 3)])
+@pytest.mark.parametrize("n_rows,n_cols,gs", [(1000, 700, 0), (513, 64, 0), (300, 1000, 50),
+                                               (257, 6000, 7), (1, 1, 0), (2000, 3, 1)])
+def test_cross_matches_exhaustive_oracle(model, d, n_rows, n_cols, gs):
+    N = 12
+    rads, obs = make_point_instance(model, N, 0, seed=n_rows + n_cols, rad=(0.015, 0.05))
+    ctx, orc = S.Context(model, rads, obs), O.Oracle(model, rads, obs)
+    rng = np.random.default_rng(n_rows * 7 + n_cols)
+    # a dense cluster so that a few percent of the pairs truly collide
+    ra, rf, rt = _edges(rng, n_rows, d, N, spread=0.5)
+    ca, cf, ct = _edges(rng, n_cols, d, N, spread=0.5)
+    g = ctx.collide_cross(ra, rf, rt, ca, cf, ct, gs)
+    o = orc.collide_cross(ra, rf, rt, ca, cf, ct, gs, nthreads=0)
+    assert g.shape == o.shape and np.array_equal(g, o)
+    if n_rows * n_cols > 10000:
+        assert o.any()
+
+
+def test_cross_degenerate_and_near_threshold():
+    """Stay edges (zero length), parallel edges, edges exactly at the contact threshold and
+    edges just outside the broad-phase radius."""
+    rads = np.array([0.02, 0.03, 0.025])
+    ctx, orc = S.Context(O.POINT2D, rads, np.zeros((0, 3))), O.Oracle(O.POINT2D, rads, np.zeros((0, 3)))
+    rng = np.random.default_rng(5)
+    n = 400
+    ra = rng.integers(0, 3, n).astype(np.int32)
+    rf = rng.uniform(0.4, 0.6, (n, 2))
+    rt = rf.copy()
+    rt[::2] += rng.normal(scale=0.02, size=(n // 2, 2))          # half stay, half move
+    ca = rng.integers(0, 3, n).astype(np.int32)
+    thr = rads[ra] + rads[ca]
+    eps = rng.choice([0.0, 1e-16, -1e-16, 1e-13, -1e-13, 1e-9, -1e-9], n)
+    cf = rf + np.stack([thr * (1 + eps), np.zeros(n)], axis=1)   # column k grazes row k
+    ct = cf + (rt - rf)                                          # parallel to the row edge
+    g = ctx.collide_cross(ra, rf, rt, ca, cf, ct, 0)
+    o = orc.collide_cross(ra, rf, rt, ca, cf, ct, 0, nthreads=0)
+    assert np.array_equal(g, o)
+    diag = (o[np.arange(n), np.arange(n) // 32] >> (np.arange(n) % 32)) & 1
+    assert 0 < diag.sum() < n
+
+
+def test_roadmap_edge_conflict_table():
+    """All roadmap edges x path edges of the other agents, OR-reduced per time step: the
+    table PP consults (pp.jl:179-189)."""
+    N, nv, T = 6, 150, 9
+    rads, obs = make_point_instance(O.POINT2D, N, 5, seed=2, rad=(0.02, 0.04))
+    ctx, orc = S.Context(O.POINT2D, rads, obs), O.Oracle(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(3)
+    nodes = rng.random((N, nv, 2))
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(0.2)
+    row_ptr, col = rm.csr()
+    # columns: for every time step t, one path edge per agent (t-major, group = N columns)
+    ca = np.tile(np.arange(N, dtype=np.int32), T)
+    vf = rng.integers(0, nv, N * T).astype(np.int32)
+    vt = rng.integers(0, nv, N * T).astype(np.int32)
+    # explicit row arrays in packed CSR order
+    rows = np.repeat(np.arange(N * nv), np.diff(row_ptr))
+    ra = (rows // nv).astype(np.int32)
+    rf = nodes[ra, rows % nv]
+    rt = nodes[ra, col]
+    cf, ct = nodes[ca, vf], nodes[ca, vt]
+    for gs in (0, N):
+        g = rm.edge_conflicts(ca, vf, vt, gs)
+        o = orc.collide_cross(ra, rf, rt, ca, cf, ct, gs, nthreads=0)
+        assert g.shape == (nnz, o.shape[1]) and np.array_equal(g, o)
+    assert o.any()
