@@ -1,0 +1,163 @@
+# MRMPB200.jl -- ccall glue: rebuilds the reference's closure API on libmrmp_b200.so.
+#
+# NOT EXECUTED in this repository's CI: there is no Julia runtime in the build image or on
+# the GPU box (see DESIGN.md).  It documents, line by line, the binding a maintainer of
+# Kei18/sssp would add; the C entry points it calls are exercised through the identical
+# ctypes binding in sssp_b200/lib.py.
+#
+# Usage inside MRMP.jl (replacing src/models/point2d.jl:42-69 and src/models/point.jl:5-36):
+#   connect = MRMPB200.gen_connect(StatePoint2D(0, 0), obstacles, rads)
+#   collide = MRMPB200.gen_collide(StatePoint2D(0, 0), rads)
+# Both return multi-method closures with the reference's signatures (1-based agent ids).
+module MRMPB200
+
+import ..MRMP: AbsState, Node, StatePoint2D, StatePoint3D, StateArm22,
+               CircleObstacle2D, CircleObstacle3D, STEP_DIST, SAFETY_DIST_LINE
+
+const LIB = get(ENV, "MRMP_B200_LIB", "libmrmp_b200.so")
+const MODEL = Dict(StatePoint2D => 0, StatePoint3D => 1, StateArm22 => 2)
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(h)
+        c = new(h)
+        finalizer(x -> ccall((:mrmp_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+function check(rc::Cint)
+    rc == 0 && return
+    error("mrmp_b200: " * unsafe_string(ccall((:mrmp_last_error, LIB), Cstring, ())))
+end
+
+# isbits structs are C-layout: Vector{StatePoint2D} == double[n][2], Vector{CircleObstacle2D}
+# == double[n][3]  (src/obstacle.jl:7-19), so they are passed without conversion.
+function make_ctx(q::State, obstacles, rads::Vector{Float64};
+                  positions = nothing, step_dist = STEP_DIST, safety_dist = SAFETY_DIST_LINE,
+                  max_dist = nothing, device = 0) where {State<:AbsState}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    base = isnothing(positions) ? C_NULL : pointer(reduce(vcat, positions))
+    check(ccall((:mrmp_ctx_create, LIB), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
+                 Ptr{Cvoid}, Float64, Float64, Float64, Cint),
+                h, MODEL[State], length(rads), rads, base, C_NULL, length(obstacles),
+                isempty(obstacles) ? C_NULL : pointer(obstacles), step_dist, safety_dist,
+                isnothing(max_dist) ? NaN : max_dist, device))
+    return Ctx(h[])
+end
+
+"""gen_connect(q, obstacles, rads) -- src/models/point2d.jl:42-69, point3d.jl:47-80"""
+function gen_connect(q::State, obstacles, ins_params...; kwargs...) where {State<:AbsState}
+    rads = ins_params[end]
+    positions = length(ins_params) == 2 ? ins_params[1] : nothing   # arm22.jl:29-37
+    ctx = make_ctx(q, obstacles, rads; positions = positions, kwargs...)
+    out = Ref{UInt8}(0)
+
+    f(q::State, i::Int64)::Bool = begin                       # point2d.jl:49-57
+        check(ccall((:mrmp_connect_point, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{State}, Ref{UInt8}), ctx.h, i - 1, q, out))
+        return out[] != 0
+    end
+    f(q_from::State, q_to::State, i::Int64)::Bool = begin     # point2d.jl:59-66
+        check(ccall((:mrmp_connect_edge, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Ref{State}, Ref{State}, Ref{UInt8}),
+                    ctx.h, i - 1, q_from, q_to, out))
+        return out[] != 0
+    end
+    # new batched method: one launch for a whole edge list
+    f(q_from::Vector{State}, q_to::Vector{State}, agents::Vector{Int32})::Vector{Bool} = begin
+        res = Vector{Bool}(undef, length(agents))
+        check(ccall((:mrmp_connect_edges, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{State}, Ptr{State}, Ptr{Bool}),
+                    ctx.h, length(agents), agents .- Int32(1), q_from, q_to, res))
+        return res
+    end
+    return f
+end
+
+"""gen_collide(q, rads) -- src/models/point.jl:5-36, arm22.jl:90-212"""
+function gen_collide(q::State, ins_params...; kwargs...) where {State<:AbsState}
+    rads = ins_params[end]
+    positions = length(ins_params) == 2 ? ins_params[1] : nothing
+    ctx = make_ctx(q, State == StatePoint3D ? CircleObstacle3D[] : CircleObstacle2D[], rads;
+                   positions = positions, kwargs...)
+    N = length(rads)
+    out = Ref{UInt8}(0)
+
+    f(a::State, b::State, c::State, d::State, i::Int64, j::Int64)::Bool = begin   # point.jl:9-12
+        check(ccall((:mrmp_collide_pair, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ref{State}, Ref{State}, Ref{State}, Ref{State},
+                     Ref{UInt8}), ctx.h, i - 1, j - 1, a, b, c, d, out))
+        return out[] != 0
+    end
+    f(q_i::State, q_j::State, i::Int64, j::Int64)::Bool = begin                   # point.jl:14-16
+        ii, jj = Int32[i - 1], Int32[j - 1]
+        check(ccall((:mrmp_collide_static_pairs, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ref{State}, Ref{State},
+                     Ref{UInt8}), ctx.h, 1, ii, jj, q_i, q_j, out))
+        return out[] != 0
+    end
+    f(Q_from::Vector{Node{State}}, Q_to::Vector{Node{State}})::Bool = begin       # point.jl:18-25
+        # Vector{Node} is an array of pointers (src/MRMP.jl:73-77): gather the states flat,
+        # exactly what the reference itself does at arm22.jl:207-209
+        qf, qt = map(v -> v.q, Q_from), map(v -> v.q, Q_to)
+        check(ccall((:mrmp_collide_configs, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Ptr{State}, Ptr{State}, Ref{UInt8}, Ptr{Int64}),
+                    ctx.h, 1, qf, qt, out, C_NULL))
+        return out[] != 0
+    end
+    f(Q::Vector{Node{State}}, q_to::State, i::Int64)::Bool = begin                # point.jl:27-33
+        qs = map(v -> v.q, Q)
+        check(ccall((:mrmp_collide_config_moves, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{State}, Int64, Ref{State}, Ref{UInt8}),
+                    ctx.h, i - 1, qs, 1, q_to, out))
+        return out[] != 0
+    end
+    # new batched method used by SSSP's successor filter (sssp.jl:196-223): all candidate
+    # successors p of agent i against the static others in one launch
+    f(Q::Vector{Node{State}}, q_tos::Vector{State}, i::Int64)::Vector{Bool} = begin
+        qs = map(v -> v.q, Q)
+        res = Vector{Bool}(undef, length(q_tos))
+        check(ccall((:mrmp_collide_config_moves, LIB), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{State}, Int64, Ptr{State}, Ptr{Bool}),
+                    ctx.h, i - 1, qs, length(q_tos), q_tos, res))
+        return res
+    end
+    return f
+end
+
+"""PRMs(config_init, config_goal, ctx, num_vertices; rad) -- src/solvers/prm.jl:251-276.
+Sampling + neighbour pass for all agents on the GPU; returns Vector{Vector{Node{State}}}."""
+function PRMs(config_init::Vector{State}, config_goal::Vector{State}, ctx::Ctx,
+              num_vertices::Int64 = 100; rad::Union{Nothing,Float64} = nothing,
+              seed::UInt64 = UInt64(0)) where {State<:AbsState}
+    N = length(config_init)
+    d = sizeof(State) ÷ 8
+    nodes = Vector{State}(undef, N * num_vertices)
+    row_ptr = Vector{Int32}(undef, N * num_vertices + 1)
+    cap = N * num_vertices * 64
+    col = Vector{Int32}(undef, cap)
+    nnz = Ref{Int64}(0)
+    rads = fill(isnothing(rad) ? NaN : rad, N)
+    rc = ccall((:mrmp_prms, LIB), Cint,
+               (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, UInt64, Ptr{State}, Ptr{State},
+                Ptr{State}, Ptr{Int32}, Ptr{Int32}, Int64, Ref{Int64}),
+               ctx.h, 0, N, num_vertices, rads, seed, config_init, config_goal, nodes, row_ptr,
+               col, cap, nnz)
+    if rc == -3          # MRMP_ERR_CAPACITY: retry with the reported size
+        resize!(col, nnz[]); cap = nnz[]
+        rc = ccall((:mrmp_prms, LIB), Cint,
+                   (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, UInt64, Ptr{State}, Ptr{State},
+                    Ptr{State}, Ptr{Int32}, Ptr{Int32}, Int64, Ref{Int64}),
+                   ctx.h, 0, N, num_vertices, rads, seed, config_init, config_goal, nodes,
+                   row_ptr, col, cap, nnz)
+    end
+    check(rc)
+    return [[Node{State}(nodes[(a - 1) * num_vertices + v], v,
+                         Int64.(col[row_ptr[(a - 1) * num_vertices + v] + 1:
+                                    row_ptr[(a - 1) * num_vertices + v + 1]]) .+ 1)
+             for v = 1:num_vertices] for a = 1:N]
+end
+
+end # module
