@@ -11,6 +11,7 @@
 
 #include "../../include/mrmp_b200.h"
 #include "mrmp_internal.cuh"
+#include "arm_model.cuh"
 
 using namespace mrmp;
 
@@ -269,6 +270,12 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cv.safety_dist = safety_dist;
     cv.max_dist = max_dist;
     cv.safety_t2 = sq_lt_threshold(safety_dist);
+    {
+        const StepRat sr = step_rat(step_dist);  // D-independent half of Julia's 0:step:D lift
+        cv.step_rat_ok = sr.ok;
+        cv.step_rat_num = sr.num;
+        cv.step_rat_den = sr.den;
+    }
 
     cudaError_t e = cudaMalloc((void **)&c->blob, h.size() * sizeof(double));
     if (e == cudaSuccess)
@@ -434,7 +441,9 @@ static int run_batch(mrmp_ctx *c, int64_t n, std::vector<Arr> &arrs, F launch) {
     return MRMP_OK;
 }
 
-static inline LaunchCfg lcfg(const mrmp_ctx *c, cudaStream_t s) { return LaunchCfg{c->sm_count, s}; }
+static inline LaunchCfg lcfg(const mrmp_ctx *c, cudaStream_t s) {
+    return LaunchCfg{c->sm_count, s, c->stats_d};
+}
 
 #define NEED(cond, msg) \
     if (!(cond)) return fail(MRMP_ERR_INVALID, msg)
@@ -655,6 +664,12 @@ extern "C" int mrmp_collide_configs_dev(mrmp_ctx *c, int64_t n_cfg, const double
                                         void *stream) {
     DEV_PROLOGUE(c, n_cfg);
     if (need_aligned(c, Q_from) || need_aligned(c, Q_to)) return MRMP_ERR_INVALID;
+    if (c->model == MRMP_MODEL_ARM22 && !first_pair_out) {
+        // the arm kernel keeps the running first hit per configuration in this array
+        int rc = ensure_scratch(c, 3, sizeof(int64_t) * (size_t)n_cfg);
+        if (rc) return rc;
+        first_pair_out = (int64_t *)c->scratch[3];
+    }
     CU(launch_collide_configs(c->cv, lcfg(c, (cudaStream_t)stream), n_cfg, Q_from, Q_to, out,
                               first_pair_out));
     return MRMP_OK;
@@ -1103,6 +1118,13 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                          const int32_t *col_vf, const int32_t *col_vt, const double *nodes,
                          int agent0, int nv_stride, int group_size, uint32_t *out,
                          cudaStream_t s) {
+    if (c->model == MRMP_MODEL_ARM22) {  // warp per (row, column) check, arm22.jl:100-146
+        CU(launch_arm_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to, n_cols,
+                                    col_agent, col_from, col_to, col_vf, col_vt, nodes, agent0,
+                                    nv_stride, group_size, cross_words(n_cols, group_size), out,
+                                    c->stats_d + 1));
+        return MRMP_OK;
+    }
     const int64_t n_tiles = (n_cols + kCrossCols - 1) / kCrossCols;
     const size_t tb = cross_tile_bytes(c->d);
     int rc = ensure_scratch(c, 0, (size_t)n_tiles * tb);

@@ -14,21 +14,41 @@
 //      case and takes norm_slow().
 //  (2) endpoint short-cut of the segment-point distance: for e == 1 / e == 0 the
 //      reference evaluates (e*a + (1-e)*b) - c, which is exactly a-c / b-c.
+//
+// The primitives are __host__ __device__: the device side is the product; the host side
+// exists only so that tests/hostprobe can run THIS source on the CPU (no GPU in the build
+// container) and compare it bit for bit with the oracle.  No library entry point calls them
+// on the host.
 #pragma once
 #include <cuda_runtime.h>
-#include <math_constants.h>
+#include <math.h>
+
+#define MRMP_HD __host__ __device__ __forceinline__
 
 namespace mrmp {
 
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
-__device__ __forceinline__ double dsqrt(double a) { return __dsqrt_rn(a); }
+#ifdef __CUDA_ARCH__
+MRMP_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+MRMP_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+MRMP_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+MRMP_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+MRMP_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+MRMP_HD double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+MRMP_HD double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+#else
+// host build (tests/hostprobe only): volatile blocks contraction / reassociation
+MRMP_HD double dadd(double a, double b) { volatile double r = a + b; return r; }
+MRMP_HD double dsub(double a, double b) { volatile double r = a - b; return r; }
+MRMP_HD double dmul(double a, double b) { volatile double r = a * b; return r; }
+MRMP_HD double ddiv(double a, double b) { volatile double r = a / b; return r; }
+MRMP_HD double dsqrt(double a) { return sqrt(a); }
+MRMP_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+MRMP_HD double dnan() { return NAN; }
+#endif
 
 // LinearAlgebra.dot on 2-3 element vectors: x1*y1 + x2*y2 (+ x3*y3), left to right
 template <int D>
-__device__ __forceinline__ double dotd(const double *a, const double *b) {
+MRMP_HD double dotd(const double *a, const double *b) {
     double s = dmul(a[0], b[0]);
 #pragma unroll
     for (int k = 1; k < D; ++k) s = dadd(s, dmul(a[k], b[k]));
@@ -37,7 +57,7 @@ __device__ __forceinline__ double dotd(const double *a, const double *b) {
 
 // sum of squares, left to right (fast path of LinearAlgebra.generic_norm2)
 template <int D>
-__device__ __forceinline__ double sumsq(const double *v) {
+MRMP_HD double sumsq(const double *v) {
     double s = dmul(v[0], v[0]);
 #pragma unroll
     for (int k = 1; k < D; ++k) s = dadd(s, dmul(v[k], v[k]));
@@ -46,12 +66,12 @@ __device__ __forceinline__ double sumsq(const double *v) {
 
 // generic_norm2 when the plain sum of squares is 0: either all-zero or underflow
 template <int D>
-__device__ __noinline__ double norm_slow(const double *v) {
+__host__ __device__ __noinline__ double norm_slow(const double *v) {
     double maxabs = fabs(v[0]);
 #pragma unroll
     for (int k = 1; k < D; ++k) {
         double a = fabs(v[k]);
-        maxabs = (isnan(maxabs) || isnan(a)) ? CUDART_NAN : (a > maxabs ? a : maxabs);
+        maxabs = (isnan(maxabs) || isnan(a)) ? dnan() : (a > maxabs ? a : maxabs);
     }
     if (maxabs == 0.0 || isinf(maxabs)) return maxabs;
     double t = ddiv(fabs(v[0]), maxabs);
@@ -66,7 +86,7 @@ __device__ __noinline__ double norm_slow(const double *v) {
 
 // full norm value (used where the distance itself is returned to the host)
 template <int D>
-__device__ __forceinline__ double norm_val(const double *v) {
+MRMP_HD double norm_val(const double *v) {
     double s = sumsq<D>(v);
     if (s == 0.0) return norm_slow<D>(v);
     return dsqrt(s);
@@ -75,7 +95,7 @@ __device__ __forceinline__ double norm_val(const double *v) {
 // norm(v) < thr.  TAB: T2 = sq_lt_threshold(thr) is available (sqrt-free exact compare);
 // otherwise the square root is taken like the reference does.
 template <int D, bool TAB = true>
-__device__ __forceinline__ bool norm_lt(const double *v, double s, double thr, double T2) {
+MRMP_HD bool norm_lt(const double *v, double s, double thr, double T2) {
     if (s == 0.0) return norm_slow<D>(v) < thr;
     if constexpr (TAB) return s < T2;
     return dsqrt(s) < thr;
@@ -84,7 +104,7 @@ __device__ __forceinline__ bool norm_lt(const double *v, double s, double thr, d
 // src/utils.jl:44-57: segment [a,b] to point c.  u = a-b and uu = dot(u,u) are passed in
 // (shared between several c).  Writes the difference vector p and returns sum p_k^2.
 template <int D>
-__device__ __forceinline__ double segpt_ss(const double *a, const double *b, const double *u,
+MRMP_HD double segpt_ss(const double *a, const double *b, const double *u,
                                            double uu, const double *c, double *p) {
     double bc[D], ac[D];
 #pragma unroll
@@ -112,7 +132,7 @@ __device__ __forceinline__ double segpt_ss(const double *a, const double *b, con
 
 // verdict  dist(a,b,c) < thr
 template <int D, bool TAB = true>
-__device__ __forceinline__ bool segpt_lt(const double *a, const double *b, const double *u,
+MRMP_HD bool segpt_lt(const double *a, const double *b, const double *u,
                                          double uu, const double *c, double thr, double T2) {
     double p[D];
     const double s = segpt_ss<D>(a, b, u, uu, c, p);
@@ -121,7 +141,7 @@ __device__ __forceinline__ bool segpt_lt(const double *a, const double *b, const
 
 // src/utils.jl:59-94: verdict  dist(p11,p12,p21,p22) < thr
 template <int D, bool TAB = true>
-__device__ __forceinline__ bool segseg_lt(const double *p11, const double *p12, const double *p21,
+MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
                                           const double *p22, double thr, double T2) {
     double v1[D], v2[D], w[D];
 #pragma unroll

@@ -220,6 +220,7 @@ static cudaError_t set_smem(K kernel, int bytes) {
 cudaError_t launch_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_t n,
                                   const int32_t *agent, const double *q, uint8_t *out) {
     if (n <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_connect_points(cv, lc, n, agent, q, out);
     const int sm = seg_smem_bytes(cv.con_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -238,6 +239,7 @@ cudaError_t launch_connect_edges(const CtxView &cv, const LaunchCfg &lc, int64_t
                                  const int32_t *agent, const double *qf, const double *qt,
                                  uint8_t *out) {
     if (n <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_connect_edges(cv, lc, n, agent, qf, qt, out);
     const int sm = seg_smem_bytes(cv.con_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -257,6 +259,7 @@ cudaError_t launch_collide_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t
                                  const double *qit, const double *qjf, const double *qjt,
                                  uint8_t *out) {
     if (n <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_collide_pairs(cv, lc, n, ai, aj, qif, qit, qjf, qjt, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -280,6 +283,7 @@ cudaError_t launch_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc,
                                          int nv_stride, uint8_t *out) {
     (void)n_local;
     if (n <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_collide_edges_indexed(cv, lc, n, ai, aj, vif, vit, vjf, vjt, nodes, agent0, nv_stride, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -299,6 +303,7 @@ cudaError_t launch_collide_static_pairs(const CtxView &cv, const LaunchCfg &lc, 
                                         const int32_t *ai, const int32_t *aj, const double *qi,
                                         const double *qj, uint8_t *out) {
     if (n <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_collide_static_pairs(cv, lc, n, ai, aj, qi, qj, out);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -318,6 +323,7 @@ cudaError_t launch_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64
                                    const double *Qf, const double *Qt, uint8_t *out,
                                    int64_t *first_pair) {
     if (n_cfg <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_collide_configs(cv, lc, n_cfg, Qf, Qt, out, first_pair, reinterpret_cast<unsigned long long *>(first_pair), lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n_cfg * 32, sm);
     cudaError_t e;
@@ -337,6 +343,7 @@ cudaError_t launch_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, 
                                         const double *Q, int64_t n_cand, const double *q_to,
                                         uint8_t *out) {
     if (n_cand <= 0) return cudaSuccess;
+    if (cv.model == 2) return launch_arm_collide_config_moves(cv, lc, agent_i, Q, n_cand, q_to, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n_cand, sm);
     cudaError_t e;

@@ -258,6 +258,7 @@ static cudaError_t set_smem(K kernel, int bytes) {
     switch ((cv).model) {                                \
     case 0: { using M = PointModel<2>; EXPR; } break;    \
     case 1: { using M = PointModel<3>; EXPR; } break;    \
+    case 2: { using M = ArmModel; EXPR; } break;         \
     default: return cudaErrorNotSupported;               \
     }
 

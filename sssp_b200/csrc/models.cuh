@@ -2,6 +2,7 @@
 // A policy exposes the reference's per-model contract (src/MRMP.jl:40-54): state
 // dimension, dist, connect(q,i), connect(q_from,q_to,i), sampler scaling.
 #pragma once
+#include "arm_model.cuh"
 #include "point_model.cuh"
 
 namespace mrmp {
@@ -37,6 +38,51 @@ struct PointModel {
 #pragma unroll
         for (int k = 0; k < D; ++k) v[k] = dsub(qa[k], qb[k]);
         return norm_val<D>(v);
+    }
+};
+
+// StateArm22 (src/models/arm22.jl): thread-per-check bodies for the roadmap kernels
+struct ArmModel {
+    static constexpr int SD = 2;
+    // StateArm22((rand(2) * 2pi)...)  arm22.jl:214-218
+    static __device__ __forceinline__ void scale_sample(double *q) {
+        q[0] = dmul(q[0], 6.283185307179586);
+        q[1] = dmul(q[1], 6.283185307179586);
+    }
+    static __device__ __forceinline__ ArmObs obs(const CtxView &cv, const ConSeg &cs) {
+        ArmObs o;
+        o.s = cs.s;
+        o.obs = cs.obs;
+        o.t2 = cs.t2;
+        o.mp = cs.mp;
+        o.n_obs = cs.n_obs;
+        (void)cv;
+        return o;
+    }
+    static __device__ __forceinline__ bool connect_point(const CtxView &cv, const ConSeg &cs,
+                                                         const double *q, int i) {
+        const int base = cv.base_off - cv.con_off;
+        return arm_connect_point(arm_ctx(cv), obs(cv, cs), q, cs.s[base + 2 * i],
+                                 cs.s[base + 2 * i + 1], cs.rad(i));
+    }
+    static __device__ __forceinline__ bool connect_edge(const CtxView &cv, const ConSeg &cs,
+                                                        const double *qf, const double *qt, int i) {
+        const int base = cv.base_off - cv.con_off;
+        return arm_connect_edge(arm_ctx(cv), obs(cv, cs), qf, qt, cs.s[base + 2 * i],
+                                cs.s[base + 2 * i + 1], cs.rad(i));
+    }
+    // dist(q_from, q_to) <= rad with dist of arm22.jl:15-20
+    static __device__ __forceinline__ bool dist_le(const CtxView &, const double *qa,
+                                                   const double *qb, double rad, double r2) {
+        double v[2];
+        arm_dist_vec(qa, qb, v);
+        const double s = sumsq<2>(v);
+        if (s == 0.0) return norm_slow<2>(v) <= rad;
+        return s <= r2;
+    }
+    static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
+                                                  const double *qb) {
+        return arm_dist(qa, qb);
     }
 };
 

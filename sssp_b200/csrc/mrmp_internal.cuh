@@ -32,6 +32,9 @@ struct CtxView {
     int t2_pair_off, g_pair_off;  // [i*N + j]
     double step_dist, safety_dist, max_dist;
     double safety_t2;  // sq_lt_threshold(safety_dist)
+    // D-independent half of Julia's rational lift of 0:step_dist:D (arm_model.cuh: step_rat)
+    int step_rat_ok;
+    long long step_rat_num, step_rat_den;
 };
 
 constexpr int kMaxStageBytes = 96 * 1024;  // larger segments are read from global (L1/L2)
@@ -90,6 +93,8 @@ __device__ __forceinline__ const double *stage_segment(const CtxView &cv, int se
 struct LaunchCfg {
     int sm_count;
     cudaStream_t stream;
+    unsigned long long *stats;  // ctx counters [4] (may be NULL): [0] cross-kernel survivors,
+                                // [1] arm link pairs that ran the exact test
 };
 
 void count_launch(int n = 1);
@@ -119,6 +124,42 @@ cudaError_t launch_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc,
                                          const int32_t *vjf, const int32_t *vjt,
                                          const double *nodes, int agent0, int n_local,
                                          int nv_stride, uint8_t *out);
+
+// kernels_arm.cu (StateArm22; the launchers above forward here when cv.model == 2)
+cudaError_t launch_arm_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                      const int32_t *agent, const double *q, uint8_t *out);
+cudaError_t launch_arm_connect_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                     const int32_t *agent, const double *qf, const double *qt,
+                                     uint8_t *out);
+cudaError_t launch_arm_collide_static_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                            const int32_t *ai, const int32_t *aj,
+                                            const double *qi, const double *qj, uint8_t *out);
+cudaError_t launch_arm_collide_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                     const int32_t *ai, const int32_t *aj, const double *qif,
+                                     const double *qit, const double *qjf, const double *qjt,
+                                     uint8_t *out, unsigned long long *stats);
+cudaError_t launch_arm_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                             const int32_t *ai, const int32_t *aj,
+                                             const int32_t *vif, const int32_t *vit,
+                                             const int32_t *vjf, const int32_t *vjt,
+                                             const double *nodes, int agent0, int nv_stride,
+                                             uint8_t *out, unsigned long long *stats);
+cudaError_t launch_arm_collide_cross(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
+                                     const int32_t *row_agent, const double *row_from,
+                                     const double *row_to, int64_t n_cols,
+                                     const int32_t *col_agent, const double *col_from,
+                                     const double *col_to, const int32_t *col_vf,
+                                     const int32_t *col_vt, const double *nodes, int agent0,
+                                     int nv_stride, int group_size, int words_per_row,
+                                     uint32_t *out, unsigned long long *stats);
+// first_scratch: n_cfg words of device scratch
+cudaError_t launch_arm_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64_t n_cfg,
+                                       const double *Qf, const double *Qt, uint8_t *out,
+                                       int64_t *first_pair, unsigned long long *first_scratch,
+                                       unsigned long long *stats);
+cudaError_t launch_arm_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, int agent_i,
+                                            const double *Q, int64_t n_cand, const double *q_to,
+                                            uint8_t *out, unsigned long long *stats);
 
 // kernels_prm.cu
 // adjacency bitmap [n_agents*nv rows][words] + row counts, exclusive scan, CSR emit

@@ -1,0 +1,111 @@
+// probe.cu -- TEST INFRASTRUCTURE: runs the device-side arithmetic headers of
+// sssp_b200/csrc (geom.cuh, trig.cuh, arm_model.cuh are __host__ __device__) on the CPU so
+// that `-m "not gpu"` tests can compare exactly the source the kernels are built from with the
+// oracle, bit for bit, in the GPU-less build container.  Not part of libmrmp_b200.so.
+#include <stdint.h>
+
+#include "../../sssp_b200/csrc/arm_model.cuh"
+
+using namespace mrmp;
+
+extern "C" {
+
+void probe_sincos(double x, double *s, double *c) { sincos_rn(x, *s, *c); }
+double probe_atan2(double y, double x) { return atan2_rn(y, x); }
+double probe_diff_angles(double a, double b) { return diff_angles(a, b); }
+
+int probe_segseg_lt(const double *p11, const double *p12, const double *p21, const double *p22,
+                    int d, double thr, double T2) {
+    return d == 2 ? segseg_lt<2, true>(p11, p12, p21, p22, thr, T2)
+                  : segseg_lt<3, true>(p11, p12, p21, p22, thr, T2);
+}
+int probe_segseg_lt_sqrt(const double *p11, const double *p12, const double *p21,
+                         const double *p22, int d, double thr) {
+    return d == 2 ? segseg_lt<2, false>(p11, p12, p21, p22, thr, 0.0)
+                  : segseg_lt<3, false>(p11, p12, p21, p22, thr, 0.0);
+}
+int probe_segpt_lt(const double *a, const double *b, const double *c, int d, double thr,
+                   double T2) {
+    double u[3];
+    for (int k = 0; k < d; ++k) u[k] = mrmp::dsub(a[k], b[k]);
+    return d == 2 ? segpt_lt<2, true>(a, b, u, dotd<2>(u, u), c, thr, T2)
+                  : segpt_lt<3, true>(a, b, u, dotd<3>(u, u), c, thr, T2);
+}
+
+// vcat(collect(0:step:D)/D, 1.0): writes min(n, cap) values, returns n
+int64_t probe_step_schedule(double step, double D, double *out, int64_t cap) {
+    const ArmSched s = arm_schedule(step_rat(step), step, D);
+    for (int64_t k = 0; k < s.n() && k < cap; ++k) out[k] = s.e(k);
+    return s.n();
+}
+
+struct ProbeArm {
+    int n_obs;
+    const double *ox, *oy, *orad, *t2;  // obstacle SoA + exact-compare table of d < o.r
+    double step, safety, safety_t2, max_dist;
+};
+
+static void unpack(const ProbeArm *p, double *buf, ArmObs &ob, ArmCtx &ac) {
+    // SoA block in the layout ArmObs expects: x[mp] y[mp] r[mp] | t2[mp]
+    const int mp = p->n_obs > 0 ? p->n_obs : 1;
+    for (int m = 0; m < p->n_obs; ++m) {
+        buf[m] = p->ox[m];
+        buf[mp + m] = p->oy[m];
+        buf[2 * mp + m] = p->orad[m];
+        buf[3 * mp + m] = p->t2[m];
+    }
+    ob.s = buf;
+    ob.obs = 0;
+    ob.t2 = 3 * mp;
+    ob.mp = mp;
+    ob.n_obs = p->n_obs;
+    ac.sr = step_rat(p->step);
+    ac.step = p->step;
+    ac.safety = p->safety;
+    ac.safety_t2 = p->safety_t2;
+    ac.max_dist = p->max_dist;
+}
+
+int probe_arm_connect_point(const ProbeArm *p, const double *q, double ax, double ay, double rad) {
+    double buf[4 * 64];
+    if (p->n_obs > 64) return -1;
+    ArmObs ob;
+    ArmCtx ac;
+    unpack(p, buf, ob, ac);
+    return arm_connect_point(ac, ob, q, ax, ay, rad);
+}
+int probe_arm_connect_edge(const ProbeArm *p, const double *qf, const double *qt, double ax,
+                           double ay, double rad) {
+    double buf[4 * 64];
+    if (p->n_obs > 64) return -1;
+    ArmObs ob;
+    ArmCtx ac;
+    unpack(p, buf, ob, ac);
+    return arm_connect_edge(ac, ob, qf, qt, ax, ay, rad);
+}
+int probe_arm_collide_static(const ProbeArm *p, const double *qi, const double *qj, double aix,
+                             double aiy, double ri, double ajx, double ajy, double rj) {
+    double buf[4 * 64];
+    ArmObs ob;
+    ArmCtx ac;
+    ProbeArm q = *p;
+    q.n_obs = 0;
+    unpack(&q, buf, ob, ac);
+    return arm_collide_static(ac, qi, qj, aix, aiy, ri, ajx, ajy, rj);
+}
+int probe_arm_collide_pair(const ProbeArm *p, const double *qif, const double *qit,
+                           const double *qjf, const double *qjt, double aix, double aiy, double ri,
+                           double ajx, double ajy, double rj) {
+    double buf[4 * 64];
+    ArmObs ob;
+    ArmCtx ac;
+    ProbeArm q = *p;
+    q.n_obs = 0;
+    unpack(&q, buf, ob, ac);
+    return arm_collide_pair_serial(ac, qif, qit, qjf, qjt, aix, aiy, ri, ajx, ajy, rj);
+}
+double probe_arm_dist(const double *q1, const double *q2) { return arm_dist(q1, q2); }
+void probe_arm_mid_status(const double *p, const double *q, double *out) {
+    arm_mid_status(p, q, out);
+}
+}

@@ -1,0 +1,201 @@
+"""The device-side arithmetic headers (geom.cuh, trig.cuh, arm_model.cuh), compiled for the
+HOST by tests/hostprobe/probe.cu, must agree bit for bit with the oracle.  This runs in the
+GPU-less container and pins the source the kernels are built from; the `-m gpu` tests then
+check the same functions as compiled for sm_100a."""
+import ctypes as C
+import math
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import make_arm_instance, near_threshold_pairs
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostprobe", "probe.cu")
+OUT = os.path.join(HERE, "_build", "libhostprobe.so")
+_dp = C.POINTER(C.c_double)
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+class ProbeArm(C.Structure):
+    _fields_ = [("n_obs", C.c_int), ("ox", _dp), ("oy", _dp), ("orad", _dp), ("t2", _dp),
+                ("step", C.c_double), ("safety", C.c_double), ("safety_t2", C.c_double),
+                ("max_dist", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def probe():
+    nvcc = _nvcc()
+    if nvcc is None:
+        pytest.skip("nvcc not available")
+    csrc = os.path.join(HERE, "..", "sssp_b200", "csrc")
+    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(p) > os.path.getmtime(OUT) for p in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17",
+                               "-O2", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-o",
+                               OUT, SRC])
+    lib = C.CDLL(OUT)
+    lib.probe_sincos.argtypes = [C.c_double, _dp, _dp]
+    lib.probe_atan2.restype = C.c_double
+    lib.probe_atan2.argtypes = [C.c_double, C.c_double]
+    lib.probe_diff_angles.restype = C.c_double
+    lib.probe_diff_angles.argtypes = [C.c_double, C.c_double]
+    lib.probe_segseg_lt.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double]
+    lib.probe_segseg_lt_sqrt.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_double]
+    lib.probe_segpt_lt.argtypes = [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double]
+    lib.probe_step_schedule.restype = C.c_int64
+    lib.probe_step_schedule.argtypes = [C.c_double, C.c_double, _dp, C.c_int64]
+    P = C.POINTER(ProbeArm)
+    lib.probe_arm_connect_point.argtypes = [P, _dp] + [C.c_double] * 3
+    lib.probe_arm_connect_edge.argtypes = [P, _dp, _dp] + [C.c_double] * 3
+    lib.probe_arm_collide_static.argtypes = [P, _dp, _dp] + [C.c_double] * 6
+    lib.probe_arm_collide_pair.argtypes = [P, _dp, _dp, _dp, _dp] + [C.c_double] * 6
+    lib.probe_arm_dist.restype = C.c_double
+    lib.probe_arm_dist.argtypes = [_dp, _dp]
+    lib.probe_arm_mid_status.argtypes = [_dp, _dp, _dp]
+    return lib
+
+
+def p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def sq_lt_threshold(thr):
+    """min{ s : RN(sqrt(s)) >= thr } (abi.cu: sq_lt_threshold)."""
+    if not thr > 0.0:
+        return 0.0
+    s = thr * thr
+    while s > 0.0 and math.sqrt(s) >= thr:
+        s = math.nextafter(s, -math.inf)
+    while math.sqrt(s) < thr:
+        s = math.nextafter(s, math.inf)
+    return s
+
+
+def bits(x):
+    return np.float64(x).view(np.uint64)
+
+
+def test_trig_bit_identical_to_oracle(probe):
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(-20, 20, 100000), rng.uniform(-1e-3, 1e-3, 5000),
+                         rng.uniform(-1e5, 1e5, 20000),
+                         np.array([0.0, -0.0, 1e-30, -1e-30, math.pi, -math.pi, math.pi / 2,
+                                   math.pi / 4, 0.7853981633974483, 0.7853981633974484,
+                                   2 * math.pi, 1e-9, 2.0 ** -26, 2.0 ** -27])])
+    L = O.lib()
+    s, c = C.c_double(), C.c_double()
+    for x in xs:
+        probe.probe_sincos(x, C.byref(s), C.byref(c))
+        assert bits(s.value) == bits(L.orc_sin(x)), x
+        assert bits(c.value) == bits(L.orc_cos(x)), x
+    ys = rng.normal(size=60000) * rng.choice([1e-12, 1e-3, 1.0, 1e3], 60000)
+    zs = rng.normal(size=60000) * rng.choice([1e-12, 1e-3, 1.0, 1e3], 60000)
+    ys[:8] = [0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 1.0, 3.0]
+    zs[:8] = [1.0, 1.0, -1.0, -1.0, 0.0, 0.0, 1.0, -0.0]
+    for y, z in zip(ys, zs):
+        assert bits(probe.probe_atan2(y, z)) == bits(L.orc_atan2(y, z)), (y, z)
+    a = rng.uniform(0, 2 * math.pi, 40000)
+    b = rng.uniform(0, 2 * math.pi, 40000)
+    a[:3], b[:3] = [1.0, math.pi, 0.0], [1.0, 0.0, math.pi]
+    for t1, t2 in zip(a, b):
+        assert bits(probe.probe_diff_angles(t1, t2)) == bits(L.orc_diff_angles(t1, t2))
+
+
+def test_step_schedule_matches_oracle(probe):
+    rng = np.random.default_rng(6)
+    Ds = list(rng.uniform(0, math.sqrt(2), 20000)) + [k / 100 for k in range(0, 143)] + \
+        [0.0, 0.29, 0.58, 0.5, 1.0, 1e-9, 0.01, 0.005, 0.015, 1.4142135623730951, 1 / 3, 2 / 7]
+    out = np.empty(8192)
+    for step in (0.01, 0.05, 0.013, 1 / 128):
+        for D in Ds:
+            n = probe.probe_step_schedule(step, D, p(out), out.size)
+            ref = O.step_schedule(step, D)
+            assert n == ref.size, (step, D)
+            assert np.array_equal(out[:n].view(np.uint64), ref.view(np.uint64)), (step, D)
+
+
+def test_segment_tests_match_oracle(probe):
+    rng = np.random.default_rng(7)
+    n = 20000
+    for d in (2, 3):
+        rads = rng.uniform(0.015, 0.03, 8)
+        ai, aj = rng.integers(0, 8, n), rng.integers(0, 8, n)
+        a, b, c, e = near_threshold_pairs(rng, n, rads, ai, aj, d)
+        a[: n // 2] = rng.random((n // 2, d))        # half plain random
+        b[: n // 2] = a[: n // 2] + rng.normal(size=(n // 2, d)) * 0.05
+        b[:50] = a[:50]                               # degenerate first segment
+        e[50:100] = c[50:100]                         # stationary second segment
+        for k in range(n):
+            thr = rads[ai[k]] + rads[aj[k]]
+            want = O.dist_ss(a[k], b[k], c[k], e[k]) < thr
+            got = probe.probe_segseg_lt(p(a[k]), p(b[k]), p(c[k]), p(e[k]), d, thr,
+                                        sq_lt_threshold(thr))
+            got2 = probe.probe_segseg_lt_sqrt(p(a[k]), p(b[k]), p(c[k]), p(e[k]), d, thr)
+            assert bool(got) == want and bool(got2) == want, (d, k)
+            want = O.dist_sp(a[k], b[k], c[k]) < thr
+            got = probe.probe_segpt_lt(p(a[k]), p(b[k]), p(c[k]), d, thr, sq_lt_threshold(thr))
+            assert bool(got) == want, (d, k)
+
+
+def _arm_probe(obs, step=0.01, safety=0.01, max_dist=math.nan):
+    ox, oy, orad = (np.ascontiguousarray(obs[:, k]) for k in range(3))
+    t2 = np.array([sq_lt_threshold(r) for r in orad])
+    pa = ProbeArm(obs.shape[0], p(ox), p(oy), p(orad), p(t2), step, safety,
+                  sq_lt_threshold(safety), max_dist)
+    pa._keep = (ox, oy, orad, t2)
+    return pa
+
+
+@pytest.mark.parametrize("max_dist", [math.nan, 0.6])
+def test_arm_bodies_match_oracle(probe, max_dist):
+    rng = np.random.default_rng(8)
+    N, M = 6, 3
+    rads, obs, base = make_arm_instance(N, M, seed=3)
+    orc = O.Oracle(O.ARM22, rads, obs, base=base, max_dist=max_dist)
+    pa = _arm_probe(obs, max_dist=max_dist)
+    n = 1500
+    q1 = rng.uniform(0, 2 * math.pi, (n, 2))
+    q2 = rng.uniform(0, 2 * math.pi, (n, 2))
+    q2[:100] = q1[:100] + rng.normal(size=(100, 2)) * 0.05     # short moves
+    q2[100:120] = q1[100:120]                                   # D == 0 (NaN first step)
+    q3 = rng.uniform(0, 2 * math.pi, (n, 2))
+    q4 = q3 + rng.normal(size=(n, 2)) * 0.3
+    ai = rng.integers(0, N, n)
+    aj = (ai + 1 + rng.integers(0, N - 1, n)) % N
+    n_free = n_edge = n_hit = 0
+    for k in range(n):
+        i, j = int(ai[k]), int(aj[k])
+        bi, bj = base[i], base[j]
+        w = orc.connect_point(q1[k], i)
+        assert bool(probe.probe_arm_connect_point(C.byref(pa), p(q1[k]), bi[0], bi[1], rads[i])) == w
+        n_free += w
+        w = orc.connect_edge(q1[k], q2[k], i)
+        assert bool(probe.probe_arm_connect_edge(C.byref(pa), p(q1[k]), p(q2[k]), bi[0], bi[1],
+                                                 rads[i])) == w, k
+        n_edge += w
+        w = orc.collide_static(q1[k], q3[k], i, j)
+        assert bool(probe.probe_arm_collide_static(C.byref(pa), p(q1[k]), p(q3[k]), bi[0], bi[1],
+                                                   rads[i], bj[0], bj[1], rads[j])) == w
+        if k < 300:
+            w = orc.collide_pair(q1[k], q2[k], q3[k], q4[k], i, j)
+            assert bool(probe.probe_arm_collide_pair(C.byref(pa), p(q1[k]), p(q2[k]), p(q3[k]),
+                                                     p(q4[k]), bi[0], bi[1], rads[i], bj[0],
+                                                     bj[1], rads[j])) == w, k
+            n_hit += w
+        assert bits(probe.probe_arm_dist(p(q1[k]), p(q2[k]))) == bits(orc.state_dist(q1[k], q2[k]))
+        mid = np.empty(2)
+        probe.probe_arm_mid_status(p(q1[k]), p(q2[k]), p(mid))
+        assert np.array_equal(mid.view(np.uint64), orc.mid_status(q1[k], q2[k]).view(np.uint64))
+    assert 0 < n_free < n and 0 < n_hit < 300   # both verdicts exercised
