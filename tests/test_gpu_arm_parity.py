@@ -39,7 +39,7 @@ def _moves(rng, n):
 def test_kats_through_the_closures():
     A = S.StateArm22
     base, rads = [[0.5, 0.5], [0.5, 0.8]], [0.2, 0.2]
-    connect = S.gen_connect(A(0, 0), [S.CircleObstacle2D(0.8, 0.5, 0.05)], base, rads)
+    connect = S.gen_connect(A(0, 0), [S.CircleObstacle2D(0.75, 0.5, 0.06)], base, rads)
     assert connect(A(math.pi / 2, 0.0), 0) is True            # up, then right: free
     assert connect(A(0.0, math.pi / 2), 0) is False           # first link runs into the obstacle
     assert connect(A(math.pi / 2, math.pi / 2), 0) is True    # straight up to y = 0.9
@@ -128,8 +128,10 @@ def test_collide_pairs_parity_fine_steps():
 
 
 def test_collide_configs_and_moves_parity():
-    N = 8
-    ctx, orc, rads, obs, base = _pair(N, 0, seed=15)
+    N = 6
+    rads, obs, base = make_arm_instance(N, 0, 18, link=(0.07, 0.1))   # sparse enough for both verdicts
+    ctx = S.Context(L.MODEL_ARM22, rads, obs, base_pos=base)
+    orc = O.Oracle(O.ARM22, rads, obs, base=base)
     rng = np.random.default_rng(25)
     n_cfg = 300
     Qf = rng.uniform(0, TWO_PI, (n_cfg, N, 2))
@@ -137,17 +139,19 @@ def test_collide_configs_and_moves_parity():
     g, gfp = ctx.collide_configs(Qf, Qt)
     o, ofp = orc.collide_configs_batch(Qf, Qt, nthreads=0)
     assert np.array_equal(g, o) and np.array_equal(gfp, ofp) and 0 < o.sum() < n_cfg
+    assert np.unique(ofp).size > 5          # first hits at several different pairs
     for i in (0, 3, N - 1):
         cand = rng.uniform(0, TWO_PI, (500, 2))
-        cand[:50] = Qf[0, i] + rng.normal(size=(50, 2)) * 0.05
-        g, o = ctx.collide_config_moves(i, Qf[0], cand), orc.collide_config_moves(i, Qf[0], cand, nthreads=0)
+        cand[:50] = Qf[1, i] + rng.normal(size=(50, 2)) * 0.05
+        g = ctx.collide_config_moves(i, Qf[1], cand)
+        o = orc.collide_config_moves(i, Qf[1], cand, nthreads=0)
         assert np.array_equal(g, o) and 0 < o.sum() < 500
 
 
 def test_roadmaps_and_cross_parity():
     # arm22.yaml: PRM num_vertices 100, rad 0.3 (scripts/config/eval/arm22.yaml:26-30)
     N, M, nv, rad = 6, 2, 100, 0.3
-    ctx, orc, rads, obs, base = _pair(N, M, seed=16)
+    ctx, orc, rads, obs, base = _pair(N, M, seed=17)   # every agent has free postures
     rng = np.random.default_rng(26)
     init = np.stack([orc.sample_free(a, 900, 1)[0][0] for a in range(N)])
     goal = np.stack([orc.sample_free(a, 901, 1)[0][0] for a in range(N)])
