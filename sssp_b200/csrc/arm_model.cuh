@@ -92,7 +92,7 @@ MRMP_HD ArmSched arm_schedule(const StepRat &sr, double step, double D) {
     s.den = sr.den;
     s.step = step;
     s.D = D;
-    if (!(D == D)) return s;  // NaN move: only e = 1 (the oracle's behaviour is undefined here)
+    if (!(D == D)) return s;  // NaN move: only e = 1 (the reference's behaviour is undefined here)
     if (sr.ok) {
         long long en, ed;
         jl_rat(D, en, ed);

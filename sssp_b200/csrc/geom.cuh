@@ -17,7 +17,7 @@
 //
 // The primitives are __host__ __device__: the device side is the product; the host side
 // exists only so that tests/hostprobe can run THIS source on the CPU (no GPU in the build
-// container) and compare it bit for bit with the oracle.  No library entry point calls them
+// container) and compare it bit for bit with the CPU checker.  No library entry point calls them
 // on the host.
 #pragma once
 #include <cuda_runtime.h>

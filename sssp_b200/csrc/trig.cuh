@@ -11,7 +11,7 @@
 // separate calls.
 //
 // Domain: |x| <= 2^20 * pi/2 (joint angles are O(10)); beyond it the device falls back to
-// libdevice and parity with the oracle (which falls back to libm there) is not claimed.
+// libdevice and bit parity with the CPU restatement (which uses libm there) is not claimed.
 #pragma once
 #include <string.h>
 
