@@ -231,6 +231,57 @@ int mrmp_sample_states(mrmp_ctx *ctx, int agent, uint64_t seed, uint64_t t0, int
 int mrmp_sample_free(mrmp_ctx *ctx, int agent, uint64_t seed, int64_t n_wanted, double *q_out,
                      int64_t *n_tried_out);
 
+/* ---- model helpers for the host-side search loops ----------------------------------------- */
+/* dist(q1, q2) of the model, n pairs: point2d.jl:12-14, point3d.jl:13-15, arm22.jl:15-20 */
+int mrmp_state_dist(mrmp_ctx *ctx, int64_t n, const double *q1, const double *q2, double *out);
+/* get_mid_status(p, q), n pairs: point2d.jl:8-10, point3d.jl:9-11, arm22.jl:8-13 */
+int mrmp_mid_status(mrmp_ctx *ctx, int64_t n, const double *p, const double *q, double *out);
+/* nearest vertex: argmin_v dist(V[v], q), or dist(q, V[v]) when reversed != 0; first minimum
+ * like Julia's argmin (sssp.jl:416-417, extend!).  V[n_v][d]. */
+int mrmp_nearest(mrmp_ctx *ctx, int n_v, const double *V, const double *q, int reversed,
+                 int32_t *idx_out, double *dist_out);
+
+/* ---- SSSP: device-resident growing roadmaps and the fused node expansion ------------------ */
+/* The reference's SSSP (src/solvers/sssp.jl:49-232) calls, for every search node it pops,
+ * expand! (:235-267, K x [steering :269-291 + nearest-distance filter :250 + conn against the
+ * whole roadmap :252-262]) and then the successor filter collide(S.Q, p.q, i) (:196-223) --
+ * thousands of closure calls.  mrmp_sssp_expand does all of it in one call on roadmaps that
+ * stay on the device; the best-first search (queue, visited set, distance tables) stays on
+ * the host, exactly as in the reference. */
+typedef struct mrmp_sssp mrmp_sssp;
+int mrmp_sssp_create(mrmp_ctx *ctx, int nv_cap, mrmp_sssp **out); /* tables grow on demand */
+void mrmp_sssp_destroy(mrmp_sssp *s);
+/* upload one agent's initial roadmap vertices (gen_RRT_connect_roadmap, sssp.jl:294-401;
+ * vertex 0 = q_init, 1 = q_goal); nodes[nv][d] */
+int mrmp_sssp_set_roadmap(mrmp_sssp *s, int agent, int nv, const double *nodes);
+int mrmp_sssp_nv(mrmp_sssp *s, int agent, int *nv_out);
+int mrmp_sssp_get_nodes(mrmp_sssp *s, int agent, double *nodes_out, int cap_vertices);
+/* One node expansion for `agent` at its vertex v_from (sssp.jl:181-223):
+ *  - samples: q_rand[n_samples][d] if non-NULL, else tries t0 .. t0+n_samples-1 of the
+ *    counter-based sampler stream (seed, agent) (same stream as mrmp_sample_states);
+ *  - steering with conn(q_from,q_to) = (epsilon is NaN || dist <= epsilon) && connect(...)
+ *    (sssp.jl:87-89, 269-291), acceptance  min_v dist(v.q, q_new) > min_dist_thread  in sample
+ *    order against the roadmap INCLUDING vertices accepted earlier in the same call (:250);
+ *  - accepted vertices get ids nv_before, nv_before+1, ...; q_new_out[n_new][d];
+ *    out_bits[r][words]: bit t set <=> edge (new r -> t), t < id_r   (sssp.jl:252-257)
+ *    in_bits [r][words]: bit t set <=> edge (t -> new r), t <= id_r  (self loop included,
+ *    sssp.jl:259-262); words_out = ceil((nv_before + n_samples) / 32); rows r >= n_new are 0.
+ *    Appending ids in ascending bit order reproduces the reference's neighbour-list order.
+ *  - successor filter: Q_ids[N] = vertex id of every agent in the popped search node
+ *    (Q_ids[agent] == v_from), old_nbrs = v_from's neighbour list before this call.
+ *    succ_ids[n_succ] = old_nbrs, then the accepted vertices that v_from now reaches
+ *    (ascending), then v_from (`vcat(v.neighbors, v.id)`, :197);
+ *    succ_collide[k] = collide(S.Q, p.q, i) (:206), or collide(S.Q, Q) (:207) when
+ *    slow_collide != 0 (no_fast_collision_check).  Both arrays hold n_old_nbrs+n_samples+1.
+ * MRMP_ERR_CAPACITY if bits_cap_words < n_samples * words_out (words_out is still written). */
+int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_samples, const double *q_rand,
+                     uint64_t seed, uint64_t t0, int steering_depth, double epsilon,
+                     double min_dist_thread, const int32_t *Q_ids, int n_old_nbrs,
+                     const int32_t *old_nbrs, int slow_collide, int32_t *n_new_out,
+                     double *q_new_out, int32_t *words_out, uint32_t *out_bits, uint32_t *in_bits,
+                     int64_t bits_cap_words, int32_t *n_succ_out, int32_t *succ_ids,
+                     uint8_t *succ_collide);
+
 #ifdef __cplusplus
 }
 #endif

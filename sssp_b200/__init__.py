@@ -7,11 +7,13 @@ gen_check_goal, src/MRMP.jl:98) on top of the C-ABI CUDA library
 from .lib import MRMPError, MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22  # noqa: F401
 from .closures import (  # noqa: F401
     StatePoint2D, StatePoint3D, StateArm22, CircleObstacle2D, CircleObstacle3D, Node,
-    Context, Roadmaps, gen_connect, gen_collide, gen_check_goal, PRMs,
+    Context, Roadmaps, SsspRoadmaps, gen_connect, gen_collide, gen_check_goal, PRMs,
 )
+from . import closures  # noqa: F401
+from .solvers import SSSP, get_distance_table  # noqa: F401
 
 __all__ = [
     "MRMPError", "MODEL_POINT2D", "MODEL_POINT3D", "MODEL_ARM22",
     "StatePoint2D", "StatePoint3D", "StateArm22", "CircleObstacle2D", "CircleObstacle3D", "Node",
-    "Context", "Roadmaps", "gen_connect", "gen_collide", "gen_check_goal", "PRMs",
+    "Context", "Roadmaps", "SsspRoadmaps", "SSSP", "gen_connect", "gen_collide", "gen_check_goal", "PRMs",
 ]

@@ -213,6 +213,31 @@ class Context:
                                            L.ptr(out, L._dp), C.byref(tried)))
         return out, int(tried.value)
 
+    # ---- model helpers used by the host search loops ----------------------------------
+    def state_dist(self, q1, q2) -> np.ndarray:
+        """dist(q1[k], q2[k]) of the model (point2d.jl:12-14, point3d.jl:13-15, arm22.jl:15-20)"""
+        a, b = _states(q1, self.d), _states(q2, self.d)
+        out = np.empty(a.shape[0])
+        L.check(self._lib.mrmp_state_dist(self._h, a.shape[0], L.ptr(a, L._dp), L.ptr(b, L._dp),
+                                          L.ptr(out, L._dp)))
+        return out
+
+    def mid_status(self, p, q) -> np.ndarray:
+        """get_mid_status(p[k], q[k]) (point2d.jl:8-10, point3d.jl:9-11, arm22.jl:8-13)"""
+        a, b = _states(p, self.d), _states(q, self.d)
+        out = np.empty_like(a)
+        L.check(self._lib.mrmp_mid_status(self._h, a.shape[0], L.ptr(a, L._dp), L.ptr(b, L._dp),
+                                          L.ptr(out, L._dp)))
+        return out
+
+    def nearest(self, V, q, reversed: bool = False):
+        """argmin_v dist(V[v], q) (reversed: dist(q, V[v])) -> (index, distance)"""
+        V, q = _states(V, self.d), _states([q] if not isinstance(q, np.ndarray) else q, self.d)
+        idx, dist = C.c_int32(-1), C.c_double(0.0)
+        L.check(self._lib.mrmp_nearest(self._h, V.shape[0], L.ptr(V, L._dp), L.ptr(q, L._dp),
+                                       int(reversed), C.byref(idx), C.byref(dist)))
+        return int(idx.value), float(dist.value)
+
     def prm_build(self, nodes, rad, agent0: int = 0):
         """nodes [n][nv][d], rad scalar/array/None -> (row_ptr [n*nv+1], col_idx [nnz])"""
         nodes = L.f64(nodes)
@@ -342,6 +367,76 @@ class Roadmaps:
                 rm.append(Node(State(*tabs[a, v]), v, col[row_ptr[r]: row_ptr[r + 1]].tolist()))
             res.append(rm)
         return res
+
+
+class SsspRoadmaps:
+    """Device-resident growing roadmaps of all agents + the fused node expansion
+    (wraps mrmp_sssp; sssp.jl:181-223, 235-291)."""
+
+    def __init__(self, ctx: Context, nv_cap: int = 256):
+        self.ctx, self._lib = ctx, ctx._lib
+        h = C.c_void_p()
+        L.check(self._lib.mrmp_sssp_create(ctx._h, int(nv_cap), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mrmp_sssp_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_roadmap(self, agent: int, nodes) -> None:
+        nodes = _states(nodes, self.ctx.d)
+        L.check(self._lib.mrmp_sssp_set_roadmap(self._h, int(agent), nodes.shape[0],
+                                                L.ptr(nodes, L._dp)))
+
+    def nv(self, agent: int) -> int:
+        n = C.c_int(0)
+        L.check(self._lib.mrmp_sssp_nv(self._h, int(agent), C.byref(n)))
+        return int(n.value)
+
+    def nodes(self, agent: int) -> np.ndarray:
+        out = np.empty((self.nv(agent), self.ctx.d))
+        L.check(self._lib.mrmp_sssp_get_nodes(self._h, int(agent), L.ptr(out, L._dp), out.shape[0]))
+        return out
+
+    def expand(self, agent: int, v_from: int, Q_ids, old_nbrs, n_samples: int, *, seed: int = 0,
+               t0: int = 0, q_rand=None, steering_depth: int = 2, epsilon: Optional[float] = None,
+               min_dist_thread: float = 0.1, slow_collide: bool = False):
+        """One node expansion.  Returns (q_new [n_new][d], out_lists, in_lists, succ_ids,
+        succ_collide): out_lists[r] / in_lists[r] are the ascending vertex ids the new vertex r
+        reaches / is reached from (its own id closes in_lists[r] when the self loop passes)."""
+        K, d = int(n_samples), self.ctx.d
+        Q_ids, old = L.i32(Q_ids).ravel(), L.i32(old_nbrs).ravel()
+        nv0 = self.nv(agent)
+        words = (nv0 + K + 31) // 32
+        q_new = np.empty((K, d))
+        out_bits = np.zeros((K, words), np.uint32)
+        in_bits = np.zeros((K, words), np.uint32)
+        cap_s = old.size + K + 1
+        succ, verdict = np.empty(cap_s, np.int32), np.empty(cap_s, np.uint8)
+        n_new, n_succ, w = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        qr = None if q_rand is None else _states(q_rand, d)
+        L.check(self._lib.mrmp_sssp_expand(
+            self._h, int(agent), int(v_from), K, None if qr is None else L.ptr(qr, L._dp),
+            int(seed), int(t0), int(steering_depth),
+            math.nan if epsilon is None else float(epsilon), float(min_dist_thread),
+            L.ptr(Q_ids, L._ip), old.size, L.ptr(old, L._ip) if old.size else None,
+            int(slow_collide), C.byref(n_new), L.ptr(q_new, L._dp), C.byref(w),
+            L.ptr(out_bits, L._vp), L.ptr(in_bits, L._vp), out_bits.size, C.byref(n_succ),
+            L.ptr(succ, L._ip), L.ptr(verdict, L._bp)))
+        n = int(n_new.value)
+
+        def ids(row):
+            return np.flatnonzero(np.unpackbits(row.view(np.uint8), bitorder="little")).tolist()
+
+        return (q_new[:n], [ids(out_bits[r]) for r in range(n)], [ids(in_bits[r]) for r in range(n)],
+                succ[: n_succ.value].copy(), verdict[: n_succ.value].copy())
 
 
 # ---------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 //   (rad === nothing || dist(q_j,q_k) <= rad) && connect(q_j,q_k)  =>  push!(neighbors_j, k)
 // Rows come out ascending in k because the bitmap is expanded in bit order.
 #include "models.cuh"
+#include "sampler.cuh"
 
 namespace mrmp {
 
@@ -13,49 +14,6 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-
-// ---- Philox4x32-10 (Salmon et al., SC'11), counter = (t_lo, t_hi, agent, block) ----------
-__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                           uint32_t k0, uint32_t k1, uint32_t *out) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0;
-        c1 = lo1;
-        c2 = n2;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0;
-    out[1] = c1;
-    out[2] = c2;
-    out[3] = c3;
-}
-
-__device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
-    // exact: 27 + 26 bits, then a power-of-two scale
-    return dmul(dadd(dmul((double)(hi >> 5), 67108864.0), (double)(lo >> 6)),
-                1.0 / 9007199254740992.0);
-}
-
-// gen_uniform_sampling: point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218
-template <class M>
-__device__ __forceinline__ void sample_state(uint64_t seed, int agent, uint64_t t, double *q) {
-    uint32_t r[4];
-    philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, 0u, (uint32_t)seed,
-               (uint32_t)(seed >> 32), r);
-    q[0] = u01_53(r[0], r[1]);
-    q[1] = u01_53(r[2], r[3]);
-    if constexpr (M::SD == 3) {
-        philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, 1u, (uint32_t)seed,
-                   (uint32_t)(seed >> 32), r);
-        q[2] = u01_53(r[0], r[1]);
-    }
-    M::scale_sample(q);
-}
 
 template <class M>
 __global__ void __launch_bounds__(kThreads)

@@ -1,0 +1,350 @@
+// kernels_sssp.cu -- the batched SSSP node expansion (src/solvers/sssp.jl:181-223, 235-291).
+//
+// One search-node expansion of the reference issues, one closure call at a time,
+//   expand!  (sssp.jl:235-267): K samples -> steering (:269-291, up to depth+1 conn tests each)
+//            -> space-filling test against every roadmap vertex (:250) -> for every accepted
+//            sample conn(q_new, v.q) and conn(v.q, q_new) against the whole roadmap (:252-262)
+//   successor filter (sssp.jl:196-223): collide(S.Q, p.q, i) for every neighbour p of v and v
+// Here the whole expansion is one short kernel sequence on the ctx stream over DEVICE-RESIDENT,
+// growing per-agent node tables; the host gets back the accepted vertices, their in/out
+// adjacency bitmaps (ascending vertex id = the reference's push! order) and the verdicts of the
+// successor filter, and keeps running the branchy best-first search itself.
+//
+// Sequential semantics kept exact: sample k sees the vertices accepted from samples k' < k of
+// the same call (sssp.jl:250 reads the roadmap after earlier push!es) -- resolved by a K x K
+// closeness matrix and one serial pass; the new vertex's out-edges exclude itself while its
+// in-edge pass includes the self loop (sssp.jl:252-262).
+#include <math_constants.h>
+
+#include "models.cuh"
+#include "sampler.cuh"
+
+namespace mrmp {
+
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+static inline int seg_smem_bytes(int seg_len) {
+    const int bytes = seg_len * 8 + 16;
+    return bytes <= kMaxStageBytes ? bytes : 0;
+}
+template <class K>
+static cudaError_t set_smem(K kernel, int bytes) {
+    if (bytes > 48 * 1024)
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaSuccess;
+}
+
+// conn(q_from, q_to) = (isnothing(epsilon) || dist(q_from,q_to) <= epsilon) && connect(...)
+// sssp.jl:87-89
+template <class M>
+__device__ __forceinline__ bool conn(const CtxView &cv, const ConSeg &cs, const SsspExpand &a,
+                                     const double *qf, const double *qt) {
+    if (a.eps == a.eps && !M::dist_le(cv, qf, qt, a.eps, a.eps_r2)) return false;
+    return M::connect_edge(cv, cs, qf, qt, a.agent);
+}
+
+// ---- stage 1: sampling, steering, space-filling test, sequential acceptance ------------------
+template <class M>
+__global__ void __launch_bounds__(256)
+k_sssp_steer(CtxView cv, SsspView view, SsspExpand a, SsspWs ws, int staged) {
+    constexpr int D = M::SD;
+    __shared__ double s_q[kMaxExpand][D];
+    __shared__ int s_near[kMaxExpand];
+    __shared__ unsigned long long s_close[kMaxExpand];
+    __shared__ int s_rank[kMaxExpand];
+    const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, staged));
+    const int tid = threadIdx.x;
+    const int nv0 = view.nv[a.agent];
+    double *tab = view.nodes + (int64_t)a.agent * view.cap * D;
+    if (tid < a.K) {
+        double q_near[D], qh[D];
+        load_state<D>(tab, a.v_from, q_near);
+        if (a.host_samples) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) qh[c] = ws.q_rand[tid * D + c];
+        } else {
+            sample_state<M>(a.seed, a.agent, a.t0 + (uint64_t)tid, qh);
+        }
+        // steering (sssp.jl:269-291)
+        if (!conn<M>(cv, cs, a, q_near, qh)) {
+            double ql[D], q[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) ql[c] = q_near[c];
+            for (int s = 0; s < a.depth; ++s) {
+                M::mid(ql, qh, q);
+                const bool ok = conn<M>(cv, cs, a, q_near, q);
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if (ok) ql[c] = q[c];
+                    else qh[c] = q[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) qh[c] = ql[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) s_q[tid][c] = qh[c];
+        s_near[tid] = 0;
+        s_close[tid] = 0ull;
+    }
+    __syncthreads();
+    // minimum(v -> dist(v.q, q_new), roadmap) > min_dist_thread  (sssp.jl:250)
+    for (int idx = tid; idx < a.K * nv0; idx += blockDim.x) {
+        const int k = idx / nv0, v = idx - k * nv0;
+        double qv[D];
+        load_state<D>(tab, v, qv);
+        if (!M::dist_gt(cv, qv, s_q[k], a.thr, a.thr_r2)) s_near[k] = 1;
+    }
+    for (int idx = tid; idx < a.K * a.K; idx += blockDim.x) {
+        const int kp = idx / a.K, k = idx - kp * a.K;
+        if (kp < k && !M::dist_gt(cv, s_q[kp], s_q[k], a.thr, a.thr_r2))
+            atomicOr(&s_close[k], 1ull << kp);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long acc = 0ull;
+        int n = 0;
+        for (int k = 0; k < a.K; ++k) {
+            if (!s_near[k] && !(s_close[k] & acc)) {
+                acc |= 1ull << k;
+                s_rank[k] = n++;
+            } else {
+                s_rank[k] = -1;
+            }
+        }
+        ws.hdr[0] = n;
+        ws.hdr[2] = nv0;
+        view.nv[a.agent] = nv0 + n;
+    }
+    __syncthreads();
+    if (tid < a.K && s_rank[tid] >= 0) {
+        const int r = s_rank[tid];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            tab[(int64_t)(nv0 + r) * D + c] = s_q[tid][c];
+            ws.q_new[r * D + c] = s_q[tid][c];
+        }
+    }
+    for (int idx = tid; idx < 2 * a.K * a.words; idx += blockDim.x) ws.out_bits[idx] = 0u;
+}
+
+// ---- stage 2: edges of the accepted vertices ------------------------------------------------
+// new vertex r (id nv0 + r): out bit t  <=> conn(q_new, q_t), t <  id   (sssp.jl:252-257)
+//                            in  bit t  <=> conn(q_t, q_new), t <= id   (sssp.jl:259-262)
+template <class M>
+__global__ void __launch_bounds__(128)
+k_sssp_conn(CtxView cv, SsspView view, SsspExpand a, SsspWs ws, int staged) {
+    constexpr int D = M::SD;
+    const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, staged));
+    const int n_new = ws.hdr[0], nv0 = ws.hdr[2];
+    const double *tab = view.nodes + (int64_t)a.agent * view.cap * D;
+    const int T = nv0 + a.K;  // targets per new vertex (upper bound)
+    const int64_t total = (int64_t)n_new * T * 2;
+    for (int64_t it = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; it < total;
+         it += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(it / (2 * T));
+        const int rem = (int)(it - (int64_t)r * 2 * T);
+        const int t = rem >> 1, dir = rem & 1;
+        const int id = nv0 + r;
+        if (t > id || (t == id && dir == 0)) continue;
+        double qu[D], qt[D];
+        load_state<D>(tab, id, qu);
+        load_state<D>(tab, t, qt);
+        const bool ok = dir == 0 ? conn<M>(cv, cs, a, qu, qt) : conn<M>(cv, cs, a, qt, qu);
+        if (ok) {
+            uint32_t *bits = (dir == 0 ? ws.out_bits : ws.in_bits) + (int64_t)r * a.words;
+            atomicOr(bits + (t >> 5), 1u << (t & 31));
+        }
+    }
+}
+
+// ---- stage 3: successor list of v_from and the operands of the collide filter ---------------
+// successors = old neighbours (host order), new neighbours (accepted u with an edge v -> u,
+// ascending), then v itself  (`for p_id in vcat(v.neighbors, v.id)`, sssp.jl:197)
+template <int D>
+__global__ void __launch_bounds__(256)
+k_sssp_gather(SsspView view, SsspExpand a, SsspWs ws, int n_agents) {
+    __shared__ int s_n;
+    const int tid = threadIdx.x;
+    const int n_new = ws.hdr[0], nv0 = ws.hdr[2];
+    const int cap_s = a.n_old + a.K + 1;
+    if (tid == 0) {
+        int n = a.n_old;
+        for (int r = 0; r < n_new; ++r)
+            if ((ws.in_bits[(int64_t)r * a.words + (a.v_from >> 5)] >> (a.v_from & 31)) & 1u)
+                ws.succ_ids[n++] = nv0 + r;
+        ws.succ_ids[n++] = a.v_from;
+        s_n = n;
+        ws.hdr[1] = n;
+    }
+    for (int k = tid; k < a.n_old; k += blockDim.x) ws.succ_ids[k] = ws.old_nbrs[k];
+    for (int j = tid; j < n_agents; j += blockDim.x) {
+        const double *tj = view.nodes + ((int64_t)j * view.cap + ws.Q_ids[j]) * D;
+#pragma unroll
+        for (int c = 0; c < D; ++c) ws.Qbuf[j * D + c] = tj[c];
+    }
+    __syncthreads();
+    const int n = s_n;
+    const double *tab = view.nodes + (int64_t)a.agent * view.cap * D;
+    for (int k = tid; k < cap_s; k += blockDim.x) {
+        const int id = k < n ? ws.succ_ids[k] : a.v_from;  // padding: the stay move
+        if (k >= n) ws.succ_ids[k] = -1;
+#pragma unroll
+        for (int c = 0; c < D; ++c) ws.cand[k * D + c] = tab[(int64_t)id * D + c];
+    }
+    if (a.slow_collide) {
+        // operands of collide(S.Q, Q) (sssp.jl:207): Q = S.Q with agent i moved to the successor
+        for (int idx = tid; idx < cap_s * n_agents; idx += blockDim.x) {
+            const int k = idx / n_agents, j = idx - k * n_agents;
+            const int id = k < n ? ws.succ_ids[k] : a.v_from;
+            const double *src = j == a.agent
+                                    ? tab + (int64_t)(id < 0 ? a.v_from : id) * D
+                                    : view.nodes + ((int64_t)j * view.cap + ws.Q_ids[j]) * D;
+            const double *from = view.nodes + ((int64_t)j * view.cap + ws.Q_ids[j]) * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                ws.cfg_to[(int64_t)idx * D + c] = src[c];
+                ws.cfg_from[(int64_t)idx * D + c] = from[c];
+            }
+        }
+    }
+}
+
+// ---- small per-state helpers for the host search loops --------------------------------------
+// op 0: out[k] = dist(q1[k], q2[k]);  op 1: out[k][:] = get_mid_status(q1[k], q2[k])
+template <class M>
+__global__ void __launch_bounds__(256)
+k_state_op(CtxView cv, int op, int64_t n, const double *__restrict__ q1,
+           const double *__restrict__ q2, double *__restrict__ out) {
+    constexpr int D = M::SD;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        double a[D], b[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            a[c] = q1[k * D + c];
+            b[c] = q2[k * D + c];
+        }
+        if (op == 0) {
+            out[k] = M::dist(cv, a, b);
+        } else {
+            double m[D];
+            M::mid(a, b, m);
+#pragma unroll
+            for (int c = 0; c < D; ++c) out[k * D + c] = m[c];
+        }
+    }
+}
+
+// argmin_v dist(V[v], q) (reversed: dist(q, V[v])); first minimum like Julia's argmin
+// (sssp.jl:416-417).  One CTA; NaN distances are never selected unless all are NaN (index 0).
+template <class M>
+__global__ void __launch_bounds__(256)
+k_nearest(CtxView cv, int n_v, const double *__restrict__ V, const double *__restrict__ q,
+          int reversed, int32_t *__restrict__ idx_out, double *__restrict__ dist_out) {
+    constexpr int D = M::SD;
+    __shared__ double s_d[256];
+    __shared__ int s_i[256];
+    double qq[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) qq[c] = q[c];
+    double best = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < n_v; v += blockDim.x) {
+        double qv[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) qv[c] = V[(int64_t)v * D + c];
+        const double dd = reversed ? M::dist(cv, qq, qv) : M::dist(cv, qv, qq);
+        if (dd < best || (dd == best && v < bi)) {
+            best = dd;
+            bi = v;
+        }
+    }
+    s_d[threadIdx.x] = best;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double d2 = s_d[threadIdx.x + o];
+            const int i2 = s_i[threadIdx.x + o];
+            if (d2 < s_d[threadIdx.x] || (d2 == s_d[threadIdx.x] && i2 < s_i[threadIdx.x])) {
+                s_d[threadIdx.x] = d2;
+                s_i[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const bool none = s_i[0] == 0x7fffffff;  // every distance NaN (or inf)
+        *idx_out = none ? 0 : s_i[0];
+        if (dist_out) {
+            double q0[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) q0[c] = V[c];
+            *dist_out = none ? (reversed ? M::dist(cv, qq, q0) : M::dist(cv, q0, qq)) : s_d[0];
+        }
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+#define MRMP_MODEL_SWITCH(cv, EXPR)                      \
+    switch ((cv).model) {                                \
+    case 0: { using M = PointModel<2>; EXPR; } break;    \
+    case 1: { using M = PointModel<3>; EXPR; } break;    \
+    case 2: { using M = ArmModel; EXPR; } break;         \
+    default: return cudaErrorNotSupported;               \
+    }
+
+cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
+                               const SsspExpand &a, const SsspWs &ws, int nv_before) {
+    if (a.K < 1 || a.K > kMaxExpand) return cudaErrorInvalidValue;
+    const int sm = seg_smem_bytes(cv.con_len);
+    cudaError_t e = cudaSuccess;
+    MRMP_MODEL_SWITCH(cv, (e = set_smem(k_sssp_steer<M>, sm),
+                           k_sssp_steer<M><<<1, 256, sm, lc.stream>>>(cv, view, a, ws, sm > 0)));
+    if (e != cudaSuccess) return e;
+    count_launch();
+    // conn tests: at most K * 2 * (nv_before + K) items, one per thread
+    const int64_t items = (int64_t)a.K * 2 * (nv_before + a.K);
+    int64_t want = (items + 127) / 128;
+    const int64_t cap = (int64_t)lc.sm_count * 8;
+    const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+    MRMP_MODEL_SWITCH(cv, (e = set_smem(k_sssp_conn<M>, sm),
+                           k_sssp_conn<M><<<grid, 128, sm, lc.stream>>>(cv, view, a, ws, sm > 0)));
+    if (e != cudaSuccess) return e;
+    count_launch();
+    if (cv.d == 3)
+        k_sssp_gather<3><<<1, 256, 0, lc.stream>>>(view, a, ws, cv.n_agents);
+    else
+        k_sssp_gather<2><<<1, 256, 0, lc.stream>>>(view, a, ws, cv.n_agents);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int cap_s = a.n_old + a.K + 1;
+    if (a.slow_collide)
+        return launch_collide_configs(cv, lc, cap_s, ws.cfg_from, ws.cfg_to, ws.succ_out,
+                                      ws.cfg_first);
+    return launch_collide_config_moves(cv, lc, a.agent, ws.Qbuf, cap_s, ws.cand, ws.succ_out);
+}
+
+cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
+                            const double *q1, const double *q2, double *out) {
+    if (n <= 0) return cudaSuccess;
+    int64_t want = (n + 255) / 256;
+    const int64_t cap = (int64_t)lc.sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    MRMP_MODEL_SWITCH(cv, (k_state_op<M><<<grid, 256, 0, lc.stream>>>(cv, op, n, q1, q2, out)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,
+                           const double *q, int reversed, int32_t *idx_out, double *dist_out) {
+    if (n_v <= 0) return cudaErrorInvalidValue;
+    MRMP_MODEL_SWITCH(cv, (k_nearest<M><<<1, 256, 0, lc.stream>>>(cv, n_v, V, q, reversed, idx_out,
+                                                                 dist_out)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace mrmp

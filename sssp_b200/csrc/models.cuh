@@ -39,6 +39,22 @@ struct PointModel {
         for (int k = 0; k < D; ++k) v[k] = dsub(qa[k], qb[k]);
         return norm_val<D>(v);
     }
+    // dist(qa, qb) > thr (false for NaN, like `minimum(...) > thr`, sssp.jl:250);
+    // r2 = sq_le_threshold(thr)
+    static __device__ __forceinline__ bool dist_gt(const CtxView &, const double *qa,
+                                                   const double *qb, double thr, double r2) {
+        double v[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] = dsub(qa[k], qb[k]);
+        const double s = sumsq<D>(v);
+        if (s == 0.0) return norm_slow<D>(v) > thr;
+        return s > r2;
+    }
+    // get_mid_status: point2d.jl:8-10, point3d.jl:9-11
+    static __device__ __forceinline__ void mid(const double *p, const double *q, double *out) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) out[k] = ddiv(dadd(p[k], q[k]), 2.0);
+    }
 };
 
 // StateArm22 (src/models/arm22.jl): thread-per-check bodies for the roadmap kernels
@@ -83,6 +99,18 @@ struct ArmModel {
     static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
                                                   const double *qb) {
         return arm_dist(qa, qb);
+    }
+    static __device__ __forceinline__ bool dist_gt(const CtxView &, const double *qa,
+                                                   const double *qb, double thr, double r2) {
+        double v[2];
+        arm_dist_vec(qa, qb, v);
+        const double s = sumsq<2>(v);
+        if (s == 0.0) return norm_slow<2>(v) > thr;
+        return s > r2;
+    }
+    // get_mid_status: arm22.jl:8-13
+    static __device__ __forceinline__ void mid(const double *p, const double *q, double *out) {
+        arm_mid_status(p, q, out);
     }
 };
 

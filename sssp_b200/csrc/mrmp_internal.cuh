@@ -179,6 +179,45 @@ cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent
                                int64_t *tries_out, int64_t max_tries);
 
 
+// kernels_sssp.cu
+constexpr int kMaxExpand = 64;  // samples per expansion call (num_vertex_expansion)
+struct SsspView {               // growing per-agent node tables of one SSSP instance
+    double *nodes;              // [N][cap][d]
+    int32_t *nv;                // [N] current vertex counts
+    int cap;
+};
+struct SsspExpand {             // scalar arguments of one expansion
+    int agent, v_from, K, depth;
+    double eps, eps_r2;         // epsilon (NaN = nothing), sq_le_threshold(epsilon)
+    double thr, thr_r2;         // min_dist_thread, sq_le_threshold(min_dist_thread)
+    unsigned long long seed, t0;
+    int host_samples;           // q_rand uploaded by the caller instead of (seed, t0 + k)
+    int words;                  // bitmap words per new vertex: ceil((nv_before + K) / 32)
+    int n_old;                  // old neighbours of v_from
+    int slow_collide;           // no_fast_collision_check: collide(S.Q, Q) instead of (S.Q, q, i)
+};
+struct SsspWs {                 // device workspace of one expansion (laid out by abi_sssp.cu)
+    const double *q_rand;       // [K][d]
+    const int32_t *Q_ids;       // [N] vertex of every agent in the search node S
+    const int32_t *old_nbrs;    // [n_old]
+    int32_t *hdr;               // [0] n_new, [1] n_succ, [2] nv_before
+    double *q_new;              // [K][d] accepted vertices, in acceptance order
+    uint32_t *out_bits;         // [K][words]; in_bits = out_bits + K*words follows directly
+    uint32_t *in_bits;
+    int32_t *succ_ids;          // [n_old + K + 1]
+    uint8_t *succ_out;          // [n_old + K + 1] collide verdict per successor
+    double *Qbuf;               // [N][d]
+    double *cand;               // [n_old + K + 1][d]
+    double *cfg_from, *cfg_to;  // slow_collide: [n_old + K + 1][N][d]
+    int64_t *cfg_first;
+};
+cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
+                               const SsspExpand &a, const SsspWs &ws, int nv_before);
+cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
+                            const double *q1, const double *q2, double *out);
+cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,
+                           const double *q, int reversed, int32_t *idx_out, double *dist_out);
+
 // kernels_cross.cu
 constexpr int kCrossCols = 64;        // columns per staged tile
 constexpr int kCrossMaxGroups = 256;  // reduced mode: groups per launch

@@ -1,0 +1,137 @@
+"""GPU parity of the SSSP hot loops: the fused node expansion (mrmp_sssp_expand) against the
+oracle's expand! / successor filter, and whole SSSP runs (sssp_b200.solvers.SSSP on the CUDA
+path) against the committed golden solutions and the live oracle -- identical solutions,
+identical roadmaps (vertices bit for bit, neighbour lists in the same order)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import sssp_b200 as S
+from sssp_b200 import lib as L, solvers
+from oracle import oracle as O
+from oracle import sssp_ref as R
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sssp_*.json")))
+STATE = {O.POINT2D: S.StatePoint2D, O.POINT3D: S.StatePoint3D, O.ARM22: S.StateArm22}
+
+
+def load(path):
+    with open(path) as f:
+        fx = json.load(f)
+    inst = fx["instance"]
+    base = None if inst["base"] is None else np.array(inst["base"])
+    orc = O.Oracle(inst["model"], inst["rads"], np.array(inst["obstacles"]), base=base)
+    return fx, inst, orc, base
+
+
+def closures(inst, base):
+    State = STATE[inst["model"]]
+    tag = State(*([0.0] * len(State._fields)))
+    params = (inst["rads"],) if base is None else (base, inst["rads"])
+    connect = S.gen_connect(tag, np.array(inst["obstacles"]), *params)
+    collide = S.gen_collide(tag, *params)
+    goal = [State(*q) for q in inst["config_goal"]]
+    return connect, collide, S.gen_check_goal(goal), State
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-5] for p in GOLD])
+def test_sssp_identical_to_golden(path):
+    fx, inst, orc, base = load(path)
+    connect, collide, check_goal, State = closures(inst, base)
+    st = {}
+    sol, rms = solvers.SSSP([State(*q) for q in inst["config_init"]],
+                            [State(*q) for q in inst["config_goal"]], connect, collide, check_goal,
+                            TIME_LIMIT=None, seed=fx["seed"], stats=st, **fx["params"])
+    assert sol is not None
+    assert st["solution_ids"] == fx["solution"] and st["expansions"] == fx["expansions"]
+    for rm, g in zip(rms, fx["roadmaps"]):
+        assert [[float(x).hex() for x in v.q] for v in rm] == g["nodes"]
+        assert [list(v.neighbors) for v in rm] == g["neighbors"]
+    # reference return shape: Vector{Vector{Node}} per time step, roadmaps per agent
+    assert len(sol[0]) == len(inst["rads"]) and isinstance(sol[0][0], S.Node)
+
+
+@pytest.mark.parametrize("model,slow", [(O.POINT2D, False), (O.POINT2D, True), (O.POINT3D, False),
+                                        (O.ARM22, False)])
+def test_expand_matches_oracle(model, slow):
+    """One fused call == expand! + successor filter of the oracle, over several consecutive
+    expansions on the same growing roadmap (the second sees the vertices of the first)."""
+    path = [p for p in GOLD if {O.POINT2D: "point2d_many", O.POINT3D: "point3d", O.ARM22: "arm22"}[model] in p][0]
+    fx, inst, orc, base = load(path)
+    N = len(inst["rads"])
+    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base)
+    # start from the golden (oracle-built) initial roadmaps truncated to their first vertices
+    rms = []
+    for g in fx["roadmaps"]:
+        keep = min(8, len(g["nodes"]))
+        rm = [R.Node([float.fromhex(x) for x in q], v, [u for u in nb if u < keep])
+              for v, (q, nb) in enumerate(zip(g["nodes"][:keep], g["neighbors"][:keep]))]
+        rms.append(rm)
+    dev = S.closures.SsspRoadmaps(ctx, nv_cap=8)            # forces the tables to grow
+    for i in range(N):
+        dev.set_roadmap(i, np.stack([v.q for v in rms[i]]))
+    eps = fx["params"].get("epsilon")
+    depth = fx["params"].get("steering_depth", 2)
+    K = 12 if model != O.ARM22 else 5
+    rng = np.random.default_rng(5)
+    t = [0] * N
+    thr = 0.08
+    for step in range(6):
+        i = step % N
+        v = int(rng.integers(0, len(rms[i])))
+        ids = [int(rng.integers(0, len(rms[j]))) for j in range(N)]
+        ids[i] = v
+        old = list(rms[i][v].neighbors)
+        q_new, outs, ins, succ, hit = dev.expand(i, v, ids, old, K, seed=9, t0=t[i], steering_depth=depth,
+                                                 epsilon=eps, min_dist_thread=thr, slow_collide=slow)
+        # oracle: same samples, sequential expand!
+        nv0 = len(rms[i])
+        samples = iter([orc.sample_state(9, i, t[i] + k) for k in range(K)])
+        t[i] += K
+        conn = lambda a, b: (eps is None or orc.state_dist(a, b) <= eps) and orc.connect_edge(a, b, i)
+        R.expand(orc, conn, lambda: next(samples), rms[i][v], rms[i], thr, K, depth)
+        new = rms[i][nv0:]
+        assert len(new) == len(q_new)
+        for r, u in enumerate(new):
+            assert np.array_equal(u.q.view(np.uint64), q_new[r].view(np.uint64))
+            assert [x for x in u.neighbors if x < u.id] == outs[r]
+            want_in = [w.id for w in rms[i][: u.id + 1] if u.id in w.neighbors]
+            assert want_in == ins[r]
+        assert succ.tolist() == list(rms[i][v].neighbors) + [v]
+        Q = np.stack([rms[j][ids[j]].q for j in range(N)])
+        for p_id, h in zip(succ.tolist(), hit.tolist()):
+            if slow:
+                Qt = Q.copy()
+                Qt[i] = rms[i][p_id].q
+                want = orc.collide_configs(Q, Qt)[0]
+            else:
+                want = orc.collide_config_move(Q, rms[i][p_id].q, i)
+            assert bool(h) == want
+        assert np.array_equal(dev.nodes(i).view(np.uint64), np.stack([w.q for w in rms[i]]).view(np.uint64))
+        thr *= 0.9
+
+
+def test_model_helpers_match_oracle():
+    rng = np.random.default_rng(3)
+    for model, d in ((O.POINT2D, 2), (O.POINT3D, 3), (O.ARM22, 2)):
+        base = rng.uniform(0.3, 0.7, (2, 2)) if model == O.ARM22 else None
+        ctx = S.Context(model, [0.05, 0.05], np.zeros((0, d + 1)), base_pos=base)
+        orc = O.Oracle(model, [0.05, 0.05], np.zeros((0, d + 1)), base=base)
+        a = rng.random((500, d)) * (2 * np.pi if model == O.ARM22 else 1)
+        b = rng.random((500, d)) * (2 * np.pi if model == O.ARM22 else 1)
+        dist = ctx.state_dist(a, b)
+        mid = ctx.mid_status(a, b)
+        for k in range(500):
+            assert dist[k].view(np.uint64) == np.float64(orc.state_dist(a[k], b[k])).view(np.uint64)
+            assert np.array_equal(mid[k].view(np.uint64), orc.mid_status(a[k], b[k]).view(np.uint64))
+        V = a[:300].copy()
+        V[17] = V[5]                      # duplicate: the first minimum wins
+        for rev in (False, True):
+            for q in (b[0], V[17]):
+                ds = [orc.state_dist(q, v) if rev else orc.state_dist(v, q) for v in V]
+                idx, dd = ctx.nearest(V, q, reversed=rev)
+                assert idx == int(np.argmin(ds)) and dd == min(ds)
