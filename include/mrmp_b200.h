@@ -145,6 +145,9 @@ int mrmp_roadmaps_sample(mrmp_roadmaps *rm, int nv, uint64_t seed, const double 
  * j != k, (rad is NaN || dist(q_j,q_k) <= rad) && connect(q_j,q_k,i); rows ascending in k.
  * rad[n_agents].  Also covers the all-pairs pass of sssp.jl:388-395 (rad = epsilon). */
 int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad);
+/* diagnostics: 1 when the last build searched neighbours through the uniform-grid spatial hash
+ * (point models, nv >= 2048, finite rad), 0 when it tested all ordered pairs */
+int mrmp_roadmaps_used_grid(mrmp_roadmaps *rm);
 int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out);
 int mrmp_roadmaps_get_nodes(mrmp_roadmaps *rm, double *nodes_out);
 /* packed CSR over all rows of all agents: row_ptr[n_agents*nv+1] (offsets into col_idx),

@@ -306,6 +306,10 @@ class Roadmaps:
         L.check(self._lib.mrmp_roadmaps_nnz(self._h, C.byref(nnz)))
         return int(nnz.value)
 
+    def used_grid(self) -> bool:
+        """True when the last build() searched neighbours through the uniform-grid hash."""
+        return bool(self._lib.mrmp_roadmaps_used_grid(self._h))
+
     def nodes(self) -> np.ndarray:
         out = np.empty((self.n, self.nv, self.ctx.d))
         L.check(self._lib.mrmp_roadmaps_get_nodes(self._h, L.ptr(out, L._dp)))

@@ -644,6 +644,14 @@ struct mrmp_roadmaps {
     double *e_from = nullptr, *e_to = nullptr;
     int64_t e_cap = 0;
     bool e_valid = false;
+    // uniform-grid spatial hash path (large nv): cell lists and the row staging buffer
+    int32_t *g_cell_start = nullptr, *g_cursor = nullptr, *g_ids = nullptr;
+    int64_t g_cells_cap = 0;
+    int64_t *g_row_off = nullptr;
+    int32_t *g_tmp = nullptr;
+    int64_t g_tmp_cap = 0;
+    unsigned long long *g_tmp_cursor = nullptr;
+    bool used_grid = false;      // diagnostics: which neighbour search the last build took
 };
 
 extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int nv_cap,
@@ -663,7 +671,7 @@ extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int n
     const int64_t rows = (int64_t)n_agents * nv_cap;
     cudaError_t e = cudaMalloc((void **)&rm->nodes_owned, sizeof(double) * c->d * rows);
     rm->nodes = rm->nodes_owned;
-    if (e == cudaSuccess) e = cudaMalloc((void **)&rm->bitmap, sizeof(uint32_t) * rows * words_cap);
+    (void)words_cap;  // the adjacency bitmap of the all-pairs path is allocated on first use
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_cnt, sizeof(int32_t) * (rows + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_ptr, sizeof(int32_t) * (rows + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->nnz_d, 16);
@@ -692,6 +700,12 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     cudaFree(rm->e_agent);
     cudaFree(rm->e_from);
     cudaFree(rm->e_to);
+    cudaFree(rm->g_cell_start);
+    cudaFree(rm->g_cursor);
+    cudaFree(rm->g_ids);
+    cudaFree(rm->g_row_off);
+    cudaFree(rm->g_tmp);
+    cudaFree(rm->g_tmp_cursor);
     delete rm;
 }
 
@@ -782,6 +796,60 @@ static int roadmaps_emit(mrmp_roadmaps *rm, cudaStream_t s) {
     return MRMP_OK;
 }
 
+static const int kGridMinNv = 2048;   // below this the all-pairs kernel is faster
+static const int kGridMinCells = 4;   // cells per dimension needed for the grid to prune
+
+// neighbour pass through the uniform-grid spatial hash; leaves row_cnt / g_row_off / g_tmp
+static int roadmaps_build_grid(mrmp_roadmaps *rm, int g, cudaStream_t s) {
+    mrmp_ctx *c = rm->ctx;
+    const int n = rm->n_agents, nv = rm->nv;
+    const int64_t rows = (int64_t)n * nv;
+    int64_t cells = 1;
+    for (int k = 0; k < c->d; ++k) cells *= g;
+    if ((int64_t)n * (cells + 1) > rm->g_cells_cap) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(rm->g_cell_start);
+        cudaFree(rm->g_cursor);
+        rm->g_cell_start = rm->g_cursor = nullptr;
+        rm->g_cells_cap = (int64_t)n * (cells + 1);
+        CU(cudaMalloc((void **)&rm->g_cell_start, sizeof(int32_t) * rm->g_cells_cap));
+        CU(cudaMalloc((void **)&rm->g_cursor, sizeof(int32_t) * rm->g_cells_cap));
+    }
+    if (!rm->g_ids) {
+        const int64_t rows_cap = (int64_t)n * rm->nv_cap;
+        CU(cudaMalloc((void **)&rm->g_ids, sizeof(int32_t) * rows_cap));
+        CU(cudaMalloc((void **)&rm->g_row_off, sizeof(int64_t) * rows_cap));
+        CU(cudaMalloc((void **)&rm->g_tmp_cursor, 16));
+    }
+    LaunchCfg lc = lcfg(c, s);
+    CU(launch_grid_bin(c->cv, lc, n, nv, g, (int)cells, rm->nodes, rm->g_cell_start, rm->g_cursor,
+                       rm->g_ids));
+    if (rm->g_tmp_cap == 0) {
+        // expected degree: nv * volume of the rad-ball, with head room
+        double rmax = 1.0 / g;
+        double ball = c->d == 2 ? 3.1416 * rmax * rmax : 4.19 * rmax * rmax * rmax;
+        double deg = (double)nv * (ball < 1.0 ? ball : 1.0) * 1.25 + 16.0;
+        rm->g_tmp_cap = (int64_t)(deg * (double)rows);
+        if (rm->g_tmp_cap > rows * (int64_t)(nv - 1)) rm->g_tmp_cap = rows * (int64_t)(nv - 1);
+        CU(cudaMalloc((void **)&rm->g_tmp, sizeof(int32_t) * rm->g_tmp_cap));
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(launch_prm_grid_adjacency(c->cv, lc, rm->agent0, n, nv, g, (int)cells, rm->g_cell_start,
+                                     rm->g_ids, rm->rad_d + n, rm->rad_d, rm->nodes, rm->row_cnt,
+                                     rm->g_row_off, rm->g_tmp, rm->g_tmp_cap, rm->g_tmp_cursor));
+        unsigned long long need = 0;
+        CU(cudaMemcpyAsync(&need, rm->g_tmp_cursor, 8, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if ((int64_t)need <= rm->g_tmp_cap) return MRMP_OK;
+        // the staging buffer was too small: now the exact size is known
+        CU(cudaFree(rm->g_tmp));
+        rm->g_tmp = nullptr;
+        rm->g_tmp_cap = (int64_t)need + 64;
+        CU(cudaMalloc((void **)&rm->g_tmp, sizeof(int32_t) * rm->g_tmp_cap));
+    }
+    return fail(MRMP_ERR_CUDA, "grid neighbour pass did not converge");
+}
+
 extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     NEED(rm && rad, "bad roadmaps / rad");
     NEED(rm->nv >= 1, "no nodes set");
@@ -793,15 +861,54 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     int rc = ensure_small(c, sizeof(double) * 2 * n + 64);
     if (rc) return rc;
     double *hr = (double *)c->small_h;
+    double rad_max = 0.0;
+    bool finite = true;
     for (int a = 0; a < n; ++a) {
         hr[a] = rad[a];
         hr[n + a] = sq_le_threshold(rad[a]);
+        finite = finite && rad[a] > 0.0 && rad[a] < 1e300;
+        if (rad[a] > rad_max) rad_max = rad[a];
     }
     CU(cudaMemcpyAsync(rm->rad_d, hr, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->s_k));
+    // neighbour search: uniform-grid spatial hash for large point roadmaps, all pairs otherwise
+    int g = 0;
+    if (finite && c->model != MRMP_MODEL_ARM22 && nv >= kGridMinNv) {
+        const double gf = floor(1.0 / rad_max);
+        const double gmax = c->d == 2 ? 1024.0 : 100.0;   // <= ~10^6 cells per agent
+        g = (int)(gf < gmax ? gf : gmax);
+    }
+    rm->used_grid = g >= kGridMinCells;
+    int64_t *h_nnz = (int64_t *)(c->small_h + align16(sizeof(double) * 2 * n));
+    if (rm->used_grid) {
+        rc = roadmaps_build_grid(rm, g, c->s_k);
+        if (rc) return rc;
+        CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
+        CU(cudaMemcpyAsync(h_nnz, rm->nnz_d, 8, cudaMemcpyDeviceToHost, c->s_k));
+        CU(cudaStreamSynchronize(c->s_k));
+        rm->nnz = *h_nnz;
+        if (rm->nnz >= ((int64_t)1 << 31))
+            return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
+        if (rm->nnz > rm->col_cap) {
+            if (rm->col_idx) CU(cudaFree(rm->col_idx));
+            rm->col_idx = nullptr;
+            rm->col_cap = rm->nnz + rm->nnz / 4 + 64;
+            CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+        }
+        CU(launch_grid_gather_rows(lcfg(c, c->s_k), rows, rm->row_ptr, rm->g_row_off, rm->g_tmp,
+                                   rm->col_idx, rm->col_cap));
+        CU(cudaStreamSynchronize(c->s_k));
+        rm->built = true;
+        rm->e_valid = false;
+        return MRMP_OK;
+    }
+    if (!rm->bitmap) {
+        const int64_t rows_cap = (int64_t)n * rm->nv_cap;
+        const int words_cap = (rm->nv_cap + 31) / 32;
+        CU(cudaMalloc((void **)&rm->bitmap, sizeof(uint32_t) * rows_cap * words_cap));
+    }
     CU(launch_prm_adjacency(c->cv, lcfg(c, c->s_k), rm->agent0, n, nv, rm->rad_d + n, rm->rad_d,
                             rm->nodes, rm->bitmap, rm->words, rm->row_cnt));
     CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
-    int64_t *h_nnz = (int64_t *)(c->small_h + align16(sizeof(double) * 2 * n));
     CU(cudaMemcpyAsync(h_nnz, rm->nnz_d, 8, cudaMemcpyDeviceToHost, c->s_k));
     rc = roadmaps_emit(rm, c->s_k);
     if (rc) return rc;
@@ -821,6 +928,9 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     rm->e_valid = false;
     return MRMP_OK;
 }
+
+/* 1 when the last mrmp_roadmaps_build used the uniform-grid spatial hash, 0 for all pairs */
+extern "C" int mrmp_roadmaps_used_grid(mrmp_roadmaps *rm) { return rm && rm->used_grid ? 1 : 0; }
 
 extern "C" int mrmp_roadmaps_set_csr_dev(mrmp_roadmaps *rm, const int32_t *row_ptr_dev,
                                          const int32_t *col_idx_dev, int64_t nnz, void *stream) {

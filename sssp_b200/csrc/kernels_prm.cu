@@ -199,6 +199,234 @@ k_prm_emit(int64_t n_rows, const uint32_t *__restrict__ bitmap, int words,
     }
 }
 
+// ---- uniform-grid spatial hash (large roadmaps) ---------------------------------------------
+// The all-pairs radius gate above is O(nv^2) per agent: fine for the reference's 10^2..10^3
+// vertices, hopeless for 10^4..10^6.  For those the vertices of every agent are binned into a
+// uniform grid with cell edge 1/g >= rad (g = floor(1/rad), so a vertex within rad of q_j can
+// only sit in the 3^d cells around q_j's cell; coordinates outside the unit cube clamp into
+// the border cells, which keeps that property because clamping is monotone).  Binning is a
+// one-pass radix (counting) sort by cell id: histogram -> exclusive scan -> scatter.  Each row
+// then tests only the vertices of its 3^d cells with the SAME exact gate + connect as the
+// brute-force kernel, collects the survivors in a per-warp shared-memory bitmap over vertex
+// ids and emits the set bits in ascending order, so the CSR is identical to the reference's
+// row-major loop (prm.jl:202-210) whatever order the cells were visited in.
+struct GridView {
+    int g;                 // cells per dimension
+    int cells;             // g^d
+    int32_t *cell_start;   // [n_agents][cells + 1]  (counts, then exclusive offsets)
+    int32_t *cursor;       // [n_agents][cells]
+    int32_t *ids;          // [n_agents][nv] vertex ids grouped by cell
+};
+
+template <int D>
+__device__ __forceinline__ int cell_coord(double x, int g) {
+    const double c = floor(x * (double)g);
+    return c < 0.0 ? 0 : (c >= (double)g ? g - 1 : (int)c);  // NaN -> last cell
+}
+template <int D>
+__device__ __forceinline__ int cell_of(const double *q, int g) {
+    int id = 0;
+#pragma unroll
+    for (int k = D - 1; k >= 0; --k) id = id * g + cell_coord<D>(q[k], g);
+    return id;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads)
+k_grid_hist(GridView gv, int n_agents, int nv, const double *__restrict__ nodes, int scatter) {
+    const int64_t total = (int64_t)n_agents * nv;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(t / nv), v = (int)(t - (int64_t)a * nv);
+        double q[D];
+        load_state<D>(nodes, t, q);
+        const int c = cell_of<D>(q, gv.g);
+        if (!scatter) {
+            atomicAdd(gv.cell_start + (int64_t)a * (gv.cells + 1) + c, 1);
+        } else {
+            const int pos = atomicAdd(gv.cursor + (int64_t)a * gv.cells + c, 1);
+            gv.ids[(int64_t)a * nv + pos] = v;
+        }
+    }
+}
+
+// per agent: counts -> exclusive offsets (cell_start[cells] = nv), cursor = offsets
+__global__ void __launch_bounds__(1024)
+k_grid_scan(GridView gv) {
+    __shared__ int part[1024];
+    int32_t *cs = gv.cell_start + (int64_t)blockIdx.x * (gv.cells + 1);
+    int32_t *cur = gv.cursor + (int64_t)blockIdx.x * gv.cells;
+    const int tid = threadIdx.x;
+    const int chunk = (gv.cells + 1023) / 1024;
+    const int lo = tid * chunk, hi = min(lo + chunk, gv.cells);
+    int s = 0;
+    for (int c = lo; c < hi; ++c) s += cs[c];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int base = tid == 0 ? 0 : part[tid - 1];
+    for (int c = lo; c < hi; ++c) {
+        const int n = cs[c];
+        cs[c] = base;
+        cur[c] = base;
+        base += n;
+    }
+    if (tid == 1023) cs[gv.cells] = part[1023];
+}
+
+// warp per row; per-warp smem: bitmap[words] + queue[64]
+template <class M>
+__global__ void __launch_bounds__(kThreads)
+k_prm_grid_adjacency(CtxView cv, GridView gv, int agent0, int n_agents, int nv,
+                     const double *__restrict__ rad, const double *__restrict__ rad_r2,
+                     const double *__restrict__ nodes, int words, int warps_per_cta,
+                     int32_t *__restrict__ row_cnt, int64_t *__restrict__ row_off,
+                     int32_t *__restrict__ tmp, int64_t tmp_cap,
+                     unsigned long long *__restrict__ tmp_cursor, int staged, int seg_bytes) {
+    constexpr int D = M::SD;
+    const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, staged));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= warps_per_cta) return;
+    uint32_t *wbits = reinterpret_cast<uint32_t *>(smem_raw + seg_bytes) + (size_t)warp * (words + 64);
+    int *queue = reinterpret_cast<int *>(wbits + words);
+    for (int t = lane; t < words; t += 32) wbits[t] = 0u;
+    __syncwarp();
+    const int64_t n_rows = (int64_t)n_agents * nv;
+    const int64_t n_warps = (int64_t)gridDim.x * warps_per_cta;
+    const int g = gv.g;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_rows; row += n_warps) {
+        const int a = (int)(row / nv), j = (int)(row - (int64_t)a * nv);
+        const int agent = agent0 + a;
+        const double *tab = nodes + (int64_t)a * nv * D;
+        const int32_t *cstart = gv.cell_start + (int64_t)a * (gv.cells + 1);
+        const int32_t *ids = gv.ids + (int64_t)a * nv;
+        const double r = rad[a], r2 = rad_r2[a];
+        double qj[D];
+        load_state<D>(tab, j, qj);
+        int cj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) cj[k] = cell_coord<D>(qj[k], g);
+        int qlen = 0, cnt = 0, lo = words, hi = -1;
+        constexpr int NB = D == 2 ? 9 : 27;
+        for (int nb = 0; nb < NB; ++nb) {
+            int cc[D], rem = nb;
+            bool inside = true;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                cc[k] = cj[k] + rem % 3 - 1;
+                rem /= 3;
+                inside &= cc[k] >= 0 && cc[k] < g;
+            }
+            if (!inside) continue;
+            int cell = 0;
+#pragma unroll
+            for (int k = D - 1; k >= 0; --k) cell = cell * g + cc[k];
+            const int beg = cstart[cell], end = cstart[cell + 1];
+            for (int p0 = beg; p0 < end; p0 += 32) {
+                const int p = p0 + lane;
+                int k = -1;
+                bool pass = false;
+                double qk[D];
+                if (p < end) {
+                    k = ids[p];
+                    if (k != j) {
+                        load_state<D>(tab, k, qk);
+                        pass = M::dist_le(cv, qj, qk, r, r2);  // prm.jl:207
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) queue[(cnt + __popc(bal & ((1u << lane) - 1u))) & 63] = k;
+                qlen += __popc(bal);
+                cnt += __popc(bal);
+                __syncwarp();
+                if (qlen >= 32) {
+                    const int k2 = queue[((cnt - qlen) + lane) & 63];
+                    load_state<D>(tab, k2, qk);
+                    if (M::connect_edge(cv, cs, qj, qk, agent)) {
+                        atomicOr(&wbits[k2 >> 5], 1u << (k2 & 31));
+                        lo = min(lo, k2 >> 5);
+                        hi = max(hi, k2 >> 5);
+                    }
+                    qlen -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane < qlen) {
+            const int k2 = queue[((cnt - qlen) + lane) & 63];
+            double qk[D];
+            load_state<D>(tab, k2, qk);
+            if (M::connect_edge(cv, cs, qj, qk, agent)) {
+                atomicOr(&wbits[k2 >> 5], 1u << (k2 & 31));
+                lo = min(lo, k2 >> 5);
+                hi = max(hi, k2 >> 5);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        __syncwarp();
+        // count, reserve, emit ascending, clear
+        int total = 0;
+        for (int t = lo + lane; t <= hi; t += 32) total += __popc(wbits[t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        long long off = 0;
+        if (lane == 0) {
+            off = total ? (long long)atomicAdd(tmp_cursor, (unsigned long long)total) : 0;
+            row_cnt[row] = total;
+            row_off[row] = off;
+        }
+        off = __shfl_sync(0xffffffffu, off, 0);
+        const bool fits = off + total <= tmp_cap;
+        long long base = off;
+        for (int t0 = lo; t0 <= hi; t0 += 32) {
+            const int t = t0 + lane;
+            const uint32_t w = t <= hi ? wbits[t] : 0u;
+            if (t <= hi) wbits[t] = 0u;
+            int c = __popc(w), incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (fits) {
+                long long pos = base + incl - c;
+                uint32_t m = w;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    tmp[pos++] = 32 * t + b;
+                }
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+    }
+}
+
+// rows were emitted at atomically reserved offsets: copy them into CSR order
+__global__ void __launch_bounds__(kThreads)
+k_grid_gather_rows(int64_t n_rows, const int32_t *__restrict__ row_ptr,
+                   const int64_t *__restrict__ row_off, const int32_t *__restrict__ tmp,
+                   int32_t *__restrict__ col_idx, int64_t col_cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows;
+         row += n_warps) {
+        const int64_t dst = row_ptr[row], n = row_ptr[row + 1] - dst, src = row_off[row];
+        for (int64_t t = lane; t < n; t += 32)
+            if (dst + t < col_cap) col_idx[dst + t] = tmp[src + t];
+    }
+}
+
 // ---- launchers ----------------------------------------------------------------------------
 static inline int seg_smem_bytes(int seg_len) {
     const int bytes = seg_len * 8 + 16;
@@ -289,6 +517,90 @@ cudaError_t launch_prm_emit(const LaunchCfg &lc, int64_t n_rows, int nv, const u
     int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     k_prm_emit<<<grid, kThreads, 0, lc.stream>>>(n_rows, bitmap, words, row_ptr, col_idx, col_cap);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ---- grid path launchers -------------------------------------------------------------------
+cudaError_t launch_grid_bin(const CtxView &cv, const LaunchCfg &lc, int n_agents, int nv, int g,
+                            int cells, const double *nodes, int32_t *cell_start, int32_t *cursor,
+                            int32_t *ids) {
+    GridView gv{g, cells, cell_start, cursor, ids};
+    cudaError_t e = cudaMemsetAsync(cell_start, 0, sizeof(int32_t) * (size_t)n_agents * (cells + 1),
+                                    lc.stream);
+    if (e != cudaSuccess) return e;
+    const int64_t total = (int64_t)n_agents * nv;
+    int64_t want = (total + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)lc.sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    if (cv.model == 0) {
+        k_grid_hist<2><<<grid, kThreads, 0, lc.stream>>>(gv, n_agents, nv, nodes, 0);
+        k_grid_scan<<<n_agents, 1024, 0, lc.stream>>>(gv);
+        k_grid_hist<2><<<grid, kThreads, 0, lc.stream>>>(gv, n_agents, nv, nodes, 1);
+    } else if (cv.model == 1) {
+        k_grid_hist<3><<<grid, kThreads, 0, lc.stream>>>(gv, n_agents, nv, nodes, 0);
+        k_grid_scan<<<n_agents, 1024, 0, lc.stream>>>(gv);
+        k_grid_hist<3><<<grid, kThreads, 0, lc.stream>>>(gv, n_agents, nv, nodes, 1);
+    } else {
+        return cudaErrorNotSupported;
+    }
+    count_launch(3);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prm_grid_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0,
+                                      int n_agents, int nv, int g, int cells,
+                                      const int32_t *cell_start, const int32_t *ids,
+                                      const double *rad_r2, const double *rad, const double *nodes,
+                                      int32_t *row_cnt, int64_t *row_off, int32_t *tmp,
+                                      int64_t tmp_cap, unsigned long long *tmp_cursor) {
+    GridView gv{g, cells, const_cast<int32_t *>(cell_start), nullptr, const_cast<int32_t *>(ids)};
+    const int words = (nv + 31) / 32;
+    int seg = seg_smem_bytes(cv.con_len);
+    const int per_warp = (words + 64) * 4;
+    int warps = kWarps;
+    while (warps > 1 && seg + warps * per_warp > 200 * 1024) warps >>= 1;
+    if (seg + warps * per_warp > 200 * 1024) seg = 0;
+    if (warps * per_warp > 220 * 1024) return cudaErrorInvalidValue;  // nv beyond ~1.7 M
+    const int sm = seg + warps * per_warp;
+    const int64_t n_rows = (int64_t)n_agents * nv;
+    int per_sm = (220 * 1024) / (sm > 0 ? sm : 1);
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t want = (n_rows + warps - 1) / warps;
+    const int64_t cap = (int64_t)lc.sm_count * per_sm;
+    const int grid = (int)(want < cap ? want : cap);
+    cudaError_t e = cudaMemsetAsync(tmp_cursor, 0, 8, lc.stream);
+    if (e != cudaSuccess) return e;
+    if (cv.model == 0) {
+        using M = PointModel<2>;
+        e = set_smem(k_prm_grid_adjacency<M>, sm);
+        k_prm_grid_adjacency<M><<<grid, kThreads, sm, lc.stream>>>(
+            cv, gv, agent0, n_agents, nv, rad, rad_r2, nodes, words, warps, row_cnt, row_off, tmp,
+            tmp_cap, tmp_cursor, seg > 0, seg);
+    } else if (cv.model == 1) {
+        using M = PointModel<3>;
+        e = set_smem(k_prm_grid_adjacency<M>, sm);
+        k_prm_grid_adjacency<M><<<grid, kThreads, sm, lc.stream>>>(
+            cv, gv, agent0, n_agents, nv, rad, rad_r2, nodes, words, warps, row_cnt, row_off, tmp,
+            tmp_cap, tmp_cursor, seg > 0, seg);
+    } else {
+        return cudaErrorNotSupported;
+    }
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_gather_rows(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_ptr,
+                                    const int64_t *row_off, const int32_t *tmp, int32_t *col_idx,
+                                    int64_t col_cap) {
+    if (n_rows <= 0) return cudaSuccess;
+    int64_t want = (n_rows + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)lc.sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    k_grid_gather_rows<<<grid, kThreads, 0, lc.stream>>>(n_rows, row_ptr, row_off, tmp, col_idx,
+                                                         col_cap);
     count_launch();
     return cudaGetLastError();
 }

@@ -171,6 +171,19 @@ cudaError_t launch_row_scan(const LaunchCfg &lc, int64_t n_rows, const int32_t *
                             int32_t *row_ptr, int64_t *nnz_total);
 cudaError_t launch_prm_emit(const LaunchCfg &lc, int64_t n_rows, int nv, const uint32_t *bitmap,
                             int words, const int32_t *row_ptr, int32_t *col_idx, int64_t col_cap);
+// uniform-grid spatial hash path (point models, large nv): bin -> adjacency -> gather
+cudaError_t launch_grid_bin(const CtxView &cv, const LaunchCfg &lc, int n_agents, int nv, int g,
+                            int cells, const double *nodes, int32_t *cell_start, int32_t *cursor,
+                            int32_t *ids);
+cudaError_t launch_prm_grid_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0,
+                                      int n_agents, int nv, int g, int cells,
+                                      const int32_t *cell_start, const int32_t *ids,
+                                      const double *rad_r2, const double *rad, const double *nodes,
+                                      int32_t *row_cnt, int64_t *row_off, int32_t *tmp,
+                                      int64_t tmp_cap, unsigned long long *tmp_cursor);
+cudaError_t launch_grid_gather_rows(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_ptr,
+                                    const int64_t *row_off, const int32_t *tmp, int32_t *col_idx,
+                                    int64_t col_cap);
 cudaError_t launch_sample_states(const CtxView &cv, const LaunchCfg &lc, int agent, uint64_t seed,
                                  uint64_t t0, int64_t n, double *q_out);
 // per agent: nodes[a][0]=init, [1]=goal, then the first nv-2 free samples in try order

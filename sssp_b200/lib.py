@@ -62,6 +62,7 @@ _SIGS = {
     "mrmp_roadmaps_sample": (C.c_int, [_vp, C.c_int, C.c_uint64, _dp, _dp, _lp]),
     "mrmp_roadmaps_build": (C.c_int, [_vp, _dp]),
     "mrmp_roadmaps_nnz": (C.c_int, [_vp, _lp]),
+    "mrmp_roadmaps_used_grid": (C.c_int, [_vp]),
     "mrmp_roadmaps_get_nodes": (C.c_int, [_vp, _dp]),
     "mrmp_roadmaps_get_csr": (C.c_int, [_vp, _ip, _ip, C.c_int64, _lp]),
     "mrmp_roadmaps_device_ptrs": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp),

@@ -92,3 +92,35 @@ def test_roadmaps_indexed_collide_and_shards():
     lo, hi = rp[3 * nv], rp[6 * nv]
     assert np.array_equal(scol, col[lo:hi]) and np.array_equal(srp, rp[3 * nv:6 * nv + 1] - lo)
     assert nnz_full == col.size
+
+
+@pytest.mark.parametrize("model,d,nv,rads_prm", [(O.POINT2D, 2, 3000, (0.05, 0.031)),
+                                                 (O.POINT3D, 3, 2500, (0.12, 0.2))])
+def test_prm_grid_hash_path_bit_exact(model, d, nv, rads_prm):
+    """nv >= 2048: neighbour search through the uniform-grid spatial hash (counting sort by
+    cell, 3^d cell scan); the CSR must still equal the reference's all-pairs row-major loop,
+    including vertices outside the unit cube and different radii per agent."""
+    N = 2
+    rads, obs = make_point_instance(model, N, 10, seed=77)
+    ctx, orc = S.Context(model, rads, obs), O.Oracle(model, rads, obs)
+    rng = np.random.default_rng(nv)
+    nodes = rng.random((N, nv, d))
+    nodes[:, :40] = rng.uniform(-0.2, 1.2, (N, 40, d))     # clamped into the border cells
+    nodes[0, 40:60] = nodes[0, 60:80]                        # duplicates (distance 0)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(np.array(rads_prm))
+    assert rm.used_grid()
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, np.array(rads_prm), nthreads=0)
+    assert nnz == int(onnz.sum()) and nnz > nv
+    for a in range(N):
+        for v in range(nv):
+            r = a * nv + v
+            assert np.array_equal(col[row_ptr[r]:row_ptr[r + 1]], ocol[a, orp[a, v]:orp[a, v + 1]]), (a, v)
+    # a second build on the same set (buffers reused) and the small-nv path on the same ctx
+    assert rm.build(np.array(rads_prm)) == nnz
+    rm2 = S.Roadmaps(ctx, 0, N, 500)
+    rm2.set_nodes(nodes[:, :500])
+    rm2.build(rads_prm[0])
+    assert not rm2.used_grid()
