@@ -75,8 +75,10 @@ int mrmp_ctx_sync(mrmp_ctx *ctx);
 /* run the ctx's kernels and small copies on a caller-owned cudaStream_t (NULL restores the
  * ctx's own stream); lets a host framework order and time the work on its stream */
 int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
-/* diagnostics: out4[0] = pairs that survived the cross kernels' broad phase (ran the exact
- * reference arithmetic) since the last reset; out4[1..3] reserved */
+/* diagnostics since the last reset: out4[0] = point-model pairs that survived the cross
+ * kernel's broad phase (ran the exact reference arithmetic); out4[1] = arm22 link pairs that ran
+ * the exact test; out4[2] = point-model pairs whose column tile survived the box test (ran the
+ * midpoint bound); out4[3] reserved */
 int mrmp_ctx_stats(mrmp_ctx *ctx, int64_t *out4, int reset);
 
 /* ---- connect -------------------------------------------------------------------- */

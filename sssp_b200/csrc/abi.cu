@@ -644,6 +644,7 @@ struct mrmp_roadmaps {
     double *e_from = nullptr, *e_to = nullptr;
     int64_t e_cap = 0;
     bool e_valid = false;
+    void *e_rows = nullptr;      // the same edges as Morton-sorted row records (point models)
     // uniform-grid spatial hash path (large nv): cell lists and the row staging buffer
     int32_t *g_cell_start = nullptr, *g_cursor = nullptr, *g_ids = nullptr;
     int64_t g_cells_cap = 0;
@@ -700,6 +701,7 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     cudaFree(rm->e_agent);
     cudaFree(rm->e_from);
     cudaFree(rm->e_to);
+    cudaFree(rm->e_rows);
     cudaFree(rm->g_cell_start);
     cudaFree(rm->g_cursor);
     cudaFree(rm->g_ids);
@@ -1107,47 +1109,57 @@ static int cross_words(int64_t n_cols, int group_size) {
     return (int)((bits + 31) / 32);
 }
 
-// rows / cols / out are device pointers; column tiles live in ctx scratch slot 0
+// rows / cols / out are device pointers.  rows_sorted: Morton-sorted row records prepared
+// earlier (roadmap edges cache them) or NULL (sorted here into scratch slot 4).  Column tiles,
+// their headers and the sort workspace live in scratch slot 0.
 static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
-                         const double *row_from, const double *row_to, int64_t n_cols,
-                         const int32_t *col_agent, const double *col_from, const double *col_to,
-                         const int32_t *col_vf, const int32_t *col_vt, const double *nodes,
-                         int agent0, int nv_stride, int group_size, uint32_t *out,
-                         cudaStream_t s) {
+                         const double *row_from, const double *row_to, const void *rows_sorted,
+                         int64_t n_cols, const int32_t *col_agent, const double *col_from,
+                         const double *col_to, const int32_t *col_vf, const int32_t *col_vt,
+                         const double *nodes, int agent0, int nv_stride, int group_size,
+                         uint32_t *out, cudaStream_t s) {
+    const int wpr = cross_words(n_cols, group_size);
     if (c->model == MRMP_MODEL_ARM22) {  // warp per (row, column) check, arm22.jl:100-146
         CU(launch_arm_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to, n_cols,
                                     col_agent, col_from, col_to, col_vf, col_vt, nodes, agent0,
-                                    nv_stride, group_size, cross_words(n_cols, group_size), out,
-                                    c->stats_d + 1));
+                                    nv_stride, group_size, wpr, out, c->stats_d + 1));
         return MRMP_OK;
     }
-    const int64_t n_tiles = (n_cols + kCrossCols - 1) / kCrossCols;
-    const size_t tb = cross_tile_bytes(c->d);
-    int rc = ensure_scratch(c, 0, (size_t)n_tiles * tb);
-    if (rc) return rc;
     LaunchCfg lc = lcfg(c, s);
-    CU(launch_cross_prep_cols(c->cv, lc, n_cols, col_agent, col_from, col_to, col_vf, col_vt,
-                              nodes, agent0, nv_stride, c->scratch[0]));
-    const int wpr = cross_words(n_cols, group_size);
-    if (group_size <= 0) {
-        CU(launch_cross_collide(c->cv, lc, n_rows, row_agent, row_from, row_to, n_cols,
-                                c->scratch[0], 0, wpr, wpr, out, c->max_rad, c->stats_d));
-        return MRMP_OK;
+    // columns per launch: everything, or kCrossMaxGroups groups in OR-reduced mode
+    const int64_t chunk_cols = group_size > 0 ? (int64_t)kCrossMaxGroups * group_size : n_cols;
+    const int64_t max_cols = n_cols < chunk_cols ? n_cols : chunk_cols;
+    const int64_t max_tiles = (max_cols + kCrossCols - 1) / kCrossCols;
+    const size_t o_cells = 0, o_work = o_cells + 4096 * 4, o_order = o_work + 16,
+                 o_hdr = align16(o_order + 4 * (size_t)max_cols),
+                 o_tiles = align16(o_hdr + cross_hdr_bytes(c->d) * (size_t)max_tiles),
+                 tot = o_tiles + cross_tile_bytes(c->d) * (size_t)max_tiles;
+    int rc = ensure_scratch(c, 0, tot);
+    if (rc) return rc;
+    unsigned char *b = c->scratch[0];
+    if (!rows_sorted) {
+        rc = ensure_scratch(c, 4, cross_row_bytes(c->d) * (size_t)n_rows);
+        if (rc) return rc;
+        CU(launch_cross_sort_rows(c->cv, lc, n_rows, row_agent, row_from, row_to,
+                                  (int32_t *)(b + o_cells), c->scratch[4]));
+        rows_sorted = c->scratch[4];
     }
-    // reduced mode: at most kCrossMaxGroups groups per launch
-    const int64_t n_groups = (n_cols + group_size - 1) / group_size;
-    for (int64_t g0 = 0; g0 < n_groups; g0 += kCrossMaxGroups) {
-        const int64_t c0 = g0 * group_size;
-        if (c0 % kCrossCols != 0)
-            return fail(MRMP_ERR_UNSUPPORTED, "group_size * %d must be a multiple of %d",
-                        kCrossMaxGroups, kCrossCols);
-        const int64_t c1 = (g0 + kCrossMaxGroups) * (int64_t)group_size < n_cols
-                               ? (g0 + kCrossMaxGroups) * (int64_t)group_size
-                               : n_cols;
-        const int w = cross_words(c1 - c0, group_size);
-        CU(launch_cross_collide(c->cv, lc, n_rows, row_agent, row_from, row_to, c1 - c0,
-                                c->scratch[0] + (size_t)(c0 / kCrossCols) * tb, group_size, w, wpr,
-                                out + g0 / 32, c->max_rad, c->stats_d));
+    if (group_size <= 0)  // full matrix: hits are OR-ed into a zeroed output
+        CU(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * wpr, s));
+    const int d = c->d;
+    for (int64_t c0 = 0; c0 < n_cols; c0 += chunk_cols) {
+        const int64_t nc = n_cols - c0 < chunk_cols ? n_cols - c0 : chunk_cols;
+        CU(launch_cross_prep_cols(c->cv, lc, nc, col_agent + c0,
+                                  col_from ? col_from + c0 * d : nullptr,
+                                  col_to ? col_to + c0 * d : nullptr, col_vf ? col_vf + c0 : nullptr,
+                                  col_vt ? col_vt + c0 : nullptr, nodes, agent0, nv_stride,
+                                  group_size, (int32_t *)(b + o_cells), (int32_t *)(b + o_order),
+                                  b + o_tiles, b + o_hdr));
+        const int64_t g0 = group_size > 0 ? c0 / group_size : 0;
+        const int w = group_size > 0 ? cross_words(nc, group_size) : wpr;
+        CU(launch_cross_collide(c->cv, lc, n_rows, rows_sorted, nc, b + o_tiles, b + o_hdr,
+                                group_size, w, wpr, out + g0 / 32, c->max_rad, c->stats_d,
+                                (unsigned int *)(b + o_work)));
     }
     return MRMP_OK;
 }
@@ -1163,8 +1175,8 @@ extern "C" int mrmp_collide_cross_dev(mrmp_ctx *c, int64_t n_rows, const int32_t
     if (need_aligned(c, row_from) || need_aligned(c, row_to) || need_aligned(c, col_from) ||
         need_aligned(c, col_to))
         return MRMP_ERR_INVALID;
-    return cross_run_dev(c, n_rows, row_agent, row_from, row_to, n_cols, col_agent, col_from,
-                         col_to, nullptr, nullptr, nullptr, 0, 0, group_size, out_bits,
+    return cross_run_dev(c, n_rows, row_agent, row_from, row_to, nullptr, n_cols, col_agent,
+                         col_from, col_to, nullptr, nullptr, nullptr, 0, 0, group_size, out_bits,
                          (cudaStream_t)stream);
 }
 
@@ -1201,7 +1213,7 @@ extern "C" int mrmp_collide_cross(mrmp_ctx *c, int64_t n_rows, const int32_t *ro
     CU(cudaMemcpyAsync(b + o_cf, col_from, sb * (size_t)n_cols, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b + o_ct, col_to, sb * (size_t)n_cols, cudaMemcpyHostToDevice, s));
     rc = cross_run_dev(c, n_rows, (const int32_t *)(b + o_ra), (const double *)(b + o_rf),
-                       (const double *)(b + o_rt), n_cols, (const int32_t *)(b + o_ca),
+                       (const double *)(b + o_rt), nullptr, n_cols, (const int32_t *)(b + o_ca),
                        (const double *)(b + o_cf), (const double *)(b + o_ct), nullptr, nullptr,
                        nullptr, 0, 0, group_size, (uint32_t *)c->scratch[2], s);
     if (rc) return rc;
@@ -1221,9 +1233,13 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
         cudaFree(rm->e_agent);
         cudaFree(rm->e_from);
         cudaFree(rm->e_to);
+        cudaFree(rm->e_rows);
         rm->e_agent = nullptr;
         rm->e_from = rm->e_to = nullptr;
+        rm->e_rows = nullptr;
         rm->e_cap = rm->nnz + rm->nnz / 8 + 64;
+        if (c->model != MRMP_MODEL_ARM22)
+            CU(cudaMalloc(&rm->e_rows, cross_row_bytes(c->d) * (size_t)rm->e_cap));
         CU(cudaMalloc((void **)&rm->e_agent, sizeof(int32_t) * rm->e_cap));
         CU(cudaMalloc((void **)&rm->e_from, sizeof(double) * c->d * rm->e_cap));
         CU(cudaMalloc((void **)&rm->e_to, sizeof(double) * c->d * rm->e_cap));
@@ -1231,6 +1247,12 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
     CU(launch_csr_expand_edges(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
                                rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes, rm->e_agent,
                                rm->e_from, rm->e_to));
+    if (rm->e_rows) {
+        int rc = ensure_scratch(c, 0, 4096 * 4 + 64);
+        if (rc) return rc;
+        CU(launch_cross_sort_rows(c->cv, lcfg(c, s), rm->nnz, rm->e_agent, rm->e_from, rm->e_to,
+                                  (int32_t *)c->scratch[0], rm->e_rows));
+    }
     rm->e_valid = true;
     return MRMP_OK;
 }
@@ -1250,9 +1272,9 @@ extern "C" int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps
     cudaStream_t s = (cudaStream_t)stream;
     int rc = roadmaps_expand_edges(rm, s);
     if (rc) return rc;
-    return cross_run_dev(c, rm->nnz, rm->e_agent, rm->e_from, rm->e_to, n_cols, col_agent,
-                         nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes, rm_cols->agent0,
-                         rm_cols->nv, group_size, out_bits, s);
+    return cross_run_dev(c, rm->nnz, rm->e_agent, rm->e_from, rm->e_to, rm->e_rows, n_cols,
+                         col_agent, nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes,
+                         rm_cols->agent0, rm_cols->nv, group_size, out_bits, s);
 }
 
 extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,

@@ -102,11 +102,13 @@ MRMP_HD bool norm_lt(const double *v, double s, double thr, double T2) {
 }
 
 // src/utils.jl:44-57: segment [a,b] to point c.  u = a-b and uu = dot(u,u) are passed in
-// (shared between several c).  Writes the difference vector p and returns sum p_k^2.
-template <int D>
-MRMP_HD double segpt_ss(const double *a, const double *b, const double *u,
-                                           double uu, const double *c, double *p) {
-    double bc[D], ac[D];
+// (shared between several c).
+// verdict dist(a,b,c) < thr; s_probe receives the squared distance (NaN propagation of
+// segseg_lt's four-way minimum)
+template <int D, bool TAB = true>
+MRMP_HD bool segpt_verdict(const double *a, const double *b, const double *u, double uu,
+                           const double *c, double thr, double T2, double &s_probe) {
+    double bc[D], ac[D], p[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         bc[k] = dsub(b[k], c[k]);
@@ -127,16 +129,17 @@ MRMP_HD double segpt_ss(const double *a, const double *b, const double *u,
 #pragma unroll
         for (int k = 0; k < D; ++k) p[k] = ac[k];
     }
-    return sumsq<D>(p);
+    const double s = sumsq<D>(p);
+    s_probe = s;
+    return norm_lt<D, TAB>(p, s, thr, T2);
 }
 
 // verdict  dist(a,b,c) < thr
 template <int D, bool TAB = true>
 MRMP_HD bool segpt_lt(const double *a, const double *b, const double *u,
                                          double uu, const double *c, double thr, double T2) {
-    double p[D];
-    const double s = segpt_ss<D>(a, b, u, uu, c, p);
-    return norm_lt<D, TAB>(p, s, thr, T2);
+    double probe;
+    return segpt_verdict<D, TAB>(a, b, u, uu, c, thr, T2, probe);
 }
 
 // src/utils.jl:59-94: verdict  dist(p11,p12,p21,p22) < thr
@@ -157,9 +160,14 @@ MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
     const double V2 = dotd<D>(v2, v2);  // :74
     const double Dd = dsub(dmul(V1, V2), dmul(Dv, Dv));  // :75
     if (Dd > 0.0) {
-        const double t1 = ddiv(dsub(dmul(D1, V2), dmul(D2, Dv)), Dd);  // :77
-        const double t2 = ddiv(dsub(dmul(D1, Dv), dmul(D2, V1)), Dd);  // :78
-        if (0.0 <= t1 && t1 <= 1.0 && 0.0 <= t2 && t2 <= 1.0) {
+        // t = RN(num / Dd) lies in [0, 1]  <=>  0 <= num <= Dd  (Dd > 0; a quotient above 1
+        // exceeds 1 by at least ulp(Dd)/Dd > 2^-53 and cannot round down to 1), so the two
+        // divisions of :77-78 are only carried out when the interior solution is taken
+        const double n1 = dsub(dmul(D1, V2), dmul(D2, Dv));
+        const double n2 = dsub(dmul(D1, Dv), dmul(D2, V1));
+        if (0.0 <= n1 && n1 <= Dd && 0.0 <= n2 && n2 <= Dd) {
+            const double t1 = ddiv(n1, Dd);  // :77
+            const double t2 = ddiv(n2, Dd);  // :78
             double q[D];
 #pragma unroll
             for (int k = 0; k < D; ++k)
@@ -167,28 +175,41 @@ MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
             return norm_lt<D, TAB>(q, sumsq<D>(q), thr, T2);
         }
     }
-    // :86-93  minimum of the four endpoint-to-segment distances (NaN-propagating)
-    double u1[D], u2[D], p[D];
+    // :86-93  minimum of the four endpoint-to-segment distances (NaN-propagating).
+    // The four evaluations of dist(a,b,c) (:44-57) are written branch-free and side by side:
+    // in a warp nearly every case (interior foot point / either end) is taken by some lane, so
+    // predicated selects cost no more than divergent branches and expose four independent
+    // dependency chains to the FP64 pipe.  Each value is computed exactly as :46-56 states;
+    // the select only chooses which of the three expressions the reference would evaluate.
+    const double *A[4] = {p11, p11, p21, p21};  // segment start  (a)
+    const double *B[4] = {p12, p12, p22, p22};  // segment end    (b)
+    const double *C[4] = {p21, p22, p11, p12};  // the point      (c)
+    double s[4];
+    bool hit = false;
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        u1[k] = dsub(p11[k], p12[k]);  // a - b of dist(p11,p12,.); dot(u1,u1) == V1 bitwise
-        u2[k] = dsub(p21[k], p22[k]);
+    for (int k = 0; k < 4; ++k) {
+        const double uu = k < 2 ? V1 : V2;  // dot(a-b, a-b) == dot(b-a, b-a) bitwise
+        double u[D], bc[D], ac[D], p[D];
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            u[x] = dsub(A[k][x], B[k][x]);
+            bc[x] = dsub(B[k][x], C[k][x]);
+            ac[x] = dsub(A[k][x], C[k][x]);
+        }
+        const double df0 = dotd<D>(u, bc);  // :46
+        const double df1 = dotd<D>(u, ac);  // :47
+        const bool inside = dmul(df0, df1) < 0.0;  // :50
+        const double e = ddiv(-df0, uu);           // :51 (only used when inside)
+        const double f = dsub(1.0, e);
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            const double blend = dsub(dadd(dmul(e, A[k][x]), dmul(f, B[k][x])), C[k][x]);  // :56
+            p[x] = inside ? blend : (df0 >= 0.0 ? bc[x] : ac[x]);  // e = 0 -> b - c, e = 1 -> a - c
+        }
+        s[k] = sumsq<D>(p);
+        hit |= norm_lt<D, TAB>(p, s[k], thr, T2);
     }
-    double s;
-    bool hit;
-    double nan_probe;
-    s = segpt_ss<D>(p11, p12, u1, V1, p21, p);
-    hit = norm_lt<D, TAB>(p, s, thr, T2);
-    nan_probe = s;
-    s = segpt_ss<D>(p11, p12, u1, V1, p22, p);
-    hit |= norm_lt<D, TAB>(p, s, thr, T2);
-    nan_probe = dadd(nan_probe, s);
-    s = segpt_ss<D>(p21, p22, u2, V2, p11, p);
-    hit |= norm_lt<D, TAB>(p, s, thr, T2);
-    nan_probe = dadd(nan_probe, s);
-    s = segpt_ss<D>(p21, p22, u2, V2, p12, p);
-    hit |= norm_lt<D, TAB>(p, s, thr, T2);
-    nan_probe = dadd(nan_probe, s);
+    const double nan_probe = dadd(dadd(s[0], s[1]), dadd(s[2], s[3]));
     return hit && !isnan(nan_probe);
 }
 

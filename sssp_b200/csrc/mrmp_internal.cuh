@@ -232,21 +232,29 @@ cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, cons
                            const double *q, int reversed, int32_t *idx_out, double *dist_out);
 
 // kernels_cross.cu
-constexpr int kCrossCols = 64;        // columns per staged tile
+constexpr int kCrossCols = 64;        // columns per tile
 constexpr int kCrossMaxGroups = 256;  // reduced mode: groups per launch
 size_t cross_tile_bytes(int d);
+size_t cross_hdr_bytes(int d);
+size_t cross_row_bytes(int d);
+// rows -> Morton-sorted row records; cells = 4096 ints of device scratch
+cudaError_t launch_cross_sort_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
+                                   const int32_t *agent, const double *qf, const double *qt,
+                                   int32_t *cells, void *rows_out);
+// columns (explicit states, or ids vf/vt into `nodes`) -> Morton-sorted tiles + headers
 cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64_t n_cols,
                                    const int32_t *agent, const double *qf, const double *qt,
                                    const int32_t *vf, const int32_t *vt, const double *nodes,
-                                   int agent0, int nv_stride, void *tiles);
+                                   int agent0, int nv_stride, int group_size, int32_t *cells,
+                                   int32_t *order, void *tiles, void *hdrs);
 cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                     int nv, int agent0, const int32_t *row_ptr,
                                     const int32_t *col_idx, const double *nodes, int32_t *e_agent,
                                     double *e_from, double *e_to);
 cudaError_t launch_cross_collide(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
-                                 const int32_t *row_agent, const double *row_from,
-                                 const double *row_to, int64_t n_cols, const void *tiles,
-                                 int group_size, int words_per_row, int64_t out_stride, uint32_t *out,
-                                 double max_rad, unsigned long long *stats);
+                                 const void *rows, int64_t n_cols, const void *tiles,
+                                 const void *hdrs, int group_size, int words_per_row,
+                                 int64_t out_stride, uint32_t *out, double max_rad,
+                                 unsigned long long *stats, unsigned int *work);
 
 }  // namespace mrmp

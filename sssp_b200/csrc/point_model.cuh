@@ -95,16 +95,11 @@ __device__ __forceinline__ bool point_connect_edge(const ConSeg &cs, const doubl
     for (int k = 0; k < D; ++k) u[k] = dsub(qf[k], qt[k]);
     const double uu = dotd<D>(u, u);
     for (int m = 0; m < cs.n_obs; ++m) {
-        double c[D], p[D];
+        double c[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) c[k] = cs.oc(k, m);
-        const double s = segpt_ss<D>(qf, qt, u, uu, c, p);
-        bool hit;
-        if (s == 0.0)
-            hit = norm_slow<D>(p) < dadd(cs.oc(D, m), r);  // dist(q_from,q_to,o) < o.r + rads[i]
-        else
-            hit = s < cs.t2_im(i, m);
-        ok &= !hit;
+        // dist(q_from,q_to,o) < o.r + rads[i]
+        ok &= !segpt_lt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(i, m));
     }
     return ok;
 }
@@ -137,11 +132,9 @@ __device__ __forceinline__ bool point_collide_move_vs_static(const ColSeg &cs, c
                                                              const double *qt, const double *u,
                                                              double uu, const double *qj, int i,
                                                              int j) {
-    double p[D];
-    const double s = segpt_ss<D>(qf, qt, u, uu, qj, p);
     const double thr = cs.thr(i, j);
-    if (cs.has_tab) return norm_lt<D, true>(p, s, thr, cs.t2_ij(i, j));
-    return norm_lt<D, false>(p, s, thr, 0.0);
+    if (cs.has_tab) return segpt_lt<D, true>(qf, qt, u, uu, qj, thr, cs.t2_ij(i, j));
+    return segpt_lt<D, false>(qf, qt, u, uu, qj, thr, 0.0);
 }
 
 }  // namespace mrmp

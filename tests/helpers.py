@@ -8,6 +8,12 @@ from oracle import oracle as O
 
 POINT2D, POINT3D, ARM22 = O.POINT2D, O.POINT3D, O.ARM22
 
+# relative offsets from the contact threshold used by the adversarial generators: rounding-level
+# ones (the reference arithmetic itself decides) and ones around the 1e-6 band in which the
+# kernels' division-free quick test hands over to the reference arithmetic (geom.cuh)
+EPS = [0.0, 1e-16, -1e-16, 1e-15, -1e-15, 1e-13, -1e-13, 1e-10, -1e-10, 2e-7, -2e-7, 4.9e-7,
+       -4.9e-7, 5.1e-7, -5.1e-7, 1e-6, -1e-6, 3e-6, -3e-6, 1e-4, -1e-4]
+
 
 def make_point_instance(model, N, M, seed, rad=(0.015625, 0.0234375), rad_obs=(0.025, 0.04)):
     """Instance in the style of gen_random_instance (utils.jl:204-245) with point2d_many's
@@ -51,7 +57,7 @@ def near_threshold_connect(rng, n, rads, obs, agent):
     nrm = rng.normal(size=(n, d))
     nrm -= (nrm * dirn).sum(1, keepdims=True) * dirn
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
-    eps = rng.choice([0.0, 1e-16, -1e-16, 1e-15, -1e-15, 1e-13, -1e-13, 1e-10, -1e-10], n)
+    eps = rng.choice(EPS, n)
     foot = c + nrm * (thr * (1 + eps))[:, None]
     la, lb = rng.uniform(-0.08, 0.08, (2, n))
     return foot + dirn * la[:, None], foot + dirn * lb[:, None]
@@ -66,7 +72,7 @@ def near_threshold_pairs(rng, n, rads, ai, aj, d):
     v = rng.normal(size=(n, d))
     v -= (v * u).sum(1, keepdims=True) * u
     v /= np.linalg.norm(v, axis=1, keepdims=True)
-    eps = rng.choice([0.0, 1e-16, -1e-16, 1e-15, -1e-15, 1e-13, -1e-13, 1e-10, -1e-10], n)
+    eps = rng.choice(EPS, n)
     off = v * (thr * (1 + eps))[:, None]
     l1, l2, l3, l4 = rng.uniform(-0.05, 0.05, (4, n))
     w = rng.normal(size=(n, d))

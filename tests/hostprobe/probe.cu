@@ -32,6 +32,28 @@ int probe_segpt_lt(const double *a, const double *b, const double *c, int d, dou
                   : segpt_lt<3, true>(a, b, u, dotd<3>(u, u), c, thr, T2);
 }
 
+// batch forms (thr / T2 looked up per pair from N x N tables, like the kernels do)
+void probe_segseg_batch(int64_t n, int d, const double *a, const double *b, const double *c,
+                        const double *e, const int32_t *ai, const int32_t *aj, int N,
+                        const double *thr, const double *T2, uint8_t *out) {
+    for (int64_t k = 0; k < n; ++k) {
+        const double t = thr[ai[k] * N + aj[k]], t2 = T2[ai[k] * N + aj[k]];
+        out[k] = d == 2 ? segseg_lt<2, true>(a + 2 * k, b + 2 * k, c + 2 * k, e + 2 * k, t, t2)
+                        : segseg_lt<3, true>(a + 3 * k, b + 3 * k, c + 3 * k, e + 3 * k, t, t2);
+    }
+}
+void probe_segpt_batch(int64_t n, int d, const double *a, const double *b, const double *c,
+                       const int32_t *ai, const int32_t *aj, int N, const double *thr,
+                       const double *T2, uint8_t *out) {
+    for (int64_t k = 0; k < n; ++k) {
+        const double t = thr[ai[k] * N + aj[k]], t2 = T2[ai[k] * N + aj[k]];
+        double u[3];
+        for (int x = 0; x < d; ++x) u[x] = mrmp::dsub(a[d * k + x], b[d * k + x]);
+        out[k] = d == 2 ? segpt_lt<2, true>(a + 2 * k, b + 2 * k, u, dotd<2>(u, u), c + 2 * k, t, t2)
+                        : segpt_lt<3, true>(a + 3 * k, b + 3 * k, u, dotd<3>(u, u), c + 3 * k, t, t2);
+    }
+}
+
 // vcat(collect(0:step:D)/D, 1.0): writes min(n, cap) values, returns n
 int64_t probe_step_schedule(double step, double D, double *out, int64_t cap) {
     const ArmSched s = arm_schedule(step_rat(step), step, D);

@@ -54,6 +54,9 @@ def probe():
     lib.probe_segseg_lt.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double]
     lib.probe_segseg_lt_sqrt.argtypes = [_dp, _dp, _dp, _dp, C.c_int, C.c_double]
     lib.probe_segpt_lt.argtypes = [_dp, _dp, _dp, C.c_int, C.c_double, C.c_double]
+    vp = C.c_void_p
+    lib.probe_segseg_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    lib.probe_segpt_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
     lib.probe_step_schedule.restype = C.c_int64
     lib.probe_step_schedule.argtypes = [C.c_double, C.c_double, _dp, C.c_int64]
     P = C.POINTER(ProbeArm)
@@ -147,6 +150,44 @@ def test_segment_tests_match_oracle(probe):
             want = O.dist_sp(a[k], b[k], c[k]) < thr
             got = probe.probe_segpt_lt(p(a[k]), p(b[k]), p(c[k]), d, thr, sq_lt_threshold(thr))
             assert bool(got) == want, (d, k)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("shift", [0.0, 1.0e3, 1.0e5])
+def test_quick_tests_never_change_a_verdict(probe, d, shift):
+    """The division-free quick tests (geom.cuh) against the oracle on 300k pairs per case:
+    radii from 1e-3 (quick path just enabled) to 0.2, contact offsets straddling the 1e-6
+    hand-over band, and the whole scene translated by up to 1e5 (the reference's own rounding
+    error grows with the coordinate magnitude; the band must still cover it)."""
+    from helpers import near_threshold_pairs
+    rng = np.random.default_rng(11 + d)
+    N, n = 12, 300_000
+    rads = np.concatenate([[5e-4, 5.1e-4, 1e-3], rng.uniform(0.002, 0.1, N - 3)])
+    ai = rng.integers(0, N, n).astype(np.int32)
+    aj = ((ai + 1 + rng.integers(0, N - 1, n)) % N).astype(np.int32)
+    a, b, c, e = near_threshold_pairs(rng, n, rads, ai, aj, d)
+    h = n // 3
+    a[:h] = rng.random((h, d))
+    b[:h] = a[:h] + rng.normal(size=(h, d)) * 0.05
+    c[:h] = a[:h] + rng.normal(size=(h, d)) * 0.05
+    e[:h] = c[:h] + rng.normal(size=(h, d)) * 0.05
+    a, b, c, e = (np.ascontiguousarray(x + shift) for x in (a, b, c, e))
+    thr = (rads[:, None] + rads[None, :]).copy()
+    T2 = np.array([[sq_lt_threshold(t) for t in row] for row in thr])
+    orc = O.Oracle(O.POINT2D if d == 2 else O.POINT3D, rads, np.zeros((0, d + 1)))
+    want = orc.collide_pairs(ai, aj, a, b, c, e, nthreads=0)
+    got = np.empty(n, np.uint8)
+    probe.probe_segseg_batch(n, d, a.ctypes.data, b.ctypes.data, c.ctypes.data, e.ctypes.data,
+                             ai.ctypes.data, aj.ctypes.data, N, thr.ctypes.data, T2.ctypes.data,
+                             got.ctypes.data)
+    assert np.array_equal(got, want) and 0.05 * n < want.sum() < 0.95 * n
+    # segment-point form: collide(Q, q_to, i) of one candidate against one static agent
+    Q = np.zeros((N, d))
+    wantp = np.array([O.dist_sp(a[k], b[k], c[k]) < thr[ai[k], aj[k]] for k in range(0, n, 10)], np.uint8)
+    gotp = np.empty(n, np.uint8)
+    probe.probe_segpt_batch(n, d, a.ctypes.data, b.ctypes.data, c.ctypes.data, ai.ctypes.data,
+                            aj.ctypes.data, N, thr.ctypes.data, T2.ctypes.data, gotp.ctypes.data)
+    assert np.array_equal(gotp[::10], wantp) and 0 < wantp.sum() < wantp.size
 
 
 def _arm_probe(obs, step=0.01, safety=0.01, max_dist=math.nan):

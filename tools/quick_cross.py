@@ -44,9 +44,11 @@ for gs in (N, 0):
     for _ in range(10): run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    surv = int(ctx.stats()[0]) / 10
+    stt = ctx.stats()
+    surv = int(stt[0]) / 10
+    tested = int(stt[2]) / 10
     pairs = nnz * len(ca)
-    res["gs=%d" % gs] = dict(ms=ms, pairs=pairs, gpairs_s=pairs / ms / 1e6, survivors=surv, surv_frac=surv / pairs,
+    res["gs=%d" % gs] = dict(ms=ms, pairs=pairs, gpairs_s=pairs / ms / 1e6, survivors=surv, surv_frac=surv / pairs, tested=tested, tested_frac=tested / pairs,
                              hits=int(torch.count_nonzero(out).item()))
     t0 = time.perf_counter(); g = rm.edge_conflicts(ca, vf, vt, gs); t1 = time.perf_counter()
     res["gs=%d" % gs]["e2e_ms"] = (t1 - t0) * 1e3
