@@ -13,9 +13,11 @@ obstacles (scripts/config/eval/point2d_many.yaml).  One STEP is one pass of the 
       steps (max_makespan of point2d_many.yaml), OR-reduced per time step -> the conflict
       table the search consults.  collide checks counted: nnz * T * (N-1).
 
-Multi-GPU (weak scaling): the roadmap build is sharded by agent, node tables and CSR are
-all-gathered over NCCL, then every rank evaluates the full table against its OWN path
-scenario (e.g. PP's random-priority restarts, pp.jl:104-128): per-GPU work is fixed.
+Multi-GPU (weak scaling): the neighbour pass of the roadmap build is sharded by agent and the
+CSR shards are exchanged by one NCCL all-gather of fixed-size slots (vertices are re-drawn on
+every rank from the counter-based sampler instead of being communicated), then every rank
+evaluates the full table against its OWN path scenario (e.g. PP's random-priority restarts,
+pp.jl:104-128): per-GPU work is fixed.
 
 `value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream.
 `e2e`    = same through the host-buffer C ABI: host init/goal and path ids in, roadmaps
@@ -251,36 +253,41 @@ def run_b200(args):
     ctx.set_stream(st)
     a0, n_local, cap = SH.agent_block(N, world, rank)
 
-    # The gathered node table IS the NCCL buffer: this rank's shard is a slice of it (the
-    # sampling kernel writes straight into the send buffer) and rm_all consumes it in place.
-    gathered = torch.zeros((world * cap, nv, d), dtype=torch.float64, device=dev)
+    # Node tables: the sampler is counter-based (any try can be generated anywhere), so every
+    # rank draws ALL agents' vertices itself (one launch, ~8 us) instead of all-gathering them;
+    # the O(nv^2) neighbour pass -- the expensive part -- is sharded by agent.
+    nodes_all = torch.zeros((N, nv, d), dtype=torch.float64, device=dev)
     rm_all = S.Roadmaps(ctx, 0, N, nv)
-    rm_all.bind_nodes(nv, gathered.data_ptr())
+    rm_all.bind_nodes(nv, nodes_all.data_ptr())
     if world > 1:
         rm_sh = S.Roadmaps(ctx, a0, max(n_local, 1), nv)
-        rm_sh.bind_nodes(nv, gathered[a0].data_ptr())
+        rm_sh.bind_nodes(nv, nodes_all[a0].data_ptr())
     else:
         rm_sh = rm_all
     radv = np.full(max(n_local, 1), inst.rad)
-    init_sh = np.ascontiguousarray(inst.q_init[a0:a0 + n_local])
-    goal_sh = np.ascontiguousarray(inst.q_goal[a0:a0 + n_local])
+    # CSR exchange: ONE all-gather of fixed-size slots (cnt[cap*nv] | col[cap_nnz]); cap_nnz is
+    # sized from a first build, with head room (a later overflow raises MRMP_ERR_CAPACITY)
+    state = {"cap_nnz": 0, "slots": None}
 
     def build_roadmaps():
-        """(A): sample + [all-gather nodes] + neighbour pass + [all-gather CSR]."""
-        rm_sh.sample(nv, inst.seed, init_sh, goal_sh)
-        if world > 1:
-            SH.allgather_nodes_inplace(gathered, cap, nv, d)
+        """(A): sample + neighbour pass of this rank's agents + [all-gather CSR shards]."""
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal)
         nnz = rm_sh.build(radv)
         if world > 1:
-            p = rm_sh.device_ptrs()
-            rp_t = torch.as_tensor(CudaArray(p["row_ptr"], (n_local * nv + 1,), "<i4"), device=dev)
-            ci_t = torch.as_tensor(CudaArray(p["col_idx"], (max(nnz, 1),), "<i4"), device=dev)[:nnz]
-            rp_g, ci_g = SH.allgather_csr(rp_t, ci_t, N, nv, world, rank)
-            rp32 = rp_g.to(torch.int32)
-            L.check(lib.mrmp_roadmaps_set_csr_dev(rm_all._h, rp32.data_ptr(), ci_g.data_ptr(),
-                                                  int(ci_g.numel()), st))
-            torch.cuda.current_stream().synchronize()  # rp32 / ci_g are consumed by now
-            return int(ci_g.numel())
+            if state["slots"] is None:
+                t = torch.tensor([nnz], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                state["cap_nnz"] = int(t.item()) * 5 // 4 + 1024
+                state["slots"] = torch.zeros((world, cap * nv + state["cap_nnz"]),
+                                             dtype=torch.int32, device=dev)
+            slots = state["slots"]
+            L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(rm_sh._h, cap, state["cap_nnz"],
+                                                         slots[rank].data_ptr(), st))
+            dist.all_gather_into_tensor(slots.view(-1), slots[rank])
+            out = C.c_int64(0)
+            L.check(lib.mrmp_roadmaps_set_csr_shards_dev(rm_all._h, world, cap, state["cap_nnz"],
+                                                         slots.data_ptr(), st, C.byref(out)))
+            return int(out.value)
         return nnz
 
     # ---- setup: one build gives the CSR the synthetic paths walk on
@@ -415,7 +422,7 @@ def run_b200(args):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-    h2d = 2 * n_local * d * 8 + 3 * n_cols * 4
+    h2d = 2 * N * d * 8 + 3 * n_cols * 4
     d2h = n_local * nv * d * 8 + (rows_sh + 1) * 4 + (nnz_total // world) * 4 + nnz_total * wpr * 4
     e2e = {"value": checks_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}

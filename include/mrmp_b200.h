@@ -160,6 +160,15 @@ int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_t *col_idx,
 /* adopt an adjacency assembled elsewhere (all-gathered shards): device arrays, packed CSR */
 int mrmp_roadmaps_set_csr_dev(mrmp_roadmaps *rm, const int32_t *row_ptr_dev,
                               const int32_t *col_idx_dev, int64_t nnz, void *stream);
+/* Multi-GPU builds: one collective instead of a size exchange.  Every rank packs the CSR of its
+ * agent block into a fixed-size slot  int32 cnt[cap_agents*nv] | int32 col[cap_nnz]  (rows beyond
+ * its agents count 0), all-gathers the slots (NCCL), and adopts the gathered slots as the CSR
+ * of the full set: row counts -> scan -> columns copied row by row, all on `stream`.
+ * pack returns MRMP_ERR_CAPACITY when the shard has more than cap_nnz edges. */
+int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agents, int64_t cap_nnz,
+                                     int32_t *slot_dev, void *stream);
+int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agents, int64_t cap_nnz,
+                                     const int32_t *slots_dev, void *stream, int64_t *nnz_out);
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
                               int32_t **row_ptr_dev, int32_t **col_idx_dev, int64_t *nnz_out);

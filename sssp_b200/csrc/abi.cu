@@ -962,6 +962,55 @@ extern "C" int mrmp_roadmaps_set_csr_dev(mrmp_roadmaps *rm, const int32_t *row_p
     return MRMP_OK;
 }
 
+// ---- CSR shards of a multi-GPU build ------------------------------------------------------------
+extern "C" int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agents, int64_t cap_nnz,
+                                                int32_t *slot_dev, void *stream) {
+    NEED(rm && slot_dev && cap_agents >= rm->n_agents && cap_nnz >= 0, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    if (rm->nnz > cap_nnz)
+        return fail(MRMP_ERR_CAPACITY, "shard holds %lld edges, slot only %lld", (long long)rm->nnz,
+                    (long long)cap_nnz);
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(launch_csr_pack_shard(lcfg(c, (cudaStream_t)stream), (int64_t)rm->n_agents * rm->nv,
+                             (int64_t)cap_agents * rm->nv, rm->row_ptr, rm->col_idx, slot_dev));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agents,
+                                                int64_t cap_nnz, const int32_t *slots_dev,
+                                                void *stream, int64_t *nnz_out) {
+    NEED(rm && slots_dev && world >= 1 && cap_agents >= 1 && cap_nnz >= 0, "bad arguments");
+    NEED(rm->nv >= 1, "no nodes set");
+    NEED((int64_t)world * cap_agents >= rm->n_agents, "shards do not cover the agents of this set");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t rows = (int64_t)rm->n_agents * rm->nv, rows_cap = (int64_t)cap_agents * rm->nv;
+    const int64_t stride = rows_cap + cap_nnz;
+    LaunchCfg lc = lcfg(c, s);
+    CU(launch_csr_shard_counts(lc, rows, rows_cap, stride, slots_dev, rm->row_cnt));
+    CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
+    if ((int64_t)world * cap_nnz > rm->col_cap) {  // upper bound of the stitched size
+        CU(cudaStreamSynchronize(s));
+        if (rm->col_idx) CU(cudaFree(rm->col_idx));
+        rm->col_idx = nullptr;
+        rm->col_cap = (int64_t)world * cap_nnz + 64;
+        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+    }
+    CU(launch_csr_stitch(lc, rows, rows_cap, stride, slots_dev, rm->row_ptr, rm->col_idx,
+                         rm->col_cap));
+    int rc = ensure_small(c, 64);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->small_h, rm->nnz_d, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    rm->nnz = *(int64_t *)c->small_h;
+    rm->built = true;
+    rm->e_valid = false;
+    if (nnz_out) *nnz_out = rm->nnz;
+    return MRMP_OK;
+}
+
 extern "C" int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out) {
     NEED(rm && nnz_total_out, "bad arguments");
     NEED(rm->built, "roadmaps not built");

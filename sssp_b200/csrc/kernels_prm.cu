@@ -521,6 +521,45 @@ cudaError_t launch_prm_emit(const LaunchCfg &lc, int64_t n_rows, int nv, const u
     return cudaGetLastError();
 }
 
+// ---- CSR shards (multi-GPU): pack this rank's rows into a fixed-size slot, stitch all slots ---
+// slot layout: int32 cnt[rows_cap] | int32 col[cap_nnz]; rows_cap = cap_agents * nv
+__global__ void __launch_bounds__(kThreads)
+k_csr_pack_shard(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ row_ptr,
+                 const int32_t *__restrict__ col_idx, int32_t *__restrict__ slot) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t r = tid; r < rows_cap; r += stride)
+        slot[r] = r < n_rows ? row_ptr[r + 1] - row_ptr[r] : 0;
+    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    for (int64_t e = tid; e < nnz; e += stride) slot[rows_cap + e] = col_idx[e];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_csr_shard_counts(int64_t n_rows, int64_t rows_cap, int64_t slot_stride,
+                   const int32_t *__restrict__ slots, int32_t *__restrict__ row_cnt) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+         r += (int64_t)gridDim.x * blockDim.x)
+        row_cnt[r] = slots[(r / rows_cap) * slot_stride + r % rows_cap];
+}
+
+// row_ptr is the global exclusive scan; a row's offset inside its shard's column block is
+// row_ptr[row] - row_ptr[first row of the shard]
+__global__ void __launch_bounds__(kThreads)
+k_csr_stitch(int64_t n_rows, int64_t rows_cap, int64_t slot_stride,
+             const int32_t *__restrict__ slots, const int32_t *__restrict__ row_ptr,
+             int32_t *__restrict__ col_idx, int64_t col_cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows;
+         row += n_warps) {
+        const int64_t shard = row / rows_cap;
+        const int64_t dst = row_ptr[row], n = row_ptr[row + 1] - dst;
+        const int32_t *src = slots + shard * slot_stride + rows_cap + (dst - row_ptr[shard * rows_cap]);
+        for (int64_t t = lane; t < n; t += 32)
+            if (dst + t < col_cap) col_idx[dst + t] = src[t];
+    }
+}
+
 // ---- grid path launchers -------------------------------------------------------------------
 cudaError_t launch_grid_bin(const CtxView &cv, const LaunchCfg &lc, int n_agents, int nv, int g,
                             int cells, const double *nodes, int32_t *cell_start, int32_t *cursor,
@@ -601,6 +640,31 @@ cudaError_t launch_grid_gather_rows(const LaunchCfg &lc, int64_t n_rows, const i
     const int grid = (int)(want < cap ? want : cap);
     k_grid_gather_rows<<<grid, kThreads, 0, lc.stream>>>(n_rows, row_ptr, row_off, tmp, col_idx,
                                                          col_cap);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csr_pack_shard(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                  const int32_t *row_ptr, const int32_t *col_idx, int32_t *slot) {
+    k_csr_pack_shard<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, row_ptr, col_idx,
+                                                                 slot);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csr_shard_counts(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                    int64_t slot_stride, const int32_t *slots, int32_t *row_cnt) {
+    k_csr_shard_counts<<<lc.sm_count * 2, kThreads, 0, lc.stream>>>(n_rows, rows_cap, slot_stride,
+                                                                   slots, row_cnt);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csr_stitch(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                              int64_t slot_stride, const int32_t *slots, const int32_t *row_ptr,
+                              int32_t *col_idx, int64_t col_cap) {
+    k_csr_stitch<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, slot_stride, slots,
+                                                             row_ptr, col_idx, col_cap);
     count_launch();
     return cudaGetLastError();
 }

@@ -184,6 +184,14 @@ cudaError_t launch_prm_grid_adjacency(const CtxView &cv, const LaunchCfg &lc, in
 cudaError_t launch_grid_gather_rows(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_ptr,
                                     const int64_t *row_off, const int32_t *tmp, int32_t *col_idx,
                                     int64_t col_cap);
+// CSR shards of a multi-GPU build: slot = int32 cnt[rows_cap] | int32 col[cap_nnz]
+cudaError_t launch_csr_pack_shard(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                  const int32_t *row_ptr, const int32_t *col_idx, int32_t *slot);
+cudaError_t launch_csr_shard_counts(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                    int64_t slot_stride, const int32_t *slots, int32_t *row_cnt);
+cudaError_t launch_csr_stitch(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                              int64_t slot_stride, const int32_t *slots, const int32_t *row_ptr,
+                              int32_t *col_idx, int64_t col_cap);
 cudaError_t launch_sample_states(const CtxView &cv, const LaunchCfg &lc, int agent, uint64_t seed,
                                  uint64_t t0, int64_t n, double *q_out);
 // per agent: nodes[a][0]=init, [1]=goal, then the first nv-2 free samples in try order

@@ -85,6 +85,8 @@ _SIGS = {
     "mrmp_roadmaps_edge_conflicts_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
                                                    _vp, _vp]),
     "mrmp_roadmaps_set_csr_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
+    "mrmp_roadmaps_pack_csr_shard_dev": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp]),
+    "mrmp_roadmaps_set_csr_shards_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _lp]),
     "mrmp_ctx_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "mrmp_sample_states": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _dp]),
     "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),

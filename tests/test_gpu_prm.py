@@ -124,3 +124,40 @@ def test_prm_grid_hash_path_bit_exact(model, d, nv, rads_prm):
     rm2.set_nodes(nodes[:, :500])
     rm2.build(rads_prm[0])
     assert not rm2.used_grid()
+
+
+def test_csr_shards_pack_and_stitch_equal_a_full_build():
+    """The multi-GPU CSR exchange (pack fixed-size slots -> all-gather -> stitch), with the ranks
+    emulated on one GPU: 7 agents in blocks of cap = 3 (the last block is short)."""
+    import ctypes as C
+    import torch
+    from sssp_b200 import lib as L
+    N, nv, rad, world, cap = 7, 200, 0.12, 3, 3
+    rads, obs = make_point_instance(O.POINT2D, N, 10, seed=9)
+    ctx = S.Context(O.POINT2D, rads, obs)
+    nodes = np.random.default_rng(2).random((N, nv, 2))
+    full = S.Roadmaps(ctx, 0, N, nv)
+    full.set_nodes(nodes)
+    nnz = full.build(rad)
+    rp_full, col_full = full.csr()
+    lib = L.load()
+    cap_nnz = nnz          # generous
+    slots = torch.full((world, cap * nv + cap_nnz), -7, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(world):
+        a0, a1 = r * cap, min(N, (r + 1) * cap)
+        sh = S.Roadmaps(ctx, a0, a1 - a0, nv)
+        sh.set_nodes(nodes[a0:a1])
+        sh.build(rad)
+        L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(sh._h, cap, cap_nnz, slots[r].data_ptr(), st))
+        torch.cuda.synchronize()
+        # a slot that is too small is refused
+        assert lib.mrmp_roadmaps_pack_csr_shard_dev(sh._h, cap, 3, slots[r].data_ptr(), st) == L.ERR_CAPACITY
+    adopt = S.Roadmaps(ctx, 0, N, nv)
+    adopt.set_nodes(nodes)
+    out = C.c_int64(0)
+    L.check(lib.mrmp_roadmaps_set_csr_shards_dev(adopt._h, world, cap, cap_nnz, slots.data_ptr(), st,
+                                                 C.byref(out)))
+    assert out.value == nnz
+    rp, col = adopt.csr()
+    assert np.array_equal(rp, rp_full) and np.array_equal(col, col_full)
