@@ -447,6 +447,8 @@ def run_b200(args):
                                     "hbm_frac": n * BYTES_CONNECT / ms_con / 1e6 / pk["hbm_gbs"]},
                   "collide_edges_indexed": {"ms": ms_idx, "checks_per_s": n / ms_idx * 1e3}}
         del con_d, cl_d, out
+        extras["sssp_expansion"] = extra_sssp_expansion(inst, nodes_h, local)
+        extras["arm22"] = extra_arm22(local, dev, st, timed)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -481,6 +483,99 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_sssp_expansion(inst, nodes_h, device):
+    """SURVEY 8(d) config 1/2 deliverable 'ms per expansion': the fused node expansion
+    (mrmp_sssp_expand: K=10 samples, steering depth 2, epsilon 0.2 as in point2d_many.yaml,
+    roadmaps of 300 vertices per agent, N=50) through the host API, against the same
+    expansion in C on one host core (a reference solver call is single-threaded)."""
+    import sssp_b200 as S
+    from oracle import oracle as O
+    N, nv0, K = inst.rads.size, 300, 10
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles, device=device)
+    orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
+    dev_rm = S.SsspRoadmaps(ctx, nv_cap=1024)
+    tabs = [np.ascontiguousarray(nodes_h[a, :nv0]) for a in range(N)]
+    for a in range(N):
+        dev_rm.set_roadmap(a, tabs[a])
+    rng = np.random.default_rng(7)
+    calls = []
+    for k in range(40):
+        a = k % N
+        ids = rng.integers(0, nv0, N).astype(np.int32)
+        old = rng.choice(nv0, 12, replace=False).astype(np.int32)
+        calls.append((a, int(ids[a]), ids, old, rng.random((K, 2))))
+    kw = dict(steering_depth=2, epsilon=0.2, min_dist_thread=0.02)
+    dev_rm.expand(calls[0][0], calls[0][1], calls[0][2], calls[0][3], K, q_rand=calls[0][4], **kw)
+    tabs[calls[0][0]] = dev_rm.nodes(calls[0][0])
+    t_gpu, t_cpu, mism, n_new = 0.0, 0.0, 0, 0
+    for a, v, ids, old, qr in calls[1:]:
+        Q = np.stack([tabs[j][ids[j]] for j in range(N)])
+        t0 = time.perf_counter()
+        q_new, outs, ins, succ, hit = dev_rm.expand(a, v, ids, old, K, q_rand=qr, **kw)
+        t1 = time.perf_counter()
+        after, ob, ib, osucc, ohit = orc.sssp_expand(a, tabs[a], v, qr, 2, 0.2, 0.02, Q, old)
+        t2 = time.perf_counter()
+        t_gpu += t1 - t0
+        t_cpu += t2 - t1
+        ok = (after.shape[0] - tabs[a].shape[0] == len(q_new) and np.array_equal(after[tabs[a].shape[0]:], q_new)
+              and np.array_equal(succ, osucc) and np.array_equal(hit, ohit))
+        mism += 0 if ok else 1
+        n_new += len(q_new)
+        tabs[a] = after
+    n = len(calls) - 1
+    return {"calls": n, "K": K, "n_agents": int(N), "roadmap_vertices": nv0,
+            "gpu_ms_per_expansion": 1e3 * t_gpu / n, "cpu_c_1core_ms_per_expansion": 1e3 * t_cpu / n,
+            "accepted_vertices": n_new, "mismatching_calls": mism}
+
+
+def extra_arm22(device, dev, st, timed):
+    """BASELINE configs[3]: StateArm22 N=10 (link 0.15-0.25, 3 obstacles): swept-link collide
+    (6-arity, arm22.jl:100-146) and edge connect (arm22.jl:56-86) on uniformly random joint
+    pairs, inputs resident in HBM; CPU = C oracle with OpenMP on a 1/16 sample."""
+    import torch
+    import sssp_b200 as S
+    from sssp_b200 import lib as L
+    from oracle import oracle as O
+    lib = L.load()
+    rng = np.random.default_rng(22)
+    N, M = 10, 3
+    rads = rng.uniform(0.15, 0.25, N)
+    base = rng.uniform(0.3, 0.7, (N, 2))
+    obs = np.concatenate([rng.random((M, 2)), rng.uniform(0.05, 0.1, (M, 1))], axis=1)
+    ctx = S.Context(L.MODEL_ARM22, rads, obs, base_pos=base, device=device)
+    orc = O.Oracle(O.ARM22, rads, obs, base=base)
+    n_col, n_con = 1 << 16, 1 << 18
+    ai = rng.integers(0, N, n_col).astype(np.int32)
+    aj = ((ai + 1 + rng.integers(0, N - 1, n_col)) % N).astype(np.int32)
+    q = [rng.uniform(0, 2 * np.pi, (n_col, 2)) for _ in range(4)]
+    ag = rng.integers(0, N, n_con).astype(np.int32)
+    cf, ct = rng.uniform(0, 2 * np.pi, (n_con, 2)), rng.uniform(0, 2 * np.pi, (n_con, 2))
+    d_ = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ai, aj, *q, ag, cf, ct)]
+    out = torch.empty(max(n_col, n_con), dtype=torch.uint8, device=dev)
+    ctx.set_stream(st)
+    ms_col = timed(lambda: L.check(lib.mrmp_collide_pairs_dev(
+        ctx._h, n_col, *[t.data_ptr() for t in d_[:6]], out.data_ptr(), st)), reps=3)
+    g_col = out[:n_col].cpu().numpy().copy()
+    ms_con = timed(lambda: L.check(lib.mrmp_connect_edges_dev(
+        ctx._h, n_con, d_[6].data_ptr(), d_[7].data_ptr(), d_[8].data_ptr(), out.data_ptr(), st)), reps=3)
+    g_con = out[:n_con].cpu().numpy().copy()
+    sl = slice(0, None, 16)
+    t0 = time.perf_counter()
+    o_col = orc.collide_pairs(ai[sl], aj[sl], *[x[sl] for x in q], nthreads=0)
+    t1 = time.perf_counter()
+    o_con = orc.connect_edges(ag[sl], cf[sl], ct[sl], nthreads=0)
+    t2 = time.perf_counter()
+    return {"n_agents": N, "n_obstacles": M,
+            "collide_pairs": {"n": n_col, "gpu_ms": ms_col, "gpu_checks_per_s": n_col / ms_col * 1e3,
+                              "cpu_checks_per_s": o_col.size / (t1 - t0), "cpu_threads": O.max_threads(),
+                              "mismatches_on_sample": int((g_col[sl] != o_col).sum()),
+                              "hit_rate": float(g_col.mean())},
+            "connect_edges": {"n": n_con, "gpu_ms": ms_con, "gpu_checks_per_s": n_con / ms_con * 1e3,
+                              "cpu_checks_per_s": o_con.size / (t2 - t1),
+                              "mismatches_on_sample": int((g_con[sl] != o_con).sum()),
+                              "free_rate": float(g_con.mean())}}
 
 
 def main():

@@ -758,3 +758,67 @@ void orc_distance_table(const orc_ctx *c, int nv, const double *nodes, const int
     }
     free(done);
 }
+
+/* ------------------------------------------------------------------------ */
+/* one SSSP node expansion: expand! (sssp.jl:235-267) followed by the        */
+/* successor filter collide(S.Q, p.q, i) (sssp.jl:196-223), as sequential C  */
+/* ------------------------------------------------------------------------ */
+/* nodes[cap][d] holds nv vertices of agent `agent` and receives the accepted ones.
+ * q_rand[K][d] are the samples in draw order.  out_bits/in_bits [K][words]: row r describes
+ * accepted vertex r (id nv+r): out bit t <=> conn(q_new, q_t) for t < id, in bit t <=>
+ * conn(q_t, q_new) for t <= id.  Q[N][d]: states of all agents in the search node (Q[agent]
+ * = nodes[v_from]); succ_ids = old_nbrs, new neighbours of v_from (ascending), v_from;
+ * succ_collide[k] = collide(Q, q_succ, agent) or collide(Q, Q') when slow != 0.
+ * Returns the number of accepted vertices; *n_succ receives the successor count. */
+int orc_sssp_expand(const orc_ctx *c, int agent, double *nodes, int nv, int v_from, int K,
+                    const double *q_rand, int depth, double epsilon, double thr, int words,
+                    uint32_t *out_bits, uint32_t *in_bits, const double *Q, int n_old,
+                    const int32_t *old_nbrs, int slow, int32_t *succ_ids, uint8_t *succ_collide,
+                    int *n_succ) {
+    const int d = c->d, N = c->n_agents;
+    const double *q_near = nodes + (size_t)d * v_from;
+    int n = nv;
+    memset(out_bits, 0, sizeof(uint32_t) * (size_t)K * words);
+    memset(in_bits, 0, sizeof(uint32_t) * (size_t)K * words);
+    for (int k = 0; k < K; ++k) {
+        double q_new[3];
+        orc_steering(c, agent, q_rand + (size_t)d * k, q_near, depth, epsilon, q_new); /* :246 */
+        double mn = INFINITY;                                                           /* :250 */
+        int has_nan = 0;
+        for (int v = 0; v < n; ++v) {
+            double dd = orc_state_dist(c, nodes + (size_t)d * v, q_new);
+            if (isnan(dd)) has_nan = 1;
+            if (dd < mn) mn = dd;
+        }
+        if (has_nan || !(mn > thr)) continue;
+        const int r = n - nv, id = n;
+        memcpy(nodes + (size_t)d * id, q_new, sizeof(double) * d);
+        for (int t = 0; t < id; ++t)                                                    /* :252-257 */
+            if (orc_conn(c, agent, q_new, nodes + (size_t)d * t, epsilon))
+                out_bits[(size_t)r * words + (t >> 5)] |= 1u << (t & 31);
+        ++n;                                                                            /* :258 */
+        for (int t = 0; t < n; ++t)                                                     /* :259-262 */
+            if (orc_conn(c, agent, nodes + (size_t)d * t, q_new, epsilon))
+                in_bits[(size_t)r * words + (t >> 5)] |= 1u << (t & 31);
+    }
+    int ns = 0;
+    for (int k = 0; k < n_old; ++k) succ_ids[ns++] = old_nbrs[k];
+    for (int r = 0; r < n - nv; ++r)
+        if ((in_bits[(size_t)r * words + (v_from >> 5)] >> (v_from & 31)) & 1u) succ_ids[ns++] = nv + r;
+    succ_ids[ns++] = v_from;
+    double *Qt = slow ? (double *)malloc(sizeof(double) * d * N) : NULL;
+    for (int k = 0; k < ns; ++k) {
+        const double *qp = nodes + (size_t)d * succ_ids[k];
+        if (!slow) {
+            succ_collide[k] = (uint8_t)orc_collide_config_move(c, Q, qp, agent);       /* :206 */
+        } else {
+            int64_t fp;
+            memcpy(Qt, Q, sizeof(double) * d * N);
+            memcpy(Qt + (size_t)d * agent, qp, sizeof(double) * d);
+            succ_collide[k] = (uint8_t)orc_collide_configs(c, Q, Qt, &fp);             /* :207 */
+        }
+    }
+    free(Qt);
+    *n_succ = ns;
+    return n - nv;
+}

@@ -139,6 +139,14 @@ int orc_conn(const orc_ctx *c, int agent, const double *qf, const double *qt, do
 void orc_distance_table(const orc_ctx *c, int nv, const double *nodes, const int32_t *row_ptr,
                         const int32_t *col_idx, int goal, double *table);
 
+/* one SSSP node expansion (expand! sssp.jl:235-267 + successor filter :196-223); see the
+ * definition for the argument layout */
+int orc_sssp_expand(const orc_ctx *c, int agent, double *nodes, int nv, int v_from, int K,
+                    const double *q_rand, int depth, double epsilon, double thr, int words,
+                    uint32_t *out_bits, uint32_t *in_bits, const double *Q, int n_old,
+                    const int32_t *old_nbrs, int slow, int32_t *succ_ids, uint8_t *succ_collide,
+                    int *n_succ);
+
 int orc_dot_is_fma(void);
 int orc_max_threads(void);
 

@@ -86,6 +86,10 @@ def _load(name: str) -> C.CDLL:
     lib.orc_steering.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_double, _dp]
     lib.orc_conn.argtypes = [C.c_void_p, C.c_int, _dp, _dp, C.c_double]
     lib.orc_distance_table.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, C.c_int, _dp]
+    lib.orc_sssp_expand.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, C.c_int, _dp,
+                                    C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
+                                    C.c_void_p, _dp, C.c_int, _ip, C.c_int, _ip, _bp,
+                                    C.POINTER(C.c_int)]
     return lib
 
 
@@ -325,6 +329,27 @@ class Oracle:
         self._lib.orc_steering(self._h, int(agent), _p(q_rand, _dp), _p(q_near, _dp), int(depth),
                                eps, _p(out, _dp))
         return out
+
+    def sssp_expand(self, agent, nodes, v_from, q_rand, depth, epsilon, thr, Q, old_nbrs,
+                    slow=False):
+        """One SSSP node expansion in C (expand! + successor filter).  nodes [nv][d] is not
+        modified; returns (nodes_after, out_bits, in_bits, succ_ids, succ_collide)."""
+        nodes, q_rand, Q = _f64(nodes), _f64(q_rand).reshape(-1, self.d), _f64(Q)
+        nv, K = nodes.shape[0], q_rand.shape[0]
+        buf = np.zeros((nv + K, self.d))
+        buf[:nv] = nodes
+        words = (nv + K + 31) // 32
+        ob, ib = np.zeros((K, words), np.uint32), np.zeros((K, words), np.uint32)
+        old = _i32(old_nbrs)
+        succ, hit = np.empty(old.size + K + 1, np.int32), np.empty(old.size + K + 1, np.uint8)
+        ns = C.c_int(0)
+        eps = math.nan if epsilon is None else epsilon
+        n_new = self._lib.orc_sssp_expand(
+            self._h, int(agent), _p(buf, _dp), nv, int(v_from), K, _p(q_rand, _dp), int(depth), eps,
+            float(thr), words, ob.ctypes.data_as(C.c_void_p), ib.ctypes.data_as(C.c_void_p),
+            _p(Q, _dp), old.size, _p(old, _ip) if old.size else None, int(slow), _p(succ, _ip),
+            _p(hit, _bp), C.byref(ns))
+        return buf[: nv + n_new], ob[:n_new], ib[:n_new], succ[: ns.value], hit[: ns.value]
 
     def distance_table(self, nodes, row_ptr, col_idx, goal=1) -> np.ndarray:
         nodes, row_ptr, col_idx = _f64(nodes), _i32(row_ptr), _i32(col_idx)

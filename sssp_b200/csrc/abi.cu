@@ -280,6 +280,22 @@ static int run_batch(mrmp_ctx *c, int64_t n, std::vector<Arr> &arrs, F launch) {
             }
         int rc = ensure_small(c, tot);
         if (rc) return rc;
+        if (n <= kTinyBatch) {
+            // closure-sized calls (one check .. a few hundred): latency is everything, so the
+            // kernel works on the mapped pinned block itself: one launch + one sync
+            unsigned char *hb = nullptr;
+            CU(cudaHostGetDevicePointer((void **)&hb, c->small_h, 0));
+            for (size_t a = 0; a < na; ++a) {
+                dptr[a] = hb + off[a];
+                if (arrs[a].in) memcpy(c->small_h + off[a], arrs[a].in, arrs[a].stride * (size_t)n);
+            }
+            CU(launch(dptr.data(), n, c->s_k));
+            CU(cudaStreamSynchronize(c->s_k));
+            for (size_t a = 0; a < na; ++a)
+                if (arrs[a].out)
+                    memcpy(arrs[a].out, c->small_h + off[a], arrs[a].stride * (size_t)n);
+            return MRMP_OK;
+        }
         for (size_t a = 0; a < na; ++a) {
             dptr[a] = c->small_d + off[a];
             if (arrs[a].in) memcpy(c->small_h + off[a], arrs[a].in, arrs[a].stride * (size_t)n);

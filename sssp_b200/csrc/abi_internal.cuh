@@ -63,6 +63,7 @@ static const double kFilterPad = 9.5367431640625e-07;  // 2^-20, absolute slack 
 static const int kSlots = 3;
 static const int64_t kChunk = 1 << 20;     // checks per pipeline chunk
 static const int64_t kSmallBatch = 1 << 16;  // single-stream fast path below this
+static const int64_t kTinyBatch = 256;       // zero-copy (mapped pinned memory) below this
 
 struct mrmp_ctx {
     int device = 0;
@@ -97,7 +98,8 @@ inline int ensure_small(mrmp_ctx *c, size_t bytes) {
     if (c->small_d) CU(cudaFree(c->small_d));
     c->small_h = c->small_d = nullptr;
     c->small_bytes = 0;
-    CU(cudaHostAlloc((void **)&c->small_h, nb, cudaHostAllocDefault));
+    // mapped: tiny batches let the kernel read / write this block directly (no copy nodes)
+    CU(cudaHostAlloc((void **)&c->small_h, nb, cudaHostAllocMapped));
     CU(cudaMalloc((void **)&c->small_d, nb));
     c->small_bytes = nb;
     return MRMP_OK;

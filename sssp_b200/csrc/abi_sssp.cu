@@ -23,7 +23,7 @@ static int sssp_io(mrmp_sssp *s, size_t bytes) {
     s->io_bytes = 0;
     size_t nb = 1 << 16;
     while (nb < bytes) nb *= 2;
-    CU(cudaHostAlloc((void **)&s->io_h, nb, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void **)&s->io_h, nb, cudaHostAllocMapped));  // the fused kernel reads/writes it
     CU(cudaMalloc((void **)&s->io_d, nb));
     s->io_bytes = nb;
     return MRMP_OK;
@@ -185,7 +185,6 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     if (n_old_nbrs) memcpy(s->io_h + o_old, old_nbrs, 4 * (size_t)n_old_nbrs);
     if (q_rand) memcpy(s->io_h + o_qrand, q_rand, sizeof(double) * d * (size_t)K);
     cudaStream_t st = c->s_k;
-    CU(cudaMemcpyAsync(s->io_d, s->io_h, in_end, cudaMemcpyHostToDevice, st));
 
     SsspView view{s->nodes, s->nv_d, s->cap};
     SsspExpand a{};
@@ -219,9 +218,24 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     ws.cfg_from = (double *)(b + o_cf);
     ws.cfg_to = (double *)(b + o_ct);
     ws.cfg_first = (int64_t *)(b + o_first);
-    CU(launch_sssp_expand(c->cv, lcfg(c, st), view, a, ws, nv0));
-    CU(cudaMemcpyAsync(s->io_h + in_end, s->io_d + in_end, out_end - in_end, cudaMemcpyDeviceToHost,
-                       st));
+    // search-sized roadmaps of the point models: one launch that works on the mapped pinned
+    // block directly; otherwise the multi-kernel path with explicit copies
+    const bool fused = c->model != MRMP_MODEL_ARM22 && K <= 32 &&
+                       (int64_t)K * 2 * (nv0 + K) <= (1 << 16) &&
+                       sssp_fused_smem(c->cv, a) <= 160 * 1024;
+    if (fused) {
+        unsigned char *hb = nullptr;
+        CU(cudaHostGetDevicePointer((void **)&hb, s->io_h, 0));
+        CU(launch_sssp_expand_fused(c->cv, lcfg(c, st), view, a, (const int32_t *)(hb + o_qids),
+                                    (const int32_t *)(hb + o_old), (const double *)(hb + o_qrand), (int32_t *)(hb + o_hdr),
+                                    (double *)(hb + o_qnew), (uint32_t *)(hb + o_bits),
+                                    (int32_t *)(hb + o_succ), (uint8_t *)(hb + o_sout)));
+    } else {
+        CU(cudaMemcpyAsync(s->io_d, s->io_h, in_end, cudaMemcpyHostToDevice, st));
+        CU(launch_sssp_expand(c->cv, lcfg(c, st), view, a, ws, nv0));
+        CU(cudaMemcpyAsync(s->io_h + in_end, s->io_d + in_end, out_end - in_end,
+                           cudaMemcpyDeviceToHost, st));
+    }
     CU(cudaStreamSynchronize(st));
 
     const int32_t *hdr = (const int32_t *)(s->io_h + o_hdr);

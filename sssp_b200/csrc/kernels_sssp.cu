@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include "models.cuh"
+#include "point_model.cuh"
 #include "sampler.cuh"
 
 namespace mrmp {
@@ -210,6 +211,230 @@ k_sssp_gather(SsspView view, SsspExpand a, SsspWs ws, int n_agents) {
     }
 }
 
+// ---- single-launch form for search-sized roadmaps (point models) ------------------------------
+// A popped search node of the reference's configs touches a roadmap of 10^1..10^3 vertices:
+// the whole expansion is ~10^4 primitive tests, i.e. a few microseconds of GPU work, so the
+// call is bound by launch and copy latency, not throughput.  This kernel runs every stage in
+// ONE CTA of 1024 threads (phases separated by __syncthreads), reads its inputs from and
+// writes its results to MAPPED PINNED host memory directly (no memcpy nodes around it), so a
+// call is one launch + one stream synchronisation.  The multi-kernel path above takes over
+// for large roadmaps and for the arm model.
+constexpr int kFusedThreads = 1024;
+
+template <class M>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__restrict__ h_in,
+                    const int32_t *__restrict__ h_old, const double *__restrict__ h_qrand, int32_t *__restrict__ h_hdr,
+                    double *__restrict__ h_qnew, uint32_t *__restrict__ h_bits,
+                    int32_t *__restrict__ h_succ, uint8_t *__restrict__ h_verdict) {
+    constexpr int D = M::SD;
+    __shared__ double s_q[kMaxExpand][D];
+    __shared__ int s_near[kMaxExpand];
+    __shared__ unsigned long long s_close[kMaxExpand];
+    __shared__ int s_rank[kMaxExpand];
+    __shared__ int s_nnew, s_nsucc;
+    const int tid = threadIdx.x, N = cv.n_agents;
+    const int cap_s = a.n_old + a.K + 1;
+    // dynamic smem: Qids[N] | succ[cap_s] | flag[cap_s] | bits[2*K*words] | Q[N][D]
+    int32_t *s_qids = reinterpret_cast<int32_t *>(smem_raw);
+    int32_t *s_succ = s_qids + N;
+    int32_t *s_flag = s_succ + cap_s;
+    uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_flag + cap_s);
+    double *s_Q = reinterpret_cast<double *>(smem_raw + ((4 * (size_t)(N + 2 * cap_s + 2 * a.K * a.words) + 15) & ~(size_t)15));
+    const ConSeg cs(cv, cv.blob + cv.con_off);
+    const ColSeg ks(cv, cv.blob + cv.col_off);
+    const int nv0 = view.nv[a.agent];
+    double *tab = view.nodes + (int64_t)a.agent * view.cap * D;
+
+    // ---- inputs from mapped host memory: Q_ids[N], old_nbrs[n_old]
+    for (int t = tid; t < N; t += blockDim.x) s_qids[t] = h_in[t];
+    for (int t = tid; t < a.n_old; t += blockDim.x) s_succ[t] = h_old[t];
+    for (int t = tid; t < cap_s; t += blockDim.x) s_flag[t] = 0;
+    for (int t = tid; t < 2 * a.K * a.words; t += blockDim.x) s_bits[t] = 0u;
+    // ---- steering: sample k on warp k (independent chains on different schedulers)
+    if ((tid & 31) == 0 && (tid >> 5) < a.K) {
+        const int k = tid >> 5;
+        double q_near[D], qh[D];
+        load_state<D>(tab, a.v_from, q_near);
+        if (a.host_samples) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) qh[c] = h_qrand[k * D + c];
+        } else {
+            sample_state<M>(a.seed, a.agent, a.t0 + (uint64_t)k, qh);
+        }
+        if (!conn<M>(cv, cs, a, q_near, qh)) {
+            double ql[D], q[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) ql[c] = q_near[c];
+            for (int s = 0; s < a.depth; ++s) {
+                M::mid(ql, qh, q);
+                const bool ok = conn<M>(cv, cs, a, q_near, q);
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    if (ok) ql[c] = q[c];
+                    else qh[c] = q[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) qh[c] = ql[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) s_q[k][c] = qh[c];
+        s_near[k] = 0;
+        s_close[k] = 0ull;
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += blockDim.x) {
+        const double *tj = view.nodes + ((int64_t)j * view.cap + s_qids[j]) * D;
+#pragma unroll
+        for (int c = 0; c < D; ++c) s_Q[j * D + c] = tj[c];
+    }
+    // ---- space-filling test (sssp.jl:250) and the K x K closeness matrix
+    for (int idx = tid; idx < a.K * nv0; idx += blockDim.x) {
+        const int k = idx / nv0, v = idx - k * nv0;
+        double qv[D];
+        load_state<D>(tab, v, qv);
+        if (!M::dist_gt(cv, qv, s_q[k], a.thr, a.thr_r2)) s_near[k] = 1;
+    }
+    for (int idx = tid; idx < a.K * a.K; idx += blockDim.x) {
+        const int kp = idx / a.K, k = idx - kp * a.K;
+        if (kp < k && !M::dist_gt(cv, s_q[kp], s_q[k], a.thr, a.thr_r2))
+            atomicOr(&s_close[k], 1ull << kp);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long acc = 0ull;
+        int n = 0;
+        for (int k = 0; k < a.K; ++k) {
+            if (!s_near[k] && !(s_close[k] & acc)) {
+                acc |= 1ull << k;
+                s_rank[k] = n++;
+            } else {
+                s_rank[k] = -1;
+            }
+        }
+        s_nnew = n;
+        view.nv[a.agent] = nv0 + n;
+    }
+    __syncthreads();
+    const int n_new = s_nnew;
+    if (tid < a.K && s_rank[tid] >= 0) {
+        const int r = s_rank[tid];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            tab[(int64_t)(nv0 + r) * D + c] = s_q[tid][c];
+            h_qnew[r * D + c] = s_q[tid][c];
+        }
+    }
+    __syncthreads();
+    // compact accepted samples to the front of s_q (rank order) for the edge tests
+    double mine[D];
+    int my_rank = -1;
+    if (tid < a.K) {
+        my_rank = s_rank[tid];
+#pragma unroll
+        for (int c = 0; c < D; ++c) mine[c] = s_q[tid][c];
+    }
+    __syncthreads();
+    if (my_rank >= 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) s_q[my_rank][c] = mine[c];
+    }
+    __syncthreads();
+    // ---- edges of the accepted vertices (sssp.jl:252-262)
+    {
+        const int T = nv0 + a.K;
+        const int total = n_new * T * 2;
+        for (int it = tid; it < total; it += blockDim.x) {
+            const int r = it / (2 * T);
+            const int rem = it - r * 2 * T;
+            const int t = rem >> 1, dir = rem & 1;
+            const int id = nv0 + r;
+            if (t > id || (t == id && dir == 0)) continue;
+            double qt[D];
+            if (t >= nv0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) qt[c] = s_q[t - nv0][c];
+            } else {
+                load_state<D>(tab, t, qt);
+            }
+            const bool ok = dir == 0 ? conn<M>(cv, cs, a, s_q[r], qt) : conn<M>(cv, cs, a, qt, s_q[r]);
+            if (ok)
+                atomicOr(s_bits + (dir == 0 ? 0 : a.K * a.words) + r * a.words + (t >> 5),
+                         1u << (t & 31));
+        }
+    }
+    __syncthreads();
+    // ---- successor list
+    if (tid == 0) {
+        int n = a.n_old;
+        const uint32_t *in_bits = s_bits + a.K * a.words;
+        for (int r = 0; r < n_new; ++r)
+            if ((in_bits[r * a.words + (a.v_from >> 5)] >> (a.v_from & 31)) & 1u) s_succ[n++] = nv0 + r;
+        s_succ[n++] = a.v_from;
+        s_nsucc = n;
+    }
+    __syncthreads();
+    const int n_succ = s_nsucc;
+    // ---- successor filter
+    double qf[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) qf[c] = s_Q[a.agent * D + c];
+    if (!a.slow_collide) {  // collide(S.Q, p.q, i): point.jl:27-33
+        for (int it = tid; it < n_succ * N; it += blockDim.x) {
+            const int k = it / N, j = it - k * N;
+            if (j == a.agent) continue;
+            const int id = s_succ[k];
+            double qt[D], u[D];
+            if (id >= nv0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) qt[c] = s_q[id - nv0][c];
+            } else {
+                load_state<D>(tab, id, qt);
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) u[c] = dsub(qf[c], qt[c]);
+            if (point_collide_move_vs_static<D>(ks, qf, qt, u, dotd<D>(u, u), s_Q + j * D, a.agent, j))
+                s_flag[k] = 1;
+        }
+    } else {  // collide(S.Q, Q): all pairs i < j of the 6-arity form (point.jl:18-25)
+        const int P = N * (N - 1) / 2;
+        for (int it = tid; it < n_succ * P; it += blockDim.x) {
+            const int k = it / P;
+            int rr = it - k * P, i = 0;
+            while (rr >= N - 1 - i) {
+                rr -= N - 1 - i;
+                ++i;
+            }
+            const int j = i + 1 + rr;
+            const int id = s_succ[k];
+            double qt[D];
+            if (id >= nv0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) qt[c] = s_q[id - nv0][c];
+            } else {
+                load_state<D>(tab, id, qt);
+            }
+            const double *fi = s_Q + i * D, *fj = s_Q + j * D;
+            const double *ti = i == a.agent ? qt : fi, *tj = j == a.agent ? qt : fj;
+            if (point_collide_pair<D>(ks, fi, ti, fj, tj, i, j)) s_flag[k] = 1;
+        }
+    }
+    __syncthreads();
+    // ---- results to mapped host memory
+    for (int t = tid; t < 2 * a.K * a.words; t += blockDim.x) h_bits[t] = s_bits[t];
+    for (int t = tid; t < n_succ; t += blockDim.x) {
+        h_succ[t] = s_succ[t];
+        h_verdict[t] = (uint8_t)s_flag[t];
+    }
+    if (tid == 0) {
+        h_hdr[0] = n_new;
+        h_hdr[1] = n_succ;
+        h_hdr[2] = nv0;
+    }
+    __threadfence_system();
+}
+
 // ---- small per-state helpers for the host search loops --------------------------------------
 // op 0: out[k] = dist(q1[k], q2[k]);  op 1: out[k][:] = get_mid_status(q1[k], q2[k])
 template <class M>
@@ -325,6 +550,38 @@ cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const Sss
         return launch_collide_configs(cv, lc, cap_s, ws.cfg_from, ws.cfg_to, ws.succ_out,
                                       ws.cfg_first);
     return launch_collide_config_moves(cv, lc, a.agent, ws.Qbuf, cap_s, ws.cand, ws.succ_out);
+}
+
+size_t sssp_fused_smem(const CtxView &cv, const SsspExpand &a) {
+    const int cap_s = a.n_old + a.K + 1;
+    const size_t ints = 4 * (size_t)(cv.n_agents + 2 * cap_s + 2 * a.K * a.words);
+    return ((ints + 15) & ~(size_t)15) + sizeof(double) * cv.d * (size_t)cv.n_agents;
+}
+
+// one launch; h_* are device-visible addresses of mapped pinned host memory
+cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
+                                     const SsspExpand &a, const int32_t *h_in,
+                                     const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
+                                     double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
+                                     uint8_t *h_verdict) {
+    if (a.K < 1 || a.K > 32 || cv.model == 2) return cudaErrorNotSupported;
+    const int sm = (int)sssp_fused_smem(cv, a);
+    if (sm > 160 * 1024) return cudaErrorNotSupported;
+    cudaError_t e = cudaSuccess;
+    if (cv.model == 0) {
+        using M = PointModel<2>;
+        e = set_smem(k_sssp_expand_fused<M>, sm);
+        k_sssp_expand_fused<M><<<1, kFusedThreads, sm, lc.stream>>>(cv, view, a, h_in, h_old, h_qrand,
+                                                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+    } else {
+        using M = PointModel<3>;
+        e = set_smem(k_sssp_expand_fused<M>, sm);
+        k_sssp_expand_fused<M><<<1, kFusedThreads, sm, lc.stream>>>(cv, view, a, h_in, h_old, h_qrand,
+                                                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+    }
+    if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,

@@ -234,6 +234,12 @@ struct SsspWs {                 // device workspace of one expansion (laid out b
 };
 cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
                                const SsspExpand &a, const SsspWs &ws, int nv_before);
+size_t sssp_fused_smem(const CtxView &cv, const SsspExpand &a);
+cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
+                                     const SsspExpand &a, const int32_t *h_in,
+                                     const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
+                                     double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
+                                     uint8_t *h_verdict);
 cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
                             const double *q1, const double *q2, double *out);
 cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,
