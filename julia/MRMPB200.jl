@@ -8,7 +8,9 @@
 # Usage inside MRMP.jl (replacing src/models/point2d.jl:42-69 and src/models/point.jl:5-36):
 #   connect = MRMPB200.gen_connect(StatePoint2D(0, 0), obstacles, rads)
 #   collide = MRMPB200.gen_collide(StatePoint2D(0, 0), rads)
-# Both return multi-method closures with the reference's signatures (1-based agent ids).
+# Both return multi-method closures with the reference's signatures (1-based agent ids); the
+# same constructors serve StatePoint3D and StateArm22 (ins_params = (positions, rads)).
+# SsspRoadmaps / expand_and_filter! (bottom of the file) are the batched node expansion.
 module MRMPB200
 
 import ..MRMP: AbsState, Node, StatePoint2D, StatePoint3D, StateArm22,
@@ -158,6 +160,68 @@ function PRMs(config_init::Vector{State}, config_goal::Vector{State}, ctx::Ctx,
                          Int64.(col[row_ptr[(a - 1) * num_vertices + v] + 1:
                                     row_ptr[(a - 1) * num_vertices + v + 1]]) .+ 1)
              for v = 1:num_vertices] for a = 1:N]
+end
+
+# ---- SSSP: device-resident growing roadmaps + one call per popped search node -------------
+# Replaces, inside src/solvers/sssp.jl:181-223, the call `expand!(...)` (:181-189) and the
+# per-successor `collide(S.Q, p.q, i)` (:206) by a single library call.  The search loop
+# itself (OPEN, VISITED, h_func, backtrack) is unchanged Julia.
+mutable struct SsspRoadmaps
+    h::Ptr{Cvoid}
+    function SsspRoadmaps(ctx::Ctx, nv_cap::Int = 256)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mrmp_sssp_create, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}),
+                    ctx.h, nv_cap, h))
+        s = new(h[])
+        finalizer(x -> ccall((:mrmp_sssp_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), s)
+        return s
+    end
+end
+
+"""upload agent i's initial roadmap (output of gen_RRT_connect_roadmap, sssp.jl:325-401)"""
+function set_roadmap!(s::SsspRoadmaps, i::Int64, roadmap::Vector{Node{State}}) where {State}
+    qs = map(v -> v.q, roadmap)
+    check(ccall((:mrmp_sssp_set_roadmap, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{State}),
+                s.h, i - 1, length(qs), qs))
+end
+
+"""
+    expand_and_filter!(s, i, v, S_Q, roadmap_i; kwargs...) -> Vector{Tuple{Int64,Bool}}
+
+expand! (sssp.jl:235-267) for agent i at vertex v plus the successor filter (:196-223):
+appends the accepted vertices and their edges to `roadmap_i` in the reference's order and
+returns `(p_id, collides)` for every `p_id in vcat(v.neighbors, v.id)`.
+"""
+function expand_and_filter!(s::SsspRoadmaps, i::Int64, v::Node{State}, S_Q::Vector{Node{State}},
+                            roadmap::Vector{Node{State}}; num_vertex_expansion::Int64 = 10,
+                            steering_depth::Int64 = 2, epsilon::Union{Nothing,Float64} = nothing,
+                            min_dist_thread::Float64 = 0.1, seed::UInt64 = UInt64(0),
+                            t0::UInt64 = UInt64(0), slow::Bool = false) where {State<:AbsState}
+    K = num_vertex_expansion
+    nv0 = length(roadmap)
+    words = (nv0 + K + 31) ÷ 32
+    q_new = Vector{State}(undef, K)
+    out_bits, in_bits = zeros(UInt32, words, K), zeros(UInt32, words, K)   # column r = row r in C
+    old = Int32.(v.neighbors .- 1)
+    succ, hit = Vector{Int32}(undef, length(old) + K + 1), Vector{UInt8}(undef, length(old) + K + 1)
+    n_new, n_succ, w = Ref{Int32}(0), Ref{Int32}(0), Ref{Int32}(0)
+    Q_ids = Int32[u.id - 1 for u in S_Q]
+    check(ccall((:mrmp_sssp_expand, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Cvoid}, UInt64, UInt64, Cint, Float64, Float64,
+                 Ptr{Int32}, Cint, Ptr{Int32}, Cint, Ref{Int32}, Ptr{State}, Ref{Int32},
+                 Ptr{UInt32}, Ptr{UInt32}, Int64, Ref{Int32}, Ptr{Int32}, Ptr{UInt8}),
+                s.h, i - 1, v.id - 1, K, C_NULL, seed, t0, steering_depth,
+                isnothing(epsilon) ? NaN : epsilon, min_dist_thread, Q_ids, length(old), old,
+                slow ? 1 : 0, n_new, q_new, w, out_bits, in_bits, length(out_bits), n_succ, succ,
+                hit))
+    bit(B, r, t) = (B[(t >> 5) + 1, r] >> (t & 31)) & 0x1 == 0x1
+    for r = 1:n_new[]                      # same push! order as sssp.jl:252-262
+        id = nv0 + r
+        u = Node{State}(q_new[r], id, [t + 1 for t = 0:id-2 if bit(out_bits, r, t)])
+        push!(roadmap, u)
+        foreach(t -> push!(roadmap[t+1].neighbors, id), [t for t = 0:id-1 if bit(in_bits, r, t)])
+    end
+    return [(Int64(succ[k]) + 1, hit[k] != 0) for k = 1:n_succ[]]
 end
 
 end # module
