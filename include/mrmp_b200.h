@@ -296,6 +296,18 @@ int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_samples, const d
                      int64_t bits_cap_words, int32_t *n_succ_out, int32_t *succ_ids,
                      uint8_t *succ_collide);
 
+/* ---- distance tables: get_distance_table(s) (src/solvers/utils.jl:146-236) ------------------ */
+/* n_graphs roadmaps at once (SSSP after every expansion that added a vertex, sssp.jl:193;
+ * PP / CBS for all agents up front, pp.jl:161, cbs.jl:197).  Graph g owns vertices
+ * v_off[g] .. v_off[g+1]-1 of nodes[V][d]; row_ptr[V+1] / col_idx is the CSR of the neighbour
+ * lists (col ids local to the graph); goal[g] is the local id of the goal vertex
+ * (roadmap[2] in the reference).  tables_out[V]: table[u] = cost from the goal along the
+ * neighbour lists with g = dist(v.q, u.q) + table[v], Inf where unreachable -- bit-identical to
+ * the reference's Dijkstra (the minimum over paths does not depend on relaxation order). */
+int mrmp_distance_tables(mrmp_ctx *ctx, int n_graphs, const int32_t *v_off, const double *nodes,
+                         const int32_t *row_ptr, const int32_t *col_idx, const int32_t *goal,
+                         double *tables_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,10 +298,17 @@ class Oracle:
         self._lib.orc_sample_state(self._h, int(seed), int(agent), int(t), _p(q, _dp))
         return q
 
-    def sample_free(self, agent, seed, n_wanted, max_tries=1 << 40):
+    def sample_free(self, agent, seed, n_wanted, max_tries=None):
+        """First n_wanted free samples in try order -> (q, tries).  Gives up (RuntimeError)
+        after 16384 tries per wanted sample, like the library (an agent without any free
+        posture would otherwise loop forever)."""
         q = np.empty((n_wanted, self.d))
+        explicit = max_tries is not None
+        max_tries = int(max_tries) if explicit else (1 << 14) * max(int(n_wanted), 1)
         tried = self._lib.orc_sample_free(self._h, int(agent), int(seed), int(n_wanted),
-                                          _p(q, _dp), int(max_tries))
+                                          _p(q, _dp), max_tries)
+        if tried < 0 and not explicit:
+            raise RuntimeError("oracle: free-space sampling gave up for agent %d" % agent)
         return q, int(tried)
 
     def prm_build(self, agent0, nodes, rad, cap=None, nthreads=1):

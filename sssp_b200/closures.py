@@ -238,6 +238,29 @@ class Context:
                                        int(reversed), C.byref(idx), C.byref(dist)))
         return int(idx.value), float(dist.value)
 
+    def distance_tables(self, graphs, goal: int = 1):
+        """get_distance_table for several roadmaps in one launch (solvers/utils.jl:146-236).
+        graphs: list of (nodes [nv][d], neighbour lists) ; returns a list of float64 tables."""
+        v_off = np.zeros(len(graphs) + 1, np.int32)
+        nodes, rp, ci = [], [np.zeros(1, np.int64)], []
+        for g, (q, nbrs) in enumerate(graphs):
+            q = _states(q, self.d)
+            v_off[g + 1] = v_off[g] + q.shape[0]
+            nodes.append(q)
+            deg = np.fromiter((len(x) for x in nbrs), np.int64, count=len(nbrs))
+            rp.append(rp[-1][-1] + np.cumsum(deg))
+            ci.append(np.fromiter((u for x in nbrs for u in x), np.int32, count=int(deg.sum())))
+        nodes = np.ascontiguousarray(np.concatenate(nodes))
+        row_ptr = np.concatenate(rp).astype(np.int32)
+        col = np.ascontiguousarray(np.concatenate(ci)) if ci else np.zeros(0, np.int32)
+        goals = np.full(len(graphs), goal, np.int32)
+        out = np.empty(nodes.shape[0])
+        L.check(self._lib.mrmp_distance_tables(self._h, len(graphs), L.ptr(v_off, L._ip),
+                                               L.ptr(nodes, L._dp), L.ptr(row_ptr, L._ip),
+                                               L.ptr(col, L._ip) if col.size else None,
+                                               L.ptr(goals, L._ip), L.ptr(out, L._dp)))
+        return [out[v_off[g]: v_off[g + 1]].copy() for g in range(len(graphs))]
+
     def prm_build(self, nodes, rad, agent0: int = 0):
         """nodes [n][nv][d], rad scalar/array/None -> (row_ptr [n*nv+1], col_idx [nnz])"""
         nodes = L.f64(nodes)

@@ -304,3 +304,54 @@ extern "C" int mrmp_nearest(mrmp_ctx *c, int n_v, const double *V, const double 
     if (dist_out) *dist_out = *(const double *)(c->small_h + o_out);
     return MRMP_OK;
 }
+
+// ---- distance tables -----------------------------------------------------------------------------
+extern "C" int mrmp_distance_tables(mrmp_ctx *c, int n_graphs, const int32_t *v_off,
+                                    const double *nodes, const int32_t *row_ptr,
+                                    const int32_t *col_idx, const int32_t *goal,
+                                    double *tables_out) {
+    NEED(c && n_graphs >= 0, "bad ctx / n_graphs");
+    if (n_graphs == 0) return MRMP_OK;
+    NEED(v_off && nodes && row_ptr && goal && tables_out, "NULL buffer");
+    const int64_t V = v_off[n_graphs];
+    NEED(v_off[0] == 0 && V >= 1, "v_off must start at 0");
+    for (int g = 0; g < n_graphs; ++g) {
+        const int nv = v_off[g + 1] - v_off[g];
+        if (nv < 1 || (unsigned)goal[g] >= (unsigned)nv)
+            return fail(MRMP_ERR_INVALID, "graph %d: empty or goal out of range", g);
+    }
+    const int64_t E = row_ptr[V];
+    NEED(E >= 0 && (E == 0 || col_idx), "bad CSR");
+    CU(cudaSetDevice(c->device));
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t o = off;
+        off = align16(off + bytes);
+        return o;
+    };
+    const size_t o_voff = take(4 * (size_t)(n_graphs + 1)), o_goal = take(4 * (size_t)n_graphs),
+                 o_rp = take(4 * (size_t)(V + 1)), o_ci = take(4 * (size_t)E),
+                 o_nodes = take(sizeof(double) * c->d * (size_t)V);
+    const size_t in_end = off;
+    const size_t o_tab = take(sizeof(double) * (size_t)V), o_w = take(sizeof(double) * (size_t)E);
+    int rc = ensure_scratch(c, 5, off);
+    if (rc) return rc;
+    rc = ensure_small(c, in_end > sizeof(double) * (size_t)V ? in_end : sizeof(double) * (size_t)V);
+    if (rc) return rc;
+    unsigned char *h = c->small_h, *b = c->scratch[5];
+    memcpy(h + o_voff, v_off, 4 * (size_t)(n_graphs + 1));
+    memcpy(h + o_goal, goal, 4 * (size_t)n_graphs);
+    memcpy(h + o_rp, row_ptr, 4 * (size_t)(V + 1));
+    if (E) memcpy(h + o_ci, col_idx, 4 * (size_t)E);
+    memcpy(h + o_nodes, nodes, sizeof(double) * c->d * (size_t)V);
+    cudaStream_t st = c->s_k;
+    CU(cudaMemcpyAsync(b, h, in_end, cudaMemcpyHostToDevice, st));
+    CU(launch_distance_tables(c->cv, lcfg(c, st), n_graphs, (const int32_t *)(b + o_voff),
+                              (const int32_t *)(b + o_rp), (const int32_t *)(b + o_ci),
+                              (const double *)(b + o_nodes), (const int32_t *)(b + o_goal),
+                              (double *)(b + o_w), (double *)(b + o_tab)));
+    CU(cudaMemcpyAsync(h, b + o_tab, sizeof(double) * (size_t)V, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(tables_out, h, sizeof(double) * (size_t)V);
+    return MRMP_OK;
+}

@@ -511,6 +511,67 @@ k_nearest(CtxView cv, int n_v, const double *__restrict__ V, const double *__res
     }
 }
 
+// ---- distance tables (solvers/utils.jl:146-179), one CTA per roadmap -------------------------
+// The reference runs Dijkstra from the goal vertex along the neighbour lists with
+// g = dist(v.q, u.q) + table[v].  Rounded addition of a non-negative weight is monotone, so the
+// table is the minimum over all paths of the left-to-right accumulated rounded sum -- a value
+// that does not depend on the order in which edges are relaxed.  Parallel relaxation of all
+// edges to a fixed point (Bellman-Ford with atomicMin on the bit patterns of non-negative
+// doubles) therefore yields bit-identical tables.
+template <class M>
+__global__ void __launch_bounds__(512)
+k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *__restrict__ row_ptr,
+                  const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
+                  const int32_t *__restrict__ goal, double *__restrict__ w,
+                  double *__restrict__ table) {
+    constexpr int D = M::SD;
+    __shared__ int s_changed;
+    const int g = blockIdx.x;
+    const int v0 = v_off[g], nv = v_off[g + 1] - v0;
+    const int64_t e0 = row_ptr[v0], e1 = row_ptr[v0 + nv];
+    const double *tab = nodes + (int64_t)v0 * D;
+    unsigned long long *T = reinterpret_cast<unsigned long long *>(table + v0);
+    // edge lengths dist(v.q, u.q), one warp per row
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int v = warp; v < nv; v += n_warps) {
+        double qv[D];
+        load_state<D>(tab, v, qv);
+        for (int64_t e = row_ptr[v0 + v] + lane; e < row_ptr[v0 + v + 1]; e += 32) {
+            double qu[D];
+            load_state<D>(tab, col_idx[e], qu);
+            w[e] = M::dist(cv, qv, qu);
+        }
+    }
+    for (int v = threadIdx.x; v < nv; v += blockDim.x)
+        T[v] = v == goal[g] ? 0ull : 0x7ff0000000000000ull;  // typemax(Float64) == Inf
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        bool changed = false;
+        for (int v = warp; v < nv; v += n_warps) {
+            const double d = __longlong_as_double((long long)T[v]);
+            if (d == CUDART_INF) continue;
+            for (int64_t e = row_ptr[v0 + v] + lane; e < row_ptr[v0 + v + 1]; e += 32) {
+                const double cand = dadd(w[e], d);  // g_func(v.q, u.q) + d   (:168)
+                if (cand == cand) {                  // NaN never wins `g < table[u]`
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(cand);
+                    if (bits < T[col_idx[e]]) {
+                        atomicMin(&T[col_idx[e]], bits);
+                        changed = true;
+                    }
+                }
+            }
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        if (!s_changed) break;
+        __syncthreads();
+    }
+    (void)e0;
+    (void)e1;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 #define MRMP_MODEL_SWITCH(cv, EXPR)                      \
     switch ((cv).model) {                                \
@@ -580,6 +641,17 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
                                                                    h_hdr, h_qnew, h_bits, h_succ, h_verdict);
     }
     if (e != cudaSuccess) return e;
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_distance_tables(const CtxView &cv, const LaunchCfg &lc, int n_graphs,
+                                   const int32_t *v_off, const int32_t *row_ptr,
+                                   const int32_t *col_idx, const double *nodes,
+                                   const int32_t *goal, double *w, double *table) {
+    if (n_graphs <= 0) return cudaSuccess;
+    MRMP_MODEL_SWITCH(cv, (k_distance_tables<M><<<n_graphs, 512, 0, lc.stream>>>(
+                              cv, v_off, row_ptr, col_idx, nodes, goal, w, table)));
     count_launch();
     return cudaGetLastError();
 }

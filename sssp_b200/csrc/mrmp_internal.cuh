@@ -240,6 +240,12 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
                                      const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
                                      double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
                                      uint8_t *h_verdict);
+// v_off[n_graphs+1] vertex offsets; row_ptr over all vertices, col_idx local to each graph;
+// w = scratch for one double per edge; table[total vertices]
+cudaError_t launch_distance_tables(const CtxView &cv, const LaunchCfg &lc, int n_graphs,
+                                   const int32_t *v_off, const int32_t *row_ptr,
+                                   const int32_t *col_idx, const double *nodes,
+                                   const int32_t *goal, double *w, double *table);
 cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
                             const double *q1, const double *q2, double *out);
 cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,

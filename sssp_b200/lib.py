@@ -93,6 +93,7 @@ _SIGS = {
     "mrmp_state_dist": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "mrmp_mid_status": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "mrmp_nearest": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, _ip, _dp]),
+    "mrmp_distance_tables": (C.c_int, [_vp, C.c_int, _ip, _dp, _ip, _ip, _ip, _dp]),
     "mrmp_sssp_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "mrmp_sssp_destroy": (None, [_vp]),
     "mrmp_sssp_set_roadmap": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),

@@ -8,11 +8,10 @@ return value `(solution, roadmaps)`.  What runs where:
       conn(q_new, v.q) / conn(v.q, q_new) against the whole roadmap (:252-262), and the
       successor filter collide(S.Q, p.q, i) / collide(S.Q, Q) (:206-207);
       the all-pairs edge pass of the initial roadmaps (:388-395) = `mrmp_prm_build`;
-      edge lengths of the distance tables (solvers/utils.jl:168) = one `mrmp_state_dist` batch.
+      the distance tables (solvers/utils.jl:146-179) = `mrmp_distance_tables`.
   host (as in the reference: branchy, sequential)
       the best-first search: OPEN / VISITED, successor generation, backtracking (:146-232);
-      RRT-Connect tree growth (:372-401) -- sequential by construction, each test one GPU call;
-      Dijkstra over the edge lengths.
+      RRT-Connect tree growth (:372-401) -- sequential by construction, each test one GPU call.
 
 Ids are 0-based.  The reference draws samples from Julia's global RNG; here `sampler()` of
 agent i is the next try of the library's counter-based stream (seed, i), so runs are
@@ -104,29 +103,16 @@ def gen_g_func(greedy: bool = False, stay_penalty: float = 0.0, ctx: Optional[Co
 
 
 def get_distance_table(ctx: Context, nodes: np.ndarray, nbrs: List[List[int]], goal: int = 1):
-    """solvers/utils.jl:146-179: Dijkstra from the goal vertex along the neighbour lists.
-    Edge lengths dist(v.q, u.q) come from the GPU in one batch."""
-    nv = len(nbrs)
-    src = np.repeat(np.arange(nv), [len(x) for x in nbrs])
-    dst = np.fromiter((u for x in nbrs for u in x), dtype=np.int64, count=src.size)
-    w = ctx.state_dist(nodes[src], nodes[dst]) if src.size else np.zeros(0)
-    start = np.concatenate([[0], np.cumsum([len(x) for x in nbrs])])
-    table = [math.inf] * nv
-    table[goal] = 0.0
-    OPEN = PriorityQueue()
-    OPEN.enqueue(goal, 0.0)
-    while len(OPEN):
-        v = OPEN.dequeue()
-        d = table[v]
-        for e in range(start[v], start[v + 1]):
-            u = int(dst[e])
-            g = float(w[e]) + d
-            if g < table[u]:
-                if u in OPEN:
-                    OPEN.delete(u)
-                table[u] = g
-                OPEN.enqueue(u, g)
-    return table
+    """solvers/utils.jl:146-179: cost-to-go from the goal vertex along the neighbour lists.
+    Runs on the GPU (mrmp_distance_tables: parallel edge relaxation to the fixed point, which
+    equals the reference's Dijkstra bit for bit)."""
+    return ctx.distance_tables([(nodes, nbrs)], goal)[0].tolist()
+
+
+def get_distance_tables(ctx: Context, roadmaps, goal: int = 1):
+    """solvers/utils.jl:226-236 for Vector{Vector{Node}} roadmaps: all agents in one launch."""
+    graphs = [(np.array([tuple(v.q) for v in rm]), [list(v.neighbors) for v in rm]) for rm in roadmaps]
+    return [t.tolist() for t in ctx.distance_tables(graphs, goal)]
 
 
 class _AgentSampler:
@@ -236,7 +222,7 @@ def SSSP(config_init: Sequence, config_goal: Sequence, connect: Callable, collid
     dev = SsspRoadmaps(ctx, nv_cap=max(64, 2 * max(t.shape[0] for t in tabs)))
     for i in range(N):
         dev.set_roadmap(i, tabs[i])
-    tables = [get_distance_table(ctx, tabs[i], nbrs[i]) for i in range(N)]
+    tables = [t.tolist() for t in ctx.distance_tables(list(zip(tabs, nbrs)))]
 
     def h_func(ids) -> float:
         if use_random_h_func:

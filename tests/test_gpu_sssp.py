@@ -135,3 +135,38 @@ def test_model_helpers_match_oracle():
                 ds = [orc.state_dist(q, v) if rev else orc.state_dist(v, q) for v in V]
                 idx, dd = ctx.nearest(V, q, reversed=rev)
                 assert idx == int(np.argmin(ds)) and dd == min(ds)
+
+
+def test_distance_tables_match_the_oracle_dijkstra():
+    """mrmp_distance_tables (parallel relaxation to the fixed point) == the reference's Dijkstra
+    (solvers/utils.jl:146-179) bit for bit, for PRM roadmaps of all three models incl. vertices
+    the goal cannot reach (Inf) and several roadmaps per launch."""
+    from helpers import make_point_instance, make_arm_instance
+    rng = np.random.default_rng(12)
+    for model, d in ((O.POINT2D, 2), (O.POINT3D, 3), (O.ARM22, 2)):
+        N, nv = 5, 260
+        if model == O.ARM22:
+            rads, obs, base = make_arm_instance(N, 2, 19)
+            nv = 90
+        else:
+            (rads, obs), base = make_point_instance(model, N, 10, seed=3), None
+        ctx = S.Context(model, rads, obs, base_pos=base)
+        orc = O.Oracle(model, rads, obs, base=base)
+        nodes = np.stack([orc.sample_free(a, 5, nv)[0] for a in range(N)])
+        if model != O.ARM22:
+            nodes[:, nv - 1] = 3.0          # outside the field: no edge leads there -> Inf
+        rad = 0.12 if model == O.POINT2D else 0.3
+        rp, col, nnz = orc.prm_build(0, nodes, rad, nthreads=0)
+        graphs, want = [], []
+        for a in range(N):
+            nb = [col[a, rp[a, v]:rp[a, v + 1]].tolist() for v in range(nv)]
+            graphs.append((nodes[a], nb))
+            want.append(orc.distance_table(nodes[a], rp[a], col[a, :nnz[a]], goal=1))
+        got = ctx.distance_tables(graphs, goal=1)
+        for a in range(N):
+            assert np.array_equal(got[a].view(np.uint64), want[a].view(np.uint64)), (model, a)
+        assert model == O.ARM22 or all(np.isinf(w[nv - 1]) for w in want)
+        assert all(np.isfinite(w).sum() > nv // 2 for w in want)
+    # the host-side helper of the solver mirror
+    t = solvers.get_distance_table(ctx, graphs[0][0], graphs[0][1])
+    assert np.array_equal(np.array(t).view(np.uint64), want[0].view(np.uint64))
