@@ -308,6 +308,17 @@ int mrmp_distance_tables(mrmp_ctx *ctx, int n_graphs, const int32_t *v_off, cons
                          const int32_t *row_ptr, const int32_t *col_idx, const int32_t *goal,
                          double *tables_out);
 
+/* ---- validate(config_init, connect, collide, check_goal, solution): utils.jl:320-367 -------- */
+/* The transition checks of validate (:345-363) for a whole solution in two launches:
+ * solution[T][N][d] (configuration per time step).  For t = 1..T-1 (0-based), in the
+ * reference's order: connect(solution[t-1][i], solution[t][i], i) for i ascending, then
+ * collide(solution[t-1], solution[t]).  ok_out = 1 when every check passes; otherwise the first
+ * failure: t_out = t, kind_out = 1 (not connected, agent i_out) or 2 (colliding, first pair
+ * i_out < j_out).  The initial-configuration and goal tests (:333-343) are O(N) equality
+ * tests and stay with the caller. */
+int mrmp_validate_solution(mrmp_ctx *ctx, int64_t T, const double *solution, int32_t *ok_out,
+                           int64_t *t_out, int32_t *kind_out, int32_t *i_out, int32_t *j_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -510,6 +510,66 @@ extern "C" int mrmp_collide_config_moves(mrmp_ctx *c, int agent_i, const double 
     });
 }
 
+// ---- validate (src/utils.jl:345-363): all transitions of a solution in two launches ----------
+extern "C" int mrmp_validate_solution(mrmp_ctx *c, int64_t T, const double *solution,
+                                      int32_t *ok_out, int64_t *t_out, int32_t *kind_out,
+                                      int32_t *i_out, int32_t *j_out) {
+    NEED(c && T >= 1 && solution && ok_out, "bad arguments");
+    const int N = c->n_agents, d = c->d;
+    *ok_out = 1;
+    if (t_out) *t_out = -1;
+    if (kind_out) *kind_out = 0;
+    if (i_out) *i_out = -1;
+    if (j_out) *j_out = -1;
+    if (T == 1) return MRMP_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t nt = T - 1, n_con = nt * N;
+    const size_t sol_b = sizeof(double) * d * (size_t)N * T;
+    const size_t o_ag = align16(sol_b), o_con = align16(o_ag + 4 * (size_t)n_con),
+                 o_col = align16(o_con + (size_t)n_con), o_fp = align16(o_col + (size_t)nt),
+                 tot = o_fp + 8 * (size_t)nt;
+    int rc = ensure_scratch(c, 1, tot);
+    if (rc) return rc;
+    std::vector<unsigned char> hbuf(tot);
+    int32_t *ag = (int32_t *)(hbuf.data() + o_ag);
+    for (int64_t k = 0; k < n_con; ++k) ag[k] = (int32_t)(k % N);
+    unsigned char *b = c->scratch[1];
+    cudaStream_t s = c->s_k;
+    CU(cudaMemcpyAsync(b, solution, sol_b, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b + o_ag, ag, 4 * (size_t)n_con, cudaMemcpyHostToDevice, s));
+    const double *sol_d = (const double *)b;
+    const double *next_d = sol_d + (size_t)N * d;  // configuration t+1 follows configuration t
+    // connect(solution[t-1][i].q, solution[t][i].q, i)  for every t, i   (:347-358)
+    CU(launch_connect_edges(c->cv, lcfg(c, s), n_con, (const int32_t *)(b + o_ag), sol_d, next_d,
+                            b + o_con));
+    // collide(solution[t-1], solution[t])  for every t, with the first colliding pair (:360)
+    CU(launch_collide_configs(c->cv, lcfg(c, s), nt, sol_d, next_d, b + o_col,
+                              (int64_t *)(b + o_fp)));
+    CU(cudaMemcpyAsync(hbuf.data() + o_con, b + o_con, tot - o_con, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint8_t *con = hbuf.data() + o_con, *col = hbuf.data() + o_col;
+    const int64_t *fp = (const int64_t *)(hbuf.data() + o_fp);
+    for (int64_t t = 0; t < nt; ++t) {  // the reference's order: per step, connectivity first
+        for (int i = 0; i < N; ++i)
+            if (!con[t * N + i]) {
+                *ok_out = 0;
+                if (t_out) *t_out = t + 1;
+                if (kind_out) *kind_out = 1;
+                if (i_out) *i_out = i;
+                return MRMP_OK;
+            }
+        if (col[t]) {
+            *ok_out = 0;
+            if (t_out) *t_out = t + 1;
+            if (kind_out) *kind_out = 2;
+            if (i_out) *i_out = (int32_t)(fp[t] / N);
+            if (j_out) *j_out = (int32_t)(fp[t] % N);
+            return MRMP_OK;
+        }
+    }
+    return MRMP_OK;
+}
+
 // ---- device-pointer forms --------------------------------------------------------------------
 #define DEV_PROLOGUE(c, n)                          \
     NEED(c && n >= 0, "bad ctx / n");               \

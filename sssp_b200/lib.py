@@ -93,6 +93,9 @@ _SIGS = {
     "mrmp_state_dist": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "mrmp_mid_status": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "mrmp_nearest": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, _ip, _dp]),
+    "mrmp_validate_solution": (C.c_int, [_vp, C.c_int64, _dp, C.POINTER(C.c_int32), _lp,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32)]),
     "mrmp_distance_tables": (C.c_int, [_vp, C.c_int, _ip, _dp, _ip, _ip, _ip, _dp]),
     "mrmp_sssp_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "mrmp_sssp_destroy": (None, [_vp]),

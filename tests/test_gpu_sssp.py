@@ -170,3 +170,54 @@ def test_distance_tables_match_the_oracle_dijkstra():
     # the host-side helper of the solver mirror
     t = solvers.get_distance_table(ctx, graphs[0][0], graphs[0][1])
     assert np.array_equal(np.array(t).view(np.uint64), want[0].view(np.uint64))
+
+
+def _oracle_validate(orc, N, sol):
+    """utils.jl:345-363 as the sequential loop over the oracle closures -> first failure."""
+    for t in range(1, len(sol)):
+        for i in range(N):
+            if not orc.connect_edge(sol[t - 1][i], sol[t][i], i):
+                return ("not connected", t, i)
+        hit, fp = orc.collide_configs(sol[t - 1], sol[t])
+        if hit:
+            return ("colliding", t, fp // N, fp % N)
+    return None
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-5] for p in GOLD])
+def test_validate_matches_the_sequential_reference_loop(path):
+    """validate (utils.jl:320-367) in two launches == the oracle's per-step loop: golden SSSP
+    solutions are valid; corrupted ones fail at the same first check."""
+    fx, inst, orc, base = load(path)
+    connect, collide, check_goal, State = closures(inst, base)
+    N = len(inst["rads"])
+    tabs = [np.array([[float.fromhex(x) for x in q] for q in g["nodes"]]) for g in fx["roadmaps"]]
+    sol = np.array([[tabs[i][ids[i]] for i in range(N)] for ids in fx["solution"]])
+    as_nodes = lambda arr: [[S.Node(State(*q), 0) for q in Q] for Q in arr]
+    init = [State(*q) for q in inst["config_init"]]
+    assert S.validate(init, connect, collide, check_goal, as_nodes(sol)) is True
+    assert _oracle_validate(orc, N, sol) is None
+    assert S.validate(init, connect, collide, check_goal, None) is True
+    assert S.is_valid_instance(init, [State(*q) for q in inst["config_goal"]], connect, collide)
+    rng = np.random.default_rng(8)
+    seen = set()
+    for trial in range(12):
+        bad = sol.copy()
+        t = int(rng.integers(1, len(sol) - 1)) if len(sol) > 2 else 1
+        i = int(rng.integers(0, N))
+        if trial % 2 == 0:      # teleport one agent for one step: usually disconnects or collides
+            bad[t, i] = tabs[i][int(rng.integers(0, len(tabs[i])))]
+        else:                   # put agent i on top of agent j's state
+            j = (i + 1) % N
+            bad[t:, i] = bad[t, j] if inst["model"] != O.ARM22 else bad[t, i] + 1.0
+        want = _oracle_validate(orc, N, bad)
+        got = S.validate(init, connect, collide, lambda Q: True, as_nodes(bad))
+        assert got is (want is None)
+        if want is not None:
+            assert S.validate.last_failure == want
+            seen.add(want[0])
+    assert seen, "no corrupted solution was rejected"
+    # a wrong first configuration is caught before any GPU work
+    bad = sol.copy()
+    bad[0, 0] = bad[0, 0] + 0.25
+    assert S.validate(init, connect, collide, check_goal, as_nodes(bad)) is False
