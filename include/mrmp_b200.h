@@ -319,6 +319,17 @@ int mrmp_distance_tables(mrmp_ctx *ctx, int n_graphs, const int32_t *v_off, cons
 int mrmp_validate_solution(mrmp_ctx *ctx, int64_t T, const double *solution, int32_t *ok_out,
                            int64_t *t_out, int32_t *kind_out, int32_t *i_out, int32_t *j_out);
 
+/* ---- first conflict of a joint plan: get_constraints (src/solvers/cbs.jl:374-412) ------------- */
+/* configs[T][N][d] = convert_paths_to_configurations(paths) (solvers/utils.jl:128-134: agents
+ * that arrived wait at their last vertex).  Scans t = 1..T-1 and pairs i < j in the reference's
+ * order; per pair the vertex conflict collide(q_i_to, q_j_to, i, j) (:391) is tested before
+ * the edge conflict collide(q_i_from, q_i_to, q_j_from, q_j_to, i, j) (:401).  t_out = -1 when
+ * the plan is conflict free, else the step, kind_out = 1 (vertex) / 2 (edge) and the pair.
+ * (With check_all_collisions the reference still returns at the first vertex conflict because
+ * of `&` at :395; later conflicts are obtained by calling again on the remaining steps.) */
+int mrmp_first_conflict(mrmp_ctx *ctx, int64_t T, const double *configs, int64_t *t_out,
+                        int32_t *kind_out, int32_t *i_out, int32_t *j_out);
+
 #ifdef __cplusplus
 }
 #endif

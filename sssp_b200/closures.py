@@ -238,6 +238,17 @@ class Context:
                                        int(reversed), C.byref(idx), C.byref(dist)))
         return int(idx.value), float(dist.value)
 
+    def first_conflict(self, configs):
+        """get_constraints' scan (cbs.jl:374-412) over configs [T][N][d]: None when conflict
+        free, else (t, kind, i, j) with kind 'vertex' / 'edge' of the first conflict."""
+        cfg = L.f64(configs).reshape(-1, self.N, self.d)
+        t, kind, i, j = C.c_int64(-1), C.c_int32(0), C.c_int32(-1), C.c_int32(-1)
+        L.check(self._lib.mrmp_first_conflict(self._h, cfg.shape[0], L.ptr(cfg, L._dp), C.byref(t),
+                                              C.byref(kind), C.byref(i), C.byref(j)))
+        if t.value < 0:
+            return None
+        return int(t.value), "vertex" if kind.value == 1 else "edge", int(i.value), int(j.value)
+
     def distance_tables(self, graphs, goal: int = 1):
         """get_distance_table for several roadmaps in one launch (solvers/utils.jl:146-236).
         graphs: list of (nodes [nv][d], neighbour lists) ; returns a list of float64 tables."""

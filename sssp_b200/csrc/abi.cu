@@ -570,6 +570,51 @@ extern "C" int mrmp_validate_solution(mrmp_ctx *c, int64_t T, const double *solu
     return MRMP_OK;
 }
 
+// ---- first conflict of a set of paths (CBS get_constraints, src/solvers/cbs.jl:374-412) ------
+extern "C" int mrmp_first_conflict(mrmp_ctx *c, int64_t T, const double *configs, int64_t *t_out,
+                                   int32_t *kind_out, int32_t *i_out, int32_t *j_out) {
+    NEED(c && T >= 1 && configs && t_out && kind_out && i_out && j_out, "bad arguments");
+    const int N = c->n_agents, d = c->d;
+    *t_out = -1;
+    *kind_out = 0;
+    *i_out = *j_out = -1;
+    if (T == 1 || N < 2) return MRMP_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t nt = T - 1;
+    const size_t sol_b = sizeof(double) * d * (size_t)N * T;
+    const size_t o_v = align16(sol_b), o_e = align16(o_v + (size_t)nt),
+                 o_vfp = align16(o_e + (size_t)nt), o_efp = o_vfp + 8 * (size_t)nt,
+                 tot = o_efp + 8 * (size_t)nt;
+    int rc = ensure_scratch(c, 1, tot);
+    if (rc) return rc;
+    unsigned char *b = c->scratch[1];
+    cudaStream_t s = c->s_k;
+    CU(cudaMemcpyAsync(b, configs, sol_b, cudaMemcpyHostToDevice, s));
+    const double *from = (const double *)b, *to = from + (size_t)N * d;
+    // vertex conflicts collide(q_i_to, q_j_to, i, j) (:391): stationary 6-arity checks at the
+    // target configuration -- for every model the reference's 6-arity arithmetic on two
+    // zero-length moves reduces to its 4-arity test (point.jl:9-16, arm22.jl:100-162)
+    CU(launch_collide_configs(c->cv, lcfg(c, s), nt, to, to, b + o_v, (int64_t *)(b + o_vfp)));
+    // edge conflicts collide(v_i_from.q, v_i_to.q, v_j_from.q, v_j_to.q, i, j) (:401)
+    CU(launch_collide_configs(c->cv, lcfg(c, s), nt, from, to, b + o_e, (int64_t *)(b + o_efp)));
+    std::vector<int64_t> fp(2 * (size_t)nt);
+    CU(cudaMemcpyAsync(fp.data(), b + o_vfp, 16 * (size_t)nt, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int64_t t = 0; t < nt; ++t) {
+        const int64_t v = fp[t], e = fp[nt + t];
+        if (v < 0 && e < 0) continue;
+        // per pair the vertex test comes first, so a tie on the pair goes to the vertex conflict
+        const bool vertex = v >= 0 && (e < 0 || v <= e);
+        const int64_t pr = vertex ? v : e;
+        *t_out = t + 1;
+        *kind_out = vertex ? 1 : 2;
+        *i_out = (int32_t)(pr / N);
+        *j_out = (int32_t)(pr % N);
+        return MRMP_OK;
+    }
+    return MRMP_OK;
+}
+
 // ---- device-pointer forms --------------------------------------------------------------------
 #define DEV_PROLOGUE(c, n)                          \
     NEED(c && n >= 0, "bad ctx / n");               \

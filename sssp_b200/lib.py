@@ -96,6 +96,8 @@ _SIGS = {
     "mrmp_validate_solution": (C.c_int, [_vp, C.c_int64, _dp, C.POINTER(C.c_int32), _lp,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int32)]),
+    "mrmp_first_conflict": (C.c_int, [_vp, C.c_int64, _dp, _lp, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mrmp_distance_tables": (C.c_int, [_vp, C.c_int, _ip, _dp, _ip, _ip, _ip, _dp]),
     "mrmp_sssp_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "mrmp_sssp_destroy": (None, [_vp]),

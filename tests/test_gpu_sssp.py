@@ -221,3 +221,46 @@ def test_validate_matches_the_sequential_reference_loop(path):
     bad = sol.copy()
     bad[0, 0] = bad[0, 0] + 0.25
     assert S.validate(init, connect, collide, check_goal, as_nodes(bad)) is False
+
+
+def _oracle_first_conflict(orc, N, cfg):
+    """get_constraints (cbs.jl:384-408) as the reference's loop over the oracle closures."""
+    for t in range(1, len(cfg)):
+        for i in range(N):
+            for j in range(i + 1, N):
+                if orc.collide_static(cfg[t][i], cfg[t][j], i, j):
+                    return (t, "vertex", i, j)
+                if orc.collide_pair(cfg[t - 1][i], cfg[t][i], cfg[t - 1][j], cfg[t][j], i, j):
+                    return (t, "edge", i, j)
+    return None
+
+
+@pytest.mark.parametrize("name", ["point2d_many", "point3d", "arm22"])
+def test_first_conflict_matches_get_constraints(name):
+    """Independent single-agent plans (random walks on the golden roadmaps) conflict somewhere:
+    the batched scan must name the same first (t, kind, i, j) as the reference's loop."""
+    fx, inst, orc, base = load([p for p in GOLD if name in p][0])
+    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base)
+    N = len(inst["rads"])
+    tabs = [np.array([[float.fromhex(x) for x in q] for q in g["nodes"]]) for g in fx["roadmaps"]]
+    nbrs = [g["neighbors"] for g in fx["roadmaps"]]
+    rng = np.random.default_rng(31)
+    kinds = set()
+    for trial in range(10):
+        T = 12
+        ids = np.zeros((T, N), int)
+        for i in range(N):
+            v = int(rng.integers(0, len(tabs[i])))
+            for t in range(T):
+                ids[t, i] = v
+                if nbrs[i][v] and rng.random() < 0.8:
+                    v = int(nbrs[i][v][int(rng.integers(0, len(nbrs[i][v])))])
+        cfg = np.array([[tabs[i][ids[t, i]] for i in range(N)] for t in range(T)])
+        want = _oracle_first_conflict(orc, N, cfg)
+        assert ctx.first_conflict(cfg) == want
+        if want:
+            kinds.add(want[1])
+    # the golden SSSP solution itself is conflict free
+    sol = np.array([[tabs[i][q[i]] for i in range(N)] for q in fx["solution"]])
+    assert ctx.first_conflict(sol) is None and _oracle_first_conflict(orc, N, sol) is None
+    assert kinds, "no conflict was exercised"
