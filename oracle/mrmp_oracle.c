@@ -157,20 +157,39 @@ double orc_diff_angles(double t1, double t2) {
 /* context                                                                   */
 /* ------------------------------------------------------------------------ */
 
-orc_ctx *orc_ctx_create(int model, int n_agents, const double *rads, const double *base,
-                        int n_obs, const double *obs_aos, double step_dist,
-                        double safety_dist, double max_dist) {
-    if (model < 0 || model > 2 || n_agents <= 0 || n_obs < 0) return NULL;
+orc_ctx *orc_ctx_create2(int model, int n_agents, const double *rads, const double *base,
+                         const double *aux, int n_obs, const double *obs_aos, double step_dist,
+                         double safety_dist, double max_dist) {
+    if (model < 0 || model > ORC_CAPSULE3D || n_agents <= 0 || n_obs < 0) return NULL;
     orc_ctx *c = (orc_ctx *)calloc(1, sizeof(orc_ctx));
     c->model = model;
-    c->d = model == ORC_POINT3D ? 3 : 2;
-    c->wd = model == ORC_POINT3D ? 3 : 2;
+    if (model >= ORC_LINE2D) {
+        c->d = orc_chain_state_dim(model);
+        c->wd = orc_chain_workspace_dim(model);
+    } else {
+        c->d = model == ORC_POINT3D ? 3 : 2;
+        c->wd = model == ORC_POINT3D ? 3 : 2;
+    }
     c->n_agents = n_agents;
     c->rads = (double *)malloc(sizeof(double) * n_agents);
     memcpy(c->rads, rads, sizeof(double) * n_agents);
-    if (model == ORC_ARM22) {
-        c->base = (double *)malloc(sizeof(double) * 2 * n_agents);
-        memcpy(c->base, base, sizeof(double) * 2 * n_agents);
+    if (model == ORC_ARM22 || model == ORC_ARM33) {
+        if (!base) {
+            free(c->rads);
+            free(c);
+            return NULL;
+        }
+        c->base = (double *)malloc(sizeof(double) * c->wd * n_agents);
+        memcpy(c->base, base, sizeof(double) * c->wd * n_agents);
+    }
+    if (model == ORC_CAPSULE3D) {
+        if (!aux) {
+            free(c->rads);
+            free(c);
+            return NULL;
+        }
+        c->aux = (double *)malloc(sizeof(double) * n_agents);
+        memcpy(c->aux, aux, sizeof(double) * n_agents);
     }
     c->n_obs = n_obs;
     c->obs = (double *)malloc(sizeof(double) * (c->wd + 1) * (n_obs > 0 ? n_obs : 1));
@@ -181,10 +200,18 @@ orc_ctx *orc_ctx_create(int model, int n_agents, const double *rads, const doubl
     return c;
 }
 
+orc_ctx *orc_ctx_create(int model, int n_agents, const double *rads, const double *base,
+                        int n_obs, const double *obs_aos, double step_dist,
+                        double safety_dist, double max_dist) {
+    return orc_ctx_create2(model, n_agents, rads, base, NULL, n_obs, obs_aos, step_dist,
+                           safety_dist, max_dist);
+}
+
 void orc_ctx_destroy(orc_ctx *c) {
     if (!c) return;
     free(c->rads);
     free(c->base);
+    free(c->aux);
     free(c->obs);
     free(c);
 }
@@ -336,11 +363,13 @@ static int arm22_links_hit(const orc_ctx *c, const double *ai, const double *bi,
 /* ------------------------------------------------------------------------ */
 
 double orc_state_dist(const orc_ctx *c, const double *q1, const double *q2) {
+    if (c->model >= ORC_LINE2D) return orc_chain_dist(c, q1, q2);
     if (c->model == ORC_ARM22) return arm22_dist(q1, q2);
     return orc_dist_pp(q1, q2, c->d); /* point2d.jl:12-14, point3d.jl:13-15 */
 }
 
 void orc_mid_status(const orc_ctx *c, const double *p, const double *q, double *out) {
+    if (c->model >= ORC_LINE2D) { orc_chain_mid_status(c, p, q, out); return; };
     if (c->model == ORC_ARM22) { /* arm22.jl:8-13 */
         out[0] = orc_diff_angles(q[0], p[0]) / 2 + p[0];
         out[1] = orc_diff_angles(q[1], p[1]) / 2 + p[1];
@@ -355,6 +384,7 @@ void orc_mid_status(const orc_ctx *c, const double *p, const double *q, double *
 
 /* connect(q, i): point2d.jl:49-57, point3d.jl:54-64, arm22.jl:40-54 */
 int orc_connect_point(const orc_ctx *c, const double *q, int i) {
+    if (c->model >= ORC_LINE2D) return orc_chain_connect_point(c, q, i);
     if (c->model == ORC_ARM22) {
         double b[2], cc[2];
         const double *a = c->base + 2 * i;
@@ -374,6 +404,7 @@ int orc_connect_point(const orc_ctx *c, const double *q, int i) {
 
 /* connect(q_from, q_to, i): point2d.jl:59-66, point3d.jl:66-77, arm22.jl:56-86 */
 int orc_connect_edge(const orc_ctx *c, const double *qf, const double *qt, int i) {
+    if (c->model >= ORC_LINE2D) return orc_chain_connect_edge(c, qf, qt, i);
     if (c->model == ORC_ARM22) {
         double D = arm22_dist(qf, qt);                      /* :57 */
         if (!isnan(c->max_dist) && D > c->max_dist) return 0; /* :58 */
@@ -406,6 +437,7 @@ int orc_connect_edge(const orc_ctx *c, const double *qf, const double *qt, int i
 /* collide(qi_from,qi_to,qj_from,qj_to,i,j): point.jl:9-12, arm22.jl:100-146 */
 int orc_collide_pair(const orc_ctx *c, const double *qif, const double *qit, const double *qjf,
                      const double *qjt, int i, int j) {
+    if (c->model >= ORC_LINE2D) return orc_chain_collide_pair(c, qif, qit, qjf, qjt, i, j);
     if (c->model == ORC_ARM22) {
         double Di = arm22_dist(qif, qit), Dj = arm22_dist(qjf, qjt);
         double dt1i = orc_diff_angles(qit[0], qif[0]), dt2i = orc_diff_angles(qit[1], qif[1]);
@@ -431,6 +463,7 @@ int orc_collide_pair(const orc_ctx *c, const double *qif, const double *qit, con
 
 /* collide(q_i,q_j,i,j): point.jl:14-16, arm22.jl:148-162 */
 int orc_collide_static(const orc_ctx *c, const double *qi, const double *qj, int i, int j) {
+    if (c->model >= ORC_LINE2D) return orc_chain_collide_static(c, qi, qj, i, j);
     if (c->model == ORC_ARM22) {
         const double *ai = c->base + 2 * i, *aj = c->base + 2 * j;
         double bi[2], ci[2], bj[2], cj[2];
@@ -457,6 +490,7 @@ int orc_collide_configs(const orc_ctx *c, const double *Qf, const double *Qt,
 
 /* collide(Q, q_to, i): point.jl:27-33, arm22.jl:173-209 */
 int orc_collide_config_move(const orc_ctx *c, const double *Q, const double *q_to, int i) {
+    if (c->model >= ORC_LINE2D) return orc_chain_collide_config_move(c, Q, q_to, i);
     int N = c->n_agents, d = c->d;
     const double *qf = Q + d * i;
     if (c->model == ORC_ARM22) {
@@ -633,6 +667,17 @@ static inline double u01_53(uint32_t hi, uint32_t lo) {
  * Try t of (seed, agent) -> counter (t_lo, t_hi, agent, block), key (seed_lo, seed_hi). */
 void orc_sample_state(const orc_ctx *c, uint64_t seed, int agent, uint64_t t, double *q) {
     uint32_t r[4];
+    if (c->model >= ORC_LINE2D) { /* uniform k of a try = pair (k % 2) of Philox block k / 2 */
+        double u[6];
+        for (int b = 0; 2 * b < c->d; ++b) {
+            orc_philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, (uint32_t)b,
+                           (uint32_t)seed, (uint32_t)(seed >> 32), r);
+            u[2 * b] = u01_53(r[0], r[1]);
+            if (2 * b + 1 < c->d) u[2 * b + 1] = u01_53(r[2], r[3]);
+        }
+        orc_chain_scale_sample(c, u, q);
+        return;
+    }
     orc_philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, 0u, (uint32_t)seed,
                    (uint32_t)(seed >> 32), r);
     q[0] = u01_53(r[0], r[1]);

@@ -27,15 +27,17 @@
 extern "C" {
 #endif
 
-enum { ORC_POINT2D = 0, ORC_POINT3D = 1, ORC_ARM22 = 2 };
+enum { ORC_POINT2D = 0, ORC_POINT3D = 1, ORC_ARM22 = 2, ORC_LINE2D = 3, ORC_SNAKE2D = 4,
+       ORC_ARM33 = 5, ORC_CAPSULE3D = 6 };
 
 typedef struct orc_ctx {
     int model;          /* ORC_* */
-    int d;              /* state dimension: 2, 3, 2 */
-    int wd;             /* workspace dimension (obstacle centre dim): 2, 3, 2 */
+    int d;              /* state dimension: 2, 3, 2, 3, 6, 6, 6 */
+    int wd;             /* workspace dimension (obstacle centre dim): 2, 3, 2, 2, 2, 3, 3 */
     int n_agents;
     double *rads;       /* [n_agents]  agent radius (points) / link length (arm22) */
-    double *base;       /* [n_agents*2] arm22 base positions, else NULL */
+    double *base;       /* [n_agents*wd] arm22 / arm33 base positions, else NULL */
+    double *aux;        /* [n_agents] capsule3d axis lengths (axises), else NULL */
     int n_obs;
     double *obs;        /* AoS [n_obs*(wd+1)]: x,y,(z),r  (src/obstacle.jl:7-19) */
     double step_dist;   /* src/MRMP.jl:65 */
@@ -46,6 +48,10 @@ typedef struct orc_ctx {
 orc_ctx *orc_ctx_create(int model, int n_agents, const double *rads, const double *base,
                         int n_obs, const double *obs_aos, double step_dist,
                         double safety_dist, double max_dist);
+/* same with the second per-agent parameter of capsule3d (axises, capsule3d.jl:61-68) */
+orc_ctx *orc_ctx_create2(int model, int n_agents, const double *rads, const double *base,
+                         const double *aux, int n_obs, const double *obs_aos, double step_dist,
+                         double safety_dist, double max_dist);
 void orc_ctx_destroy(orc_ctx *c);
 
 /* geometry: src/utils.jl:17-99 */
@@ -146,6 +152,19 @@ int orc_sssp_expand(const orc_ctx *c, int agent, double *nodes, int nv, int v_fr
                     uint32_t *out_bits, uint32_t *in_bits, const double *Q, int n_old,
                     const int32_t *old_nbrs, int slow, int32_t *succ_ids, uint8_t *succ_collide,
                     int *n_succ);
+
+/* orc_chain.c: line2d / snake2d / arm33 / capsule3d (dispatched to by the functions above) */
+int orc_chain_state_dim(int model);
+int orc_chain_workspace_dim(int model);
+double orc_chain_dist(const orc_ctx *c, const double *q1, const double *q2);
+void orc_chain_mid_status(const orc_ctx *c, const double *p, const double *q, double *out);
+int orc_chain_connect_point(const orc_ctx *c, const double *q, int i);
+int orc_chain_connect_edge(const orc_ctx *c, const double *qf, const double *qt, int i);
+int orc_chain_collide_static(const orc_ctx *c, const double *qi, const double *qj, int i, int j);
+int orc_chain_collide_pair(const orc_ctx *c, const double *qif, const double *qit,
+                           const double *qjf, const double *qjt, int i, int j);
+int orc_chain_collide_config_move(const orc_ctx *c, const double *Q, const double *q_to, int i);
+void orc_chain_scale_sample(const orc_ctx *c, const double *u, double *q);
 
 int orc_dot_is_fma(void);
 int orc_max_threads(void);

@@ -14,8 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-POINT2D, POINT3D, ARM22 = 0, 1, 2
-_D = {POINT2D: 2, POINT3D: 3, ARM22: 2}
+POINT2D, POINT3D, ARM22, LINE2D, SNAKE2D, ARM33, CAPSULE3D = 0, 1, 2, 3, 4, 5, 6
+_D = {POINT2D: 2, POINT3D: 3, ARM22: 2, LINE2D: 3, SNAKE2D: 6, ARM33: 6, CAPSULE3D: 6}   # state dim
+_W = {POINT2D: 2, POINT3D: 3, ARM22: 2, LINE2D: 2, SNAKE2D: 2, ARM33: 3, CAPSULE3D: 3}   # workspace dim
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -38,6 +39,9 @@ def _load(name: str) -> C.CDLL:
     lib.orc_ctx_create.restype = C.c_void_p
     lib.orc_ctx_create.argtypes = [C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_double,
                                    C.c_double, C.c_double]
+    lib.orc_ctx_create2.restype = C.c_void_p
+    lib.orc_ctx_create2.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _dp, C.c_double,
+                                    C.c_double, C.c_double]
     lib.orc_ctx_destroy.argtypes = [C.c_void_p]
     for f in ("orc_norm", "orc_dist_pp", "orc_dist_sp", "orc_dist_ss", "orc_diff_angles",
               "orc_sin", "orc_cos", "orc_atan2", "orc_state_dist", "orc_dot"):
@@ -162,21 +166,26 @@ def philox4x32(ctr, key):
 class Oracle:
     """CPU restatement of gen_connect / gen_collide closures for one instance."""
 
-    def __init__(self, model, rads, obstacles, base=None, step_dist=0.01, safety_dist=0.01,
-                 max_dist=math.nan, dot_fma=False):
+    def __init__(self, model, rads, obstacles, base=None, step_dist=None, safety_dist=0.01,
+                 max_dist=math.nan, dot_fma=False, aux=None):
         self.model = int(model)
         self.d = _D[self.model]
+        self.wd = _W[self.model]
         self.rads = _f64(rads).ravel()
         self.N = self.rads.size
-        self.obs = _f64(obstacles).reshape(-1, self.d + 1) if np.size(obstacles) else \
-            np.zeros((0, self.d + 1))
-        self.base = None if base is None else _f64(base).reshape(self.N, 2)
+        self.obs = _f64(obstacles).reshape(-1, self.wd + 1) if np.size(obstacles) else \
+            np.zeros((0, self.wd + 1))
+        self.base = None if base is None else _f64(base).reshape(self.N, self.wd)
+        self.aux = None if aux is None else _f64(aux).ravel()
         self._lib = lib(dot_fma)
         if max_dist is None:
             max_dist = math.nan
-        self._h = self._lib.orc_ctx_create(
+        if step_dist is None:   # STEP_DIST (MRMP.jl:65); snake2d.jl:3 / capsule3d.jl:3 use 0.05
+            step_dist = 0.05 if self.model in (SNAKE2D, CAPSULE3D) else 0.01
+        self._h = self._lib.orc_ctx_create2(
             self.model, self.N, _p(self.rads, _dp),
             _p(self.base, _dp) if self.base is not None else None,
+            _p(self.aux, _dp) if self.aux is not None else None,
             self.obs.shape[0], _p(self.obs, _dp) if self.obs.size else None,
             step_dist, safety_dist, max_dist)
         if not self._h:

@@ -80,3 +80,41 @@ def near_threshold_pairs(rng, n, rads, ai, aj, d):
     w /= np.linalg.norm(w, axis=1, keepdims=True)
     return (p + u * l1[:, None], p + u * l2[:, None],
             p + off + w * l3[:, None], p + off + w * l4[:, None])
+
+
+LINE2D, SNAKE2D, ARM33, CAPSULE3D = O.LINE2D, O.SNAKE2D, O.ARM33, O.CAPSULE3D
+CHAIN_MODELS = (LINE2D, SNAKE2D, ARM33, CAPSULE3D)
+
+
+def make_chain_instance(model, N, M, seed):
+    """Instances in the spirit of the reference's eval configs (scripts/config/eval/*.yaml) with
+    bodies small enough that N agents fit: returns dict(rads, obs, base, aux)."""
+    rng = np.random.default_rng(seed)
+    wd = O._W[model]
+    obs = np.concatenate([rng.random((M, wd)), rng.uniform(0.05, 0.1, (M, 1))], axis=1) if M \
+        else np.zeros((0, wd + 1))
+    base = aux = None
+    if model == LINE2D:
+        rads = rng.uniform(0.06, 0.12, N)
+    elif model == SNAKE2D:
+        rads = rng.uniform(0.03, 0.05, N)
+    elif model == ARM33:
+        rads = rng.uniform(0.08, 0.12, N)
+        base = rng.uniform(0.35, 0.65, (N, 3))
+    else:
+        rads = rng.uniform(0.03, 0.05, N)
+        aux = rng.uniform(0.08, 0.15, N)
+    return dict(rads=rads, obs=obs, base=base, aux=aux)
+
+
+def chain_states(rng, model, n, near=None, spread=0.15):
+    """n random states of a chain model (positions in [0.2, 0.8], angles in [0, 2pi)); with
+    `near` (an array of states) perturbations of those instead."""
+    sd = O._D[model]
+    npos = {LINE2D: 2, SNAKE2D: 2, ARM33: 0, CAPSULE3D: 3}[model]
+    if near is not None:
+        q = near + rng.normal(size=near.shape) * spread
+        return q
+    q = rng.uniform(0, 2 * np.pi, (n, sd))
+    q[:, :npos] = rng.uniform(0.2, 0.8, (n, npos))
+    return q

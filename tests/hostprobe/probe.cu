@@ -4,7 +4,7 @@
 // oracle, bit for bit, in the GPU-less build container.  Not part of libmrmp_b200.so.
 #include <stdint.h>
 
-#include "../../sssp_b200/csrc/arm_model.cuh"
+#include "../../sssp_b200/csrc/chain_model.cuh"
 
 using namespace mrmp;
 
@@ -129,5 +129,74 @@ int probe_arm_collide_pair(const ProbeArm *p, const double *qif, const double *q
 double probe_arm_dist(const double *q1, const double *q2) { return arm_dist(q1, q2); }
 void probe_arm_mid_status(const double *p, const double *q, double *out) {
     arm_mid_status(p, q, out);
+}
+}  // extern "C"
+
+// ---- line2d / snake2d / arm33 / capsule3d (chain_model.cuh) ------------------------------------
+struct ProbeChain {
+    int model, n_obs;
+    const double *obs_soa;  // [(W+1)][n_obs]: coordinates then radius
+    const double *t2;       // [n_obs] exact-compare table of this agent's obstacle threshold
+    double step, safety, safety_t2, max_dist;
+};
+
+template <int MODEL>
+static int chain_dispatch(int what, const ProbeChain *p, const double *g1, const double *g2,
+                          const double *a, const double *b, const double *c, const double *d,
+                          double thr, double T2, double *out) {
+    ChainPar cp;
+    cp.sr = step_rat(p->step);
+    cp.step = p->step;
+    cp.safety = p->safety;
+    cp.safety_t2 = p->safety_t2;
+    cp.max_dist = p->max_dist;
+    ChainObs ob;
+    ob.s = p->obs_soa;
+    ob.obs = 0;
+    ob.mp = p->n_obs > 0 ? p->n_obs : 1;
+    ob.n_obs = p->n_obs;
+    ob.t2 = 0;
+    ChainObs obt = ob;  // T2 lives in a separate array: point the accessor at it
+    ChainGeom gi, gj;
+    for (int x = 0; x < 3; ++x) {
+        gi.base[x] = g1[x];
+        gj.base[x] = g2 ? g2[x] : 0.0;
+    }
+    gi.len = g1[3];
+    gi.rad = g1[4];
+    gj.len = g2 ? g2[3] : 0.0;
+    gj.rad = g2 ? g2[4] : 0.0;
+    // ChainObs reads coordinates and T2 through one base pointer: pack both into one buffer
+    double buf[5 * 64];
+    const int mp = ob.mp;
+    for (int k = 0; k <= Chain<MODEL>::W; ++k)
+        for (int m = 0; m < p->n_obs; ++m) buf[k * mp + m] = p->obs_soa[k * p->n_obs + m];
+    for (int m = 0; m < p->n_obs; ++m) buf[(Chain<MODEL>::W + 1) * mp + m] = p->t2[m];
+    obt.s = buf;
+    obt.t2 = (Chain<MODEL>::W + 1) * mp;
+    switch (what) {
+    case 0: return chain_connect_point<MODEL>(cp, obt, gi, a);
+    case 1: return chain_connect_edge<MODEL>(cp, obt, gi, a, b);
+    case 2: return chain_collide_static<MODEL>(gi, gj, a, b, thr, T2);
+    case 3: return chain_collide_pair_serial<MODEL>(cp, gi, gj, a, b, c, d, thr, T2);
+    case 4: *out = Chain<MODEL>::dist(a, b); return 0;
+    default: Chain<MODEL>::mid(a, b, out); return 0;
+    }
+}
+
+extern "C" {
+// what: 0 connect(q,i) [a], 1 connect(qf,qt,i) [a,b], 2 collide static [a,b], 3 collide 6-arity
+// [a,b,c,d], 4 dist [a,b] -> out[0], 5 mid status [a,b] -> out[SD].  g = {base[3], len, rad}.
+int probe_chain(int what, const ProbeChain *p, const double *g1, const double *g2, const double *a,
+                const double *b, const double *c, const double *d, double thr, double T2,
+                double *out) {
+    if (p->n_obs > 64) return -1;
+    switch (p->model) {
+    case kModelLine2D: return chain_dispatch<kModelLine2D>(what, p, g1, g2, a, b, c, d, thr, T2, out);
+    case kModelSnake2D: return chain_dispatch<kModelSnake2D>(what, p, g1, g2, a, b, c, d, thr, T2, out);
+    case kModelArm33: return chain_dispatch<kModelArm33>(what, p, g1, g2, a, b, c, d, thr, T2, out);
+    case kModelCapsule3D: return chain_dispatch<kModelCapsule3D>(what, p, g1, g2, a, b, c, d, thr, T2, out);
+    default: return -2;
+    }
 }
 }

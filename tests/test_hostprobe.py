@@ -64,6 +64,7 @@ def probe():
     lib.probe_arm_connect_edge.argtypes = [P, _dp, _dp] + [C.c_double] * 3
     lib.probe_arm_collide_static.argtypes = [P, _dp, _dp] + [C.c_double] * 6
     lib.probe_arm_collide_pair.argtypes = [P, _dp, _dp, _dp, _dp] + [C.c_double] * 6
+    lib.probe_chain.argtypes = [C.c_int, C.c_void_p, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.probe_arm_dist.restype = C.c_double
     lib.probe_arm_dist.argtypes = [_dp, _dp]
     lib.probe_arm_mid_status.argtypes = [_dp, _dp, _dp]
@@ -240,3 +241,71 @@ def test_arm_bodies_match_oracle(probe, max_dist):
         probe.probe_arm_mid_status(p(q1[k]), p(q2[k]), p(mid))
         assert np.array_equal(mid.view(np.uint64), orc.mid_status(q1[k], q2[k]).view(np.uint64))
     assert 0 < n_free < n and 0 < n_hit < 300   # both verdicts exercised
+
+
+class ProbeChain(C.Structure):
+    _fields_ = [("model", C.c_int), ("n_obs", C.c_int), ("obs_soa", _dp), ("t2", _dp),
+                ("step", C.c_double), ("safety", C.c_double), ("safety_t2", C.c_double),
+                ("max_dist", C.c_double)]
+
+
+@pytest.mark.parametrize("model", [O.LINE2D, O.SNAKE2D, O.ARM33, O.CAPSULE3D])
+@pytest.mark.parametrize("max_dist", [math.nan, 0.5])
+def test_chain_models_match_oracle(probe, model, max_dist):
+    """line2d / snake2d / arm33 / capsule3d: chain_model.cuh compiled for the host against the
+    oracle's per-model restatement (oracle/orc_chain.c): connect (both forms), collide (4- and
+    6-arity), dist, get_mid_status -- verdicts equal, values bit-identical."""
+    from helpers import make_chain_instance, chain_states
+    rng = np.random.default_rng(40 + model)
+    N, M = 5, 3
+    ins = make_chain_instance(model, N, M, seed=model)
+    orc = O.Oracle(model, ins["rads"], ins["obs"], base=ins["base"], aux=ins["aux"], max_dist=max_dist)
+    sd, wd = O._D[model], O._W[model]
+    step = 0.05 if model in (O.SNAKE2D, O.CAPSULE3D) else 0.01
+    obs_soa = np.ascontiguousarray(ins["obs"].T)
+    geoms, t2s = [], []
+    for i in range(N):
+        base = ins["base"][i] if ins["base"] is not None else np.zeros(3)
+        ln = ins["aux"][i] if model == O.CAPSULE3D else ins["rads"][i]
+        geoms.append(np.array([*np.resize(base, 3), ln, ins["rads"][i]]))
+        thr = ins["obs"][:, wd] + (ins["rads"][i] if model == O.CAPSULE3D else 0.0)
+        t2s.append(np.array([sq_lt_threshold(t) for t in thr]))
+    n = 400
+    q1 = chain_states(rng, model, n)
+    q2 = chain_states(rng, model, n, near=q1, spread=0.12)
+    q2[:20] = q1[:20]                       # D == 0
+    q3 = chain_states(rng, model, n, near=q1, spread=0.1)
+    q4 = chain_states(rng, model, n, near=q3, spread=0.12)
+    ai = rng.integers(0, N, n)
+    aj = (ai + 1 + rng.integers(0, N - 1, n)) % N
+    out = np.empty(8)
+    tally = dict(free=0, edge=0, hit4=0, hit6=0)
+    for k in range(n):
+        i, j = int(ai[k]), int(aj[k])
+        pc = ProbeChain(model, M, p(obs_soa), p(t2s[i]), step, 0.01, sq_lt_threshold(0.01), max_dist)
+        thr = ins["rads"][i] + ins["rads"][j] if model == O.CAPSULE3D else 0.01
+        T2 = sq_lt_threshold(thr)
+        args = lambda what, a, b=None, c=None, d=None: probe.probe_chain(
+            what, C.byref(pc), geoms[i].ctypes.data, geoms[j].ctypes.data, a.ctypes.data,
+            None if b is None else b.ctypes.data, None if c is None else c.ctypes.data,
+            None if d is None else d.ctypes.data, thr, T2, out.ctypes.data)
+        w = orc.connect_point(q1[k], i)
+        assert bool(args(0, q1[k])) == w, (k, "point")
+        tally["free"] += w
+        w = orc.connect_edge(q1[k], q2[k], i)
+        assert bool(args(1, q1[k], q2[k])) == w, (k, "edge")
+        tally["edge"] += w
+        w = orc.collide_static(q1[k], q3[k], i, j)
+        assert bool(args(2, q1[k], q3[k])) == w, (k, "static")
+        tally["hit4"] += w
+        if k < 150:
+            w = orc.collide_pair(q1[k], q2[k], q3[k], q4[k], i, j)
+            assert bool(args(3, q1[k], q2[k], q3[k], q4[k])) == w, (k, "pair")
+            tally["hit6"] += w
+        args(4, q1[k], q2[k])
+        assert bits(out[0]) == bits(orc.state_dist(q1[k], q2[k]))
+        args(5, q1[k], q2[k])
+        assert np.array_equal(out[:sd].view(np.uint64), orc.mid_status(q1[k], q2[k]).view(np.uint64))
+    assert 0 < tally["free"] < n and 0 < tally["hit4"] < n and 0 < tally["hit6"] < 150, tally
+    if math.isnan(max_dist):
+        assert 0 < tally["edge"] < n, tally
