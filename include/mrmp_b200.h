@@ -42,6 +42,10 @@ extern "C" {
 #define MRMP_MODEL_POINT2D 0 /* src/models/point2d.jl */
 #define MRMP_MODEL_POINT3D 1 /* src/models/point3d.jl */
 #define MRMP_MODEL_ARM22 2   /* src/models/arm22.jl   */
+#define MRMP_MODEL_LINE2D 3    /* src/models/line2d.jl:    state (x, y, theta) */
+#define MRMP_MODEL_SNAKE2D 4   /* src/models/snake2d.jl:   state (x, y, theta1..4) */
+#define MRMP_MODEL_ARM33 5     /* src/models/arm33.jl:     state (theta1, phi1, ..., theta3, phi3) */
+#define MRMP_MODEL_CAPSULE3D 6 /* src/models/capsule3d.jl: state (x, y, z, roll, pitch, yaw) */
 
 typedef struct mrmp_ctx mrmp_ctx;           /* one problem instance (obstacles, radii) */
 typedef struct mrmp_roadmaps mrmp_roadmaps; /* device-resident per-agent roadmaps */
@@ -62,9 +66,14 @@ int mrmp_host_free(void *ptr);
 /* gen_connect(q, obstacles, ins_params...; step_dist, max_dist, safety_dist) and
  * gen_collide(q, ins_params...; step_dist, safety_dist):
  *   point2d.jl:42-69, point3d.jl:47-80, point.jl:5-36, arm22.jl:29-37, arm22.jl:90-96.
- * rads[n_agents]; base_pos[n_agents*2] only for ARM22 (positions, arm22.jl:32) else NULL;
- * aux reserved (NULL); obstacles_aos[n_obs*(d+1)] = x,y,(z),r; step_dist / safety_dist
- * only used by ARM22 (src/MRMP.jl:65-66); max_dist NaN == nothing; device = CUDA ordinal. */
+ * and the same constructors of line2d.jl:22-28,72-77, snake2d.jl:61-68,127-132,
+ * arm33.jl:42-50,116-122, capsule3d.jl:61-68,107-112.
+ * rads[n_agents]; base_pos = positions, [n_agents*2] for ARM22 (arm22.jl:32), [n_agents*3]
+ * for ARM33 (arm33.jl:45), else NULL; aux = axises[n_agents] for CAPSULE3D (capsule3d.jl:65),
+ * else NULL; obstacles_aos[n_obs*(w+1)] = x,y,(z),r with w the workspace dimension;
+ * step_dist / safety_dist are used by the discretised models (STEP_DIST / SAFETY_DIST_LINE,
+ * src/MRMP.jl:65-66; snake2d.jl:3 and capsule3d.jl:3 default to step 0.05); max_dist NaN ==
+ * nothing; device = CUDA ordinal.  State layouts: the reference's isbits structs. */
 int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const double *rads,
                     const double *base_pos, const double *aux, int n_obs,
                     const double *obstacles_aos, double step_dist, double safety_dist,

@@ -699,7 +699,7 @@ int64_t orc_sample_free(const orc_ctx *c, int agent, uint64_t seed, int64_t n_wa
     int d = c->d;
     int64_t got = 0, t = 0;
     while (got < n_wanted && t < max_tries) {
-        double q[3];
+        double q[6];
         orc_sample_state(c, seed, agent, (uint64_t)t, q);
         ++t;
         if (orc_connect_point(c, q, agent)) {
@@ -758,7 +758,7 @@ int orc_conn(const orc_ctx *c, int agent, const double *qf, const double *qt, do
 void orc_steering(const orc_ctx *c, int agent, const double *q_rand, const double *q_near,
                   int depth, double epsilon, double *q_out) {
     int d = c->d;
-    double qh[3], ql[3], q[3];
+    double qh[6], ql[6], q[6];
     memcpy(qh, q_rand, sizeof(double) * d);
     if (!orc_conn(c, agent, q_near, qh, epsilon)) { /* :277 */
         memcpy(ql, q_near, sizeof(double) * d);
@@ -826,7 +826,7 @@ int orc_sssp_expand(const orc_ctx *c, int agent, double *nodes, int nv, int v_fr
     memset(out_bits, 0, sizeof(uint32_t) * (size_t)K * words);
     memset(in_bits, 0, sizeof(uint32_t) * (size_t)K * words);
     for (int k = 0; k < K; ++k) {
-        double q_new[3];
+        double q_new[6];
         orc_steering(c, agent, q_rand + (size_t)d * k, q_near, depth, epsilon, q_new); /* :246 */
         double mn = INFINITY;                                                           /* :250 */
         int has_nan = 0;

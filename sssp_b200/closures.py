@@ -46,6 +46,43 @@ class StateArm22(NamedTuple):  # src/models/arm22.jl:3-6
     theta2: float
 
 
+class StateLine2D(NamedTuple):  # src/models/line2d.jl:3-7
+    x: float
+    y: float
+    theta: float
+
+
+class StateSnake2D(NamedTuple):  # src/models/snake2d.jl:5-12
+    x: float
+    y: float
+    theta1: float
+    theta2: float
+    theta3: float
+    theta4: float
+
+
+class StateArm33(NamedTuple):  # src/models/arm33.jl:3-10
+    theta1: float
+    phi1: float
+    theta2: float
+    phi2: float
+    theta3: float
+    phi3: float
+
+
+class StateCapsule3D(NamedTuple):  # src/models/capsule3d.jl:5-12
+    x: float
+    y: float
+    z: float
+    phi: float
+    theta: float
+    psi: float
+
+
+STEP_DIST_SNAKE2D = 0.05    # src/models/snake2d.jl:3
+STEP_DIST_CAPSULE3D = 0.05  # src/models/capsule3d.jl:3
+
+
 class CircleObstacle2D(NamedTuple):  # src/obstacle.jl:7-11
     x: float
     y: float
@@ -67,9 +104,10 @@ class Node:  # src/MRMP.jl:73-77
 
 
 _MODEL_OF = {StatePoint2D: L.MODEL_POINT2D, StatePoint3D: L.MODEL_POINT3D,
-             StateArm22: L.MODEL_ARM22}
-_STATE_OF = {L.MODEL_POINT2D: StatePoint2D, L.MODEL_POINT3D: StatePoint3D,
-             L.MODEL_ARM22: StateArm22}
+             StateArm22: L.MODEL_ARM22, StateLine2D: L.MODEL_LINE2D, StateSnake2D: L.MODEL_SNAKE2D,
+             StateArm33: L.MODEL_ARM33, StateCapsule3D: L.MODEL_CAPSULE3D}
+_STATE_OF = {m: t for t, m in _MODEL_OF.items()}
+_DEFAULT_STEP = {L.MODEL_SNAKE2D: STEP_DIST_SNAKE2D, L.MODEL_CAPSULE3D: STEP_DIST_CAPSULE3D}
 
 
 def _model_of(q) -> int:
@@ -90,23 +128,29 @@ def _states(qs, d: int) -> np.ndarray:
 class Context:
     """One problem instance on one GPU (wraps mrmp_ctx)."""
 
-    def __init__(self, model: int, rads, obstacles=(), base_pos=None, step_dist=STEP_DIST,
-                 safety_dist=SAFETY_DIST_LINE, max_dist: Optional[float] = None, device: int = 0):
+    def __init__(self, model: int, rads, obstacles=(), base_pos=None, step_dist=None,
+                 safety_dist=SAFETY_DIST_LINE, max_dist: Optional[float] = None, device: int = 0,
+                 aux=None):
         self.model = int(model)
         self.d = L.STATE_DIM[self.model]
+        self.wd = L.WORK_DIM[self.model]
         self.rads = L.f64(rads).ravel()
         self.N = int(self.rads.size)
         obs = L.f64([tuple(o) for o in obstacles] if not isinstance(obstacles, np.ndarray)
-                    else obstacles).reshape(-1, self.d + 1)
+                    else obstacles).reshape(-1, self.wd + 1)
         self.obstacles = obs
-        base = None if base_pos is None else L.f64(base_pos).reshape(self.N, 2)
+        base = None if base_pos is None else L.f64(base_pos).reshape(self.N, self.wd)
         self.base_pos = base
+        self.aux = None if aux is None else L.f64(aux).ravel()
+        if step_dist is None:
+            step_dist = _DEFAULT_STEP.get(self.model, STEP_DIST)
         self.device = int(device)
         self._lib = L.load()
         h = C.c_void_p()
         L.check(self._lib.mrmp_ctx_create(
             C.byref(h), self.model, self.N, L.ptr(self.rads, L._dp),
-            L.ptr(base, L._dp) if base is not None else None, None, obs.shape[0],
+            L.ptr(base, L._dp) if base is not None else None,
+            L.ptr(self.aux, L._dp) if self.aux is not None else None, obs.shape[0],
             L.ptr(obs, L._dp) if obs.size else None, float(step_dist), float(safety_dist),
             math.nan if max_dist is None else float(max_dist), self.device))
         self._h = h
@@ -481,20 +525,25 @@ class SsspRoadmaps:
 # closure constructors
 # ---------------------------------------------------------------------------------------
 def _split_ins_params(model: int, ins_params):
-    if model == L.MODEL_ARM22:  # (positions, rads)  arm22.jl:29-37
+    """ins_params of the reference's constructors -> (rads, positions, axises)."""
+    if model in (L.MODEL_ARM22, L.MODEL_ARM33):   # (positions, rads)  arm22.jl:29-37, arm33.jl:42-50
         positions, rads = ins_params
-        return L.f64(rads).ravel(), L.f64(positions).reshape(-1, 2)
-    (rads,) = ins_params        # (rads,)  point2d.jl:42-46
-    return L.f64(rads).ravel(), None
+        return L.f64(rads).ravel(), L.f64(positions).reshape(-1, L.WORK_DIM[model]), None
+    if model == L.MODEL_CAPSULE3D:                # (rads, axises)  capsule3d.jl:61-68
+        rads, axises = ins_params
+        return L.f64(rads).ravel(), None, L.f64(axises).ravel()
+    (rads,) = ins_params                          # (rads,)  point2d.jl:42-46, line2d.jl:22-28
+    return L.f64(rads).ravel(), None, None
 
 
-def gen_connect(q, obstacles, *ins_params, step_dist: float = STEP_DIST,
+def gen_connect(q, obstacles, *ins_params, step_dist: Optional[float] = None,
                 max_dist: Optional[float] = None, safety_dist: float = SAFETY_DIST_LINE,
                 device: int = 0):
-    """gen_connect(q, obstacles, ins_params...) -> f;  f(q, i) / f(q_from, q_to, i)."""
+    """gen_connect(q, obstacles, ins_params...) -> f;  f(q, i) / f(q_from, q_to, i).
+    step_dist defaults to the model's constant (STEP_DIST, or 0.05 for snake2d / capsule3d)."""
     model = _model_of(q)
-    rads, base = _split_ins_params(model, ins_params)
-    ctx = Context(model, rads, obstacles, base, step_dist, safety_dist, max_dist, device)
+    rads, base, aux = _split_ins_params(model, ins_params)
+    ctx = Context(model, rads, obstacles, base, step_dist, safety_dist, max_dist, device, aux=aux)
 
     def f(*args) -> bool:
         if len(args) == 2:    # f(q, i)
@@ -509,12 +558,12 @@ def gen_connect(q, obstacles, *ins_params, step_dist: float = STEP_DIST,
     return f
 
 
-def gen_collide(q, *ins_params, step_dist: float = STEP_DIST,
+def gen_collide(q, *ins_params, step_dist: Optional[float] = None,
                 safety_dist: float = SAFETY_DIST_LINE, device: int = 0):
     """gen_collide(q, ins_params...) -> f with the reference's four methods."""
     model = _model_of(q)
-    rads, base = _split_ins_params(model, ins_params)
-    ctx = Context(model, rads, (), base, step_dist, safety_dist, None, device)
+    rads, base, aux = _split_ins_params(model, ins_params)
+    ctx = Context(model, rads, (), base, step_dist, safety_dist, None, device, aux=aux)
     State = _STATE_OF[model]
 
     def _is_config(x) -> bool:

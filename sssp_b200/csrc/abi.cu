@@ -66,15 +66,19 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
                                const double *base_pos, const double *aux, int n_obs,
                                const double *obstacles_aos, double step_dist,
                                double safety_dist, double max_dist, int device) {
-    (void)aux;
     if (!out) return fail(MRMP_ERR_INVALID, "out is NULL");
     *out = nullptr;
-    if (model < 0 || model > 2) return fail(MRMP_ERR_INVALID, "unknown model %d", model);
+    if (model < 0 || model > MRMP_MODEL_CAPSULE3D)
+        return fail(MRMP_ERR_INVALID, "unknown model %d", model);
     if (n_agents <= 0 || !rads) return fail(MRMP_ERR_INVALID, "need n_agents > 0 and rads");
     if (n_obs < 0 || (n_obs > 0 && !obstacles_aos))
         return fail(MRMP_ERR_INVALID, "need obstacles_aos for n_obs > 0");
-    if (model == MRMP_MODEL_ARM22 && !base_pos)
-        return fail(MRMP_ERR_INVALID, "arm22 needs base_pos (positions)");
+    if ((model == MRMP_MODEL_ARM22 || model == MRMP_MODEL_ARM33) && !base_pos)
+        return fail(MRMP_ERR_INVALID, "arm models need base_pos (positions)");
+    if (model == MRMP_MODEL_CAPSULE3D && !aux)
+        return fail(MRMP_ERR_INVALID, "capsule3d needs aux (axises)");
+    if (model == MRMP_MODEL_CAPSULE3D && n_agents > 1024)
+        return fail(MRMP_ERR_UNSUPPORTED, "capsule3d supports at most 1024 agents per ctx");
     if ((int64_t)n_agents * (n_obs > 0 ? n_obs : 1) > (int64_t)1 << 24)
         return fail(MRMP_ERR_UNSUPPORTED, "n_agents * n_obs too large");
     int ndev = 0;
@@ -90,8 +94,9 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     if (!c) return fail(MRMP_ERR_NOMEM, "out of host memory");
     c->device = device;
     c->model = model;
-    c->d = model == MRMP_MODEL_POINT3D ? 3 : 2;
-    const int wd = c->d;  // workspace dimension of obstacle centres (2 for arm22 as well)
+    static const int kStateDim[] = {2, 3, 2, 3, 6, 6, 6}, kWorkDim[] = {2, 3, 2, 2, 2, 3, 3};
+    c->d = kStateDim[model];
+    const int wd = kWorkDim[model];  // workspace dimension of obstacle centres / joint points
     c->n_agents = n_agents;
     c->n_obs = n_obs;
     c->h_rads.assign(rads, rads + n_agents);
@@ -101,9 +106,14 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
 
     const int N = n_agents, M = n_obs;
     const int mp = pad2(M > 0 ? M : 1), np = pad2(N);
-    const bool arm = model == MRMP_MODEL_ARM22;
-    const int n_thr_rows = arm ? 1 : N;  // arm22 compares with o.r alone (arm22.jl:46,77)
-    const bool pair_tab = !arm && N <= 1024;
+    const bool arm = model == MRMP_MODEL_ARM22 || model == MRMP_MODEL_ARM33;  // fixed bases
+    // obstacle threshold o.r + rads[i] (points, capsule3d.jl:76) or o.r alone (arm22.jl:46,
+    // line2d.jl:39, snake2d.jl:78, arm33.jl:60); pair threshold rads[i] + rads[j] (point.jl:11,
+    // capsule3d.jl:163) or safety_dist
+    const bool rad_thr = model == MRMP_MODEL_POINT2D || model == MRMP_MODEL_POINT3D ||
+                         model == MRMP_MODEL_CAPSULE3D;
+    const int n_thr_rows = rad_thr ? N : 1;
+    const bool pair_tab = rad_thr && N <= 1024;
 
     std::vector<double> h;
     auto section = [&](size_t len) {
@@ -114,6 +124,7 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     CtxView &cv = c->cv;
     cv.model = model;
     cv.d = c->d;
+    cv.wd = wd;
     cv.n_agents = N;
     cv.n_obs = M;
     cv.mp = mp;
@@ -129,15 +140,18 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     }
     cv.rads_off = section(np);
     for (int i = 0; i < N; ++i) h[cv.rads_off + i] = rads[i];
-    cv.base_off = section(arm ? 2 * np : 0);
+    cv.base_off = section(arm ? wd * np : 0);
     if (arm)
-        for (int i = 0; i < 2 * N; ++i) h[cv.base_off + i] = base_pos[i];
+        for (int i = 0; i < wd * N; ++i) h[cv.base_off + i] = base_pos[i];
+    cv.aux_off = section(aux ? np : 0);
+    if (aux)
+        for (int i = 0; i < N; ++i) h[cv.aux_off + i] = aux[i];
     cv.t2_obs_off = section((size_t)n_thr_rows * mp);
     cv.g_obs_off = section((size_t)n_thr_rows * mp);
     for (int i = 0; i < n_thr_rows; ++i)
         for (int m = 0; m < mp; ++m) {
             const double orad = h[cv.obs_off + wd * mp + m];
-            const double thr = arm ? orad : orad + rads[i];  // o.r + rads[i]  point2d.jl:54,63
+            const double thr = rad_thr ? orad + rads[i] : orad;  // o.r + rads[i]  point2d.jl:54,63
             h[cv.t2_obs_off + i * mp + m] = m < M ? sq_lt_threshold(thr) : 0.0;
             const double tp = (thr > 0 ? thr : 0.0) + kFilterPad;
             h[cv.g_obs_off + i * mp + m] = 2.0 * tp * tp * (1.0 + 1e-9);
@@ -147,9 +161,12 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cv.col_off = (int)h.size();
     cv.crads_off = section(np);
     for (int i = 0; i < N; ++i) h[cv.crads_off + i] = rads[i];
-    cv.cbase_off = section(arm ? 2 * np : 0);
+    cv.cbase_off = section(arm ? wd * np : 0);
     if (arm)
-        for (int i = 0; i < 2 * N; ++i) h[cv.cbase_off + i] = base_pos[i];
+        for (int i = 0; i < wd * N; ++i) h[cv.cbase_off + i] = base_pos[i];
+    cv.caux_off = section(aux ? np : 0);
+    if (aux)
+        for (int i = 0; i < N; ++i) h[cv.caux_off + i] = aux[i];
     cv.has_pair_tab = pair_tab ? 1 : 0;
     cv.t2_pair_off = section(pair_tab ? (size_t)N * N : 0);
     cv.g_pair_off = section(pair_tab ? (size_t)N * N : 0);
@@ -671,7 +688,7 @@ extern "C" int mrmp_collide_configs_dev(mrmp_ctx *c, int64_t n_cfg, const double
                                         void *stream) {
     DEV_PROLOGUE(c, n_cfg);
     if (need_aligned(c, Q_from) || need_aligned(c, Q_to)) return MRMP_ERR_INVALID;
-    if (c->model == MRMP_MODEL_ARM22 && !first_pair_out) {
+    if (c->model >= MRMP_MODEL_ARM22 && !first_pair_out) {
         // the arm kernel keeps the running first hit per configuration in this array
         int rc = ensure_scratch(c, 3, sizeof(int64_t) * (size_t)n_cfg);
         if (rc) return rc;
@@ -995,7 +1012,7 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     CU(cudaMemcpyAsync(rm->rad_d, hr, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->s_k));
     // neighbour search: uniform-grid spatial hash for large point roadmaps, all pairs otherwise
     int g = 0;
-    if (finite && c->model != MRMP_MODEL_ARM22 && nv >= kGridMinNv) {
+    if (finite && c->model <= MRMP_MODEL_POINT3D && nv >= kGridMinNv) {
         const double gf = floor(1.0 / rad_max);
         const double gmax = c->d == 2 ? 1024.0 : 100.0;   // <= ~10^6 cells per agent
         g = (int)(gf < gmax ? gf : gmax);
@@ -1289,10 +1306,16 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                          const double *nodes, int agent0, int nv_stride, int group_size,
                          uint32_t *out, cudaStream_t s) {
     const int wpr = cross_words(n_cols, group_size);
-    if (c->model == MRMP_MODEL_ARM22) {  // warp per (row, column) check, arm22.jl:100-146
-        CU(launch_arm_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to, n_cols,
-                                    col_agent, col_from, col_to, col_vf, col_vt, nodes, agent0,
-                                    nv_stride, group_size, wpr, out, c->stats_d + 1));
+    if (c->model >= MRMP_MODEL_ARM22) {  // discretised models: warp per (row, column) check
+        if (c->model == MRMP_MODEL_ARM22)
+            CU(launch_arm_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to,
+                                        n_cols, col_agent, col_from, col_to, col_vf, col_vt, nodes,
+                                        agent0, nv_stride, group_size, wpr, out, c->stats_d + 1));
+        else
+            CU(launch_chain_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to,
+                                          n_cols, col_agent, col_from, col_to, col_vf, col_vt,
+                                          nodes, agent0, nv_stride, group_size, wpr, out,
+                                          c->stats_d + 1));
         return MRMP_OK;
     }
     LaunchCfg lc = lcfg(c, s);
@@ -1408,7 +1431,7 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
         rm->e_from = rm->e_to = nullptr;
         rm->e_rows = nullptr;
         rm->e_cap = rm->nnz + rm->nnz / 8 + 64;
-        if (c->model != MRMP_MODEL_ARM22)
+        if (c->model <= MRMP_MODEL_POINT3D)
             CU(cudaMalloc(&rm->e_rows, cross_row_bytes(c->d) * (size_t)rm->e_cap));
         CU(cudaMalloc((void **)&rm->e_agent, sizeof(int32_t) * rm->e_cap));
         CU(cudaMalloc((void **)&rm->e_from, sizeof(double) * c->d * rm->e_cap));

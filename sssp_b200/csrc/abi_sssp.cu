@@ -220,7 +220,7 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     ws.cfg_first = (int64_t *)(b + o_first);
     // search-sized roadmaps of the point models: one launch that works on the mapped pinned
     // block directly; otherwise the multi-kernel path with explicit copies
-    const bool fused = c->model != MRMP_MODEL_ARM22 && K <= 32 &&
+    const bool fused = c->model <= MRMP_MODEL_POINT3D && K <= 32 &&
                        (int64_t)K * 2 * (nv0 + K) <= (1 << 16) &&
                        sssp_fused_smem(c->cv, a) <= 160 * 1024;
     if (fused) {

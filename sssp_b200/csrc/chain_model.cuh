@@ -6,7 +6,7 @@
 // A move is discretised like arm22's (arm_model.cuh: ArmSched, Julia's 0:step:D): at every
 // step positions are interpolated as (1-e)*from + e*to and angles as
 // from + e*diff_angles(to, from) (line2d.jl:53-55), the joint points are rebuilt and tested.
-// Everything is __host__ __device__ (tests/hostprobe runs it on the CPU against the oracle).
+// Everything is __host__ __device__ (tests/hostprobe runs it on the CPU against the checker).
 #pragma once
 #include "arm_model.cuh"
 

@@ -564,11 +564,14 @@ cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int6
     int64_t want = (n_rows_csr + 7) / 8;
     int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
-    if (cv.model == 0 || cv.model == 2)  // StateArm22 is two doubles as well
+    if (cv.d == 2)  // StatePoint2D, StateArm22
         k_csr_expand_edges<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
                                                           nodes, e_agent, e_from, e_to);
-    else if (cv.model == 1)
+    else if (cv.d == 3)  // StatePoint3D, StateLine2D
         k_csr_expand_edges<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
+                                                          nodes, e_agent, e_from, e_to);
+    else if (cv.d == 6)  // StateSnake2D, StateArm33, StateCapsule3D
+        k_csr_expand_edges<6><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
                                                           nodes, e_agent, e_from, e_to);
     else
         return cudaErrorNotSupported;

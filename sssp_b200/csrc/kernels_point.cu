@@ -221,6 +221,7 @@ cudaError_t launch_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_
                                   const int32_t *agent, const double *q, uint8_t *out) {
     if (n <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_connect_points(cv, lc, n, agent, q, out);
+    if (cv.model >= 3) return launch_chain_connect_points(cv, lc, n, agent, q, out);
     const int sm = seg_smem_bytes(cv.con_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -240,6 +241,7 @@ cudaError_t launch_connect_edges(const CtxView &cv, const LaunchCfg &lc, int64_t
                                  uint8_t *out) {
     if (n <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_connect_edges(cv, lc, n, agent, qf, qt, out);
+    if (cv.model >= 3) return launch_chain_connect_edges(cv, lc, n, agent, qf, qt, out);
     const int sm = seg_smem_bytes(cv.con_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -260,6 +262,7 @@ cudaError_t launch_collide_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t
                                  uint8_t *out) {
     if (n <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_collide_pairs(cv, lc, n, ai, aj, qif, qit, qjf, qjt, out, lc.stats ? lc.stats + 1 : nullptr);
+    if (cv.model >= 3) return launch_chain_collide_pairs(cv, lc, n, ai, aj, qif, qit, qjf, qjt, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -284,6 +287,7 @@ cudaError_t launch_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc,
     (void)n_local;
     if (n <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_collide_edges_indexed(cv, lc, n, ai, aj, vif, vit, vjf, vjt, nodes, agent0, nv_stride, out, lc.stats ? lc.stats + 1 : nullptr);
+    if (cv.model >= 3) return launch_chain_collide_edges_indexed(cv, lc, n, ai, aj, vif, vit, vjf, vjt, nodes, agent0, nv_stride, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -304,6 +308,7 @@ cudaError_t launch_collide_static_pairs(const CtxView &cv, const LaunchCfg &lc, 
                                         const double *qj, uint8_t *out) {
     if (n <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_collide_static_pairs(cv, lc, n, ai, aj, qi, qj, out);
+    if (cv.model >= 3) return launch_chain_collide_static_pairs(cv, lc, n, ai, aj, qi, qj, out);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n, sm);
     cudaError_t e;
@@ -324,6 +329,7 @@ cudaError_t launch_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64
                                    int64_t *first_pair) {
     if (n_cfg <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_collide_configs(cv, lc, n_cfg, Qf, Qt, out, first_pair, reinterpret_cast<unsigned long long *>(first_pair), lc.stats ? lc.stats + 1 : nullptr);
+    if (cv.model >= 3) return launch_chain_collide_configs(cv, lc, n_cfg, Qf, Qt, out, first_pair, reinterpret_cast<unsigned long long *>(first_pair), lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n_cfg * 32, sm);
     cudaError_t e;
@@ -344,6 +350,7 @@ cudaError_t launch_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, 
                                         uint8_t *out) {
     if (n_cand <= 0) return cudaSuccess;
     if (cv.model == 2) return launch_arm_collide_config_moves(cv, lc, agent_i, Q, n_cand, q_to, out, lc.stats ? lc.stats + 1 : nullptr);
+    if (cv.model >= 3) return launch_chain_collide_config_moves(cv, lc, agent_i, Q, n_cand, q_to, out, lc.stats ? lc.stats + 1 : nullptr);
     const int sm = seg_smem_bytes(cv.col_len);
     const int grid = grid_for(lc, n_cand, sm);
     cudaError_t e;

@@ -445,6 +445,10 @@ static cudaError_t set_smem(K kernel, int bytes) {
     case 0: { using M = PointModel<2>; EXPR; } break;    \
     case 1: { using M = PointModel<3>; EXPR; } break;    \
     case 2: { using M = ArmModel; EXPR; } break;         \
+    case 3: { using M = ChainModel<3>; EXPR; } break;    \
+    case 4: { using M = ChainModel<4>; EXPR; } break;    \
+    case 5: { using M = ChainModel<5>; EXPR; } break;    \
+    case 6: { using M = ChainModel<6>; EXPR; } break;    \
     default: return cudaErrorNotSupported;               \
     }
 

@@ -578,6 +578,10 @@ k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *
     case 0: { using M = PointModel<2>; EXPR; } break;    \
     case 1: { using M = PointModel<3>; EXPR; } break;    \
     case 2: { using M = ArmModel; EXPR; } break;         \
+    case 3: { using M = ChainModel<3>; EXPR; } break;    \
+    case 4: { using M = ChainModel<4>; EXPR; } break;    \
+    case 5: { using M = ChainModel<5>; EXPR; } break;    \
+    case 6: { using M = ChainModel<6>; EXPR; } break;    \
     default: return cudaErrorNotSupported;               \
     }
 
@@ -599,7 +603,9 @@ cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const Sss
                            k_sssp_conn<M><<<grid, 128, sm, lc.stream>>>(cv, view, a, ws, sm > 0)));
     if (e != cudaSuccess) return e;
     count_launch();
-    if (cv.d == 3)
+    if (cv.d == 6)
+        k_sssp_gather<6><<<1, 256, 0, lc.stream>>>(view, a, ws, cv.n_agents);
+    else if (cv.d == 3)
         k_sssp_gather<3><<<1, 256, 0, lc.stream>>>(view, a, ws, cv.n_agents);
     else
         k_sssp_gather<2><<<1, 256, 0, lc.stream>>>(view, a, ws, cv.n_agents);
@@ -625,7 +631,7 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
                                      const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
                                      double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
                                      uint8_t *h_verdict) {
-    if (a.K < 1 || a.K > 32 || cv.model == 2) return cudaErrorNotSupported;
+    if (a.K < 1 || a.K > 32 || cv.model >= 2) return cudaErrorNotSupported;
     const int sm = (int)sssp_fused_smem(cv, a);
     if (sm > 160 * 1024) return cudaErrorNotSupported;
     cudaError_t e = cudaSuccess;

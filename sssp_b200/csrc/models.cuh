@@ -3,6 +3,7 @@
 // dimension, dist, connect(q,i), connect(q_from,q_to,i), sampler scaling.
 #pragma once
 #include "arm_model.cuh"
+#include "chain_model.cuh"
 #include "point_model.cuh"
 
 namespace mrmp {
@@ -111,6 +112,81 @@ struct ArmModel {
     // get_mid_status: arm22.jl:8-13
     static __device__ __forceinline__ void mid(const double *p, const double *q, double *out) {
         arm_mid_status(p, q, out);
+    }
+};
+
+// line2d / snake2d / arm33 / capsule3d: thread-per-check bodies for the roadmap kernels
+template <int MODEL>
+struct ChainModel {
+    using C = Chain<MODEL>;
+    static constexpr int SD = C::SD;
+    // positions rand(), angles rand() * 2pi (line2d.jl:165-169, snake2d.jl:261-265,
+    // arm33.jl:288-292, capsule3d.jl:216-220)
+    static __device__ __forceinline__ void scale_sample(double *q) {
+#pragma unroll
+        for (int k = C::NPOS; k < SD; ++k) q[k] = dmul(q[k], 6.283185307179586);
+    }
+    static __device__ __forceinline__ ChainPar par(const CtxView &cv) {
+        ChainPar p;
+        p.sr.ok = cv.step_rat_ok;
+        p.sr.num = cv.step_rat_num;
+        p.sr.den = cv.step_rat_den;
+        p.step = cv.step_dist;
+        p.safety = cv.safety_dist;
+        p.safety_t2 = cv.safety_t2;
+        p.max_dist = cv.max_dist;
+        return p;
+    }
+    static __device__ __forceinline__ ChainGeom geom(const CtxView &cv, const ConSeg &cs, int i) {
+        ChainGeom g;
+        g.rad = cs.rad(i);
+        g.len = MODEL == kModelCapsule3D ? cs.s[cv.aux_off - cv.con_off + i] : g.rad;
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+            g.base[x] = (ChainTraits<MODEL>::kHasBase && x < C::W)
+                            ? cs.s[cv.base_off - cv.con_off + C::W * i + x]
+                            : 0.0;
+        return g;
+    }
+    static __device__ __forceinline__ ChainObs obs(const ConSeg &cs, int i) {
+        ChainObs o;
+        o.s = cs.s;
+        o.obs = cs.obs;
+        o.t2 = cs.t2 + (ChainTraits<MODEL>::kObsAddsRad ? i * cs.mp : 0);
+        o.mp = cs.mp;
+        o.n_obs = cs.n_obs;
+        return o;
+    }
+    static __device__ __forceinline__ bool connect_point(const CtxView &cv, const ConSeg &cs,
+                                                         const double *q, int i) {
+        return chain_connect_point<MODEL>(par(cv), obs(cs, i), geom(cv, cs, i), q);
+    }
+    static __device__ __forceinline__ bool connect_edge(const CtxView &cv, const ConSeg &cs,
+                                                        const double *qf, const double *qt, int i) {
+        return chain_connect_edge<MODEL>(par(cv), obs(cs, i), geom(cv, cs, i), qf, qt);
+    }
+    static __device__ __forceinline__ bool dist_le(const CtxView &, const double *qa,
+                                                   const double *qb, double rad, double r2) {
+        double v[SD];
+        C::dist_vec(qa, qb, v);
+        const double s = sumsq<SD>(v);
+        if (s == 0.0) return norm_slow<SD>(v) <= rad;
+        return s <= r2;
+    }
+    static __device__ __forceinline__ bool dist_gt(const CtxView &, const double *qa,
+                                                   const double *qb, double thr, double r2) {
+        double v[SD];
+        C::dist_vec(qa, qb, v);
+        const double s = sumsq<SD>(v);
+        if (s == 0.0) return norm_slow<SD>(v) > thr;
+        return s > r2;
+    }
+    static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
+                                                  const double *qb) {
+        return C::dist(qa, qb);
+    }
+    static __device__ __forceinline__ void mid(const double *p, const double *q, double *out) {
+        C::mid(p, q, out);
     }
 };
 

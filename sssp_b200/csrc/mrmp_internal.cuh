@@ -10,24 +10,27 @@ namespace mrmp {
 // Device-side view of one problem instance.  `blob` is one contiguous array of doubles in
 // HBM; offsets are in doubles.  Layout (each section padded to a multiple of 2 doubles so
 // that every section start is 16-byte aligned for the 1-D TMA bulk copy):
-//   [CONNECT SEGMENT]  obs SoA: x[mp] y[mp] (z[mp]) r[mp] | rads[np] | base[2*np] |
-//                      t2_obs[N][mp] | g_obs[N][mp]
-//   [COLLIDE SEGMENT]  rads[np] | base[2*np] | t2_pair[N][N] | g_pair[N][N] (when has_pair_tab)
+//   [CONNECT SEGMENT]  obs SoA: x[mp] y[mp] (z[mp]) r[mp] | rads[np] | base[wd*np] | aux[np] |
+//                      t2_obs[N or 1][mp] | g_obs[N or 1][mp]
+//   [COLLIDE SEGMENT]  rads[np] | base[wd*np] | aux[np] | t2_pair[N][N] | g_pair[N][N]
+//                      (pair tables when the pair threshold is rads[i] + rads[j])
 // t2_* = sq_lt_threshold(thr) (sqrt-free exact compare), g_* = broad-phase bound; the
 // thresholds themselves (o.r + rads[i], rads[i] + rads[j]) are recomputed on the fly where
 // the rare slow path needs them.
 struct CtxView {
     const double *blob;
-    int model, d, n_agents, n_obs;
+    int model, d, n_agents, n_obs;  // d = state dimension
+    int wd;                         // workspace dimension (obstacle centres, joint points)
     int mp, np;          // padded obstacle / agent counts
     // connect segment
     int con_off, con_len;  // segment [con_off, con_off+con_len) is staged to smem
     int obs_off;           // SoA base: coordinate k of obstacle m at obs_off + k*mp + m; radius at k = wd
-    int rads_off, base_off;
+    int rads_off, base_off;     // base: wd doubles per agent (arm22, arm33)
+    int aux_off;                // capsule3d axis lengths (axises[i])
     int t2_obs_off, g_obs_off;  // [agent*mp + m]
     // collide segment
     int col_off, col_len;
-    int crads_off, cbase_off;
+    int crads_off, cbase_off, caux_off;
     int has_pair_tab;
     int t2_pair_off, g_pair_off;  // [i*N + j]
     double step_dist, safety_dist, max_dist;
@@ -158,6 +161,42 @@ cudaError_t launch_arm_collide_configs(const CtxView &cv, const LaunchCfg &lc, i
                                        int64_t *first_pair, unsigned long long *first_scratch,
                                        unsigned long long *stats);
 cudaError_t launch_arm_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, int agent_i,
+                                            const double *Q, int64_t n_cand, const double *q_to,
+                                            uint8_t *out, unsigned long long *stats);
+
+// kernels_chain.cu (line2d / snake2d / arm33 / capsule3d; forwarded to when cv.model >= 3)
+cudaError_t launch_chain_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                      const int32_t *agent, const double *q, uint8_t *out);
+cudaError_t launch_chain_connect_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                     const int32_t *agent, const double *qf, const double *qt,
+                                     uint8_t *out);
+cudaError_t launch_chain_collide_static_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                            const int32_t *ai, const int32_t *aj,
+                                            const double *qi, const double *qj, uint8_t *out);
+cudaError_t launch_chain_collide_pairs(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                     const int32_t *ai, const int32_t *aj, const double *qif,
+                                     const double *qit, const double *qjf, const double *qjt,
+                                     uint8_t *out, unsigned long long *stats);
+cudaError_t launch_chain_collide_edges_indexed(const CtxView &cv, const LaunchCfg &lc, int64_t n,
+                                             const int32_t *ai, const int32_t *aj,
+                                             const int32_t *vif, const int32_t *vit,
+                                             const int32_t *vjf, const int32_t *vjt,
+                                             const double *nodes, int agent0, int nv_stride,
+                                             uint8_t *out, unsigned long long *stats);
+cudaError_t launch_chain_collide_cross(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
+                                     const int32_t *row_agent, const double *row_from,
+                                     const double *row_to, int64_t n_cols,
+                                     const int32_t *col_agent, const double *col_from,
+                                     const double *col_to, const int32_t *col_vf,
+                                     const int32_t *col_vt, const double *nodes, int agent0,
+                                     int nv_stride, int group_size, int words_per_row,
+                                     uint32_t *out, unsigned long long *stats);
+// first_scratch: n_cfg words of device scratch
+cudaError_t launch_chain_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64_t n_cfg,
+                                       const double *Qf, const double *Qt, uint8_t *out,
+                                       int64_t *first_pair, unsigned long long *first_scratch,
+                                       unsigned long long *stats);
+cudaError_t launch_chain_collide_config_moves(const CtxView &cv, const LaunchCfg &lc, int agent_i,
                                             const double *Q, int64_t n_cand, const double *q_to,
                                             uint8_t *out, unsigned long long *stats);
 

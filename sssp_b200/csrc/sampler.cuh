@@ -38,15 +38,14 @@ __device__ __forceinline__ double u01_53(uint32_t hi, uint32_t lo) {
 // gen_uniform_sampling: point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218
 template <class M>
 __device__ __forceinline__ void sample_state(uint64_t seed, int agent, uint64_t t, double *q) {
-    uint32_t r[4];
-    philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, 0u, (uint32_t)seed,
-               (uint32_t)(seed >> 32), r);
-    q[0] = u01_53(r[0], r[1]);
-    q[1] = u01_53(r[2], r[3]);
-    if constexpr (M::SD == 3) {
-        philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, 1u, (uint32_t)seed,
+    // uniform k of a try = pair (k % 2) of Philox block k / 2
+#pragma unroll
+    for (int b = 0; 2 * b < M::SD; ++b) {
+        uint32_t r[4];
+        philox4x32((uint32_t)t, (uint32_t)(t >> 32), (uint32_t)agent, (uint32_t)b, (uint32_t)seed,
                    (uint32_t)(seed >> 32), r);
-        q[2] = u01_53(r[0], r[1]);
+        q[2 * b] = u01_53(r[0], r[1]);
+        if (2 * b + 1 < M::SD) q[2 * b + 1] = u01_53(r[2], r[3]);
     }
     M::scale_sample(q);
 }

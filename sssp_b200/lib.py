@@ -14,7 +14,11 @@ from . import build as _build
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22 = 0, 1, 2
-STATE_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2}
+MODEL_LINE2D, MODEL_SNAKE2D, MODEL_ARM33, MODEL_CAPSULE3D = 3, 4, 5, 6
+STATE_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2, MODEL_LINE2D: 3, MODEL_SNAKE2D: 6,
+             MODEL_ARM33: 6, MODEL_CAPSULE3D: 6}
+WORK_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2, MODEL_LINE2D: 2, MODEL_SNAKE2D: 2,
+            MODEL_ARM33: 3, MODEL_CAPSULE3D: 3}
 
 # every buffer argument is declared void* so that numpy arrays (ndarray.ctypes.data_as),
 # torch pinned tensors (data_ptr()) and raw device pointers can all be passed
