@@ -17,20 +17,24 @@ from oracle import sssp_ref as R        # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def gen_instance(model, N, num_obs, rad, rad_obs, seed, base_box=(0.25, 0.75)):
+NPOS = {O.POINT2D: 2, O.POINT3D: 3, O.ARM22: 0, O.LINE2D: 2, O.SNAKE2D: 2, O.ARM33: 0, O.CAPSULE3D: 3}
+
+
+def gen_instance(model, N, num_obs, rad, rad_obs, seed, base_box=(0.25, 0.75), axis=(0.08, 0.12)):
     """utils.jl:204-245 / :160-201: obstacles, radii, then per agent a start and a goal that are
     free (connect(q,i)) and do not collide with the starts / goals chosen so far."""
     rng = np.random.default_rng(seed)
-    d = 3 if model == O.POINT3D else 2
-    wd = d
+    d, wd = O._D[model], O._W[model]
     obs = np.array([list(rng.random(wd)) + [rng.uniform(*rad_obs)] for _ in range(num_obs)]).reshape(-1, wd + 1)
     rads = np.array([rng.uniform(*rad) for _ in range(N)])
-    base = rng.uniform(*base_box, size=(N, 2)) if model == O.ARM22 else None
-    orc = O.Oracle(model, rads, obs, base=base)
+    base = rng.uniform(*base_box, size=(N, wd)) if model in (O.ARM22, O.ARM33) else None
+    aux = rng.uniform(*axis, size=N) if model == O.CAPSULE3D else None
+    orc = O.Oracle(model, rads, obs, base=base, aux=aux)
 
-    def sample():
+    def sample():   # gen_uniform_sampling: positions rand(), angles rand() * 2pi
         q = rng.random(d)
-        return q * (2 * np.pi) if model == O.ARM22 else q
+        q[NPOS[model]:] *= 2 * np.pi
+        return q
 
     init, goal = [], []
     for i in range(N):
@@ -45,6 +49,7 @@ def gen_instance(model, N, num_obs, rad, rad_obs, seed, base_box=(0.25, 0.75)):
                 raise RuntimeError("instance generation stalled")
     return dict(model=int(model), rads=rads.tolist(), obstacles=obs.tolist(),
                 base=None if base is None else base.tolist(),
+                aux=None if aux is None else aux.tolist(),
                 config_init=[q.tolist() for q in init], config_goal=[q.tolist() for q in goal])
 
 
@@ -71,6 +76,15 @@ CASES = {
     "sssp_arm22_n3_seed2": dict(model=O.ARM22, N=3, num_obs=1, rad=(0.12, 0.16),
                                 rad_obs=(0.05, 0.08), seed=2,
                                 params=dict(steering_depth=4, num_vertex_expansion=5)),
+    # the other discretised models with their eval-config solver parameters
+    # (scripts/config/eval/line2d.yaml, capsule3d.yaml), bodies sized so that N agents fit
+    "sssp_line2d_n4_seed5": dict(model=O.LINE2D, N=4, num_obs=3, rad=(0.06, 0.1),
+                                 rad_obs=(0.05, 0.08), seed=5,
+                                 params=dict(steering_depth=2, num_vertex_expansion=10)),
+    "sssp_capsule3d_n3_seed7": dict(model=O.CAPSULE3D, N=3, num_obs=3, rad=(0.03, 0.05),
+                                    rad_obs=(0.05, 0.1), seed=7,
+                                    params=dict(steering_depth=2, num_vertex_expansion=10,
+                                                init_min_dist_thread=0.2)),
 }
 
 
@@ -78,7 +92,8 @@ def main():
     for name, c in CASES.items():
         inst = gen_instance(c["model"], c["N"], c["num_obs"], c["rad"], c["rad_obs"], c["seed"])
         orc = O.Oracle(c["model"], inst["rads"], np.array(inst["obstacles"]),
-                       base=None if inst["base"] is None else np.array(inst["base"]))
+                       base=None if inst["base"] is None else np.array(inst["base"]),
+                       aux=None if inst["aux"] is None else np.array(inst["aux"]))
         sol, rms, st = R.SSSP(orc, inst["config_init"], inst["config_goal"], seed=c["seed"],
                               **c["params"])
         out = dict(instance=inst, params=c["params"], seed=c["seed"], solution=sol,

@@ -16,7 +16,9 @@ from oracle import sssp_ref as R
 
 pytestmark = pytest.mark.gpu
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sssp_*.json")))
-STATE = {O.POINT2D: S.StatePoint2D, O.POINT3D: S.StatePoint3D, O.ARM22: S.StateArm22}
+STATE = {O.POINT2D: S.StatePoint2D, O.POINT3D: S.StatePoint3D, O.ARM22: S.StateArm22,
+         O.LINE2D: S.StateLine2D, O.SNAKE2D: S.StateSnake2D, O.ARM33: S.StateArm33,
+         O.CAPSULE3D: S.StateCapsule3D}
 
 
 def load(path):
@@ -24,7 +26,8 @@ def load(path):
         fx = json.load(f)
     inst = fx["instance"]
     base = None if inst["base"] is None else np.array(inst["base"])
-    orc = O.Oracle(inst["model"], inst["rads"], np.array(inst["obstacles"]), base=base)
+    aux = None if inst.get("aux") is None else np.array(inst["aux"])
+    orc = O.Oracle(inst["model"], inst["rads"], np.array(inst["obstacles"]), base=base, aux=aux)
     return fx, inst, orc, base
 
 
@@ -32,6 +35,8 @@ def closures(inst, base):
     State = STATE[inst["model"]]
     tag = State(*([0.0] * len(State._fields)))
     params = (inst["rads"],) if base is None else (base, inst["rads"])
+    if inst.get("aux") is not None:
+        params = (inst["rads"], inst["aux"])
     connect = S.gen_connect(tag, np.array(inst["obstacles"]), *params)
     collide = S.gen_collide(tag, *params)
     goal = [State(*q) for q in inst["config_goal"]]
@@ -63,7 +68,8 @@ def test_expand_matches_oracle(model, slow):
     path = [p for p in GOLD if {O.POINT2D: "point2d_many", O.POINT3D: "point3d", O.ARM22: "arm22"}[model] in p][0]
     fx, inst, orc, base = load(path)
     N = len(inst["rads"])
-    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base)
+    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base,
+                    aux=inst.get("aux"))
     # start from the golden (oracle-built) initial roadmaps truncated to their first vertices
     rms = []
     for g in fx["roadmaps"]:
@@ -240,7 +246,8 @@ def test_first_conflict_matches_get_constraints(name):
     """Independent single-agent plans (random walks on the golden roadmaps) conflict somewhere:
     the batched scan must name the same first (t, kind, i, j) as the reference's loop."""
     fx, inst, orc, base = load([p for p in GOLD if name in p][0])
-    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base)
+    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base,
+                    aux=inst.get("aux"))
     N = len(inst["rads"])
     tabs = [np.array([[float.fromhex(x) for x in q] for q in g["nodes"]]) for g in fx["roadmaps"]]
     nbrs = [g["neighbors"] for g in fx["roadmaps"]]
