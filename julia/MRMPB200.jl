@@ -13,11 +13,17 @@
 # SsspRoadmaps / expand_and_filter! (bottom of the file) are the batched node expansion.
 module MRMPB200
 
-import ..MRMP: AbsState, Node, StatePoint2D, StatePoint3D, StateArm22,
-               CircleObstacle2D, CircleObstacle3D, STEP_DIST, SAFETY_DIST_LINE
+import ..MRMP: AbsState, Node, StatePoint2D, StatePoint3D, StateArm22, StateLine2D, StateSnake2D,
+               StateArm33, StateCapsule3D, CircleObstacle2D, CircleObstacle3D, STEP_DIST,
+               SAFETY_DIST_LINE, STEP_DIST_SNAKE2D, STEP_DIST_CAPSULE3D
 
 const LIB = get(ENV, "MRMP_B200_LIB", "libmrmp_b200.so")
-const MODEL = Dict(StatePoint2D => 0, StatePoint3D => 1, StateArm22 => 2)
+const MODEL = Dict(StatePoint2D => 0, StatePoint3D => 1, StateArm22 => 2, StateLine2D => 3,
+                   StateSnake2D => 4, StateArm33 => 5, StateCapsule3D => 6)
+# per-model default of the step_dist keyword (snake2d.jl:3, capsule3d.jl:3)
+default_step(::Type{StateSnake2D}) = STEP_DIST_SNAKE2D
+default_step(::Type{StateCapsule3D}) = STEP_DIST_CAPSULE3D
+default_step(::Type) = STEP_DIST
 
 mutable struct Ctx
     h::Ptr{Cvoid}
@@ -36,14 +42,16 @@ end
 # isbits structs are C-layout: Vector{StatePoint2D} == double[n][2], Vector{CircleObstacle2D}
 # == double[n][3]  (src/obstacle.jl:7-19), so they are passed without conversion.
 function make_ctx(q::State, obstacles, rads::Vector{Float64};
-                  positions = nothing, step_dist = STEP_DIST, safety_dist = SAFETY_DIST_LINE,
-                  max_dist = nothing, device = 0) where {State<:AbsState}
+                  positions = nothing, axises = nothing, step_dist = default_step(State),
+                  safety_dist = SAFETY_DIST_LINE, max_dist = nothing,
+                  device = 0) where {State<:AbsState}
     h = Ref{Ptr{Cvoid}}(C_NULL)
     base = isnothing(positions) ? C_NULL : pointer(reduce(vcat, positions))
+    aux = isnothing(axises) ? C_NULL : pointer(axises)          # capsule3d.jl:65
     check(ccall((:mrmp_ctx_create, LIB), Cint,
                 (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
                  Ptr{Cvoid}, Float64, Float64, Float64, Cint),
-                h, MODEL[State], length(rads), rads, base, C_NULL, length(obstacles),
+                h, MODEL[State], length(rads), rads, base, aux, length(obstacles),
                 isempty(obstacles) ? C_NULL : pointer(obstacles), step_dist, safety_dist,
                 isnothing(max_dist) ? NaN : max_dist, device))
     return Ctx(h[])
@@ -51,9 +59,12 @@ end
 
 """gen_connect(q, obstacles, rads) -- src/models/point2d.jl:42-69, point3d.jl:47-80"""
 function gen_connect(q::State, obstacles, ins_params...; kwargs...) where {State<:AbsState}
-    rads = ins_params[end]
-    positions = length(ins_params) == 2 ? ins_params[1] : nothing   # arm22.jl:29-37
-    ctx = make_ctx(q, obstacles, rads; positions = positions, kwargs...)
+    # ins_params: (rads,) | (positions, rads) for arm22 / arm33 | (rads, axises) for capsule3d
+    capsule = State == StateCapsule3D
+    rads = capsule ? ins_params[1] : ins_params[end]
+    positions = (!capsule && length(ins_params) == 2) ? ins_params[1] : nothing   # arm22.jl:29-37
+    ctx = make_ctx(q, obstacles, rads; positions = positions,
+                   axises = capsule ? ins_params[2] : nothing, kwargs...)
     out = Ref{UInt8}(0)
 
     f(q::State, i::Int64)::Bool = begin                       # point2d.jl:49-57
@@ -80,10 +91,12 @@ end
 
 """gen_collide(q, rads) -- src/models/point.jl:5-36, arm22.jl:90-212"""
 function gen_collide(q::State, ins_params...; kwargs...) where {State<:AbsState}
-    rads = ins_params[end]
-    positions = length(ins_params) == 2 ? ins_params[1] : nothing
-    ctx = make_ctx(q, State == StatePoint3D ? CircleObstacle3D[] : CircleObstacle2D[], rads;
-                   positions = positions, kwargs...)
+    capsule = State == StateCapsule3D
+    rads = capsule ? ins_params[1] : ins_params[end]
+    positions = (!capsule && length(ins_params) == 2) ? ins_params[1] : nothing
+    ws3 = State in (StatePoint3D, StateArm33, StateCapsule3D)
+    ctx = make_ctx(q, ws3 ? CircleObstacle3D[] : CircleObstacle2D[], rads;
+                   positions = positions, axises = capsule ? ins_params[2] : nothing, kwargs...)
     N = length(rads)
     out = Ref{UInt8}(0)
 
