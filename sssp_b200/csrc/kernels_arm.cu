@@ -29,9 +29,9 @@ namespace mrmp {
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
 constexpr int kThreads = 256;      // thread-per-check and connect kernels
-constexpr int kPairWarps = 4;      // warps per CTA in the table kernels
+constexpr int kPairWarps = 8;      // warps per CTA in the table kernels
 constexpr int kPairThreads = 32 * kPairWarps;
-constexpr int kArmCap = 128;       // postures per table tile
+constexpr int kArmCap = 64;        // postures per table tile (8 KB of tables per warp)
 constexpr int kQueueCap = 160;     // < 32 left over + up to 128 new per sweep iteration
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -41,7 +41,9 @@ struct IEntry {  // posture of the first agent: joints b, c and the midpoints of
 struct JEntry {  // posture of the second agent: base, joints, cull bound of the agent pair
     double ax, ay, bx, by, cx, cy, G, pad;
 };
-constexpr int kWarpTableBytes = kArmCap * (int)(sizeof(IEntry) + sizeof(JEntry)) + kQueueCap * 4;
+__host__ __device__ constexpr int warp_table_bytes(int cap) {
+    return cap * (int)(sizeof(IEntry) + sizeof(JEntry)) + kQueueCap * 4;
+}
 
 static inline int seg_smem_bytes(int seg_len) {
     const int bytes = seg_len * 8 + 16;
@@ -294,7 +296,7 @@ __device__ __forceinline__ bool warp_arm_collide_pair(const ArmCtx &ac, const Ar
                                                       const double *qif, const double *qit,
                                                       const double *qjf, const double *qjt, int i,
                                                       int j, IEntry *I, JEntry *J, unsigned *queue,
-                                                      int lane, unsigned &n_exact) {
+                                                      int cap, int lane, unsigned &n_exact) {
     ArmMove mi, mj;
     warp_arm_moves(ac, lane, qif, qit, qjf, qjt, mi, mj, true);
     mi.ax = sg.bx(i), mi.ay = sg.by(i), mi.rad = sg.rad(i);
@@ -308,12 +310,12 @@ __device__ __forceinline__ bool warp_arm_collide_pair(const ArmCtx &ac, const Ar
     }
     const double G = arm_pair_bound(ac.safety, mi.rad, mj.rad);
     const long long ni = mi.sch.n(), nj = mj.sch.n();
-    for (long long i0 = 0; i0 < ni; i0 += kArmCap) {
-        const int ci = (int)(ni - i0 < kArmCap ? ni - i0 : kArmCap);
+    for (long long i0 = 0; i0 < ni; i0 += cap) {
+        const int ci = (int)(ni - i0 < cap ? ni - i0 : cap);
         fill_I(I, mi, i0, ci, lane);
-        for (long long j0 = 0; j0 < nj; j0 += kArmCap) {
-            const int cj = (int)(nj - j0 < kArmCap ? nj - j0 : kArmCap);
-            if (i0 == 0 || nj > kArmCap) fill_J(J, mj, j0, cj, G, lane);
+        for (long long j0 = 0; j0 < nj; j0 += cap) {
+            const int cj = (int)(nj - j0 < cap ? nj - j0 : cap);
+            if (i0 == 0 || nj > cap) fill_J(J, mj, j0, cj, G, lane);
             __syncwarp();
             if (warp_sweep(I, ci, mi.ax, mi.ay, J, cj, queue, ac, lane, n_exact)) return true;
             __syncwarp();
@@ -443,25 +445,30 @@ struct ConfigSrc {  // collide(Q_from, Q_to): arm22.jl:164-171, pairs i < j in r
 };
 
 template <class Src>
-__global__ void __launch_bounds__(kPairThreads)
-k_arm_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats, int staged,
-              int seg_bytes) {
+__global__ void __launch_bounds__(kPairThreads, 3)
+k_arm_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
+              unsigned long long *work, int staged, int seg_bytes, int cap) {
     const ArmSeg sg = arm_col(cv, stage_segment(cv, cv.col_off, cv.col_len, smem_raw, staged));
     const ArmCtx ac = arm_ctx(cv);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wb = smem_raw + seg_bytes + (size_t)warp * kWarpTableBytes;
+    unsigned char *wb = smem_raw + seg_bytes + (size_t)warp * warp_table_bytes(cap);
     IEntry *I = reinterpret_cast<IEntry *>(wb);
-    JEntry *J = reinterpret_cast<JEntry *>(wb + kArmCap * sizeof(IEntry));
-    unsigned *queue = reinterpret_cast<unsigned *>(wb + kArmCap * (sizeof(IEntry) + sizeof(JEntry)));
+    JEntry *J = reinterpret_cast<JEntry *>(wb + cap * sizeof(IEntry));
+    unsigned *queue = reinterpret_cast<unsigned *>(wb + cap * (sizeof(IEntry) + sizeof(JEntry)));
     unsigned n_exact = 0;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += n_warps) {
+    // checks differ in cost by orders of magnitude (S_i x S_j posture pairs, early exits):
+    // warps pull the next check from a counter instead of striding
+    for (;;) {
+        unsigned long long kk = 0;
+        if (lane == 0) kk = atomicAdd(work, 1ull);
+        const int64_t k = (int64_t)__shfl_sync(kFull, kk, 0);
+        if (k >= n) break;
         PairCheck p;
         const bool run = src.fetch(k, p);  // warp-uniform
         bool hit = false;
         if (run)
             hit = warp_arm_collide_pair(ac, sg, p.qif, p.qit, p.qjf, p.qjt, p.i, p.j, I, J, queue,
-                                        lane, n_exact);
+                                        cap, lane, n_exact);
         if (lane == 0) src.emit(k, run, hit);
         __syncwarp();
     }
@@ -580,20 +587,30 @@ cudaError_t launch_arm_connect_edges(const CtxView &cv, const LaunchCfg &lc, int
 template <class Src>
 static cudaError_t launch_arm_collide_src(const CtxView &cv, const LaunchCfg &lc, int64_t n,
                                           const Src &src, unsigned long long *stats) {
+    // bulk batches: 8 warps per CTA with 64-posture table tiles (3 CTAs = 24 warps per SM);
+    // small batches are bound by their slowest check: fewer warps per CTA spread them over more
+    // SMs, and 128-posture tiles hold a whole move (no table refills)
+    int warps = kPairWarps;
+    while (warps > 1 && (n + warps - 1) / warps < (int64_t)lc.sm_count * 3) warps >>= 1;
+    const int cap = warps <= 4 ? 2 * kArmCap : kArmCap;
     int seg = seg_smem_bytes(cv.col_len);
-    const int tables = kPairWarps * kWarpTableBytes;
+    const int tables = warps * warp_table_bytes(cap);
     if (seg + tables > 200 * 1024) seg = 0;
     const int sm = seg + tables;
     cudaError_t e = set_smem(k_arm_collide<Src>, sm);
     if (e != cudaSuccess) return e;
     int per_sm = (220 * 1024) / sm;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    int64_t want = (n + kPairWarps - 1) / kPairWarps;
-    const int64_t cap = (int64_t)lc.sm_count * per_sm;
+    if (per_sm > 12) per_sm = 12;
+    int64_t want = (n + warps - 1) / warps;
+    const int64_t cap_ctas = (int64_t)lc.sm_count * per_sm;
     if (want < 1) want = 1;
-    const int grid = (int)(want < cap ? want : cap);
-    k_arm_collide<Src><<<grid, kPairThreads, sm, lc.stream>>>(cv, n, src, stats, seg > 0, seg);
+    const int grid = (int)(want < cap_ctas ? want : cap_ctas);
+    // work counter: the ctx's reserved counter slot, zeroed in stream order before the launch
+    unsigned long long *work = lc.stats + 3;
+    e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), lc.stream);
+    if (e != cudaSuccess) return e;
+    k_arm_collide<Src><<<grid, 32 * warps, sm, lc.stream>>>(cv, n, src, stats, work, seg > 0, seg, cap);
     count_launch();
     return cudaGetLastError();
 }

@@ -498,8 +498,8 @@ struct ConfigSrcN {
 
 template <int MODEL, class Src>
 __global__ void __launch_bounds__(kPairThreads)
-k_chain_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats, int staged,
-                int seg_bytes) {
+k_chain_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
+                unsigned long long *work, int staged, int seg_bytes) {
     using Y = Lay<MODEL>;
     constexpr int SD = Chain<MODEL>::SD;
     const double *col = stage_segment(cv, cv.col_off, cv.col_len, smem_raw, staged);
@@ -510,8 +510,13 @@ k_chain_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats, int s
     double *J = I + Y::CAP * Y::IE;
     unsigned *queue = reinterpret_cast<unsigned *>(J + Y::CAP * Y::JE);
     unsigned n_exact = 0;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += n_warps) {
+    // checks differ in cost by orders of magnitude (S_i x S_j posture pairs, early exits):
+    // warps pull the next check from a counter instead of striding
+    for (;;) {
+        unsigned long long kk = 0;
+        if (lane == 0) kk = atomicAdd(work, 1ull);
+        const int64_t k = (int64_t)__shfl_sync(kFull, kk, 0);
+        if (k >= n) break;
         PairCheckN<SD> p;
         const bool run = src.fetch(k, p);
         bool hit = false;
@@ -664,7 +669,11 @@ static cudaError_t launch_chain_collide_src(const CtxView &cv, const LaunchCfg &
     const int64_t cap = (int64_t)lc.sm_count * per_sm;
     if (want < 1) want = 1;
     const int grid = (int)(want < cap ? want : cap);
-    k_chain_collide<MODEL, Src><<<grid, kPairThreads, sm, lc.stream>>>(cv, n, src, stats, seg > 0, seg);
+    unsigned long long *work = lc.stats + 3;  // ctx counter slot, zeroed in stream order
+    e = cudaMemsetAsync(work, 0, sizeof(unsigned long long), lc.stream);
+    if (e != cudaSuccess) return e;
+    k_chain_collide<MODEL, Src><<<grid, kPairThreads, sm, lc.stream>>>(cv, n, src, stats, work, seg > 0,
+                                                                      seg);
     count_launch();
     return cudaGetLastError();
 }
