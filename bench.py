@@ -491,6 +491,7 @@ def extra_sssp_expansion(inst, nodes_h, device):
     roadmaps of 300 vertices per agent, N=50) through the host API, against the same
     expansion in C on one host core (a reference solver call is single-threaded)."""
     import sssp_b200 as S
+    from sssp_b200 import lib as L
     from oracle import oracle as O
     N, nv0, K = inst.rads.size, 300, 10
     ctx = S.Context(inst.model, inst.rads, inst.obstacles, device=device)
@@ -506,27 +507,46 @@ def extra_sssp_expansion(inst, nodes_h, device):
         ids = rng.integers(0, nv0, N).astype(np.int32)
         old = rng.choice(nv0, 12, replace=False).astype(np.int32)
         calls.append((a, int(ids[a]), ids, old, rng.random((K, 2))))
-    kw = dict(steering_depth=2, epsilon=0.2, min_dist_thread=0.02)
-    dev_rm.expand(calls[0][0], calls[0][1], calls[0][2], calls[0][3], K, q_rand=calls[0][4], **kw)
+    # timed through the C ABI itself (the drop-in boundary) with caller-owned buffers, exactly
+    # what the Julia glue passes; decoding the bitmaps is host bookkeeping outside the call
+    lib = L.load()
+    words_cap = (nv0 + 64 * K + 31) // 32
+    q_new = np.empty((K, 2))
+    ob_g, ib_g = np.zeros((K, words_cap), np.uint32), np.zeros((K, words_cap), np.uint32)
+    succ, hit = np.empty(12 + K + 1, np.int32), np.empty(12 + K + 1, np.uint8)
+    n_new, n_succ, w = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+
+    def call(a, v, ids, old, qr):
+        L.check(lib.mrmp_sssp_expand(dev_rm._h, a, v, K, qr.ctypes.data, 0, 0, 2, 0.2, 0.02,
+                                     ids.ctypes.data, old.size, old.ctypes.data, 0, C.byref(n_new),
+                                     q_new.ctypes.data, C.byref(w), ob_g.ctypes.data, ib_g.ctypes.data,
+                                     ob_g.size, C.byref(n_succ), succ.ctypes.data, hit.ctypes.data))
+
+    call(*calls[0])
     tabs[calls[0][0]] = dev_rm.nodes(calls[0][0])
-    t_gpu, t_cpu, mism, n_new = 0.0, 0.0, 0, 0
+    t_gpu, t_cpu, mism, n_acc = 0.0, 0.0, 0, 0
     for a, v, ids, old, qr in calls[1:]:
         Q = np.stack([tabs[j][ids[j]] for j in range(N)])
         t0 = time.perf_counter()
-        q_new, outs, ins, succ, hit = dev_rm.expand(a, v, ids, old, K, q_rand=qr, **kw)
+        call(a, v, ids, old, qr)
         t1 = time.perf_counter()
         after, ob, ib, osucc, ohit = orc.sssp_expand(a, tabs[a], v, qr, 2, 0.2, 0.02, Q, old)
         t2 = time.perf_counter()
         t_gpu += t1 - t0
         t_cpu += t2 - t1
-        ok = (after.shape[0] - tabs[a].shape[0] == len(q_new) and np.array_equal(after[tabs[a].shape[0]:], q_new)
-              and np.array_equal(succ, osucc) and np.array_equal(hit, ohit))
+        k, ns, wd_ = n_new.value, n_succ.value, w.value
+        ok = (after.shape[0] - tabs[a].shape[0] == k and np.array_equal(after[tabs[a].shape[0]:], q_new[:k])
+              and np.array_equal(succ[:ns], osucc) and np.array_equal(hit[:ns], ohit)
+              and np.array_equal(ob_g.reshape(-1)[:K * wd_].reshape(K, wd_)[:k, :ob.shape[1]], ob)
+              and np.array_equal(ib_g.reshape(-1)[:K * wd_].reshape(K, wd_)[:k, :ib.shape[1]], ib))
         mism += 0 if ok else 1
-        n_new += len(q_new)
+        n_acc += k
         tabs[a] = after
+    n_new = n_acc
     n = len(calls) - 1
     return {"calls": n, "K": K, "n_agents": int(N), "roadmap_vertices": nv0,
             "gpu_ms_per_expansion": 1e3 * t_gpu / n, "cpu_c_1core_ms_per_expansion": 1e3 * t_cpu / n,
+            "timed": "mrmp_sssp_expand through the C ABI (host buffers in, results out)",
             "accepted_vertices": n_new, "mismatching_calls": mism}
 
 

@@ -14,6 +14,7 @@
 // the same call (sssp.jl:250 reads the roadmap after earlier push!es) -- resolved by a K x K
 // closeness matrix and one serial pass; the new vertex's out-edges exclude itself while its
 // in-edge pass includes the self loop (sssp.jl:252-262).
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "models.cuh"
@@ -215,11 +216,41 @@ k_sssp_gather(SsspView view, SsspExpand a, SsspWs ws, int n_agents) {
 // A popped search node of the reference's configs touches a roadmap of 10^1..10^3 vertices:
 // the whole expansion is ~10^4 primitive tests, i.e. a few microseconds of GPU work, so the
 // call is bound by launch and copy latency, not throughput.  This kernel runs every stage in
-// ONE CTA of 1024 threads (phases separated by __syncthreads), reads its inputs from and
-// writes its results to MAPPED PINNED host memory directly (no memcpy nodes around it), so a
-// call is one launch + one stream synchronisation.  The multi-kernel path above takes over
-// for large roadmaps and for the arm model.
+// ONE launch of one thread-block CLUSTER of 8 CTAs x 1024 threads: the leader CTA keeps the
+// state of the expansion in its shared memory and runs the serial stages; the 2*K'*nv edge
+// tests -- the bulk of the work -- are spread over all 8 CTAs, which read the accepted
+// vertices from, and OR their verdict bits into, the leader's shared memory through
+// distributed shared memory (cluster.map_shared_rank).  Inputs are read from and results
+// written to MAPPED PINNED host memory directly (no memcpy nodes around the kernel), so a call
+// is one launch + one stream synchronisation.  Steering runs one sample per warp with the
+// obstacles of each conn test spread over the lanes.  The multi-kernel path above takes
+// over for large roadmaps and for the discretised models.
+
+// conn(q_from, q_to) of a point model with the obstacle loop spread over the lanes of a warp
+// (point2d.jl:59-66 / point3d.jl:66-77 + the epsilon gate of sssp.jl:87-89); warp-uniform result
+template <class M>
+__device__ __forceinline__ bool warp_conn_point(const CtxView &cv, const ConSeg &cs,
+                                                const SsspExpand &a, const double *qf,
+                                                const double *qt, int lane) {
+    constexpr int D = M::SD;
+    if (a.eps == a.eps && !M::dist_le(cv, qf, qt, a.eps, a.eps_r2)) return false;
+    const double r = cs.rad(a.agent);
+    bool ok = !out_of_field<D>(qt, r);
+    double u[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) u[k] = dsub(qf[k], qt[k]);
+    const double uu = dotd<D>(u, u);
+    for (int m = lane; m < cs.n_obs; m += 32) {
+        double c[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) c[k] = cs.oc(k, m);
+        ok &= !segpt_lt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(a.agent, m));
+    }
+    return __all_sync(0xffffffffu, ok);
+}
 constexpr int kFusedThreads = 1024;
+constexpr int kFusedCluster = 8;  // CTAs of the thread-block cluster that share the edge tests
+namespace cg = cooperative_groups;
 
 template <class M>
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -232,7 +263,10 @@ k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__re
     __shared__ int s_near[kMaxExpand];
     __shared__ unsigned long long s_close[kMaxExpand];
     __shared__ int s_rank[kMaxExpand];
-    __shared__ int s_nnew, s_nsucc;
+    __shared__ int s_nnew, s_nsucc, s_nv0;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+    const bool leader = crank == 0;
     const int tid = threadIdx.x, N = cv.n_agents;
     const int cap_s = a.n_old + a.K + 1;
     // dynamic smem: Qids[N] | succ[cap_s] | flag[cap_s] | bits[2*K*words] | Q[N][D]
@@ -243,128 +277,139 @@ k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__re
     double *s_Q = reinterpret_cast<double *>(smem_raw + ((4 * (size_t)(N + 2 * cap_s + 2 * a.K * a.words) + 15) & ~(size_t)15));
     const ConSeg cs(cv, cv.blob + cv.con_off);
     const ColSeg ks(cv, cv.blob + cv.col_off);
-    const int nv0 = view.nv[a.agent];
     double *tab = view.nodes + (int64_t)a.agent * view.cap * D;
-
-    // ---- inputs from mapped host memory: Q_ids[N], old_nbrs[n_old]
-    for (int t = tid; t < N; t += blockDim.x) s_qids[t] = h_in[t];
-    for (int t = tid; t < a.n_old; t += blockDim.x) s_succ[t] = h_old[t];
-    for (int t = tid; t < cap_s; t += blockDim.x) s_flag[t] = 0;
-    for (int t = tid; t < 2 * a.K * a.words; t += blockDim.x) s_bits[t] = 0u;
-    // ---- steering: sample k on warp k (independent chains on different schedulers)
-    if ((tid & 31) == 0 && (tid >> 5) < a.K) {
-        const int k = tid >> 5;
-        double q_near[D], qh[D];
-        load_state<D>(tab, a.v_from, q_near);
-        if (a.host_samples) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int nv0 = 0, n_new = 0;
+    if (leader) {
+        nv0 = view.nv[a.agent];
+        // ---- inputs from mapped host memory: Q_ids[N], old_nbrs[n_old]
+        for (int t = tid; t < N; t += blockDim.x) s_qids[t] = h_in[t];
+        for (int t = tid; t < a.n_old; t += blockDim.x) s_succ[t] = h_old[t];
+        for (int t = tid; t < cap_s; t += blockDim.x) s_flag[t] = 0;
+        for (int t = tid; t < 2 * a.K * a.words; t += blockDim.x) s_bits[t] = 0u;
+        // ---- steering (sssp.jl:269-291): sample k on warp k, obstacles over the lanes
+        if (warp < a.K) {
+            const int k = warp;
+            double q_near[D], qh[D];
+            load_state<D>(tab, a.v_from, q_near);
+            if (a.host_samples) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) qh[c] = h_qrand[k * D + c];
-        } else {
-            sample_state<M>(a.seed, a.agent, a.t0 + (uint64_t)k, qh);
+                for (int c = 0; c < D; ++c) qh[c] = h_qrand[k * D + c];
+            } else {
+                sample_state<M>(a.seed, a.agent, a.t0 + (uint64_t)k, qh);
+            }
+            if (!warp_conn_point<M>(cv, cs, a, q_near, qh, lane)) {
+                double ql[D], q[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) ql[c] = q_near[c];
+                for (int st = 0; st < a.depth; ++st) {
+                    M::mid(ql, qh, q);
+                    const bool ok = warp_conn_point<M>(cv, cs, a, q_near, q, lane);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        if (ok) ql[c] = q[c];
+                        else qh[c] = q[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) qh[c] = ql[c];
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) s_q[k][c] = qh[c];
+                s_near[k] = 0;
+                s_close[k] = 0ull;
+            }
         }
-        if (!conn<M>(cv, cs, a, q_near, qh)) {
-            double ql[D], q[D];
+        __syncthreads();
+        for (int j = tid; j < N; j += blockDim.x) {
+            const double *tj = view.nodes + ((int64_t)j * view.cap + s_qids[j]) * D;
 #pragma unroll
-            for (int c = 0; c < D; ++c) ql[c] = q_near[c];
-            for (int s = 0; s < a.depth; ++s) {
-                M::mid(ql, qh, q);
-                const bool ok = conn<M>(cv, cs, a, q_near, q);
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    if (ok) ql[c] = q[c];
-                    else qh[c] = q[c];
+            for (int c = 0; c < D; ++c) s_Q[j * D + c] = tj[c];
+        }
+        // ---- space-filling test (sssp.jl:250) and the K x K closeness matrix
+        for (int idx = tid; idx < a.K * nv0; idx += blockDim.x) {
+            const int k = idx / nv0, v = idx - k * nv0;
+            double qv[D];
+            load_state<D>(tab, v, qv);
+            if (!M::dist_gt(cv, qv, s_q[k], a.thr, a.thr_r2)) s_near[k] = 1;
+        }
+        for (int idx = tid; idx < a.K * a.K; idx += blockDim.x) {
+            const int kp = idx / a.K, k = idx - kp * a.K;
+            if (kp < k && !M::dist_gt(cv, s_q[kp], s_q[k], a.thr, a.thr_r2))
+                atomicOr(&s_close[k], 1ull << kp);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long acc = 0ull;
+            int n = 0;
+            for (int k = 0; k < a.K; ++k) {
+                if (!s_near[k] && !(s_close[k] & acc)) {
+                    acc |= 1ull << k;
+                    s_rank[k] = n++;
+                } else {
+                    s_rank[k] = -1;
                 }
             }
-#pragma unroll
-            for (int c = 0; c < D; ++c) qh[c] = ql[c];
+            s_nnew = n;
+            s_nv0 = nv0;
+            view.nv[a.agent] = nv0 + n;
         }
+        __syncthreads();
+        // accepted samples: to the node table, the result block, and compacted to the front of
+        // s_q in acceptance order for the edge tests
+        double mine[D];
+        int my_rank = -1;
+        if (tid < a.K) {
+            my_rank = s_rank[tid];
 #pragma unroll
-        for (int c = 0; c < D; ++c) s_q[k][c] = qh[c];
-        s_near[k] = 0;
-        s_close[k] = 0ull;
-    }
-    __syncthreads();
-    for (int j = tid; j < N; j += blockDim.x) {
-        const double *tj = view.nodes + ((int64_t)j * view.cap + s_qids[j]) * D;
+            for (int c = 0; c < D; ++c) mine[c] = s_q[tid][c];
+        }
+        __syncthreads();
+        if (my_rank >= 0) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) s_Q[j * D + c] = tj[c];
-    }
-    // ---- space-filling test (sssp.jl:250) and the K x K closeness matrix
-    for (int idx = tid; idx < a.K * nv0; idx += blockDim.x) {
-        const int k = idx / nv0, v = idx - k * nv0;
-        double qv[D];
-        load_state<D>(tab, v, qv);
-        if (!M::dist_gt(cv, qv, s_q[k], a.thr, a.thr_r2)) s_near[k] = 1;
-    }
-    for (int idx = tid; idx < a.K * a.K; idx += blockDim.x) {
-        const int kp = idx / a.K, k = idx - kp * a.K;
-        if (kp < k && !M::dist_gt(cv, s_q[kp], s_q[k], a.thr, a.thr_r2))
-            atomicOr(&s_close[k], 1ull << kp);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long acc = 0ull;
-        int n = 0;
-        for (int k = 0; k < a.K; ++k) {
-            if (!s_near[k] && !(s_close[k] & acc)) {
-                acc |= 1ull << k;
-                s_rank[k] = n++;
-            } else {
-                s_rank[k] = -1;
+            for (int c = 0; c < D; ++c) {
+                s_q[my_rank][c] = mine[c];
+                tab[(int64_t)(nv0 + my_rank) * D + c] = mine[c];
+                h_qnew[my_rank * D + c] = mine[c];
             }
         }
-        s_nnew = n;
-        view.nv[a.agent] = nv0 + n;
     }
-    __syncthreads();
-    const int n_new = s_nnew;
-    if (tid < a.K && s_rank[tid] >= 0) {
-        const int r = s_rank[tid];
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            tab[(int64_t)(nv0 + r) * D + c] = s_q[tid][c];
-            h_qnew[r * D + c] = s_q[tid][c];
-        }
-    }
-    __syncthreads();
-    // compact accepted samples to the front of s_q (rank order) for the edge tests
-    double mine[D];
-    int my_rank = -1;
-    if (tid < a.K) {
-        my_rank = s_rank[tid];
-#pragma unroll
-        for (int c = 0; c < D; ++c) mine[c] = s_q[tid][c];
-    }
-    __syncthreads();
-    if (my_rank >= 0) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) s_q[my_rank][c] = mine[c];
-    }
-    __syncthreads();
-    // ---- edges of the accepted vertices (sssp.jl:252-262)
+    cluster.sync();  // the leader's s_q / s_nnew / s_nv0 are final
+
+    // ---- edges of the accepted vertices (sssp.jl:252-262), spread over the cluster: every CTA
+    // reads the accepted vertices from the leader's shared memory and ORs into its bitmaps
     {
+        const double(*l_q)[D] = reinterpret_cast<const double(*)[D]>(cluster.map_shared_rank(&s_q[0][0], 0));
+        uint32_t *l_bits = cluster.map_shared_rank(s_bits, 0);
+        n_new = *cluster.map_shared_rank(&s_nnew, 0);
+        nv0 = *cluster.map_shared_rank(&s_nv0, 0);
         const int T = nv0 + a.K;
         const int total = n_new * T * 2;
-        for (int it = tid; it < total; it += blockDim.x) {
+        for (int it = crank * blockDim.x + tid; it < total; it += csize * blockDim.x) {
             const int r = it / (2 * T);
             const int rem = it - r * 2 * T;
             const int t = rem >> 1, dir = rem & 1;
             const int id = nv0 + r;
             if (t > id || (t == id && dir == 0)) continue;
-            double qt[D];
+            double qu[D], qt[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) qu[c] = l_q[r][c];
             if (t >= nv0) {
 #pragma unroll
-                for (int c = 0; c < D; ++c) qt[c] = s_q[t - nv0][c];
+                for (int c = 0; c < D; ++c) qt[c] = l_q[t - nv0][c];
             } else {
-                load_state<D>(tab, t, qt);
+                load_state<D>(tab, t, qt);  // vertices that existed before this launch
             }
-            const bool ok = dir == 0 ? conn<M>(cv, cs, a, s_q[r], qt) : conn<M>(cv, cs, a, qt, s_q[r]);
+            const bool ok = dir == 0 ? conn<M>(cv, cs, a, qu, qt) : conn<M>(cv, cs, a, qt, qu);
             if (ok)
-                atomicOr(s_bits + (dir == 0 ? 0 : a.K * a.words) + r * a.words + (t >> 5),
+                atomicOr(l_bits + (dir == 0 ? 0 : a.K * a.words) + r * a.words + (t >> 5),
                          1u << (t & 31));
         }
     }
-    __syncthreads();
+    cluster.sync();  // all verdict bits have landed in the leader's shared memory
+    if (!leader) return;
+
     // ---- successor list
     if (tid == 0) {
         int n = a.n_old;
@@ -634,17 +679,32 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
     if (a.K < 1 || a.K > 32 || cv.model >= 2) return cudaErrorNotSupported;
     const int sm = (int)sssp_fused_smem(cv, a);
     if (sm > 160 * 1024) return cudaErrorNotSupported;
+    // one thread-block cluster of kFusedCluster CTAs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kFusedCluster, 1, 1);
+    cfg.blockDim = dim3(kFusedThreads, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)sm;
+    cfg.stream = lc.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kFusedCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     cudaError_t e = cudaSuccess;
     if (cv.model == 0) {
         using M = PointModel<2>;
         e = set_smem(k_sssp_expand_fused<M>, sm);
-        k_sssp_expand_fused<M><<<1, kFusedThreads, sm, lc.stream>>>(cv, view, a, h_in, h_old, h_qrand,
-                                                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+        if (e == cudaSuccess)
+            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, h_in, h_old, h_qrand,
+                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
     } else {
         using M = PointModel<3>;
         e = set_smem(k_sssp_expand_fused<M>, sm);
-        k_sssp_expand_fused<M><<<1, kFusedThreads, sm, lc.stream>>>(cv, view, a, h_in, h_old, h_qrand,
-                                                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+        if (e == cudaSuccess)
+            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, h_in, h_old, h_qrand,
+                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
     }
     if (e != cudaSuccess) return e;
     count_launch();
