@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import sys
 from dataclasses import dataclass, field
 from typing import List, NamedTuple, Optional, Sequence
 
@@ -161,6 +162,10 @@ class Context:
             self._lib.mrmp_ctx_destroy(h)
 
     def __del__(self):
+        # at interpreter shutdown the CUDA runtime may already be gone: leave the handle to the
+        # OS instead of calling into the library from a finaliser
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -354,6 +359,10 @@ class Roadmaps:
             self._lib.mrmp_roadmaps_destroy(h)
 
     def __del__(self):
+        # at interpreter shutdown the CUDA runtime may already be gone: leave the handle to the
+        # OS instead of calling into the library from a finaliser
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -467,6 +476,10 @@ class SsspRoadmaps:
             self._lib.mrmp_sssp_destroy(h)
 
     def __del__(self):
+        # at interpreter shutdown the CUDA runtime may already be gone: leave the handle to the
+        # OS instead of calling into the library from a finaliser
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:

@@ -220,14 +220,18 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     ws.cfg_first = (int64_t *)(b + o_first);
     // search-sized roadmaps of the point models: one launch that works on the mapped pinned
     // block directly; otherwise the multi-kernel path with explicit copies
-    const bool fused = c->model <= MRMP_MODEL_POINT3D && K <= 32 &&
+    const bool fused = c->model <= MRMP_MODEL_POINT3D && K <= kFusedMaxK && N <= kFusedMaxAgents &&
+                       n_old_nbrs <= kFusedMaxOld &&
                        (int64_t)K * 2 * (nv0 + K) <= (1 << 16) &&
                        sssp_fused_smem(c->cv, a) <= 160 * 1024;
     if (fused) {
         unsigned char *hb = nullptr;
         CU(cudaHostGetDevicePointer((void **)&hb, s->io_h, 0));
-        CU(launch_sssp_expand_fused(c->cv, lcfg(c, st), view, a, (const int32_t *)(hb + o_qids),
-                                    (const int32_t *)(hb + o_old), (const double *)(hb + o_qrand), (int32_t *)(hb + o_hdr),
+        SsspFusedIn in;
+        memcpy(in.q_ids, Q_ids, 4 * (size_t)N);
+        if (n_old_nbrs) memcpy(in.old_nbrs, old_nbrs, 4 * (size_t)n_old_nbrs);
+        if (q_rand) memcpy(in.q_rand, q_rand, sizeof(double) * d * (size_t)K);
+        CU(launch_sssp_expand_fused(c->cv, lcfg(c, st), view, a, in, (int32_t *)(hb + o_hdr),
                                     (double *)(hb + o_qnew), (uint32_t *)(hb + o_bits),
                                     (int32_t *)(hb + o_succ), (uint8_t *)(hb + o_sout)));
     } else {

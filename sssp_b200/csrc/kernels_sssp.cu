@@ -254,8 +254,8 @@ namespace cg = cooperative_groups;
 
 template <class M>
 __global__ void __launch_bounds__(kFusedThreads, 1)
-k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__restrict__ h_in,
-                    const int32_t *__restrict__ h_old, const double *__restrict__ h_qrand, int32_t *__restrict__ h_hdr,
+k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const __grid_constant__ SsspFusedIn in,
+                    int32_t *__restrict__ h_hdr,
                     double *__restrict__ h_qnew, uint32_t *__restrict__ h_bits,
                     int32_t *__restrict__ h_succ, uint8_t *__restrict__ h_verdict) {
     constexpr int D = M::SD;
@@ -282,9 +282,9 @@ k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__re
     int nv0 = 0, n_new = 0;
     if (leader) {
         nv0 = view.nv[a.agent];
-        // ---- inputs from mapped host memory: Q_ids[N], old_nbrs[n_old]
-        for (int t = tid; t < N; t += blockDim.x) s_qids[t] = h_in[t];
-        for (int t = tid; t < a.n_old; t += blockDim.x) s_succ[t] = h_old[t];
+        // ---- inputs from the kernel parameters: Q_ids[N], old_nbrs[n_old]
+        for (int t = tid; t < N; t += blockDim.x) s_qids[t] = in.q_ids[t];
+        for (int t = tid; t < a.n_old; t += blockDim.x) s_succ[t] = in.old_nbrs[t];
         for (int t = tid; t < cap_s; t += blockDim.x) s_flag[t] = 0;
         for (int t = tid; t < 2 * a.K * a.words; t += blockDim.x) s_bits[t] = 0u;
         // ---- steering (sssp.jl:269-291): sample k on warp k, obstacles over the lanes
@@ -294,7 +294,7 @@ k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const int32_t *__re
             load_state<D>(tab, a.v_from, q_near);
             if (a.host_samples) {
 #pragma unroll
-                for (int c = 0; c < D; ++c) qh[c] = h_qrand[k * D + c];
+                for (int c = 0; c < D; ++c) qh[c] = in.q_rand[k * D + c];
             } else {
                 sample_state<M>(a.seed, a.agent, a.t0 + (uint64_t)k, qh);
             }
@@ -672,11 +672,12 @@ size_t sssp_fused_smem(const CtxView &cv, const SsspExpand &a) {
 
 // one launch; h_* are device-visible addresses of mapped pinned host memory
 cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
-                                     const SsspExpand &a, const int32_t *h_in,
-                                     const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
+                                     const SsspExpand &a, const SsspFusedIn &in, int32_t *h_hdr,
                                      double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
                                      uint8_t *h_verdict) {
-    if (a.K < 1 || a.K > 32 || cv.model >= 2) return cudaErrorNotSupported;
+    if (a.K < 1 || a.K > kFusedMaxK || cv.model >= 2 || cv.n_agents > kFusedMaxAgents ||
+        a.n_old > kFusedMaxOld)
+        return cudaErrorNotSupported;
     const int sm = (int)sssp_fused_smem(cv, a);
     if (sm > 160 * 1024) return cudaErrorNotSupported;
     // one thread-block cluster of kFusedCluster CTAs
@@ -697,14 +698,14 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
         using M = PointModel<2>;
         e = set_smem(k_sssp_expand_fused<M>, sm);
         if (e == cudaSuccess)
-            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, h_in, h_old, h_qrand,
-                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, in, h_hdr, h_qnew, h_bits,
+                                   h_succ, h_verdict);
     } else {
         using M = PointModel<3>;
         e = set_smem(k_sssp_expand_fused<M>, sm);
         if (e == cudaSuccess)
-            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, h_in, h_old, h_qrand,
-                                   h_hdr, h_qnew, h_bits, h_succ, h_verdict);
+            e = cudaLaunchKernelEx(&cfg, k_sssp_expand_fused<M>, cv, view, a, in, h_hdr, h_qnew, h_bits,
+                                   h_succ, h_verdict);
     }
     if (e != cudaSuccess) return e;
     count_launch();

@@ -273,10 +273,17 @@ struct SsspWs {                 // device workspace of one expansion (laid out b
 };
 cudaError_t launch_sssp_expand(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
                                const SsspExpand &a, const SsspWs &ws, int nv_before);
+// small inputs of one expansion travel in the kernel parameter space (no host-memory reads
+// on the kernel's critical path)
+constexpr int kFusedMaxAgents = 128, kFusedMaxOld = 128, kFusedMaxK = 32;
+struct SsspFusedIn {
+    int32_t q_ids[kFusedMaxAgents];
+    int32_t old_nbrs[kFusedMaxOld];
+    double q_rand[kFusedMaxK * 3];
+};
 size_t sssp_fused_smem(const CtxView &cv, const SsspExpand &a);
 cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, const SsspView &view,
-                                     const SsspExpand &a, const int32_t *h_in,
-                                     const int32_t *h_old, const double *h_qrand, int32_t *h_hdr,
+                                     const SsspExpand &a, const SsspFusedIn &in, int32_t *h_hdr,
                                      double *h_qnew, uint32_t *h_bits, int32_t *h_succ,
                                      uint8_t *h_verdict);
 // v_off[n_graphs+1] vertex offsets; row_ptr over all vertices, col_idx local to each graph;
