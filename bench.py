@@ -272,7 +272,7 @@ def run_b200(args):
 
     def build_roadmaps():
         """(A): sample + neighbour pass of this rank's agents + [all-gather CSR shards]."""
-        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
         nnz = rm_sh.build(radv)
         if world > 1:
             if state["slots"] is None:

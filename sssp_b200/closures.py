@@ -378,13 +378,16 @@ class Roadmaps:
         L.check(self._lib.mrmp_roadmaps_bind_nodes(self._h, int(nv), nodes_dev_ptr))
         self.nv = int(nv)
 
-    def sample(self, nv: int, seed: int, q_init, q_goal) -> np.ndarray:
+    def sample(self, nv: int, seed: int, q_init, q_goal, tries: bool = True):
+        """Draw the vertex tables on the device. With ``tries=False`` the call does not wait for
+        the device: a sampler that gave up is then reported by the next build()/nodes()."""
         qi, qg = _states(q_init, self.ctx.d), _states(q_goal, self.ctx.d)
-        tries = np.empty(self.n, np.int64)
+        out = np.empty(self.n, np.int64) if tries else None
         L.check(self._lib.mrmp_roadmaps_sample(self._h, int(nv), int(seed), L.ptr(qi, L._dp),
-                                               L.ptr(qg, L._dp), L.ptr(tries, L._lp)))
+                                               L.ptr(qg, L._dp),
+                                               L.ptr(out, L._lp) if tries else None))
         self.nv = int(nv)
-        return tries
+        return out
 
     def build(self, rad) -> int:
         radv = np.broadcast_to(L.f64(math.nan if rad is None else rad), (self.n,)).copy()
@@ -637,7 +640,7 @@ def PRMs(config_init, config_goal, connect, num_vertices: int = 100, *, rad=None
     ctx: Context = connect.ctx
     N = len(config_init)
     rm = Roadmaps(ctx, 0, N, max(2, num_vertices))
-    rm.sample(num_vertices, seed, config_init, config_goal)
+    rm.sample(num_vertices, seed, config_init, config_goal, tries=False)
     rm.build(rads if rads is not None else rad)
     out = rm.to_nodes()
     rm.close()

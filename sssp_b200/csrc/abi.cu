@@ -105,7 +105,8 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
 
     const int N = n_agents, M = n_obs;
-    const int mp = pad2(M > 0 ? M : 1), np = pad2(N);
+    // obstacle arrays are padded to a multiple of 8 (kernels read them in groups of 8)
+    const int mp = (pad2(M > 0 ? M : 1) + 7) & ~7, np = pad2(N);
     const bool arm = model == MRMP_MODEL_ARM22 || model == MRMP_MODEL_ARM33;  // fixed bases
     // obstacle threshold o.r + rads[i] (points, capsule3d.jl:76) or o.r alone (arm22.jl:46,
     // line2d.jl:39, snake2d.jl:78, arm33.jl:60); pair threshold rads[i] + rads[j] (point.jl:11,
@@ -773,6 +774,8 @@ struct mrmp_roadmaps {
     int32_t *row_cnt = nullptr, *row_ptr = nullptr, *col_idx = nullptr;
     int64_t col_cap = 0;
     int64_t *nnz_d = nullptr;    // device scalar
+    long long *chunk_ws = nullptr;  // row-scan workspace: one partial sum per 1024 rows
+    int64_t chunk_ws_len = 0;
     int64_t *tries_d = nullptr;  // [n_agents]
     double *rad_d = nullptr;     // [2][n_agents]: rad, r2
     int64_t nnz = -1;            // host copy after build
@@ -791,7 +794,34 @@ struct mrmp_roadmaps {
     int64_t g_tmp_cap = 0;
     unsigned long long *g_tmp_cursor = nullptr;
     bool used_grid = false;      // diagnostics: which neighbour search the last build took
+    // pinned staging owned by the object: [2*d*n] init/goal, [2*n] rad/r2, [n] tries, [2] nnz
+    unsigned char *stage_h = nullptr;
+    unsigned char *stage_d = nullptr;  // device alias of stage_h (mapped: kernels read the tiny
+                                       // inputs and write the verdict scalars in place)
+    bool tries_pending = false;  // sampling verdicts copied to stage_h but not yet examined
+    double *st_ends() { return (double *)stage_h; }
+    double *st_rad() { return st_ends() + (size_t)2 * ctx->d * n_agents; }
+    int64_t *st_tries() { return (int64_t *)(st_rad() + (size_t)2 * n_agents); }
+    int64_t *st_nnz() { return st_tries() + n_agents; }
+    template <class T>
+    T *dev(T *host_ptr) { return (T *)(stage_d + ((unsigned char *)host_ptr - stage_h)); }
 };
+
+// Examine the sampling verdicts of a mrmp_roadmaps_sample call that deferred its synchronise.
+static int roadmaps_settle(mrmp_roadmaps *rm, bool synced) {
+    if (!rm->tries_pending) return MRMP_OK;
+    if (!synced) CU(cudaStreamSynchronize(rm->ctx->s_k));
+    rm->tries_pending = false;
+    const int64_t *tries = rm->st_tries();
+    for (int a = 0; a < rm->n_agents; ++a)
+        if (tries[a] < 0) {
+            rm->nv = 0;
+            rm->built = false;
+            return fail(MRMP_ERR_CAPACITY, "free-space sampling gave up for agent %d",
+                        rm->agent0 + a);
+        }
+    return MRMP_OK;
+}
 
 extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int nv_cap,
                                     mrmp_roadmaps **out) {
@@ -814,8 +844,16 @@ extern "C" int mrmp_roadmaps_create(mrmp_ctx *c, int agent0, int n_agents, int n
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_cnt, sizeof(int32_t) * (rows + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->row_ptr, sizeof(int32_t) * (rows + 1));
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->nnz_d, 16);
+    rm->chunk_ws_len = (rows + 1023) / 1024 + 1;
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&rm->chunk_ws, sizeof(long long) * rm->chunk_ws_len);
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->tries_d, sizeof(int64_t) * n_agents);
     if (e == cudaSuccess) e = cudaMalloc((void **)&rm->rad_d, sizeof(double) * 2 * n_agents);
+    if (e == cudaSuccess)
+        e = cudaHostAlloc((void **)&rm->stage_h,
+                          sizeof(double) * ((size_t)2 * c->d + 3) * n_agents + 64,
+                          cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&rm->stage_d, rm->stage_h, 0);
     if (e != cudaSuccess) {
         mrmp_roadmaps_destroy(rm);
         return fail(MRMP_ERR_CUDA, "roadmaps alloc: %s", cudaGetErrorString(e));
@@ -834,6 +872,7 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     cudaFree(rm->row_ptr);
     cudaFree(rm->col_idx);
     cudaFree(rm->nnz_d);
+    cudaFree(rm->chunk_ws);
     cudaFree(rm->tries_d);
     cudaFree(rm->rad_d);
     cudaFree(rm->e_agent);
@@ -846,6 +885,7 @@ extern "C" void mrmp_roadmaps_destroy(mrmp_roadmaps *rm) {
     cudaFree(rm->g_row_off);
     cudaFree(rm->g_tmp);
     cudaFree(rm->g_tmp_cursor);
+    cudaFreeHost(rm->stage_h);
     delete rm;
 }
 
@@ -855,6 +895,7 @@ extern "C" int mrmp_roadmaps_set_nodes(mrmp_roadmaps *rm, int nv, const double *
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     rm->nv = nv;
+    rm->tries_pending = false;
     rm->built = false;
     CU(cudaMemcpyAsync(rm->nodes, nodes, sizeof(double) * c->d * (size_t)nv * rm->n_agents,
                        cudaMemcpyHostToDevice, c->s_k));
@@ -869,6 +910,7 @@ extern "C" int mrmp_roadmaps_set_nodes_dev(mrmp_roadmaps *rm, int nv, const doub
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     rm->nv = nv;
+    rm->tries_pending = false;
     rm->built = false;
     CU(cudaMemcpyAsync(rm->nodes, nodes_dev, sizeof(double) * c->d * (size_t)nv * rm->n_agents,
                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -879,7 +921,8 @@ extern "C" int mrmp_roadmaps_bind_nodes(mrmp_roadmaps *rm, int nv, double *nodes
     NEED(rm, "bad roadmaps");
     if (!nodes_dev) {  // back to the set's own storage
         rm->nodes = rm->nodes_owned;
-        rm->built = false;
+        rm->tries_pending = false;
+    rm->built = false;
         return MRMP_OK;
     }
     NEED(nv >= 1 && nv <= rm->nv_cap, "nv out of range");
@@ -901,27 +944,24 @@ extern "C" int mrmp_roadmaps_sample(mrmp_roadmaps *rm, int nv, uint64_t seed, co
     const int d = c->d, n = rm->n_agents;
     // vertices 0 / 1 = init / goal (prm.jl:232)
     const size_t sb = sizeof(double) * d;
-    int rc = ensure_small(c, 2 * sb * n);
-    if (rc) return rc;
+    if (rm->tries_pending) CU(cudaStreamSynchronize(c->s_k));  // stage_h is about to be rewritten
+    rm->tries_pending = false;
+    unsigned char *ends = rm->stage_h;
     for (int a = 0; a < n; ++a) {
-        memcpy(c->small_h + (2 * a) * sb, q_init + (size_t)a * d, sb);
-        memcpy(c->small_h + (2 * a + 1) * sb, q_goal + (size_t)a * d, sb);
+        memcpy(ends + (2 * a) * sb, q_init + (size_t)a * d, sb);
+        memcpy(ends + (2 * a + 1) * sb, q_goal + (size_t)a * d, sb);
     }
-    CU(cudaMemcpy2DAsync(rm->nodes, sb * nv, c->small_h, 2 * sb, 2 * sb, n, cudaMemcpyHostToDevice,
-                         c->s_k));
+    // the kernel reads init / goal from, and writes the per-agent verdicts to, mapped memory
     CU(launch_sample_free(c->cv, lcfg(c, c->s_k), rm->agent0, n, 2, nv, nv, seed, rm->nodes,
-                          rm->tries_d, kMaxTriesFactor * (int64_t)nv));
-    std::vector<int64_t> tries(n);
-    CU(cudaMemcpyAsync(tries.data(), rm->tries_d, sizeof(int64_t) * n, cudaMemcpyDeviceToHost,
-                       c->s_k));
+                          rm->dev(rm->st_tries()), kMaxTriesFactor * (int64_t)nv,
+                          rm->dev(rm->st_ends())));
+    rm->tries_pending = true;
+    // Without a tries_out the verdicts are examined at the next call that synchronises anyway
+    // (build / get_nodes / device_ptrs), which saves one host round trip per roadmap set.
+    if (!tries_out) return MRMP_OK;
     CU(cudaStreamSynchronize(c->s_k));
-    for (int a = 0; a < n; ++a) {
-        if (tries_out) tries_out[a] = tries[a];
-        if (tries[a] < 0)
-            return fail(MRMP_ERR_CAPACITY, "free-space sampling gave up for agent %d",
-                        rm->agent0 + a);
-    }
-    return MRMP_OK;
+    for (int a = 0; a < n; ++a) tries_out[a] = rm->st_tries()[a];
+    return roadmaps_settle(rm, true);
 }
 
 static int roadmaps_emit(mrmp_roadmaps *rm, cudaStream_t s) {
@@ -998,9 +1038,8 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     const int n = rm->n_agents, nv = rm->nv;
     const int64_t rows = (int64_t)n * nv;
     rm->words = (nv + 31) / 32;
-    int rc = ensure_small(c, sizeof(double) * 2 * n + 64);
-    if (rc) return rc;
-    double *hr = (double *)c->small_h;
+    int rc = MRMP_OK;
+    double *hr = rm->st_rad();
     double rad_max = 0.0;
     bool finite = true;
     for (int a = 0; a < n; ++a) {
@@ -1009,7 +1048,6 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
         finite = finite && rad[a] > 0.0 && rad[a] < 1e300;
         if (rad[a] > rad_max) rad_max = rad[a];
     }
-    CU(cudaMemcpyAsync(rm->rad_d, hr, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->s_k));
     // neighbour search: uniform-grid spatial hash for large point roadmaps, all pairs otherwise
     int g = 0;
     if (finite && c->model <= MRMP_MODEL_POINT3D && nv >= kGridMinNv) {
@@ -1018,13 +1056,17 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
         g = (int)(gf < gmax ? gf : gmax);
     }
     rm->used_grid = g >= kGridMinCells;
-    int64_t *h_nnz = (int64_t *)(c->small_h + align16(sizeof(double) * 2 * n));
+    int64_t *h_nnz = rm->st_nnz();
     if (rm->used_grid) {
+        CU(cudaMemcpyAsync(rm->rad_d, hr, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->s_k));
         rc = roadmaps_build_grid(rm, g, c->s_k);
         if (rc) return rc;
-        CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
+        CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
+                           rm->chunk_ws, rm->chunk_ws_len));
         CU(cudaMemcpyAsync(h_nnz, rm->nnz_d, 8, cudaMemcpyDeviceToHost, c->s_k));
         CU(cudaStreamSynchronize(c->s_k));
+        rc = roadmaps_settle(rm, true);
+        if (rc) return rc;
         rm->nnz = *h_nnz;
         if (rm->nnz >= ((int64_t)1 << 31))
             return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
@@ -1046,13 +1088,16 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
         const int words_cap = (rm->nv_cap + 31) / 32;
         CU(cudaMalloc((void **)&rm->bitmap, sizeof(uint32_t) * rows_cap * words_cap));
     }
-    CU(launch_prm_adjacency(c->cv, lcfg(c, c->s_k), rm->agent0, n, nv, rm->rad_d + n, rm->rad_d,
-                            rm->nodes, rm->bitmap, rm->words, rm->row_cnt));
-    CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
-    CU(cudaMemcpyAsync(h_nnz, rm->nnz_d, 8, cudaMemcpyDeviceToHost, c->s_k));
+    // rad / r2 are read from, and nnz is written to, the mapped staging block
+    CU(launch_prm_adjacency(c->cv, lcfg(c, c->s_k), rm->agent0, n, nv, rm->dev(hr) + n,
+                            rm->dev(hr), rm->nodes, rm->bitmap, rm->words, rm->row_cnt));
+    CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
+                       rm->chunk_ws, rm->chunk_ws_len, rm->dev(h_nnz)));
     rc = roadmaps_emit(rm, c->s_k);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->s_k));
+    rc = roadmaps_settle(rm, true);
+    if (rc) return rc;
     rm->nnz = *h_nnz;
     if (rm->nnz >= ((int64_t)1 << 31)) return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
     if (rm->nnz > rm->col_cap) {  // rare: grow and re-emit
@@ -1128,7 +1173,8 @@ extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, in
     const int64_t stride = rows_cap + cap_nnz;
     LaunchCfg lc = lcfg(c, s);
     CU(launch_csr_shard_counts(lc, rows, rows_cap, stride, slots_dev, rm->row_cnt));
-    CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d));
+    CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
+                           rm->chunk_ws, rm->chunk_ws_len));
     if ((int64_t)world * cap_nnz > rm->col_cap) {  // upper bound of the stitched size
         CU(cudaStreamSynchronize(s));
         if (rm->col_idx) CU(cudaFree(rm->col_idx));
@@ -1164,7 +1210,7 @@ extern "C" int mrmp_roadmaps_get_nodes(mrmp_roadmaps *rm, double *nodes_out) {
     CU(cudaMemcpyAsync(nodes_out, rm->nodes, sizeof(double) * c->d * (size_t)rm->nv * rm->n_agents,
                        cudaMemcpyDeviceToHost, c->s_k));
     CU(cudaStreamSynchronize(c->s_k));
-    return MRMP_OK;
+    return roadmaps_settle(rm, true);
 }
 
 extern "C" int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_t *col_idx,
@@ -1195,6 +1241,10 @@ extern "C" int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double 
                                          int32_t **row_ptr_dev, int32_t **col_idx_dev,
                                          int64_t *nnz_out) {
     NEED(rm, "bad roadmaps");
+    {
+        int rc = roadmaps_settle(rm, false);
+        if (rc) return rc;
+    }
     if (nv_out) *nv_out = rm->nv;
     if (nodes_dev) *nodes_dev = rm->nodes;
     if (row_ptr_dev) *row_ptr_dev = rm->row_ptr;

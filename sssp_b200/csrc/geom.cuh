@@ -142,6 +142,40 @@ MRMP_HD bool segpt_lt(const double *a, const double *b, const double *u,
     return segpt_verdict<D, TAB>(a, b, u, uu, c, thr, T2, probe);
 }
 
+// Branch-free statement of :44-57 for SIMT callers: in a warp nearly every case (interior foot
+// point / either end) is taken by some lane, so one predicated select of e costs no more than
+// divergent branches and leaves one straight dependency chain per point that the caller can
+// interleave with its neighbours.  p = e*a + (1-e)*b - c is evaluated as :56 writes it for all
+// three values of e, which also reproduces the reference's NaN / Inf propagation (0 * b).
+// Returns sumsq(p).
+template <int D>
+MRMP_HD double segpt_foot_sq(const double *a, const double *b, const double *u, double uu,
+                             const double *c, double *p) {
+    double bc[D], ac[D];
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+        bc[x] = dsub(b[x], c[x]);
+        ac[x] = dsub(a[x], c[x]);
+    }
+    const double df0 = dotd<D>(u, bc);  // :46
+    const double df1 = dotd<D>(u, ac);  // :47
+    const bool inside = dmul(df0, df1) < 0.0;  // :50
+    const double e_in = ddiv(-df0, uu);        // :51 (only used when inside)
+    const double e = inside ? e_in : (df0 >= 0.0 ? 0.0 : 1.0);  // :49-54
+    const double f = dsub(1.0, e);
+#pragma unroll
+    for (int x = 0; x < D; ++x) p[x] = dsub(dadd(dmul(e, a[x]), dmul(f, b[x])), c[x]);  // :56
+    return sumsq<D>(p);
+}
+
+template <int D, bool TAB = true>
+MRMP_HD bool segpt_lt_simt(const double *a, const double *b, const double *u, double uu,
+                           const double *c, double thr, double T2) {
+    double p[D];
+    const double s = segpt_foot_sq<D>(a, b, u, uu, c, p);
+    return norm_lt<D, TAB>(p, s, thr, T2);
+}
+
 // src/utils.jl:59-94: verdict  dist(p11,p12,p21,p22) < thr
 template <int D, bool TAB = true>
 MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
@@ -176,11 +210,8 @@ MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
         }
     }
     // :86-93  minimum of the four endpoint-to-segment distances (NaN-propagating).
-    // The four evaluations of dist(a,b,c) (:44-57) are written branch-free and side by side:
-    // in a warp nearly every case (interior foot point / either end) is taken by some lane, so
-    // predicated selects cost no more than divergent branches and expose four independent
-    // dependency chains to the FP64 pipe.  Each value is computed exactly as :46-56 states;
-    // the select only chooses which of the three expressions the reference would evaluate.
+    // The four evaluations of dist(a,b,c) (:44-57) run branch-free and side by side
+    // (segpt_foot_sq): four independent dependency chains for the FP64 pipe.
     const double *A[4] = {p11, p11, p21, p21};  // segment start  (a)
     const double *B[4] = {p12, p12, p22, p22};  // segment end    (b)
     const double *C[4] = {p21, p22, p11, p12};  // the point      (c)
@@ -189,24 +220,10 @@ MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double uu = k < 2 ? V1 : V2;  // dot(a-b, a-b) == dot(b-a, b-a) bitwise
-        double u[D], bc[D], ac[D], p[D];
+        double u[D], p[D];
 #pragma unroll
-        for (int x = 0; x < D; ++x) {
-            u[x] = dsub(A[k][x], B[k][x]);
-            bc[x] = dsub(B[k][x], C[k][x]);
-            ac[x] = dsub(A[k][x], C[k][x]);
-        }
-        const double df0 = dotd<D>(u, bc);  // :46
-        const double df1 = dotd<D>(u, ac);  // :47
-        const bool inside = dmul(df0, df1) < 0.0;  // :50
-        const double e = ddiv(-df0, uu);           // :51 (only used when inside)
-        const double f = dsub(1.0, e);
-#pragma unroll
-        for (int x = 0; x < D; ++x) {
-            const double blend = dsub(dadd(dmul(e, A[k][x]), dmul(f, B[k][x])), C[k][x]);  // :56
-            p[x] = inside ? blend : (df0 >= 0.0 ? bc[x] : ac[x]);  // e = 0 -> b - c, e = 1 -> a - c
-        }
-        s[k] = sumsq<D>(p);
+        for (int x = 0; x < D; ++x) u[x] = dsub(A[k][x], B[k][x]);
+        s[k] = segpt_foot_sq<D>(A[k], B[k], u, uu, C[k], p);
         hit |= norm_lt<D, TAB>(p, s[k], thr, T2);
     }
     const double nan_probe = dadd(dadd(s[0], s[1]), dadd(s[2], s[3]));

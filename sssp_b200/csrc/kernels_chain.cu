@@ -19,7 +19,6 @@ constexpr int kThreads = 256;
 constexpr int kPairWarps = 4;
 constexpr int kPairThreads = 32 * kPairWarps;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr double kPad = 9.5367431640625e-07;  // 2^-20
 constexpr int kTableBudget = 12 * 1024;       // bytes of posture tables per warp
 
 static inline int seg_smem_bytes(int seg_len) {

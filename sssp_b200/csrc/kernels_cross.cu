@@ -39,7 +39,6 @@ constexpr int kCols = 64;        // column edges per tile
 constexpr int kRedWords = 8;     // reduced mode: up to 256 groups per launch
 constexpr int kWarpsPerCta = 8;
 constexpr int kSortCells = 4096;  // Morton grid: 64 x 64 (2-D), 16^3 (3-D)
-constexpr double kPad = 9.5367431640625e-07;  // 2^-20
 
 template <int D>
 struct RowRec {  // one row edge, in Morton order
@@ -180,18 +179,6 @@ k_cols_scatter(EdgeList<D> el, int64_t n, int32_t *__restrict__ cursor,
         el.get(k, a, b);
         order[atomicAdd(cursor + morton_cell<D>(a, b), 1)] = (int)k;
     }
-}
-
-// half length of an edge, rounded up
-template <int D>
-__device__ __forceinline__ double half_len_up(const double *a, const double *b) {
-    double v[D];
-#pragma unroll
-    for (int x = 0; x < D; ++x) v[x] = b[x] - a[x];
-    double s = v[0] * v[0];
-#pragma unroll
-    for (int x = 1; x < D; ++x) s += v[x] * v[x];
-    return 0.5 * sqrt(s) * (1.0 + 1e-9);
 }
 
 // ---- column tiles: one warp builds one tile (2 columns per lane) and its header ------------

@@ -27,14 +27,19 @@ k_sample_states(int agent, uint64_t seed, uint64_t t0, int64_t n, double *__rest
     }
 }
 
-// One CTA per agent.  Round r tests tries [r*T, (r+1)*T); accepted tries are compacted in try
-// order (ballot + warp prefix), so the result equals the sequential loop of prm.jl:193-199.
+constexpr int kSampleThreads = 1024;
+constexpr int kSampleWarps = kSampleThreads / 32;
+
+// One CTA per agent (1024 threads: a 500-vertex roadmap usually fills in a single round).
+// Round r tests tries [r*T, (r+1)*T); accepted tries are compacted in try order (ballot + warp
+// prefix), so the result equals the sequential loop of prm.jl:193-199.  fixed_src (may be
+// mapped host memory) holds the n_fixed leading vertices of every agent (init / goal).
 template <class M>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kSampleThreads)
 k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64_t seed,
               double *__restrict__ nodes, int64_t *__restrict__ tries_out, int64_t max_tries,
-              int staged) {
-    __shared__ int warp_cnt[kWarps];
+              const double *__restrict__ fixed_src, int staged) {
+    __shared__ int warp_cnt[kSampleWarps];
     __shared__ int accepted_sh;
     const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, staged));
     const int a = blockIdx.x;
@@ -42,9 +47,12 @@ k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64
     const int wanted = nv - n_fixed;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *out = nodes + ((int64_t)a * nv_stride + n_fixed) * M::SD;
+    if (fixed_src && threadIdx.x < n_fixed * M::SD)
+        nodes[(int64_t)a * nv_stride * M::SD + threadIdx.x] =
+            fixed_src[(int64_t)a * n_fixed * M::SD + threadIdx.x];
     int accepted = 0;
     int64_t tries = wanted <= 0 ? 0 : -1;
-    for (int64_t t0 = 0; accepted < wanted && t0 < max_tries; t0 += kThreads) {
+    for (int64_t t0 = 0; accepted < wanted && t0 < max_tries; t0 += kSampleThreads) {
         const int64_t t = t0 + threadIdx.x;
         double q[M::SD];
         sample_state<M>(seed, agent, (uint64_t)t, q);
@@ -62,7 +70,7 @@ k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64
         }
         if (threadIdx.x == 0) {
             int tot = 0;
-            for (int w = 0; w < kWarps; ++w) tot += warp_cnt[w];
+            for (int w = 0; w < kSampleWarps; ++w) tot += warp_cnt[w];
             accepted_sh = accepted + tot;
         }
         __syncthreads();
@@ -72,110 +80,333 @@ k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64
     if (threadIdx.x == 0 && tries_out && (accepted < wanted || wanted <= 0)) tries_out[a] = tries;
 }
 
-// ---- adjacency bitmap: one warp per row (agent, j) ------------------------------------------
-// Phase A: radius gate for every k (ballot -> one 32-bit word per 32 vertices).
-// Phase B: the sparse survivors are compacted into a per-warp queue so that the expensive
-//          edge-vs-obstacle test runs on dense lanes; failures clear their bit.
+// ---- all-pairs neighbour pass -------------------------------------------------------------
+// One CTA = (agent, chunk of that agent's rows); the agent's vertex table is staged in shared
+// memory once per CTA.  A warp walks its rows j through a small pipeline of per-warp rings so
+// that every expensive stage runs on 32 dense lanes, across row boundaries:
+//   gate   every lane tests kAdjGroup candidates k per round (prm.jl:207, branch-free,
+//          independent FP64 chains); survivors (j,k) are compacted into ring 1;
+//   edge   (prm.jl:208) generic models: connect(q_j, q_k) per lane, a passing edge sets its bit
+//          in the (row-zeroed) global bitmap and bumps the row count with L2 reductions;
+//          point models: the field test of q_k, then the bit is set optimistically and the edge
+//          is tested against every obstacle with the conservative midpoint cull of
+//          point_model.cuh; only (edge, obstacle) pairs that survive go to ring 2;
+//   exact  (point models) the reference's segment-point test on ring 2; a hit clears the bit
+//          again (the first clear also takes the row count back).
+// Bits and counts are order-independent, so it does not matter when a pair leaves a ring.
+constexpr int kRing1 = 256;      // (j,k) entries per warp; in flight <= 31 + 32 * kGateGroup
+constexpr int kGateGroup = 4;    // bitmap words gated per compaction round
+constexpr int kRing2 = 512;      // (j,k,m) entries per warp; in flight <= 31 + 32 * kCullGroup
+constexpr int kCullGroup = 8;    // obstacles culled per compaction round (ctx pads to 8)
+constexpr int kAdjStageBytes = 96 * 1024;  // vertex tables up to this size are staged in smem
+constexpr double kGateRadMin = 1e-150;     // above this, dist <= rad  <=>  dist_sq <= r2
+
 template <class M>
-__global__ void __launch_bounds__(kThreads)
-k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, const double *__restrict__ rad,
-                const double *__restrict__ rad_r2, const double *__restrict__ nodes,
-                uint32_t *__restrict__ bitmap, int words, int32_t *__restrict__ row_cnt,
-                int staged, int seg_bytes) {
-    const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, staged));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp scratch behind the staged segment: words bitmap + 64-entry queue
-    uint32_t *wbits = reinterpret_cast<uint32_t *>(smem_raw + seg_bytes) + warp * (words + 64);
-    int *queue = reinterpret_cast<int *>(wbits + words);
-    const int64_t n_rows = (int64_t)n_agents * nv;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows;
-         row += n_warps) {
-        const int a = (int)(row / nv), j = (int)(row - (int64_t)a * nv);
-        const int agent = agent0 + a;
-        const double *tab = nodes + (int64_t)a * nv * M::SD;
-        const double r = rad[a], r2 = rad_r2[a];
-        const bool gate_all = isnan(r);
-        double qj[M::SD];
-        load_state<M::SD>(tab, j, qj);
-        int qlen = 0;  // warp-uniform queue length
-        int cnt = 0;
-        for (int t = 0; t < words; ++t) {
-            const int k = 32 * t + lane;
-            bool pass = false;
-            double qk[M::SD];
-            if (k < nv && k != j) {
-                load_state<M::SD>(tab, k, qk);
-                pass = gate_all || M::dist_le(cv, qj, qk, r, r2);  // prm.jl:207
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (lane == 0) wbits[t] = bal;
-            if (pass) queue[(cnt + __popc(bal & ((1u << lane) - 1u))) & 63] = k;
-            qlen += __popc(bal);
-            cnt += __popc(bal);
-            __syncwarp();
-            if (qlen >= 32) {
-                // dense flush of 32 queued candidates (oldest first)
-                const int head = (cnt - qlen) & 63;  // ring position of the oldest entry
-                const int k2 = queue[(head + lane) & 63];
-                load_state<M::SD>(tab, k2, qk);
-                const bool ok = M::connect_edge(cv, cs, qj, qk, agent);
-                if (!ok) atomicAnd(&wbits[k2 >> 5], ~(1u << (k2 & 31)));
-                qlen -= 32;
-                __syncwarp();
-            }
-        }
-        if (qlen > 0) {
-            const int head = (cnt - qlen) & 63;
-            if (lane < qlen) {
-                const int k2 = queue[(head + lane) & 63];
-                double qk[M::SD];
-                load_state<M::SD>(tab, k2, qk);
-                const bool ok = M::connect_edge(cv, cs, qj, qk, agent);
-                if (!ok) atomicAnd(&wbits[k2 >> 5], ~(1u << (k2 & 31)));
-            }
-        }
-        __syncwarp();
-        int total = 0;
-        for (int t = lane; t < words; t += 32) {
-            const uint32_t w = wbits[t];
-            bitmap[row * words + t] = w;
-            total += __popc(w);
-        }
+struct AdjTraits {
+    static constexpr bool kCull = false;
+};
+template <int D>
+struct AdjTraits<PointModel<D>> {
+    static constexpr bool kCull = true;
+};
+
+template <int SD>
+__device__ __forceinline__ void load_node(const double *tab, int k, double *q) {
+    if constexpr (SD % 2 == 0) {
+        const double2 *p = reinterpret_cast<const double2 *>(tab + (int64_t)SD * k);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-        if (lane == 0) row_cnt[row] = total;
-        __syncwarp();
+        for (int c = 0; c < SD / 2; ++c) {
+            const double2 t = p[c];
+            q[2 * c] = t.x;
+            q[2 * c + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < SD; ++c) q[c] = tab[(int64_t)SD * k + c];
     }
 }
 
-// ---- exclusive scan of the row counts (single CTA; n_rows is at most a few 10^6) -----------
-__global__ void __launch_bounds__(1024)
-k_row_scan(int64_t n_rows, const int32_t *__restrict__ row_cnt, int32_t *__restrict__ row_ptr,
-           int64_t *__restrict__ nnz_total) {
-    __shared__ long long part[1024];
-    const int tid = threadIdx.x;
-    const int64_t chunk = (n_rows + 1023) / 1024;
-    const int64_t lo = tid * chunk, hi = lo + chunk < n_rows ? lo + chunk : n_rows;
-    long long s = 0;
-    for (int64_t r = lo; r < hi; ++r) s += row_cnt[r];
-    part[tid] = s;
+// exclusive prefix of c over the warp; total = sum over all lanes
+__device__ __forceinline__ int warp_offsets(int c, int lane, int &total) {
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - c;
+}
+
+// SMEM: the connect segment and the agent's vertex table (padded to 32 * words entries) are
+// staged in shared memory -- the normal case; the other instantiation reads both from global.
+template <class M, bool SMEM>
+__global__ void __launch_bounds__(kThreads, 3)
+k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
+                const double *__restrict__ rad, const double *__restrict__ rad_r2,
+                const double *__restrict__ nodes, uint32_t *__restrict__ bitmap, int words,
+                int32_t *__restrict__ row_cnt, int seg_bytes) {
+    constexpr int SD = M::SD;
+    constexpr bool kCull = AdjTraits<M>::kCull;
+    const int a = blockIdx.x / chunks, chunk = blockIdx.x - a * chunks;
+    // rad / r2 may live in mapped host memory: issue the reads before the staging waits
+    const double r = rad[a], r2 = rad_r2[a];
+    const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, SMEM));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int agent = agent0 + a;
+    unsigned char *sp = smem_raw + (SMEM ? seg_bytes : 0);
+    int2 *ring1 = reinterpret_cast<int2 *>(sp) + warp * kRing1;
+    sp += kWarps * kRing1 * 8;
+    unsigned long long *ring2 = reinterpret_cast<unsigned long long *>(sp) + warp * kRing2;
+    if (kCull) sp += kWarps * kRing2 * 8;
+    const double *tab = nodes + (int64_t)a * nv * SD;
+    if constexpr (SMEM) {
+        double *st = reinterpret_cast<double *>(sp);
+        const int n_dbl = nv * SD, n_pad = words * 32 * SD;
+        for (int i = threadIdx.x; i < n_pad; i += kThreads) st[i] = i < n_dbl ? __ldg(tab + i) : 0.0;
+        __syncthreads();
+        tab = st;
+    }
+    const bool gate_all = isnan(r);
+    const bool fast_gate = r >= kGateRadMin;  // false for NaN
+    uint32_t *bits_a = bitmap + (int64_t)a * nv * words;
+    int32_t *cnt_a = row_cnt + (int64_t)a * nv;
+    const double rad_i = cs.rad(agent);
+    (void)rad_i;
+    (void)ring2;
+
+    int head = 0, tail = 0;    // ring 1, warp-uniform
+    int head2 = 0, tail2 = 0;  // ring 2 (point models)
+
+    // generic models: the whole edge test on one lane
+    auto connect_lane = [&](int2 e) {
+        double qa[SD], qb[SD];
+        load_node<SD>(tab, e.x, qa);
+        load_node<SD>(tab, e.y, qb);
+        if (M::connect_edge(cv, cs, qa, qb, agent)) {
+            atomicOr(bits_a + (int64_t)e.x * words + (e.y >> 5), 1u << (e.y & 31));
+            atomicAdd(cnt_a + e.x, 1);
+        }
+    };
+    // point models, exact stage: dist(q_j, q_k, o_m) < o_m.r + rads[i]  (point2d.jl:63-65)
+    auto exact_lane = [&](unsigned long long e) {
+        if constexpr (kCull) {
+            const int j = (int)(e >> 44), k = (int)((e >> 24) & 0xfffffu), m = (int)(e & 0xffffffu);
+            double qa[SD], qb[SD], u[SD], c[SD];
+            load_node<SD>(tab, j, qa);
+            load_node<SD>(tab, k, qb);
+#pragma unroll
+            for (int x = 0; x < SD; ++x) {
+                u[x] = dsub(qa[x], qb[x]);
+                c[x] = cs.oc(x, m);
+            }
+            if (segpt_lt_simt<SD, true>(qa, qb, u, dotd<SD>(u, u), c, dadd(cs.oc(SD, m), rad_i),
+                                        cs.t2_im(agent, m))) {
+                const uint32_t bit = 1u << (k & 31);
+                const uint32_t old = atomicAnd(bits_a + (int64_t)j * words + (k >> 5), ~bit);
+                if (old & bit) atomicSub(cnt_a + j, 1);
+            }
+        }
+    };
+    // point models, edge stage for up to 32 ring-1 entries (warp-collective)
+    auto cull_batch = [&](int n_valid) {
+        if constexpr (kCull) {
+            const bool valid = lane < n_valid;
+            const int2 e = ring1[(head + lane) & (kRing1 - 1)];
+            double mid[SD], R = 0.0;
+            bool ok = false, wide = false;
+            if (valid) {
+                double qa[SD], qb[SD];
+                load_node<SD>(tab, e.x, qa);
+                load_node<SD>(tab, e.y, qb);
+                ok = !out_of_field<SD>(qb, rad_i);  // q_to only (point2d.jl:60)
+                if (ok) {
+                    atomicOr(bits_a + (int64_t)e.x * words + (e.y >> 5), 1u << (e.y & 31));
+                    atomicAdd(cnt_a + e.x, 1);
+                }
+                const double h = half_len_up<SD>(qa, qb);
+                R = rad_i + kPad + h;
+                wide = !(h < kCullCoordMax);
+#pragma unroll
+                for (int x = 0; x < SD; ++x) {
+                    mid[x] = 0.5 * (qa[x] + qb[x]);
+                    wide |= !(fabs(mid[x]) < kCullCoordMax);
+                }
+            }
+            const unsigned long long key = ((unsigned long long)(unsigned)e.x << 44) |
+                                           ((unsigned long long)(unsigned)e.y << 24);
+            // the ctx pads the obstacle arrays to a multiple of kCullGroup with far-away,
+            // zero-radius entries, so a group is read without clamping
+            for (int m0 = 0; m0 < cs.n_obs; m0 += kCullGroup) {
+                unsigned near = 0;
+                if (ok) {
+                    const double *oc = cs.s + cs.obs + m0;
+#pragma unroll
+                    for (int u = 0; u < kCullGroup; ++u) {
+                        double w2 = 0.0;
+#pragma unroll
+                        for (int x = 0; x < SD; ++x) {
+                            const double w = oc[x * cs.mp + u] - mid[x];
+                            w2 += w * w;
+                        }
+                        const double orad = oc[SD * cs.mp + u];
+                        const double reach = R + orad;
+                        const bool far = w2 > reach * reach && fabs(orad) < kCullCoordMax;
+                        near |= (m0 + u < cs.n_obs && (wide || !far) ? 1u : 0u) << u;
+                    }
+                }
+                int total;
+                int pos = tail2 + warp_offsets(__popc(near), lane, total);
+                while (near) {
+                    const int u = __ffs(near) - 1;
+                    near &= near - 1;
+                    ring2[pos & (kRing2 - 1)] = key | (unsigned)(m0 + u);
+                    ++pos;
+                }
+                tail2 += total;
+                __syncwarp();
+                while (tail2 - head2 >= 32) {
+                    exact_lane(ring2[(head2 + lane) & (kRing2 - 1)]);
+                    head2 += 32;
+                }
+            }
+        }
+    };
+
+    for (int j = chunk * kWarps + warp; j < nv; j += chunks * kWarps) {
+        for (int t = lane; t < words; t += 32) bits_a[(int64_t)j * words + t] = 0u;
+        if (lane == 0) cnt_a[j] = 0;
+        double qj[SD];
+        load_node<SD>(tab, j, qj);
+        for (int t0 = 0; t0 < words; t0 += kGateGroup) {
+            unsigned m = 0;
+            const int k0 = 32 * t0 + lane;
+            if (fast_gate) {
+                // branch-free, independent chains; candidates past nv are masked out (staged
+                // tables are padded, global ones are read at a clamped index)
+#pragma unroll
+                for (int u = 0; u < kGateGroup; ++u) {
+                    const int k = k0 + 32 * u;
+                    const bool valid = k < nv && k != j;
+                    double qk[SD];
+                    if constexpr (SMEM) {
+                        if (t0 + u < words) load_node<SD>(tab, k, qk);  // warp-uniform guard
+                        else load_node<SD>(tab, j, qk);
+                    } else {
+                        load_node<SD>(tab, valid ? k : j, qk);
+                    }
+                    const double s = M::dist_sq(qj, qk);  // prm.jl:207
+                    m |= (valid && s <= r2 ? 1u : 0u) << u;
+                }
+            } else {
+                for (int u = 0; u < kGateGroup; ++u) {
+                    const int k = k0 + 32 * u;
+                    if (k < nv && k != j) {
+                        double qk[SD];
+                        load_node<SD>(tab, k, qk);
+                        if (gate_all || M::dist_le(cv, qj, qk, r, r2)) m |= 1u << u;
+                    }
+                }
+            }
+            // compaction by ballots: with only kGateGroup slots per lane this is cheaper than a
+            // prefix sum plus a divergent loop over the set bits
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int u = 0; u < kGateGroup; ++u) {
+                const bool pass = (m >> u) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) ring1[(tail + __popc(bal & lt)) & (kRing1 - 1)] = make_int2(j, k0 + 32 * u);
+                tail += __popc(bal);
+            }
+            __syncwarp();  // ring writes (and this row's zeroing) before the reads / reductions
+            while (tail - head >= 32) {
+                if constexpr (kCull) cull_batch(32);
+                else connect_lane(ring1[(head + lane) & (kRing1 - 1)]);
+                head += 32;
+            }
+        }
+    }
+    __syncwarp();
+    if (tail - head > 0) {
+        if constexpr (kCull) {
+            cull_batch(tail - head);
+        } else {
+            if (lane < tail - head) connect_lane(ring1[(head + lane) & (kRing1 - 1)]);
+        }
+    }
+    if constexpr (kCull) {
+        __syncwarp();
+        if (lane < tail2 - head2) exact_lane(ring2[(head2 + lane) & (kRing2 - 1)]);
+    }
+}
+
+// ---- exclusive scan of the row counts ------------------------------------------------------
+// CTA b owns rows [1024 b, 1024 b + 1024).  Its base offset is the sum of everything before:
+// read from chunk_sum[0..b) when the caller ran k_chunk_sums first (many chunks), otherwise
+// summed straight from row_cnt (few chunks: every load is independent, so the redundant reads
+// pipeline and the whole scan is one short, fully parallel launch).
+__device__ __forceinline__ long long block_sum_1024(long long v, long long *sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp] = v;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (int o = 1; o < 1024; o <<= 1) {
-        long long v = tid >= o ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
+    long long w = sh[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    __syncthreads();
+    return w;
+}
+
+__global__ void __launch_bounds__(1024)
+k_chunk_sums(int64_t n_rows, const int32_t *__restrict__ row_cnt, long long *__restrict__ chunk_sum) {
+    __shared__ long long sh[32];
+    const int64_t r = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const long long s = block_sum_1024(r < n_rows ? row_cnt[r] : 0, sh);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_row_scan(int64_t n_rows, const int32_t *__restrict__ row_cnt,
+           const long long *__restrict__ chunk_sum, int32_t *__restrict__ row_ptr,
+           int64_t *__restrict__ nnz_total, int64_t *__restrict__ nnz_mirror) {
+    __shared__ long long sh[32];
+    __shared__ long long warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base_row = (int64_t)blockIdx.x * 1024;
+    long long part = 0;
+    if (chunk_sum) {
+        for (int64_t c = tid; c < blockIdx.x; c += 1024) part += chunk_sum[c];
+    } else {
+        for (int64_t r = tid; r < base_row; r += 1024) part += row_cnt[r];
     }
-    long long base = tid == 0 ? 0 : part[tid - 1];
-    for (int64_t r = lo; r < hi; ++r) {
-        row_ptr[r] = (int32_t)base;
-        base += row_cnt[r];
+    const int64_t r = base_row + tid;
+    const long long v = r < n_rows ? row_cnt[r] : 0;
+    const long long base = block_sum_1024(part, sh);
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (tid == 1023) {
-        row_ptr[n_rows] = (int32_t)part[1023];
-        *nnz_total = part[1023];
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        long long w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_tot[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const long long before = base + (warp ? warp_tot[warp - 1] : 0) + incl - v;
+    if (r < n_rows) row_ptr[r] = (int32_t)before;
+    if (r == n_rows - 1) {
+        row_ptr[n_rows] = (int32_t)(before + v);
+        *nnz_total = before + v;
+        if (nnz_mirror) *nnz_mirror = before + v;  // mapped host copy: no D2H copy node
     }
 }
 
@@ -188,13 +419,20 @@ k_prm_emit(int64_t n_rows, const uint32_t *__restrict__ bitmap, int words,
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows;
          row += n_warps) {
         int64_t base = row_ptr[row];
-        for (int t = 0; t < words; ++t) {
-            const uint32_t w = __ldg(bitmap + row * words + t);
-            if ((w >> lane) & 1u) {
-                const int64_t pos = base + __popc(w & ((1u << lane) - 1u));
-                if (pos < col_cap) col_idx[pos] = 32 * t + lane;
+        for (int t0 = 0; t0 < words; t0 += 32) {
+            // lane t owns word t0 + t: the bitmap is sparse (a few bits per word), so a prefix
+            // over the popcounts plus a short loop over the set bits beats one pass per word
+            uint32_t w = t0 + lane < words ? __ldg(bitmap + row * words + t0 + lane) : 0u;
+            int total;
+            int64_t pos = base + warp_offsets(__popc(w), lane, total);
+            const int k0 = 32 * (t0 + lane);
+            while (w) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                if (pos < col_cap) col_idx[pos] = k0 + bit;
+                ++pos;
             }
-            base += __popc(w);
+            base += total;
         }
     }
 }
@@ -466,17 +704,52 @@ cudaError_t launch_sample_states(const CtxView &cv, const LaunchCfg &lc, int age
 
 cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                int n_fixed, int nv, int nv_stride, uint64_t seed, double *nodes,
-                               int64_t *tries_out, int64_t max_tries) {
+                               int64_t *tries_out, int64_t max_tries, const double *fixed_src) {
     if (n_agents <= 0) return cudaSuccess;
+    if (fixed_src && n_fixed * cv.d > kSampleThreads) return cudaErrorInvalidValue;
     const int sm = seg_smem_bytes(cv.con_len);
     cudaError_t e = cudaSuccess;
     MRMP_MODEL_SWITCH(cv, (e = set_smem(k_sample_free<M>, sm),
-                           k_sample_free<M><<<n_agents, kThreads, sm, lc.stream>>>(
+                           k_sample_free<M><<<n_agents, kSampleThreads, sm, lc.stream>>>(
                                cv, agent0, n_fixed, nv, nv_stride, seed, nodes, tries_out,
-                               max_tries, sm > 0)));
+                               max_tries, fixed_src, sm > 0)));
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
+}
+
+// resident CTAs per SM of one adjacency instantiation, cached per (model, staging, smem size)
+template <class K>
+static int adj_occupancy(K kernel, int slot, int smem) {
+    static int cached_smem[16], cached_occ[16];
+    if (cached_occ[slot] == 0 || cached_smem[slot] != smem) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) !=
+                cudaSuccess || occ < 1)
+            occ = 1;
+        cached_smem[slot] = smem;
+        cached_occ[slot] = occ;
+    }
+    return cached_occ[slot];
+}
+
+// one wave: (agent, chunk) CTAs fill the resident slots without a ragged second wave
+template <class M, bool SMEM>
+static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
+                                int nv, const double *rad_r2, const double *rad,
+                                const double *nodes, uint32_t *bitmap, int words,
+                                int32_t *row_cnt, int seg, int sm) {
+    auto kern = k_prm_adjacency<M, SMEM>;
+    cudaError_t e = set_smem(kern, sm);
+    if (e != cudaSuccess) return e;
+    const int slots = lc.sm_count * adj_occupancy(kern, 2 * cv.model + (SMEM ? 1 : 0), sm);
+    const int max_chunks = (nv + kWarps - 1) / kWarps;  // at most one row per warp
+    int chunks = slots / n_agents;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    kern<<<n_agents * chunks, kThreads, sm, lc.stream>>>(cv, agent0, n_agents, nv, chunks, rad,
+                                                         rad_r2, nodes, bitmap, words, row_cnt, seg);
+    return cudaSuccess;
 }
 
 cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
@@ -484,31 +757,40 @@ cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int age
                                  const double *nodes, uint32_t *bitmap, int words,
                                  int32_t *row_cnt) {
     if (n_agents <= 0 || nv <= 0) return cudaSuccess;
-    int seg = seg_smem_bytes(cv.con_len);
-    const int scratch = kWarps * (words + 64) * 4;
-    if (seg + scratch > 200 * 1024) seg = 0;  // very large nv: leave the segment in global
-    if (scratch > 200 * 1024) return cudaErrorInvalidValue;
-    const int sm = seg + scratch;
-    const int64_t n_rows = (int64_t)n_agents * nv;
-    int per_sm = (220 * 1024) / (sm > 0 ? sm : 1);
-    if (per_sm > 8) per_sm = 8;
-    if (per_sm < 1) per_sm = 1;
-    int64_t want = (n_rows + kWarps - 1) / kWarps;
-    int64_t cap = (int64_t)lc.sm_count * per_sm;
-    const int grid = (int)(want < cap ? want : cap);
+    const bool cull = cv.model <= 1;  // AdjTraits<PointModel<D>>::kCull: second ring
+    if (cull && (cv.n_obs >= (1 << 24) || nv > (1 << 20) || cv.mp % kCullGroup != 0))
+        return cudaErrorInvalidValue;
+    const int rings = kWarps * 8 * (kRing1 + (cull ? kRing2 : 0));
+    const int seg = (seg_smem_bytes(cv.con_len) + 15) & ~15;
+    const int64_t tab = (int64_t)words * 32 * cv.d * 8;
+    const bool smem_on = seg > 0 && tab <= kAdjStageBytes;
+    const int sm = rings + (smem_on ? seg + (int)tab : 0);
     cudaError_t e = cudaSuccess;
-    MRMP_MODEL_SWITCH(cv, (e = set_smem(k_prm_adjacency<M>, sm),
-                           k_prm_adjacency<M><<<grid, kThreads, sm, lc.stream>>>(
-                               cv, agent0, n_agents, nv, rad, rad_r2, nodes, bitmap, words,
-                               row_cnt, seg > 0, seg)));
+    if (smem_on) {
+        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, true>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
+                                                         nodes, bitmap, words, row_cnt, seg, sm)));
+    } else {
+        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, false>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
+                                                          nodes, bitmap, words, row_cnt, seg, sm)));
+    }
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t launch_row_scan(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_cnt,
-                            int32_t *row_ptr, int64_t *nnz_total) {
-    k_row_scan<<<1, 1024, 0, lc.stream>>>(n_rows, row_cnt, row_ptr, nnz_total);
+                            int32_t *row_ptr, int64_t *nnz_total, long long *chunk_ws,
+                            int64_t chunk_ws_len, int64_t *nnz_mirror) {
+    if (n_rows <= 0) return cudaErrorInvalidValue;
+    const int64_t chunks = (n_rows + 1023) / 1024;
+    const bool two_level = chunks > 64;
+    if (two_level) {
+        if (!chunk_ws || chunk_ws_len < chunks) return cudaErrorInvalidValue;
+        k_chunk_sums<<<(int)chunks, 1024, 0, lc.stream>>>(n_rows, row_cnt, chunk_ws);
+        count_launch();
+    }
+    k_row_scan<<<(int)chunks, 1024, 0, lc.stream>>>(n_rows, row_cnt, two_level ? chunk_ws : nullptr,
+                                                     row_ptr, nnz_total, nnz_mirror);
     count_launch();
     return cudaGetLastError();
 }

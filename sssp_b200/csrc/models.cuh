@@ -32,6 +32,14 @@ struct PointModel {
         if (s == 0.0) return norm_slow<D>(v) <= rad;
         return s <= r2;
     }
+    // s with: dist(qa, qb) <= rad  <=>  s <= sq_le_threshold(rad), for rad >= kGateRadMin
+    // (s == 0 then means a distance below 1e-153, see dist_le)
+    static __device__ __forceinline__ double dist_sq(const double *qa, const double *qb) {
+        double v[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) v[k] = dsub(qa[k], qb[k]);
+        return sumsq<D>(v);
+    }
     // dist(qa, qb) as a value
     static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
                                                   const double *qb) {
@@ -96,6 +104,11 @@ struct ArmModel {
         const double s = sumsq<2>(v);
         if (s == 0.0) return norm_slow<2>(v) <= rad;
         return s <= r2;
+    }
+    static __device__ __forceinline__ double dist_sq(const double *qa, const double *qb) {
+        double v[2];
+        arm_dist_vec(qa, qb, v);
+        return sumsq<2>(v);
     }
     static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
                                                   const double *qb) {
@@ -180,6 +193,11 @@ struct ChainModel {
         const double s = sumsq<SD>(v);
         if (s == 0.0) return norm_slow<SD>(v) > thr;
         return s > r2;
+    }
+    static __device__ __forceinline__ double dist_sq(const double *qa, const double *qb) {
+        double v[SD];
+        C::dist_vec(qa, qb, v);
+        return sumsq<SD>(v);
     }
     static __device__ __forceinline__ double dist(const CtxView &, const double *qa,
                                                   const double *qb) {

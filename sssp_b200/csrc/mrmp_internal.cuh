@@ -207,7 +207,8 @@ cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int age
                                  const double *rad /*[n]*/, const double *nodes,
                                  uint32_t *bitmap, int words, int32_t *row_cnt);
 cudaError_t launch_row_scan(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_cnt,
-                            int32_t *row_ptr, int64_t *nnz_total);
+                            int32_t *row_ptr, int64_t *nnz_total, long long *chunk_ws,
+                            int64_t chunk_ws_len, int64_t *nnz_mirror = nullptr);
 cudaError_t launch_prm_emit(const LaunchCfg &lc, int64_t n_rows, int nv, const uint32_t *bitmap,
                             int words, const int32_t *row_ptr, int32_t *col_idx, int64_t col_cap);
 // uniform-grid spatial hash path (point models, large nv): bin -> adjacency -> gather
@@ -236,7 +237,8 @@ cudaError_t launch_sample_states(const CtxView &cv, const LaunchCfg &lc, int age
 // per agent: nodes[a][0]=init, [1]=goal, then the first nv-2 free samples in try order
 cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                int n_fixed, int nv, int nv_stride, uint64_t seed, double *nodes,
-                               int64_t *tries_out, int64_t max_tries);
+                               int64_t *tries_out, int64_t max_tries,
+                               const double *fixed_src = nullptr);
 
 
 // kernels_sssp.cu

@@ -42,6 +42,28 @@ struct ColSeg {
     __device__ __forceinline__ double g_ij(int i, int j) const { return s[g + i * n + j]; }
 };
 
+// ---- conservative culling (kernels_cross.cu, kernels_prm.cu) -----------------------------
+// A segment whose midpoint is farther from a point (or another midpoint) than
+//   thr + kPad + half length(s)
+// cannot produce `dist < thr` in the reference's arithmetic: the true distance then exceeds
+// thr by kPad = 2^-20, while the reference's computed distance is within a few ulp of the
+// coordinate magnitude (< 2^-28 for |coordinates| < 2^20) of the true one.  Callers disable
+// the cull for larger or non-finite coordinates.
+constexpr double kPad = 9.5367431640625e-07;  // 2^-20
+constexpr double kCullCoordMax = 1048576.0;   // 2^20
+
+// half length of an edge, rounded up
+template <int D>
+__device__ __forceinline__ double half_len_up(const double *a, const double *b) {
+    double v[D];
+#pragma unroll
+    for (int x = 0; x < D; ++x) v[x] = b[x] - a[x];
+    double s = v[0] * v[0];
+#pragma unroll
+    for (int x = 1; x < D; ++x) s += v[x] * v[x];
+    return 0.5 * sqrt(s) * (1.0 + 1e-9);
+}
+
 template <int D>
 __device__ __forceinline__ void load_state(const double *__restrict__ base, int64_t k, double *q) {
     if constexpr (D == 2) {
@@ -94,12 +116,13 @@ __device__ __forceinline__ bool point_connect_edge(const ConSeg &cs, const doubl
 #pragma unroll
     for (int k = 0; k < D; ++k) u[k] = dsub(qf[k], qt[k]);
     const double uu = dotd<D>(u, u);
+#pragma unroll 2
     for (int m = 0; m < cs.n_obs; ++m) {
         double c[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) c[k] = cs.oc(k, m);
         // dist(q_from,q_to,o) < o.r + rads[i]
-        ok &= !segpt_lt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(i, m));
+        ok &= !segpt_lt_simt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(i, m));
     }
     return ok;
 }

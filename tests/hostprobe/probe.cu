@@ -28,8 +28,12 @@ int probe_segpt_lt(const double *a, const double *b, const double *c, int d, dou
                    double T2) {
     double u[3];
     for (int k = 0; k < d; ++k) u[k] = mrmp::dsub(a[k], b[k]);
-    return d == 2 ? segpt_lt<2, true>(a, b, u, dotd<2>(u, u), c, thr, T2)
-                  : segpt_lt<3, true>(a, b, u, dotd<3>(u, u), c, thr, T2);
+    const int v = d == 2 ? segpt_lt<2, true>(a, b, u, dotd<2>(u, u), c, thr, T2)
+                         : segpt_lt<3, true>(a, b, u, dotd<3>(u, u), c, thr, T2);
+    // the branch-free form the SIMT callers use must give the same verdict: -1 flags a mismatch
+    const int w = d == 2 ? segpt_lt_simt<2, true>(a, b, u, dotd<2>(u, u), c, thr, T2)
+                         : segpt_lt_simt<3, true>(a, b, u, dotd<3>(u, u), c, thr, T2);
+    return v == w ? v : -1;
 }
 
 // batch forms (thr / T2 looked up per pair from N x N tables, like the kernels do)
@@ -51,6 +55,10 @@ void probe_segpt_batch(int64_t n, int d, const double *a, const double *b, const
         for (int x = 0; x < d; ++x) u[x] = mrmp::dsub(a[d * k + x], b[d * k + x]);
         out[k] = d == 2 ? segpt_lt<2, true>(a + 2 * k, b + 2 * k, u, dotd<2>(u, u), c + 2 * k, t, t2)
                         : segpt_lt<3, true>(a + 3 * k, b + 3 * k, u, dotd<3>(u, u), c + 3 * k, t, t2);
+        const uint8_t w =
+            d == 2 ? segpt_lt_simt<2, true>(a + 2 * k, b + 2 * k, u, dotd<2>(u, u), c + 2 * k, t, t2)
+                   : segpt_lt_simt<3, true>(a + 3 * k, b + 3 * k, u, dotd<3>(u, u), c + 3 * k, t, t2);
+        if (w != out[k]) out[k] = 255;  // branch-free form disagrees: poison the verdict
     }
 }
 

@@ -161,3 +161,67 @@ def test_csr_shards_pack_and_stitch_equal_a_full_build():
     assert out.value == nnz
     rp, col = adopt.csr()
     assert np.array_equal(rp, rp_full) and np.array_equal(col, col_full)
+
+
+def _assert_csr_equal(N, nv, row_ptr, col, orp, ocol):
+    for a in range(N):
+        for v in range(nv):
+            r = a * nv + v
+            assert np.array_equal(col[row_ptr[r]:row_ptr[r + 1]], ocol[a, orp[a, v]:orp[a, v + 1]]), (a, v)
+
+
+def _edge_case_nodes(N, nv, d, seed):
+    rng = np.random.default_rng(seed)
+    nodes = rng.random((N, nv, d))
+    nodes[:, :30] = rng.uniform(-0.3, 1.3, (N, 30, d))       # outside the field
+    nodes[:, 30:45] = nodes[:, 45:60]                          # duplicates: distance 0, a == b edges
+    nodes[:, 60:64] = nodes[:, 64:68] + 1e-170                 # below the squared-norm underflow
+    nodes[:, 70] = 3.0e6                                       # beyond the cull's coordinate range
+    nodes[:, 71] = 3.0e6 + 0.05
+    nodes[0, 72, 0] = np.nan
+    return nodes
+
+
+@pytest.mark.parametrize("model,d", [(O.POINT2D, 2), (O.POINT3D, 3)])
+def test_prm_all_pairs_edge_cases(model, d):
+    """The all-pairs neighbour pass (branch-free gate, obstacle cull + exact stage) on inputs
+    that leave the cull's comfort zone: vertices outside the field, duplicates, coordinates
+    beyond 2^20, a NaN vertex, and per-agent radii down to 1e-160 and up to 'connect all'."""
+    N, nv = 4, 300
+    rads, obs = make_point_instance(model, N, 13, seed=31, rad_obs=(0.03, 0.12))
+    obs[12, :d] = 3.0e6 + 0.02                                 # an obstacle next to the far pair
+    ctx, orc = S.Context(model, rads, obs), O.Oracle(model, rads, obs)
+    nodes = _edge_case_nodes(N, nv, d, 5)
+    rads_prm = np.array([0.1, 1e-160, 0.45, 0.2])
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(rads_prm)
+    assert not rm.used_grid()
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, rads_prm, nthreads=0)
+    assert nnz == int(onnz.sum())
+    _assert_csr_equal(N, nv, row_ptr, col, orp, ocol)
+    assert onnz[1] > 0 and onnz[2] > 20 * nv
+    # rad = nothing: every pair is a candidate
+    nnz = rm.build(None)
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, None, nthreads=0)
+    assert nnz == int(onnz.sum())
+    _assert_csr_equal(N, nv, row_ptr, col, orp, ocol)
+
+
+def test_prm_all_pairs_table_too_large_for_shared_memory():
+    """nv = 6200 with rad = 0.26 (fewer than 4 grid cells per axis -> all pairs): the vertex
+    table (99 KB) is not staged, the kernel instantiation that reads it from global runs."""
+    N, nv, d = 1, 6200, 2
+    rads, obs = make_point_instance(O.POINT2D, N, 10, seed=3)
+    ctx, orc = S.Context(O.POINT2D, rads, obs), O.Oracle(O.POINT2D, rads, obs)
+    nodes = np.random.default_rng(8).random((N, nv, d))
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(0.26)
+    assert not rm.used_grid()
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, 0.26, nthreads=0)
+    assert nnz == int(onnz.sum()) and nnz > 100 * nv
+    assert np.array_equal(row_ptr, orp[0]) and np.array_equal(col, ocol[0, :nnz])

@@ -185,9 +185,10 @@ def test_quick_tests_never_change_a_verdict(probe, d, shift):
     # segment-point form: collide(Q, q_to, i) of one candidate against one static agent
     Q = np.zeros((N, d))
     wantp = np.array([O.dist_sp(a[k], b[k], c[k]) < thr[ai[k], aj[k]] for k in range(0, n, 10)], np.uint8)
-    gotp = np.empty(n, np.uint8)
+    gotp = np.empty(n, np.uint8)  # 255 = branchy and branch-free device forms disagree
     probe.probe_segpt_batch(n, d, a.ctypes.data, b.ctypes.data, c.ctypes.data, ai.ctypes.data,
                             aj.ctypes.data, N, thr.ctypes.data, T2.ctypes.data, gotp.ctypes.data)
+    assert gotp.max() <= 1
     assert np.array_equal(gotp[::10], wantp) and 0 < wantp.sum() < wantp.size
 
 
