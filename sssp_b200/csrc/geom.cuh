@@ -149,6 +149,18 @@ MRMP_HD bool segpt_lt(const double *a, const double *b, const double *u,
 // three values of e, which also reproduces the reference's NaN / Inf propagation (0 * b).
 // Returns sumsq(p).
 template <int D>
+MRMP_HD double segpt_foot_core(const double *a, const double *b, const double *c, double uu,
+                               double df0, double df1, double *p) {
+    const bool inside = dmul(df0, df1) < 0.0;  // :50
+    const double e_in = ddiv(-df0, uu);        // :51 (only used when inside)
+    const double e = inside ? e_in : (df0 >= 0.0 ? 0.0 : 1.0);  // :49-54
+    const double f = dsub(1.0, e);
+#pragma unroll
+    for (int x = 0; x < D; ++x) p[x] = dsub(dadd(dmul(e, a[x]), dmul(f, b[x])), c[x]);  // :56
+    return sumsq<D>(p);
+}
+
+template <int D>
 MRMP_HD double segpt_foot_sq(const double *a, const double *b, const double *u, double uu,
                              const double *c, double *p) {
     double bc[D], ac[D];
@@ -159,13 +171,7 @@ MRMP_HD double segpt_foot_sq(const double *a, const double *b, const double *u, 
     }
     const double df0 = dotd<D>(u, bc);  // :46
     const double df1 = dotd<D>(u, ac);  // :47
-    const bool inside = dmul(df0, df1) < 0.0;  // :50
-    const double e_in = ddiv(-df0, uu);        // :51 (only used when inside)
-    const double e = inside ? e_in : (df0 >= 0.0 ? 0.0 : 1.0);  // :49-54
-    const double f = dsub(1.0, e);
-#pragma unroll
-    for (int x = 0; x < D; ++x) p[x] = dsub(dadd(dmul(e, a[x]), dmul(f, b[x])), c[x]);  // :56
-    return sumsq<D>(p);
+    return segpt_foot_core<D>(a, b, c, uu, df0, df1, p);
 }
 
 template <int D, bool TAB = true>
@@ -211,21 +217,39 @@ MRMP_HD bool segseg_lt(const double *p11, const double *p12, const double *p21,
     }
     // :86-93  minimum of the four endpoint-to-segment distances (NaN-propagating).
     // The four evaluations of dist(a,b,c) (:44-57) run branch-free and side by side
-    // (segpt_foot_sq): four independent dependency chains for the FP64 pipe.
-    const double *A[4] = {p11, p11, p21, p21};  // segment start  (a)
-    const double *B[4] = {p12, p12, p22, p22};  // segment end    (b)
-    const double *C[4] = {p21, p22, p11, p12};  // the point      (c)
-    double s[4];
-    bool hit = false;
+    // (segpt_foot_core): four independent dependency chains for the FP64 pipe.  Their
+    // difference vectors are shared: RN(x - y) = -RN(y - x) exactly, a negated operand negates
+    // every product and sum of an un-fused dot exactly, and signs of zero cannot reach a verdict
+    // (they only meet comparisons against 0, squares, and products with finite values), so
+    //   a - b  is  -v1 / -v2,   p11 - p21 = -w,   p21 - p11 = w,
+    //   p22 - p11 = -(p11 - p22),  p22 - p12 = -(p12 - p22),  p21 - p12 = -(p12 - p21),
+    // and dot(a - b, a - c) of the first / third call is D1 / -D2.
+    double g0[D], g1[D], g2[D], nv1[D], nv2[D], ng0[D], ng1[D], ng2[D];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const double uu = k < 2 ? V1 : V2;  // dot(a-b, a-b) == dot(b-a, b-a) bitwise
-        double u[D], p[D];
-#pragma unroll
-        for (int x = 0; x < D; ++x) u[x] = dsub(A[k][x], B[k][x]);
-        s[k] = segpt_foot_sq<D>(A[k], B[k], u, uu, C[k], p);
-        hit |= norm_lt<D, TAB>(p, s[k], thr, T2);
+    for (int x = 0; x < D; ++x) {
+        g0[x] = dsub(p12[x], p21[x]);
+        g1[x] = dsub(p12[x], p22[x]);
+        g2[x] = dsub(p11[x], p22[x]);
+        nv1[x] = -v1[x];
+        nv2[x] = -v2[x];
+        ng0[x] = -g0[x];
+        ng1[x] = -g1[x];
+        ng2[x] = -g2[x];
     }
+    double s[4], p[D];
+    bool hit = false;
+    // dist(p11, p12, p21): u = -v1, b - c = g0, a - c = -w
+    s[0] = segpt_foot_core<D>(p11, p12, p21, V1, dotd<D>(nv1, g0), D1, p);
+    hit |= norm_lt<D, TAB>(p, s[0], thr, T2);
+    // dist(p11, p12, p22): u = -v1, b - c = g1, a - c = g2
+    s[1] = segpt_foot_core<D>(p11, p12, p22, V1, dotd<D>(nv1, g1), dotd<D>(nv1, g2), p);
+    hit |= norm_lt<D, TAB>(p, s[1], thr, T2);
+    // dist(p21, p22, p11): u = -v2, b - c = -g2, a - c = w
+    s[2] = segpt_foot_core<D>(p21, p22, p11, V2, dotd<D>(nv2, ng2), -D2, p);
+    hit |= norm_lt<D, TAB>(p, s[2], thr, T2);
+    // dist(p21, p22, p12): u = -v2, b - c = -g1, a - c = -g0
+    s[3] = segpt_foot_core<D>(p21, p22, p12, V2, dotd<D>(nv2, ng1), dotd<D>(nv2, ng0), p);
+    hit |= norm_lt<D, TAB>(p, s[3], thr, T2);
     const double nan_probe = dadd(dadd(s[0], s[1]), dadd(s[2], s[3]));
     return hit && !isnan(nan_probe);
 }

@@ -186,7 +186,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 k_cross_prep_cols(EdgeList<D> el, int64_t n_cols, const int32_t *__restrict__ order,
                   int group_size, ColTile<D> *__restrict__ tiles, TileHdr<D> *__restrict__ hdrs,
-                  int64_t n_tiles) {
+                  int64_t n_tiles, const double *__restrict__ rads, int n_agents) {
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles;
@@ -216,7 +216,9 @@ k_cross_prep_cols(EdgeList<D> el, int64_t n_cols, const int32_t *__restrict__ or
             const int64_t src = order[c];
             double a[D], b[D];
             const int j = el.get(src, a, b);
-            const double h = half_len_up<D>(a, b);
+            // reach of the column: half length + its agent's radius (an id outside the ctx is
+            // rejected by the exact stage; it must not be culled here)
+            const double h = half_len_up<D>(a, b) + (j >= 0 && j < n_agents ? __ldg(rads + j) : 1e300);
 #pragma unroll
             for (int x = 0; x < D; ++x) {
                 const double m = dmul(dadd(a[x], b[x]), 0.5);
@@ -334,8 +336,9 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
                 S.row_ab[lane][D + x] = rec.b[x];
                 lo[x] = hi[x] = m1[x];
             }
-            // reach of this row: largest threshold it can meet + slack + its own half length
-            R = __ldg(rads + i) + max_rad + kPad + half_len_up<D>(rec.a, rec.b);
+            // reach of this row: its radius + slack + its own half length (the column's
+            // radius and half length are in T.sa[c].h)
+            R = __ldg(rads + i) + kPad + half_len_up<D>(rec.a, rec.b);
         } else {
 #pragma unroll
             for (int x = 0; x < D; ++x) {
@@ -510,9 +513,9 @@ cudaError_t launch_cross_sort_rows(const CtxView &cv, const LaunchCfg &lc, int64
 }
 
 template <int D>
-static cudaError_t prep_cols_t(const LaunchCfg &lc, const EdgeList<D> &el, int64_t n_cols,
-                               int group_size, int32_t *cells, int32_t *order, void *tiles,
-                               void *hdrs) {
+static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const EdgeList<D> &el,
+                               int64_t n_cols, int group_size, int32_t *cells, int32_t *order,
+                               void *tiles, void *hdrs) {
     const int64_t n_tiles = (n_cols + kCols - 1) / kCols;
     cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * kSortCells, lc.stream);
     if (e != cudaSuccess) return e;
@@ -521,7 +524,8 @@ static cudaError_t prep_cols_t(const LaunchCfg &lc, const EdgeList<D> &el, int64
     k_cell_scan<<<1, 1024, 0, lc.stream>>>(cells);
     k_cols_scatter<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells, order);
     k_cross_prep_cols<D><<<grid_for_n(lc, n_tiles * 32, 256), 256, 0, lc.stream>>>(
-        el, n_cols, order, group_size, (ColTile<D> *)tiles, (TileHdr<D> *)hdrs, n_tiles);
+        el, n_cols, order, group_size, (ColTile<D> *)tiles, (TileHdr<D> *)hdrs, n_tiles,
+        cv.blob + cv.crads_off, cv.n_agents);
     count_launch(4);
     return cudaGetLastError();
 }
@@ -535,10 +539,10 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
     if (n_cols <= 0) return cudaSuccess;
     if (n_cols >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (cv.model == 0)
-        return prep_cols_t<2>(lc, EdgeList<2>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
+        return prep_cols_t<2>(cv, lc, EdgeList<2>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
                               n_cols, group_size, cells, order, tiles, hdrs);
     if (cv.model == 1)
-        return prep_cols_t<3>(lc, EdgeList<3>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
+        return prep_cols_t<3>(cv, lc, EdgeList<3>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
                               n_cols, group_size, cells, order, tiles, hdrs);
     return cudaErrorNotSupported;
 }
