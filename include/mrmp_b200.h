@@ -316,6 +316,11 @@ int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_samples, const d
 int mrmp_distance_tables(mrmp_ctx *ctx, int n_graphs, const int32_t *v_off, const double *nodes,
                          const int32_t *row_ptr, const int32_t *col_idx, const int32_t *goal,
                          double *tables_out);
+/* the same with the edge cost of gen_g_func(stay_penalty = p) (solvers/utils.jl:29-39), which
+ * PP / CBS pass as g_func (pp.jl:54,161): dist(v.q, u.q) + (v.q == u.q ? p : 0). */
+int mrmp_distance_tables_g(mrmp_ctx *ctx, int n_graphs, const int32_t *v_off, const double *nodes,
+                           const int32_t *row_ptr, const int32_t *col_idx, const int32_t *goal,
+                           double stay_penalty, double *tables_out);
 
 /* ---- validate(config_init, connect, collide, check_goal, solution): utils.jl:320-367 -------- */
 /* The transition checks of validate (:345-363) for a whole solution in two launches:

@@ -16,10 +16,11 @@ from .closures import (  # noqa: F401
 from . import closures  # noqa: F401
 from .solvers import SSSP, get_distance_table, get_distance_tables  # noqa: F401
 from .validation import validate, is_valid_instance  # noqa: F401
+from .pp import PP, PP_on_roadmaps  # noqa: F401
 
 __all__ = [
     "MRMPError", "MODEL_POINT2D", "MODEL_POINT3D", "MODEL_ARM22",
     "StatePoint2D", "StatePoint3D", "StateArm22", "StateLine2D", "StateSnake2D", "StateArm33",
     "StateCapsule3D", "CircleObstacle2D", "CircleObstacle3D", "Node",
-    "Context", "Roadmaps", "SsspRoadmaps", "SSSP", "validate", "is_valid_instance", "gen_connect", "gen_collide", "gen_check_goal", "PRMs",
+    "Context", "Roadmaps", "SsspRoadmaps", "SSSP", "PP", "PP_on_roadmaps", "validate", "is_valid_instance", "gen_connect", "gen_collide", "gen_check_goal", "PRMs",
 ]

@@ -298,9 +298,10 @@ class Context:
             return None
         return int(t.value), "vertex" if kind.value == 1 else "edge", int(i.value), int(j.value)
 
-    def distance_tables(self, graphs, goal: int = 1):
+    def distance_tables(self, graphs, goal: int = 1, stay_penalty: float = 0.0):
         """get_distance_table for several roadmaps in one launch (solvers/utils.jl:146-236).
-        graphs: list of (nodes [nv][d], neighbour lists) ; returns a list of float64 tables."""
+        graphs: list of (nodes [nv][d], neighbour lists) ; returns a list of float64 tables.
+        stay_penalty: the edge cost is gen_g_func(stay_penalty)'s (solvers/utils.jl:34-36)."""
         v_off = np.zeros(len(graphs) + 1, np.int32)
         nodes, rp, ci = [], [np.zeros(1, np.int64)], []
         for g, (q, nbrs) in enumerate(graphs):
@@ -315,10 +316,11 @@ class Context:
         col = np.ascontiguousarray(np.concatenate(ci)) if ci else np.zeros(0, np.int32)
         goals = np.full(len(graphs), goal, np.int32)
         out = np.empty(nodes.shape[0])
-        L.check(self._lib.mrmp_distance_tables(self._h, len(graphs), L.ptr(v_off, L._ip),
-                                               L.ptr(nodes, L._dp), L.ptr(row_ptr, L._ip),
-                                               L.ptr(col, L._ip) if col.size else None,
-                                               L.ptr(goals, L._ip), L.ptr(out, L._dp)))
+        L.check(self._lib.mrmp_distance_tables_g(self._h, len(graphs), L.ptr(v_off, L._ip),
+                                                 L.ptr(nodes, L._dp), L.ptr(row_ptr, L._ip),
+                                                 L.ptr(col, L._ip) if col.size else None,
+                                                 L.ptr(goals, L._ip), float(stay_penalty),
+                                                 L.ptr(out, L._dp)))
         return [out[v_off[g]: v_off[g + 1]].copy() for g in range(len(graphs))]
 
     def prm_build(self, nodes, rad, agent0: int = 0):

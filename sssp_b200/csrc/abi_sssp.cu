@@ -314,7 +314,16 @@ extern "C" int mrmp_distance_tables(mrmp_ctx *c, int n_graphs, const int32_t *v_
                                     const double *nodes, const int32_t *row_ptr,
                                     const int32_t *col_idx, const int32_t *goal,
                                     double *tables_out) {
+    return mrmp_distance_tables_g(c, n_graphs, v_off, nodes, row_ptr, col_idx, goal, 0.0,
+                                  tables_out);
+}
+
+extern "C" int mrmp_distance_tables_g(mrmp_ctx *c, int n_graphs, const int32_t *v_off,
+                                      const double *nodes, const int32_t *row_ptr,
+                                      const int32_t *col_idx, const int32_t *goal,
+                                      double stay_penalty, double *tables_out) {
     NEED(c && n_graphs >= 0, "bad ctx / n_graphs");
+    NEED(stay_penalty == stay_penalty, "stay_penalty is NaN");
     if (n_graphs == 0) return MRMP_OK;
     NEED(v_off && nodes && row_ptr && goal && tables_out, "NULL buffer");
     const int64_t V = v_off[n_graphs];
@@ -353,7 +362,7 @@ extern "C" int mrmp_distance_tables(mrmp_ctx *c, int n_graphs, const int32_t *v_
     CU(launch_distance_tables(c->cv, lcfg(c, st), n_graphs, (const int32_t *)(b + o_voff),
                               (const int32_t *)(b + o_rp), (const int32_t *)(b + o_ci),
                               (const double *)(b + o_nodes), (const int32_t *)(b + o_goal),
-                              (double *)(b + o_w), (double *)(b + o_tab)));
+                              stay_penalty, (double *)(b + o_w), (double *)(b + o_tab)));
     CU(cudaMemcpyAsync(h, b + o_tab, sizeof(double) * (size_t)V, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(tables_out, h, sizeof(double) * (size_t)V);

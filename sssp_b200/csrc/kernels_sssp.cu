@@ -567,7 +567,7 @@ template <class M>
 __global__ void __launch_bounds__(512)
 k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *__restrict__ row_ptr,
                   const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
-                  const int32_t *__restrict__ goal, double *__restrict__ w,
+                  const int32_t *__restrict__ goal, double stay_penalty, double *__restrict__ w,
                   double *__restrict__ table) {
     constexpr int D = M::SD;
     __shared__ int s_changed;
@@ -584,7 +584,13 @@ k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *
         for (int64_t e = row_ptr[v0 + v] + lane; e < row_ptr[v0 + v + 1]; e += 32) {
             double qu[D];
             load_state<D>(tab, col_idx[e], qu);
-            w[e] = M::dist(cv, qv, qu);
+            // gen_g_func (solvers/utils.jl:34-36): dist + (q_from == q_to ? stay_penalty : 0);
+            // `==` of two immutable states is egality: every field bit-identical
+            bool same = true;
+#pragma unroll
+            for (int x = 0; x < D; ++x)
+                same &= __double_as_longlong(qv[x]) == __double_as_longlong(qu[x]);
+            w[e] = dadd(M::dist(cv, qv, qu), same ? stay_penalty : 0.0);
         }
     }
     for (int v = threadIdx.x; v < nv; v += blockDim.x)
@@ -715,10 +721,11 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
 cudaError_t launch_distance_tables(const CtxView &cv, const LaunchCfg &lc, int n_graphs,
                                    const int32_t *v_off, const int32_t *row_ptr,
                                    const int32_t *col_idx, const double *nodes,
-                                   const int32_t *goal, double *w, double *table) {
+                                   const int32_t *goal, double stay_penalty, double *w,
+                                   double *table) {
     if (n_graphs <= 0) return cudaSuccess;
     MRMP_MODEL_SWITCH(cv, (k_distance_tables<M><<<n_graphs, 512, 0, lc.stream>>>(
-                              cv, v_off, row_ptr, col_idx, nodes, goal, w, table)));
+                              cv, v_off, row_ptr, col_idx, nodes, goal, stay_penalty, w, table)));
     count_launch();
     return cudaGetLastError();
 }

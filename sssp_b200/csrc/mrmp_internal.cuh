@@ -293,7 +293,7 @@ cudaError_t launch_sssp_expand_fused(const CtxView &cv, const LaunchCfg &lc, con
 cudaError_t launch_distance_tables(const CtxView &cv, const LaunchCfg &lc, int n_graphs,
                                    const int32_t *v_off, const int32_t *row_ptr,
                                    const int32_t *col_idx, const double *nodes,
-                                   const int32_t *goal, double *w, double *table);
+                                   const int32_t *goal, double stay_penalty, double *w, double *table);
 cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
                             const double *q1, const double *q2, double *out);
 cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,

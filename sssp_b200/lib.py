@@ -103,6 +103,7 @@ _SIGS = {
     "mrmp_first_conflict": (C.c_int, [_vp, C.c_int64, _dp, _lp, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mrmp_distance_tables": (C.c_int, [_vp, C.c_int, _ip, _dp, _ip, _ip, _ip, _dp]),
+    "mrmp_distance_tables_g": (C.c_int, [_vp, C.c_int, _ip, _dp, _ip, _ip, _ip, C.c_double, _dp]),
     "mrmp_sssp_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "mrmp_sssp_destroy": (None, [_vp]),
     "mrmp_sssp_set_roadmap": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),

@@ -109,10 +109,10 @@ def get_distance_table(ctx: Context, nodes: np.ndarray, nbrs: List[List[int]], g
     return ctx.distance_tables([(nodes, nbrs)], goal)[0].tolist()
 
 
-def get_distance_tables(ctx: Context, roadmaps, goal: int = 1):
+def get_distance_tables(ctx: Context, roadmaps, goal: int = 1, stay_penalty: float = 0.0):
     """solvers/utils.jl:226-236 for Vector{Vector{Node}} roadmaps: all agents in one launch."""
     graphs = [(np.array([tuple(v.q) for v in rm]), [list(v.neighbors) for v in rm]) for rm in roadmaps]
-    return [t.tolist() for t in ctx.distance_tables(graphs, goal)]
+    return [t.tolist() for t in ctx.distance_tables(graphs, goal, stay_penalty)]
 
 
 class _AgentSampler:
