@@ -7,9 +7,10 @@ with the reference's signatures and return value `(solution, roadmaps)`.  What r
   GPU, once per planned agent i (instead of one `collide` call per generated search node):
       * the conflict table  bit[(v -> u), (t, j)] = collide(v.q, u.q, p_j[t-1], p_j[t], i, j)
         for every move of roadmap i (its edges plus the "stay" moves v -> v) against every
-        already planned agent j at every time step t <= max_makespan -- one cross-product
-        launch (`mrmp_collide_cross`); `invalid()` (pp.jl:171-193) and the extra goal
-        constraints (pp.jl:195-213) become table look-ups;
+        already planned agent j at every time step t <= max_makespan -- two cross-product
+        launches (`mrmp_collide_cross`: all moves with the OR over j taken on the device, and
+        the stay moves per (t, j)); `invalid()` (pp.jl:171-193) and the extra goal constraints
+        (pp.jl:195-213) become table look-ups;
       * the move costs dist(v.q, u.q) of the same moves (`mrmp_state_dist`);
       * beforehand, for all agents: the roadmaps (`PRMs`) and the distance tables with
         gen_g_func's edge cost (`mrmp_distance_tables_g`, pp.jl:161).
@@ -78,15 +79,17 @@ class _AgentTables:
             cf[:, k] = qj[p[np.minimum(t - 1, l) - 1]]   # paths[j][min(t - 1, l)]
             ct[:, k] = qj[p[np.minimum(t, l) - 1]]       # paths[j][min(t, l)]
             live[:, k] = t <= l
-        bits = ctx.collide_cross(np.full(dst.size, i, np.int32), rf, rt, ca,
-                                 cf.reshape(-1, ctx.d), ct.reshape(-1, ctx.d))
-        hit = np.unpackbits(bits.view(np.uint8), axis=1, bitorder="little")[:, :T * K]
-        hit = hit.reshape(dst.size, T, K).astype(bool)
-        self.blocked = hit.any(axis=2)
+        cf, ct = cf.reshape(-1, ctx.d), ct.reshape(-1, ctx.d)
+        # invalid() (pp.jl:171-193) tests every planned agent at time t: OR over the K columns
+        # of a time step, reduced on the device (group_size = K)
+        bits = ctx.collide_cross(np.full(dst.size, i, np.int32), rf, rt, ca, cf, ct, group_size=K)
+        self.blocked = np.unpackbits(bits.view(np.uint8), axis=1,
+                                     bitorder="little")[:, :T].astype(bool)
         # check_goal_i (pp.jl:195-213): the stay move of v against paths[j][t-1 -> t] for
-        # t = S.t + 1 .. length(paths[j]) only
-        stay_rows = self.row0[1:] - 1                # v -> v is the last move of each vertex
-        g = (hit[stay_rows] & live[None, :, :]).any(axis=2)        # [v][t - 2]
+        # t = S.t + 1 .. length(paths[j]) only -> per-agent bits of the nv stay moves
+        sbits = ctx.collide_cross(np.full(nv, i, np.int32), q, q, ca, cf, ct)
+        hit = np.unpackbits(sbits.view(np.uint8), axis=1, bitorder="little")[:, :T * K]
+        g = (hit.reshape(nv, T, K).astype(bool) & live[None, :, :]).any(axis=2)   # [v][t - 2]
         later = np.zeros((nv, max_makespan + 1), bool)             # index S.t - 1
         # later[v][s - 1] = any g[v][t - 2] for t >= s + 1
         acc = np.zeros(nv, bool)
@@ -228,13 +231,20 @@ def PP(config_init: Sequence, config_goal: Sequence, connect: Callable, collide:
     def timeover():
         return TIME_LIMIT is not None and time.monotonic() - t_s > TIME_LIMIT
 
-    kw = dict(stay_penalty=stay_penalty, max_makespan=max_makespan,
-              order_randomize=order_randomize, order=order, seed=seed, stats=stats)
+    rng = np.random.default_rng(seed)
+
+    def kw():
+        # a fresh randperm(N) for every attempt (pp.jl:165), unless the caller fixed the order
+        o = order
+        if o is None:
+            o = rng.permutation(len(config_init)).tolist() if order_randomize else None
+        return dict(stay_penalty=stay_penalty, max_makespan=max_makespan, order_randomize=False,
+                    order=o, stats=stats)
     roadmaps = PRMs(config_init, config_goal, connect, num_vertices, rad=rad, rads=rads, seed=seed)
     if timeover():
         return None, roadmaps
     solution, roadmaps = PP_on_roadmaps(roadmaps, collide, check_goal, g_func, TIME_LIMIT=left(),
-                                        **kw)
+                                        **kw())
     while solution is None and roadmaps_growing_rate is not None and not timeover():
         num_vertices = int(math.floor(num_vertices * roadmaps_growing_rate))
         fresh = PRMs(config_init, config_goal, connect, num_vertices, rad=rad, rads=rads,
@@ -242,6 +252,8 @@ def PP(config_init: Sequence, config_goal: Sequence, connect: Callable, collide:
         roadmaps = _grow(roadmaps, fresh)
         if timeover():
             break
+        if stats is not None:
+            stats["attempts"] = stats.get("attempts", 1) + 1
         solution, roadmaps = PP_on_roadmaps(roadmaps, collide, check_goal, g_func,
-                                            TIME_LIMIT=left(), **kw)
+                                            TIME_LIMIT=left(), **kw())
     return solution, roadmaps
