@@ -237,4 +237,46 @@ function expand_and_filter!(s::SsspRoadmaps, i::Int64, v::Node{State}, S_Q::Vect
     return [(Int64(succ[k]) + 1, hit[k] != 0) for k = 1:n_succ[]]
 end
 
+# ---- PP (pp.jl:140-260): conflict tables for the agent that is planned next ------------------
+"""
+    pp_conflict_tables(ctx, roadmaps, i, paths, max_makespan) -> (blocked, stay_hits, planned)
+
+Everything `invalid` (pp.jl:171-193) and `check_goal_i` (pp.jl:195-213) ask about agent `i`,
+in two cross-product launches instead of one `collide` call per generated search node.
+Rows are agent i's moves in expansion order `vcat(v.neighbors, v.id)` (solvers/utils.jl:107),
+columns `(paths[j][min(t-1,l)], paths[j][min(t,l)])` for `t = 2:max_makespan`, j over the
+planned agents.  `blocked[move, t-1]` is the OR over j (taken on the device, group_size = K);
+`stay_hits[v, (t-2)*K + k]` is the verdict of the stay move of vertex v against planned[k] at t.
+"""
+function pp_conflict_tables(ctx::Ctx, roadmaps::Vector{Vector{Node{State}}}, i::Int64,
+                            paths::Vector{Vector{Node{State}}},
+                            max_makespan::Int64) where {State<:AbsState}
+    rm = roadmaps[i]
+    planned = [j for j = 1:length(roadmaps) if j != i && !isempty(paths[j])]
+    K, T = length(planned), max_makespan - 1
+    rf = State[v.q for v in rm for _ in 1:(length(v.neighbors) + 1)]
+    rt = State[rm[k].q for v in rm for k in vcat(v.neighbors, v.id)]
+    ca = Int32[j - 1 for _ = 2:max_makespan for j in planned]
+    cf = State[paths[j][min(t - 1, length(paths[j]))].q for t = 2:max_makespan for j in planned]
+    ct = State[paths[j][min(t, length(paths[j]))].q for t = 2:max_makespan for j in planned]
+    ra = fill(Int32(i - 1), length(rf))
+    wpr = (T + 31) ÷ 32
+    bits = zeros(UInt32, wpr, length(rf))                  # column r = row r in C
+    check(ccall((:mrmp_collide_cross, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{State}, Ptr{State}, Int64, Ptr{Int32},
+                 Ptr{State}, Ptr{State}, Cint, Ptr{UInt32}),
+                ctx.h, length(rf), ra, rf, rt, length(ca), ca, cf, ct, K, bits))
+    blocked = [(bits[(c >> 5) + 1, r] >> (c & 31)) & 0x1 == 0x1 for r = 1:length(rf), c = 0:T-1]
+    sq = State[v.q for v in rm]
+    swpr = (T * K + 31) ÷ 32
+    sbits = zeros(UInt32, swpr, length(rm))
+    check(ccall((:mrmp_collide_cross, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{State}, Ptr{State}, Int64, Ptr{Int32},
+                 Ptr{State}, Ptr{State}, Cint, Ptr{UInt32}),
+                ctx.h, length(rm), fill(Int32(i - 1), length(rm)), sq, sq, length(ca), ca, cf, ct,
+                0, sbits))
+    stay_hits = [(sbits[(c >> 5) + 1, v] >> (c & 31)) & 0x1 == 0x1 for v = 1:length(rm), c = 0:T*K-1]
+    return blocked, stay_hits, planned
+end
+
 end # module
