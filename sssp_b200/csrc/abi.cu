@@ -1192,7 +1192,7 @@ extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, in
     rm->built = true;
     rm->e_valid = false;
     if (nnz_out) *nnz_out = rm->nnz;
-    return MRMP_OK;
+    return roadmaps_settle(rm, false);  // a deferred sampling verdict of this set, if any
 }
 
 extern "C" int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out) {

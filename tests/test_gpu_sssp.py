@@ -271,3 +271,30 @@ def test_first_conflict_matches_get_constraints(name):
     sol = np.array([[tabs[i][q[i]] for i in range(N)] for q in fx["solution"]])
     assert ctx.first_conflict(sol) is None and _oracle_first_conflict(orc, N, sol) is None
     assert kinds, "no conflict was exercised"
+
+
+def test_distance_tables_with_stay_penalty_edge_cost():
+    """mrmp_distance_tables_g: the edge cost of gen_g_func(stay_penalty) (solvers/utils.jl:34-36)
+    -- dist + stay_penalty between bit-identical states -- as PP / CBS build their tables
+    (pp.jl:161).  Duplicated vertices make the penalty reachable through the neighbour lists."""
+    from helpers import make_point_instance
+    from oracle import pp_ref
+    from oracle.sssp_ref import Node as ONode
+    N, nv = 3, 120
+    rads, obs = make_point_instance(O.POINT2D, N, 6, seed=9)
+    ctx, orc = S.Context(O.POINT2D, rads, obs), O.Oracle(O.POINT2D, rads, obs)
+    nodes = np.stack([orc.sample_free(a, 7, nv)[0] for a in range(N)])
+    nodes[:, 40:60] = nodes[:, 60:80]            # exact duplicates: dist 0, q_from == q_to
+    nodes[:, 1] = nodes[:, 41]                   # the goal itself has a twin
+    rp, col, nnz = orc.prm_build(0, nodes, 0.2, nthreads=0)
+    graphs = [(nodes[a], [col[a, rp[a, v]:rp[a, v + 1]].tolist() for v in range(nv)])
+              for a in range(N)]
+    for pen in (0.1, 0.0, 2.5):
+        g = pp_ref.gen_g_func(orc, False, pen)
+        got = ctx.distance_tables(graphs, goal=1, stay_penalty=pen)
+        for a in range(N):
+            rm = [ONode(nodes[a, v], v, graphs[a][1][v]) for v in range(nv)]
+            want = np.array(pp_ref.get_distance_table(rm, g, 1))
+            assert np.array_equal(got[a].view(np.uint64), want.view(np.uint64)), (pen, a)
+    twin = ctx.distance_tables(graphs, goal=1, stay_penalty=0.1)[0][41]
+    assert twin == 0.1                           # one hop goal -> its twin costs the penalty
