@@ -105,8 +105,7 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
 
     const int N = n_agents, M = n_obs;
-    // obstacle arrays are padded to a multiple of 8 (kernels read them in groups of 8)
-    const int mp = (pad2(M > 0 ? M : 1) + 7) & ~7, np = pad2(N);
+    const int mp = pad2(M > 0 ? M : 1), np = pad2(N);
     const bool arm = model == MRMP_MODEL_ARM22 || model == MRMP_MODEL_ARM33;  // fixed bases
     // obstacle threshold o.r + rads[i] (points, capsule3d.jl:76) or o.r alone (arm22.jl:46,
     // line2d.jl:39, snake2d.jl:78, arm33.jl:60); pair threshold rads[i] + rads[j] (point.jl:11,

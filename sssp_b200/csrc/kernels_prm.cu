@@ -97,7 +97,7 @@ k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64
 constexpr int kRing1 = 256;      // (j,k) entries per warp; in flight <= 31 + 32 * kGateGroup
 constexpr int kGateGroup = 4;    // bitmap words gated per compaction round
 constexpr int kRing2 = 512;      // (j,k,m) entries per warp; in flight <= 31 + 32 * kCullGroup
-constexpr int kCullGroup = 8;    // obstacles culled per compaction round (ctx pads to 8)
+constexpr int kCullGroup = 8;    // obstacles culled per compaction round
 constexpr int kAdjStageBytes = 96 * 1024;  // vertex tables up to this size are staged in smem
 constexpr double kGateRadMin = 1e-150;     // above this, dist <= rad  <=>  dist_sq <= r2
 
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 3)
 k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
                 const double *__restrict__ rad, const double *__restrict__ rad_r2,
                 const double *__restrict__ nodes, uint32_t *__restrict__ bitmap, int words,
-                int32_t *__restrict__ row_cnt, int seg_bytes) {
+                int32_t *__restrict__ row_cnt, int seg_bytes, int obs_pad) {
     constexpr int SD = M::SD;
     constexpr bool kCull = AdjTraits<M>::kCull;
     const int a = blockIdx.x / chunks, chunk = blockIdx.x - a * chunks;
@@ -159,6 +159,17 @@ k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
     sp += kWarps * kRing1 * 8;
     unsigned long long *ring2 = reinterpret_cast<unsigned long long *>(sp) + warp * kRing2;
     if (kCull) sp += kWarps * kRing2 * 8;
+    // point models: obstacle SoA re-packed with the count padded to a multiple of kCullGroup
+    // (far-away, zero-radius entries), so that a cull round reads at immediate offsets
+    double *opad = reinterpret_cast<double *>(sp);
+    if (kCull && obs_pad > 0) {
+        for (int t = threadIdx.x; t < (SD + 1) * obs_pad; t += kThreads) {
+            const int x = t / obs_pad, m = t - x * obs_pad;
+            opad[t] = m < cs.n_obs ? cs.oc(x, m) : (x < SD ? 1.0e300 : 0.0);
+        }
+        sp += (SD + 1) * obs_pad * 8;
+        if (!SMEM) __syncthreads();
+    }
     const double *tab = nodes + (int64_t)a * nv * SD;
     if constexpr (SMEM) {
         double *st = reinterpret_cast<double *>(sp);
@@ -235,21 +246,35 @@ k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
             }
             const unsigned long long key = ((unsigned long long)(unsigned)e.x << 44) |
                                            ((unsigned long long)(unsigned)e.y << 24);
-            // the ctx pads the obstacle arrays to a multiple of kCullGroup with far-away,
-            // zero-radius entries, so a group is read without clamping
             for (int m0 = 0; m0 < cs.n_obs; m0 += kCullGroup) {
                 unsigned near = 0;
-                if (ok) {
-                    const double *oc = cs.s + cs.obs + m0;
+                if (ok && obs_pad > 0) {
+                    const double *oc = opad + m0;
 #pragma unroll
                     for (int u = 0; u < kCullGroup; ++u) {
                         double w2 = 0.0;
 #pragma unroll
                         for (int x = 0; x < SD; ++x) {
-                            const double w = oc[x * cs.mp + u] - mid[x];
+                            const double w = oc[x * obs_pad + u] - mid[x];
                             w2 += w * w;
                         }
-                        const double orad = oc[SD * cs.mp + u];
+                        const double orad = oc[SD * obs_pad + u];
+                        const double reach = R + orad;
+                        const bool far = w2 > reach * reach && fabs(orad) < kCullCoordMax;
+                        near |= (m0 + u < cs.n_obs && (wide || !far) ? 1u : 0u) << u;
+                    }
+                } else if (ok) {  // very many obstacles: read the ctx arrays at a clamped index
+                    const double *oc = cs.s + cs.obs;
+#pragma unroll
+                    for (int u = 0; u < kCullGroup; ++u) {
+                        const int m = m0 + u < cs.n_obs ? m0 + u : cs.n_obs - 1;
+                        double w2 = 0.0;
+#pragma unroll
+                        for (int x = 0; x < SD; ++x) {
+                            const double w = oc[x * cs.mp + m] - mid[x];
+                            w2 += w * w;
+                        }
+                        const double orad = oc[SD * cs.mp + m];
                         const double reach = R + orad;
                         const bool far = w2 > reach * reach && fabs(orad) < kCullCoordMax;
                         near |= (m0 + u < cs.n_obs && (wide || !far) ? 1u : 0u) << u;
@@ -738,7 +763,7 @@ template <class M, bool SMEM>
 static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                 int nv, const double *rad_r2, const double *rad,
                                 const double *nodes, uint32_t *bitmap, int words,
-                                int32_t *row_cnt, int seg, int sm) {
+                                int32_t *row_cnt, int seg, int sm, int obs_pad) {
     auto kern = k_prm_adjacency<M, SMEM>;
     cudaError_t e = set_smem(kern, sm);
     if (e != cudaSuccess) return e;
@@ -748,7 +773,8 @@ static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agen
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     kern<<<n_agents * chunks, kThreads, sm, lc.stream>>>(cv, agent0, n_agents, nv, chunks, rad,
-                                                         rad_r2, nodes, bitmap, words, row_cnt, seg);
+                                                         rad_r2, nodes, bitmap, words, row_cnt, seg,
+                                                         obs_pad);
     return cudaSuccess;
 }
 
@@ -758,20 +784,25 @@ cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int age
                                  int32_t *row_cnt) {
     if (n_agents <= 0 || nv <= 0) return cudaSuccess;
     const bool cull = cv.model <= 1;  // AdjTraits<PointModel<D>>::kCull: second ring
-    if (cull && (cv.n_obs >= (1 << 24) || nv > (1 << 20) || cv.mp % kCullGroup != 0))
+    if (cull && (cv.n_obs >= (1 << 24) || nv > (1 << 20)))
         return cudaErrorInvalidValue;
     const int rings = kWarps * 8 * (kRing1 + (cull ? kRing2 : 0));
     const int seg = (seg_smem_bytes(cv.con_len) + 15) & ~15;
     const int64_t tab = (int64_t)words * 32 * cv.d * 8;
     const bool smem_on = seg > 0 && tab <= kAdjStageBytes;
-    const int sm = rings + (smem_on ? seg + (int)tab : 0);
+    int obs_pad = 0;  // padded obstacle count of the re-packed smem copy (point models)
+    if (cull && cv.n_obs > 0 && (int64_t)cv.n_obs * (cv.d + 1) * 8 <= 32 * 1024)
+        obs_pad = (cv.n_obs + kCullGroup - 1) / kCullGroup * kCullGroup;
+    const int sm = rings + obs_pad * (cv.d + 1) * 8 + (smem_on ? seg + (int)tab : 0);
     cudaError_t e = cudaSuccess;
     if (smem_on) {
         MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, true>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
-                                                         nodes, bitmap, words, row_cnt, seg, sm)));
+                                                         nodes, bitmap, words, row_cnt, seg, sm,
+                                                         obs_pad)));
     } else {
         MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, false>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
-                                                          nodes, bitmap, words, row_cnt, seg, sm)));
+                                                          nodes, bitmap, words, row_cnt, seg, sm,
+                                                          obs_pad)));
     }
     if (e != cudaSuccess) return e;
     count_launch();

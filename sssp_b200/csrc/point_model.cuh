@@ -116,13 +116,13 @@ __device__ __forceinline__ bool point_connect_edge(const ConSeg &cs, const doubl
 #pragma unroll
     for (int k = 0; k < D; ++k) u[k] = dsub(qf[k], qt[k]);
     const double uu = dotd<D>(u, u);
-#pragma unroll 2
     for (int m = 0; m < cs.n_obs; ++m) {
         double c[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) c[k] = cs.oc(k, m);
-        // dist(q_from,q_to,o) < o.r + rads[i]
-        ok &= !segpt_lt_simt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(i, m));
+        // dist(q_from,q_to,o) < o.r + rads[i]   (branchy form: most lanes of a list kernel take
+        // an end-point case, which skips the division)
+        ok &= !segpt_lt<D, true>(qf, qt, u, uu, c, dadd(cs.oc(D, m), r), cs.t2_im(i, m));
     }
     return ok;
 }
