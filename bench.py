@@ -13,11 +13,14 @@ obstacles (scripts/config/eval/point2d_many.yaml).  One STEP is one pass of the 
       steps (max_makespan of point2d_many.yaml), OR-reduced per time step -> the conflict
       table the search consults.  collide checks counted: nnz * T * (N-1).
 
-Multi-GPU (weak scaling): the neighbour pass of the roadmap build is sharded by agent and the
-CSR shards are exchanged by one NCCL all-gather of fixed-size slots (vertices are re-drawn on
-every rank from the counter-based sampler instead of being communicated), then every rank
-evaluates the full table against its OWN path scenario (e.g. PP's random-priority restarts,
-pp.jl:104-128): per-GPU work is fixed.
+Multi-GPU (weak scaling): every rank evaluates the full table against its OWN path scenario
+(e.g. PP's random-priority restarts, pp.jl:104-128): per-GPU work is fixed.  The roadmap build
+has two modes (--build): "sharded" = the neighbour pass is sharded by agent and the CSR shards
+are exchanged by one NCCL all-gather of fixed-size slots (vertices are re-drawn on every rank
+from the counter-based sampler instead of being communicated); "replicated" = every rank
+builds all roadmaps itself, no exchange.  "auto" (default) times both at start-up and takes
+the faster one; both timings are reported (`multi_gpu_build`).  The connect checks of the
+build are counted once per step in either mode.
 
 `value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream.
 `e2e`    = same through the host-buffer C ABI: host init/goal and path ids in, roadmaps
@@ -66,6 +69,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--build", default="auto", choices=["auto", "sharded", "replicated"],
+                    help="multi-GPU roadmap build: neighbour pass sharded by agent + CSR "
+                         "all-gather, or every rank builds all roadmaps (no exchange); auto "
+                         "times both at start-up and takes the faster")
     return ap.parse_args()
 
 
@@ -82,6 +89,8 @@ def config_dict(world):
                         "roadmap edges x other agents' path edges, T=64) per GPU",
             "n_agents": N_AGENTS, "num_vertices": NV, "rad": RAD, "path_steps": T_STEPS,
             "n_obstacles": 10, "path_scenarios": world,
+            "parallelism": "single GPU" if world == 1 else
+                           "weak scaling: one path scenario per GPU, roadmap build per --build",
             "l2": "L2 flushed between timed steps (256 MB memset); per-step inputs are KB-sized"}
 
 
@@ -270,7 +279,10 @@ def run_b200(args):
     # sized from a first build, with head room (a later overflow raises MRMP_ERR_CAPACITY)
     state = {"cap_nnz": 0, "slots": None}
 
-    def build_roadmaps():
+    radv_all = np.full(N, inst.rad)
+    build_mode = {"mode": "sharded" if world > 1 else "single"}
+
+    def build_sharded():
         """(A): sample + neighbour pass of this rank's agents + [all-gather CSR shards]."""
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
         nnz = rm_sh.build(radv)
@@ -291,9 +303,39 @@ def run_b200(args):
             return int(out.value)
         return nnz
 
+    def build_replicated():
+        """(A'): every rank builds all N roadmaps itself -- no exchange.  Cheaper than the
+        sharded build whenever the whole build takes less than the all-gather round trip."""
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        return rm_all.build(radv_all)
+
+    def build_roadmaps():
+        return build_replicated() if build_mode["mode"] == "replicated" else build_sharded()
+
     # ---- setup: one build gives the CSR the synthetic paths walk on
     nnz_total = build_roadmaps()
     torch.cuda.synchronize()
+    build_modes_ms = None
+    if world > 1:
+        def wall_ms(fn, reps=10):
+            for _ in range(3):
+                fn()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([(time.perf_counter() - t0) / reps * 1e3], dtype=torch.float64,
+                             device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        build_modes_ms = {"sharded": wall_ms(build_sharded), "replicated": wall_ms(build_replicated)}
+        if args.build == "auto":
+            build_mode["mode"] = min(build_modes_ms, key=build_modes_ms.get)
+        else:
+            build_mode["mode"] = args.build
+        assert build_roadmaps() == nnz_total   # both modes give the same roadmaps
     nodes_h = rm_all.nodes()
     row_ptr_h, col_h = rm_all.csr()
     gate = W.gate_pass_count(nodes_h, RAD)
@@ -309,8 +351,11 @@ def run_b200(args):
     cols_d = [t.to(dev) for t in cols_h]
     bits_d = torch.zeros((nnz_total, wpr), dtype=torch.int32, device=dev)
     bits_h = torch.zeros((nnz_total, wpr), dtype=torch.int32).pin_memory()
-    rows_sh = max(n_local, 1) * nv
-    nodes_out_h = torch.empty((max(n_local, 1), nv, d), dtype=torch.float64).pin_memory()
+    # e2e returns the roadmaps this rank built to the host: its shard, or all of them
+    rm_ret = rm_all if build_mode["mode"] == "replicated" else rm_sh
+    n_ret = N if build_mode["mode"] == "replicated" else max(n_local, 1)
+    rows_sh = n_ret * nv
+    nodes_out_h = torch.empty((n_ret, nv, d), dtype=torch.float64).pin_memory()
     rowptr_out_h = torch.empty(rows_sh + 1, dtype=torch.int32).pin_memory()
     colidx_out_h = torch.empty(max(nnz_total, 1), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -327,9 +372,9 @@ def run_b200(args):
     def step_e2e():
         build_roadmaps()
         # roadmaps back to the host (what PRMs() returns to the solver)
-        L.check(lib.mrmp_roadmaps_get_nodes(rm_sh._h, nodes_out_h.data_ptr()))
+        L.check(lib.mrmp_roadmaps_get_nodes(rm_ret._h, nodes_out_h.data_ptr()))
         nnz = C.c_int64(0)
-        L.check(lib.mrmp_roadmaps_get_csr(rm_sh._h, rowptr_out_h.data_ptr(),
+        L.check(lib.mrmp_roadmaps_get_csr(rm_ret._h, rowptr_out_h.data_ptr(),
                                           colidx_out_h.data_ptr(), colidx_out_h.numel(),
                                           C.byref(nnz)))
         L.check(lib.mrmp_roadmaps_edge_conflicts(rm_all._h, None, n_cols, cols_h[0].data_ptr(),
@@ -427,7 +472,8 @@ def run_b200(args):
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     h2d = 2 * N * d * 8 + 3 * n_cols * 4
-    d2h = n_local * nv * d * 8 + (rows_sh + 1) * 4 + (nnz_total // world) * 4 + nnz_total * wpr * 4
+    nnz_ret = nnz_total if build_mode["mode"] == "replicated" else nnz_total // world
+    d2h = n_ret * nv * d * 8 + (rows_sh + 1) * 4 + nnz_ret * 4 + nnz_total * wpr * 4
     e2e = {"value": checks_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
 
@@ -481,6 +527,8 @@ def run_b200(args):
             "config": config_dict(world),
             "checks_per_step": {"connect": gate, "collide": world * pair_checks},
             "roadmap_build_ms": ms_build, "roadmap_nnz": nnz_total,
+            "multi_gpu_build": None if world == 1 else dict(mode=build_mode["mode"],
+                                                            wall_ms=build_modes_ms),
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
