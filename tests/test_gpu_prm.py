@@ -225,3 +225,26 @@ def test_prm_all_pairs_table_too_large_for_shared_memory():
     orp, ocol, onnz = orc.prm_build(0, nodes, 0.26, nthreads=0)
     assert nnz == int(onnz.sum()) and nnz > 100 * nv
     assert np.array_equal(row_ptr, orp[0]) and np.array_equal(col, ocol[0, :nnz])
+
+
+def test_prm_all_pairs_with_more_obstacles_than_the_padded_copy_holds():
+    """1500 small obstacles: the re-packed obstacle copy of the neighbour pass (32 KB) is not
+    used, the cull reads the ctx arrays at clamped indices; many (edge, obstacle) pairs reach
+    the exact stage."""
+    N, nv, M = 2, 220, 1500
+    rng = np.random.default_rng(17)
+    obs = np.concatenate([rng.random((M, 2)), rng.uniform(0.0005, 0.003, (M, 1))], axis=1)
+    rads = np.array([0.002, 0.004])
+    ctx, orc = S.Context(O.POINT2D, rads, obs), O.Oracle(O.POINT2D, rads, obs)
+    nodes = rng.random((N, nv, 2)) * 0.96 + 0.02
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(np.array([0.15, 0.2]))
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, np.array([0.15, 0.2]), nthreads=0)
+    assert nnz == int(onnz.sum()) and 0 < nnz
+    _assert_csr_equal(N, nv, row_ptr, col, orp, ocol)
+    # a fair share of the gated pairs is blocked by an obstacle, the rest is connected
+    gated = sum(int((np.linalg.norm(nodes[a][:, None] - nodes[a][None], axis=2) <= r).sum()) - nv
+                for a, r in ((0, 0.15), (1, 0.2)))
+    assert 0.05 * gated < nnz < 0.95 * gated
