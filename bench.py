@@ -371,15 +371,16 @@ def run_b200(args):
 
     def step_e2e():
         build_roadmaps()
-        # roadmaps back to the host (what PRMs() returns to the solver)
-        L.check(lib.mrmp_roadmaps_get_nodes(rm_ret._h, nodes_out_h.data_ptr()))
+        # roadmaps back to the host (what PRMs() returns to the solver): on the copy stream,
+        # beside the conflict-table kernel
         nnz = C.c_int64(0)
-        L.check(lib.mrmp_roadmaps_get_csr(rm_ret._h, rowptr_out_h.data_ptr(),
-                                          colidx_out_h.data_ptr(), colidx_out_h.numel(),
-                                          C.byref(nnz)))
+        L.check(lib.mrmp_roadmaps_read_async(rm_ret._h, nodes_out_h.data_ptr(),
+                                             rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
+                                             colidx_out_h.numel(), C.byref(nnz)))
         L.check(lib.mrmp_roadmaps_edge_conflicts(rm_all._h, None, n_cols, cols_h[0].data_ptr(),
                                                  cols_h[1].data_ptr(), cols_h[2].data_ptr(), N,
                                                  bits_h.data_ptr(), bits_h.numel()))
+        L.check(lib.mrmp_roadmaps_read_wait(rm_ret._h))
 
     def barrier():
         if world > 1:

@@ -178,6 +178,14 @@ int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agents, int64_t 
                                      int32_t *slot_dev, void *stream);
 int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agents, int64_t cap_nnz,
                                      const int32_t *slots_dev, void *stream, int64_t *nnz_out);
+/* Asynchronous read-back of a built roadmap set (what PRMs returns, prm.jl:251-276) into PINNED
+ * host buffers on the ctx's copy stream: returns at once, so the caller can launch the next
+ * batch (e.g. the conflict table) while the roadmaps travel.  mrmp_roadmaps_read_wait() blocks
+ * until they have arrived.  The set must not be rebuilt in between. */
+int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
+                             int32_t *col_idx, int64_t col_cap, int64_t *nnz_out);
+int mrmp_roadmaps_read_wait(mrmp_roadmaps *rm);
+
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
                               int32_t **row_ptr_dev, int32_t **col_idx_dev, int64_t *nnz_out);

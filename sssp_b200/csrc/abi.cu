@@ -1236,6 +1236,37 @@ extern "C" int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_
     return MRMP_OK;
 }
 
+extern "C" int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
+                                        int32_t *col_idx, int64_t col_cap, int64_t *nnz_out) {
+    NEED(rm && nodes_out && row_ptr && nnz_out, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    *nnz_out = rm->nnz;
+    if (col_cap < rm->nnz)
+        return fail(MRMP_ERR_CAPACITY, "col_cap %lld < nnz %lld", (long long)col_cap,
+                    (long long)rm->nnz);
+    NEED(col_idx || rm->nnz == 0, "col_idx is NULL");
+    // build() has synchronised the kernel stream, so the copy stream may start at once and
+    // runs beside whatever the caller launches next
+    const int64_t rows = (int64_t)rm->n_agents * rm->nv;
+    CU(cudaMemcpyAsync(nodes_out, rm->nodes, sizeof(double) * c->d * (size_t)rows,
+                       cudaMemcpyDeviceToHost, c->s_out));
+    CU(cudaMemcpyAsync(row_ptr, rm->row_ptr, sizeof(int32_t) * (rows + 1), cudaMemcpyDeviceToHost,
+                       c->s_out));
+    if (rm->nnz > 0)
+        CU(cudaMemcpyAsync(col_idx, rm->col_idx, sizeof(int32_t) * rm->nnz, cudaMemcpyDeviceToHost,
+                           c->s_out));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_read_wait(mrmp_roadmaps *rm) {
+    NEED(rm, "bad roadmaps");
+    CU(cudaSetDevice(rm->ctx->device));
+    CU(cudaStreamSynchronize(rm->ctx->s_out));
+    return roadmaps_settle(rm, false);
+}
+
 extern "C" int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
                                          int32_t **row_ptr_dev, int32_t **col_idx_dev,
                                          int64_t *nnz_out) {
@@ -1547,13 +1578,26 @@ extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm
     CU(cudaMemcpyAsync(b, col_agent, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b + ib, col_vfrom, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b + 2 * ib, col_vto, 4 * (size_t)n_cols, cudaMemcpyHostToDevice, s));
+    // OR-reduced tables of the point models write each output word exactly once with plain
+    // stores: when the caller's buffer is pinned (mapped) host memory the kernel writes it in
+    // place, the result travels while the kernel runs and no copy follows
+    uint32_t *direct = nullptr;
+    if (group_size > 0 && c->model <= MRMP_MODEL_POINT3D) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out_bits) == cudaSuccess &&
+            at.type == cudaMemoryTypeHost && at.devicePointer)
+            direct = (uint32_t *)at.devicePointer;
+        else
+            cudaGetLastError();  // clear the sticky error of an unregistered pointer
+    }
     rc = mrmp_roadmaps_edge_conflicts_dev(rm, rm_cols, n_cols, (const int32_t *)b,
                                           (const int32_t *)(b + ib),
                                           (const int32_t *)(b + 2 * ib), group_size,
-                                          (uint32_t *)c->scratch[2], s);
+                                          direct ? direct : (uint32_t *)c->scratch[2], s);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(out_bits, c->scratch[2], sizeof(uint32_t) * (size_t)rm->nnz * wpr,
-                       cudaMemcpyDeviceToHost, s));
+    if (!direct)
+        CU(cudaMemcpyAsync(out_bits, c->scratch[2], sizeof(uint32_t) * (size_t)rm->nnz * wpr,
+                           cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return MRMP_OK;
 }

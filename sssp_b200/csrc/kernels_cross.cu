@@ -461,8 +461,15 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
             }
         }
         if (REDUCED && live) {
-            for (int w = 0; w < words_per_row; ++w)
-                out[(int64_t)orig * out_stride + w] = S.obits[lane][w];
+            // every word of the row is written exactly once (the output may be mapped host
+            // memory: plain stores, two words per transaction where the layout allows)
+            uint32_t *dst = out + (int64_t)orig * out_stride;
+            if ((words_per_row & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                for (int w = 0; w < words_per_row; w += 2)
+                    *reinterpret_cast<uint2 *>(dst + w) = make_uint2(S.obits[lane][w], S.obits[lane][w + 1]);
+            } else {
+                for (int w = 0; w < words_per_row; ++w) dst[w] = S.obits[lane][w];
+            }
         }
         __syncwarp();
     }

@@ -248,3 +248,64 @@ def test_prm_all_pairs_with_more_obstacles_than_the_padded_copy_holds():
     gated = sum(int((np.linalg.norm(nodes[a][:, None] - nodes[a][None], axis=2) <= r).sum()) - nv
                 for a, r in ((0, 0.15), (1, 0.2)))
     assert 0.05 * gated < nnz < 0.95 * gated
+
+
+def test_roadmaps_async_read_back_equals_the_blocking_getters():
+    import ctypes as C
+    from sssp_b200 import lib as L
+    N, nv = 5, 150
+    rads, obs = make_point_instance(O.POINT2D, N, 8, seed=4)
+    ctx = S.Context(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(2)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, 9, rng.random((N, 2)) * 0.8 + 0.1, rng.random((N, 2)) * 0.8 + 0.1, tries=False)
+    nnz = rm.build(0.2)
+    nodes, (row_ptr, col) = rm.nodes(), rm.csr()
+    n2, rp2, c2 = np.empty_like(nodes), np.empty_like(row_ptr), np.empty(nnz + 7, np.int32)
+    got = C.c_int64(-1)
+    lib = L.load()
+    L.check(lib.mrmp_roadmaps_read_async(rm._h, n2.ctypes.data, rp2.ctypes.data, c2.ctypes.data,
+                                         c2.size, C.byref(got)))
+    bits = rm.edge_conflicts(np.zeros(4, np.int32), np.arange(4, dtype=np.int32),
+                             np.arange(1, 5, dtype=np.int32))        # a batch in between
+    L.check(lib.mrmp_roadmaps_read_wait(rm._h))
+    assert got.value == nnz and bits.shape[0] == nnz
+    assert np.array_equal(n2, nodes) and np.array_equal(rp2, row_ptr)
+    assert np.array_equal(c2[:nnz], col)
+    with pytest.raises(S.MRMPError):
+        lib_rc = lib.mrmp_roadmaps_read_async(rm._h, n2.ctypes.data, rp2.ctypes.data,
+                                              c2.ctypes.data, nnz - 1, C.byref(got))
+        L.check(lib_rc)
+
+
+def test_edge_conflicts_written_in_place_into_pinned_host_memory():
+    """OR-reduced conflict table of a point model: with a pinned output buffer the kernel
+    stores the bits straight into host memory; the result must equal the staged copy."""
+    import ctypes as C
+    import torch
+    from sssp_b200 import lib as L
+    N, nv, T = 6, 120, 40
+    rads, obs = make_point_instance(O.POINT2D, N, 8, seed=14)
+    ctx = S.Context(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(3)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, 3, rng.random((N, 2)) * 0.8 + 0.1, rng.random((N, 2)) * 0.8 + 0.1, tries=False)
+    nnz = rm.build(0.25)
+    row_ptr, col = rm.csr()
+    # columns: T time steps x N agents, random roadmap edges
+    ca = np.tile(np.arange(N, dtype=np.int32), T)
+    vf = rng.integers(0, nv, ca.size).astype(np.int32)
+    vt = np.array([col[rng.integers(row_ptr[a * nv + v], max(row_ptr[a * nv + v + 1], row_ptr[a * nv + v] + 1))]
+                   if row_ptr[a * nv + v + 1] > row_ptr[a * nv + v] else v
+                   for a, v in zip(ca, vf)], np.int32)
+    want = rm.edge_conflicts(ca, vf, vt, group_size=N)                  # pageable: staged copy
+    wpr = want.shape[1]
+    for odd in (0, 1):                                                  # 8- and 4-byte aligned rows
+        pinned = torch.full((nnz * wpr + 1,), -1, dtype=torch.int32).pin_memory()
+        L.check(L.load().mrmp_roadmaps_edge_conflicts(
+            rm._h, None, ca.size, ca.ctypes.data, vf.ctypes.data, vt.ctypes.data, N,
+            pinned.data_ptr() + 4 * odd, nnz * wpr))
+        got = pinned.numpy()[odd:odd + nnz * wpr].view(np.uint32).reshape(nnz, wpr)
+        assert np.array_equal(got, want)
+        assert pinned[nnz * wpr if odd == 0 else 0] == -1
+    assert want.any()
