@@ -53,7 +53,8 @@ N_AGENTS, NV, RAD, T_STEPS = 50, 500, 0.1, 64
 CPU_ROW_STRIDE = 64            # reference arm: every 64th roadmap edge as a row of (B)
 
 # algorithmic work per unit (DESIGN.md "Kernels"), FP64 flops with add/mul/cmp = 1 each
-FLOPS_BROAD = 8                # midpoint bound per tested pair: 2 sub, 2 mul, 2 add, 1 mul, 1 cmp
+FLOPS_BROAD = 17               # capsule bound per tested pair (2-D): w 2, |w|^2 3, w.u 3, perp^2 2,
+                               # excess 2, d^2 2, reach 2, compare 1
 FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
 FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
 NCU_DRAM_BYTES_PER_LAUNCH = 16.12e6   # profiles/r1_d_ncu_full_summary.md (read 16.12 MB, written 1.5 KB)
@@ -454,7 +455,7 @@ def run_b200(args):
                               "per_tested_pair": FLOPS_BROAD, "survivors": survivors,
                               "per_survivor_exact": FLOPS_EXACT,
                               "note": "work the kernel performs: pairs whose column tile "
-                                      "survives the box test x 8 + pairs on the exact reference "
+                                      "survives the box test x 17 + pairs on the exact reference "
                                       "path x 170 (SURVEY 8d); the reference itself spends 170 "
                                       "per pair"},
         "reference_equivalent_tflops": n_pairs * FLOPS_EXACT / (ms_table * 1e-3) / 1e12,

@@ -324,7 +324,10 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
         const bool live = r < n_rows;
         int i = -2, orig = 0;
         double m1[D], R = 0.0;
+        double u1[D], h1 = 0.0, Rc = 0.0;  // unit direction, half length, reach without h1
         double lo[D], hi[D];
+#pragma unroll
+        for (int x = 0; x < D; ++x) u1[x] = 0.0;
         if (live) {
             const RowRec<D> rec = rows[r];
             i = rec.agent;
@@ -338,7 +341,19 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
             }
             // reach of this row: its radius + slack + its own half length (the column's
             // radius and half length are in T.sa[c].h)
-            R = __ldg(rads + i) + kPad + half_len_up<D>(rec.a, rec.b);
+            h1 = half_len_up<D>(rec.a, rec.b);
+            Rc = __ldg(rads + i) + kPad;
+            R = Rc + h1;
+            // direction of the row edge for the capsule bound (a zero-length edge keeps u1 = 0:
+            // its capsule is the disc of the midpoint bound)
+            double len2 = 0.0;
+#pragma unroll
+            for (int x = 0; x < D; ++x) len2 += (rec.b[x] - rec.a[x]) * (rec.b[x] - rec.a[x]);
+            if (len2 > 0.0 && len2 < 1e300) {
+                const double inv = 1.0 / sqrt(len2);
+#pragma unroll
+                for (int x = 0; x < D; ++x) u1[x] = (rec.b[x] - rec.a[x]) * inv;
+            }
         } else {
 #pragma unroll
             for (int x = 0; x < D; ++x) {
@@ -393,19 +408,29 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
                 unsigned long long mask = 0ull;
 #pragma unroll 8
                 for (int c = 0; c < kCols; ++c) {
-                    double w2;
+                    // capsule bound: the column's midpoint against the row SEGMENT --
+                    // dist(seg_r, seg_c) >= dist(m_c, seg_r) - h_c, and
+                    // dist(m_c, seg_r)^2 = |w_perp|^2 + max(|w_par| - h_r, 0)^2 with w = m_c - m_r
+                    double w2, par;
                     if constexpr (D == 2) {
                         const double2 mm = __ldg(reinterpret_cast<const double2 *>(&T.mm[c][0]));
-                        const double wx = dsub(mm.x, m1[0]), wy = dsub(mm.y, m1[1]);
-                        w2 = dadd(dmul(wx, wx), dmul(wy, wy));
+                        const double wx = mm.x - m1[0], wy = mm.y - m1[1];
+                        w2 = wx * wx + wy * wy;
+                        par = wx * u1[0] + wy * u1[1];
                     } else {
-                        double w[D];
+                        w2 = 0.0;
+                        par = 0.0;
 #pragma unroll
-                        for (int x = 0; x < D; ++x) w[x] = dsub(__ldg(&T.mm[c][x]), m1[x]);
-                        w2 = sumsq<D>(w);
+                        for (int x = 0; x < D; ++x) {
+                            const double w = __ldg(&T.mm[c][x]) - m1[x];
+                            w2 += w * w;
+                            par += w * u1[x];
+                        }
                     }
-                    const double reach = dadd(R, __ldg(&T.sa[c].h));
-                    const bool far = w2 > dmul(reach, reach);
+                    const double ex = fmax(fabs(par) - h1, 0.0);
+                    const double d2 = (w2 - par * par) + ex * ex;
+                    const double reach = Rc + __ldg(&T.sa[c].h);
+                    const bool far = d2 > reach * reach;
                     mask |= (unsigned long long)(far ? 0 : 1) << c;
                 }
                 if (!live) mask = 0ull;
