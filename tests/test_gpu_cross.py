@@ -85,3 +85,43 @@ def test_roadmap_edge_conflict_table():
         o = orc.collide_cross(ra, rf, rt, ca, cf, ct, gs, nthreads=0)
         assert g.shape == (nnz, o.shape[1]) and np.array_equal(g, o)
     assert o.any()
+
+
+def test_full_size_bench_step_matches_the_oracle_bit_for_bit():
+    """BASELINE configs[1] at full size -- point2d_many N=50, PRMs(500, rad=0.1), all 396 166
+    roadmap edges x 64 time steps of the other agents' path edges (1.24e9 collide checks) --
+    the whole step of bench.py: roadmaps (vertices + CSR) and the OR-reduced conflict table
+    are compared in full with the CPU restatement (about 10 s on the host cores)."""
+    from sssp_b200 import workload as W
+    T = 64
+    inst = W.point2d_many(50, seed=0, nv=500, rad=0.1)
+    N, nv = 50, inst.nv
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles)
+    orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+    nnz = rm.build(inst.rad)
+    nodes, (row_ptr, col) = rm.nodes(), rm.csr()
+    # roadmaps: the oracle draws the same counter-based stream and runs the all-pairs pass
+    o_nodes = np.empty_like(nodes)
+    for a in range(N):
+        o_nodes[a, 0], o_nodes[a, 1] = inst.q_init[a], inst.q_goal[a]
+        o_nodes[a, 2:] = orc.sample_free(a, inst.seed, nv - 2)[0]
+    assert np.array_equal(nodes, o_nodes)
+    orp, ocol, onnz = orc.prm_build(0, o_nodes, inst.rad, nthreads=0)
+    assert nnz == int(onnz.sum()) == 396166
+    for a in range(N):
+        lo, hi = row_ptr[a * nv], row_ptr[(a + 1) * nv]
+        assert np.array_equal(col[lo:hi], ocol[a, :onnz[a]]), a
+        assert np.array_equal(row_ptr[a * nv:(a + 1) * nv + 1] - lo, orp[a]), a
+    # conflict table
+    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr, col, T, seed=4321)
+    got = rm.edge_conflicts(ca, vf, vt, group_size=N)
+    rows = np.repeat(np.arange(N * nv), np.diff(row_ptr))
+    ra = (rows // nv).astype(np.int32)
+    rf, rt = nodes[ra, rows % nv], nodes[ra, col]
+    want = orc.collide_cross(ra, rf, rt, ca, nodes[ca, vf], nodes[ca, vt], N, nthreads=0)
+    assert got.shape == want.shape == (nnz, 2)
+    assert np.array_equal(got, want)
+    density = np.unpackbits(want.view(np.uint8)).mean()
+    assert 0.05 < density < 0.95
