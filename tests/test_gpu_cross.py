@@ -125,3 +125,40 @@ def test_full_size_bench_step_matches_the_oracle_bit_for_bit():
     assert np.array_equal(got, want)
     density = np.unpackbits(want.view(np.uint8)).mean()
     assert 0.05 < density < 0.95
+
+
+def test_point3d_config_roadmaps_and_conflict_table_match_the_oracle():
+    """BASELINE configs[2]: StatePoint3D N=20 with sphere obstacles, PRMs(200, rad=0.3)
+    (point3d.yaml:26-30; radii per SURVEY 8d), every roadmap edge x 32 time steps of the other
+    agents' random-walk path edges, compared in full."""
+    from sssp_b200 import workload as W
+    N, nv, T, rad = 20, 200, 32, 0.3
+    rng = np.random.default_rng(5)
+    obs = np.concatenate([rng.random((10, 3)), rng.uniform(0.05, 0.1, (10, 1))], axis=1)
+    rads = rng.uniform(0.04, 0.05, N)
+    ctx, orc = S.Context(O.POINT3D, rads, obs), O.Oracle(O.POINT3D, rads, obs)
+    ends = np.stack([orc.sample_free(a, 99, 2)[0] for a in range(N)])
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, 7, ends[:, 0], ends[:, 1], tries=False)
+    nnz = rm.build(rad)
+    nodes, (row_ptr, col) = rm.nodes(), rm.csr()
+    o_nodes = np.empty_like(nodes)
+    for a in range(N):
+        o_nodes[a, :2] = ends[a]
+        o_nodes[a, 2:] = orc.sample_free(a, 7, nv - 2)[0]
+    assert np.array_equal(nodes, o_nodes)
+    orp, ocol, onnz = orc.prm_build(0, o_nodes, rad, nthreads=0)
+    assert nnz == int(onnz.sum()) and nnz > 10 * N * nv
+    for a in range(N):
+        lo, hi = row_ptr[a * nv], row_ptr[(a + 1) * nv]
+        assert np.array_equal(col[lo:hi], ocol[a, :onnz[a]]), a
+    inst = W.Instance(O.POINT3D, rads, obs, ends[:, 0], ends[:, 1], nv, rad, 7)
+    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr, col, T, seed=11)
+    rows = np.repeat(np.arange(N * nv), np.diff(row_ptr))
+    ra = (rows // nv).astype(np.int32)
+    rf, rt = nodes[ra, rows % nv], nodes[ra, col]
+    for gs in (N, 0):
+        got = rm.edge_conflicts(ca, vf, vt, group_size=gs)
+        want = orc.collide_cross(ra, rf, rt, ca, nodes[ca, vf], nodes[ca, vt], gs, nthreads=0)
+        assert np.array_equal(got, want), gs
+    assert want.any()
