@@ -140,7 +140,7 @@ __device__ __forceinline__ int warp_offsets(int c, int lane, int &total) {
 
 // SMEM: the connect segment and the agent's vertex table (padded to 32 * words entries) are
 // staged in shared memory -- the normal case; the other instantiation reads both from global.
-template <class M, bool SMEM>
+template <class M, bool SMEM, bool OPAD>
 __global__ void __launch_bounds__(kThreads, 3)
 k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
                 const double *__restrict__ rad, const double *__restrict__ rad_r2,
@@ -162,7 +162,7 @@ k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
     // point models: obstacle SoA re-packed with the count padded to a multiple of kCullGroup
     // (far-away, zero-radius entries), so that a cull round reads at immediate offsets
     double *opad = reinterpret_cast<double *>(sp);
-    if (kCull && obs_pad > 0) {
+    if (kCull && OPAD) {
         for (int t = threadIdx.x; t < (SD + 1) * obs_pad; t += kThreads) {
             const int x = t / obs_pad, m = t - x * obs_pad;
             opad[t] = m < cs.n_obs ? cs.oc(x, m) : (x < SD ? 1.0e300 : 0.0);
@@ -248,7 +248,7 @@ k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
                                            ((unsigned long long)(unsigned)e.y << 24);
             for (int m0 = 0; m0 < cs.n_obs; m0 += kCullGroup) {
                 unsigned near = 0;
-                if (ok && obs_pad > 0) {
+                if (ok && OPAD) {
                     const double *oc = opad + m0;
 #pragma unroll
                     for (int u = 0; u < kCullGroup; ++u) {
@@ -263,7 +263,7 @@ k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
                         const bool far = w2 > reach * reach && fabs(orad) < kCullCoordMax;
                         near |= (m0 + u < cs.n_obs && (wide || !far) ? 1u : 0u) << u;
                     }
-                } else if (ok) {  // very many obstacles: read the ctx arrays at a clamped index
+                } else if (ok && !OPAD) {  // very many obstacles: read the ctx arrays at a clamped index
                     const double *oc = cs.s + cs.obs;
 #pragma unroll
                     for (int u = 0; u < kCullGroup; ++u) {
@@ -746,7 +746,7 @@ cudaError_t launch_sample_free(const CtxView &cv, const LaunchCfg &lc, int agent
 // resident CTAs per SM of one adjacency instantiation, cached per (model, staging, smem size)
 template <class K>
 static int adj_occupancy(K kernel, int slot, int smem) {
-    static int cached_smem[16], cached_occ[16];
+    static int cached_smem[32], cached_occ[32];
     if (cached_occ[slot] == 0 || cached_smem[slot] != smem) {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) !=
@@ -759,15 +759,15 @@ static int adj_occupancy(K kernel, int slot, int smem) {
 }
 
 // one wave: (agent, chunk) CTAs fill the resident slots without a ragged second wave
-template <class M, bool SMEM>
+template <class M, bool SMEM, bool OPAD>
 static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                 int nv, const double *rad_r2, const double *rad,
                                 const double *nodes, uint32_t *bitmap, int words,
                                 int32_t *row_cnt, int seg, int sm, int obs_pad) {
-    auto kern = k_prm_adjacency<M, SMEM>;
+    auto kern = k_prm_adjacency<M, SMEM, OPAD>;
     cudaError_t e = set_smem(kern, sm);
     if (e != cudaSuccess) return e;
-    const int slots = lc.sm_count * adj_occupancy(kern, 2 * cv.model + (SMEM ? 1 : 0), sm);
+    const int slots = lc.sm_count * adj_occupancy(kern, 4 * cv.model + (SMEM ? 1 : 0) + (OPAD ? 2 : 0), sm);
     const int max_chunks = (nv + kWarps - 1) / kWarps;  // at most one row per warp
     int chunks = slots / n_agents;
     if (chunks > max_chunks) chunks = max_chunks;
@@ -795,15 +795,21 @@ cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int age
         obs_pad = (cv.n_obs + kCullGroup - 1) / kCullGroup * kCullGroup;
     const int sm = rings + obs_pad * (cv.d + 1) * 8 + (smem_on ? seg + (int)tab : 0);
     cudaError_t e = cudaSuccess;
-    if (smem_on) {
-        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, true>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
-                                                         nodes, bitmap, words, row_cnt, seg, sm,
-                                                         obs_pad)));
+#define ADJ_ARGS cv, lc, agent0, n_agents, nv, rad_r2, rad, nodes, bitmap, words, row_cnt, seg, sm, obs_pad
+    if (obs_pad > 0) {  // point models with a re-packed obstacle copy
+        if (smem_on) {
+            if (cv.model == 0) e = launch_adj_t<PointModel<2>, true, true>(ADJ_ARGS);
+            else e = launch_adj_t<PointModel<3>, true, true>(ADJ_ARGS);
+        } else {
+            if (cv.model == 0) e = launch_adj_t<PointModel<2>, false, true>(ADJ_ARGS);
+            else e = launch_adj_t<PointModel<3>, false, true>(ADJ_ARGS);
+        }
+    } else if (smem_on) {
+        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, true, false>(ADJ_ARGS)));
     } else {
-        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, false>(cv, lc, agent0, n_agents, nv, rad_r2, rad,
-                                                          nodes, bitmap, words, row_cnt, seg, sm,
-                                                          obs_pad)));
+        MRMP_MODEL_SWITCH(cv, (e = launch_adj_t<M, false, false>(ADJ_ARGS)));
     }
+#undef ADJ_ARGS
     if (e != cudaSuccess) return e;
     count_launch();
     return cudaGetLastError();
