@@ -84,7 +84,7 @@ k_sample_free(CtxView cv, int agent0, int n_fixed, int nv, int nv_stride, uint64
 // One CTA = (agent, chunk of that agent's rows); the agent's vertex table is staged in shared
 // memory once per CTA.  A warp walks its rows j through a small pipeline of per-warp rings so
 // that every expensive stage runs on 32 dense lanes, across row boundaries:
-//   gate   every lane tests kAdjGroup candidates k per round (prm.jl:207, branch-free,
+//   gate   every lane tests kGateGroup candidates k per round (prm.jl:207, branch-free,
 //          independent FP64 chains); survivors (j,k) are compacted into ring 1;
 //   edge   (prm.jl:208) generic models: connect(q_j, q_k) per lane, a passing edge sets its bit
 //          in the (row-zeroed) global bitmap and bumps the row count with L2 reductions;
