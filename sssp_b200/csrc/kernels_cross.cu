@@ -434,6 +434,18 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
                     mask |= (unsigned long long)(far ? 0 : 1) << c;
                 }
                 if (!live) mask = 0ull;
+                if (REDUCED) {
+                    // the output is an OR over each column group: a pair whose bit this row
+                    // has already set (by an earlier tile) cannot change it -- drop it here,
+                    // before the compaction, so the exact stage stays dense
+                    unsigned long long m2 = mask;
+                    while (m2) {
+                        const int c = __ffsll((long long)m2) - 1;
+                        m2 &= m2 - 1;
+                        const int bit = __ldg(&T.sa[c].bit);
+                        if ((S.obits[lane][bit >> 5] >> (bit & 31)) & 1u) mask &= ~(1ull << c);
+                    }
+                }
                 ++n_tiles_read;
                 // ---- compaction into the warp queue
                 const int cnt = __popcll(mask);
