@@ -35,7 +35,7 @@ namespace mrmp {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
-constexpr int kCols = 64;        // column edges per tile
+constexpr int kCols = 32;        // column edges per tile (must equal kCrossCols)
 constexpr int kRedWords = 8;     // reduced mode: up to 256 groups per launch
 constexpr int kWarpsPerCta = 8;
 constexpr int kSortCells = 4096;  // Morton grid: 64 x 64 (2-D), 16^3 (3-D)
@@ -200,7 +200,7 @@ k_cross_prep_cols(EdgeList<D> el, int64_t n_cols, const int32_t *__restrict__ or
         }
         bool poison = false;  // a NaN midpoint must never be culled by the box test
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < kCols / 32; ++half) {
             const int k = half * 32 + lane;
             const int64_t c = t * kCols + k;
             if (c >= n_cols) {  // padding column: infinitely far, never selected

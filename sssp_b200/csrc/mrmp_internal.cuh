@@ -300,7 +300,7 @@ cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, cons
                            const double *q, int reversed, int32_t *idx_out, double *dist_out);
 
 // kernels_cross.cu
-constexpr int kCrossCols = 64;        // columns per tile
+constexpr int kCrossCols = 32;        // columns per tile
 constexpr int kCrossMaxGroups = 256;  // reduced mode: groups per launch
 size_t cross_tile_bytes(int d);
 size_t cross_hdr_bytes(int d);
