@@ -57,7 +57,7 @@ FLOPS_BROAD = 17               # capsule bound per tested pair (2-D): w 2, |w|^2
                                # excess 2, d^2 2, reach 2, compare 1
 FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
 FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
-NCU_DRAM_BYTES_PER_LAUNCH = 16.12e6   # profiles/r1_i_ncu_full_summary.md (read 16.12 MB, written 8.2 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 16.12e6   # profiles/r1_i_ncu_full_summary.md, last table (read 16.13 MB, written 16 KB)
 BYTES_CONNECT = 2 * 16 + 4 + 1
 BYTES_COLLIDE = 4 * 16 + 8 + 1
 
