@@ -26,6 +26,7 @@
 #ifndef MRMP_B200_H
 #define MRMP_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -185,6 +186,11 @@ int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agent
 int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
                              int32_t *col_idx, int64_t col_cap, int64_t *nnz_out);
 int mrmp_roadmaps_read_wait(mrmp_roadmaps *rm);
+/* Pin (page-lock and map) / unpin a host buffer of the caller: host code without a CUDA binding of
+ * its own (the reference's Julia: `Vector`s passed to ccall) gets the asynchronous read-back and
+ * the in-place output of OR-reduced conflict tables for its ordinary arrays. */
+int mrmp_host_register(void *ptr, size_t bytes);
+int mrmp_host_unregister(void *ptr);
 
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,

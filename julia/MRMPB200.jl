@@ -279,4 +279,22 @@ function pp_conflict_tables(ctx::Ctx, roadmaps::Vector{Vector{Node{State}}}, i::
     return blocked, stay_hits, planned
 end
 
+# ---- pinned host arrays: async read-back / in-place conflict tables ---------------------------
+"""
+    with_pinned(f, arrays...)
+
+Page-locks the given `Array`s for the duration of `f()` (mrmp_host_register): OR-reduced conflict
+tables are then written by the kernel straight into the Julia array, and `read_async!` /
+`read_wait` overlap the roadmap read-back with the next batch.
+"""
+function with_pinned(f, arrays...)
+    foreach(a -> check(ccall((:mrmp_host_register, LIB), Cint, (Ptr{Cvoid}, Csize_t), a, sizeof(a))),
+            arrays)
+    try
+        return f()
+    finally
+        foreach(a -> ccall((:mrmp_host_unregister, LIB), Cint, (Ptr{Cvoid},), a), arrays)
+    end
+end
+
 end # module

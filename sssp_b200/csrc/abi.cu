@@ -1236,6 +1236,21 @@ extern "C" int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_
     return MRMP_OK;
 }
 
+/* Pin (page-lock and map) / unpin a host buffer of the caller, so that host code without a CUDA
+ * binding of its own (the reference's Julia) gets the asynchronous read-back and the in-place
+ * table output for its ordinary arrays. */
+extern "C" int mrmp_host_register(void *ptr, size_t bytes) {
+    NEED(ptr && bytes > 0, "bad buffer");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_host_unregister(void *ptr) {
+    NEED(ptr, "bad buffer");
+    CU(cudaHostUnregister(ptr));
+    return MRMP_OK;
+}
+
 extern "C" int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
                                         int32_t *col_idx, int64_t col_cap, int64_t *nnz_out) {
     NEED(rm && nodes_out && row_ptr && nnz_out, "bad arguments");

@@ -71,6 +71,8 @@ _SIGS = {
     "mrmp_roadmaps_get_csr": (C.c_int, [_vp, _ip, _ip, C.c_int64, _lp]),
     "mrmp_roadmaps_read_async": (C.c_int, [_vp, _dp, _ip, _ip, C.c_int64, _lp]),
     "mrmp_roadmaps_read_wait": (C.c_int, [_vp]),
+    "mrmp_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "mrmp_host_unregister": (C.c_int, [_vp]),
     "mrmp_roadmaps_device_ptrs": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(_vp),
                                             C.POINTER(_vp), C.POINTER(_vp), _lp]),
     "mrmp_roadmaps_set_nodes_dev": (C.c_int, [_vp, C.c_int, _vp, _vp]),

@@ -309,3 +309,30 @@ def test_edge_conflicts_written_in_place_into_pinned_host_memory():
         assert np.array_equal(got, want)
         assert pinned[nnz * wpr if odd == 0 else 0] == -1
     assert want.any()
+
+
+def test_registered_numpy_buffer_takes_the_in_place_path():
+    """mrmp_host_register pins an ordinary host array (what a Julia caller has): the OR-reduced
+    table is then written in place and must equal the staged result."""
+    from sssp_b200 import lib as L
+    N, nv, T = 5, 100, 20
+    rads, obs = make_point_instance(O.POINT2D, N, 6, seed=21)
+    ctx = S.Context(O.POINT2D, rads, obs)
+    rng = np.random.default_rng(4)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, 5, rng.random((N, 2)) * 0.8 + 0.1, rng.random((N, 2)) * 0.8 + 0.1, tries=False)
+    nnz = rm.build(0.3)
+    ca = np.tile(np.arange(N, dtype=np.int32), T)
+    vf = rng.integers(0, nv, ca.size).astype(np.int32)
+    vt = rng.integers(0, nv, ca.size).astype(np.int32)
+    want = rm.edge_conflicts(ca, vf, vt, group_size=N)
+    out = np.full(want.shape, 0xdeadbeef, np.uint32)
+    lib = L.load()
+    L.check(lib.mrmp_host_register(out.ctypes.data, out.nbytes))
+    try:
+        L.check(lib.mrmp_roadmaps_edge_conflicts(rm._h, None, ca.size, ca.ctypes.data,
+                                                 vf.ctypes.data, vt.ctypes.data, N,
+                                                 out.ctypes.data, out.size))
+    finally:
+        L.check(lib.mrmp_host_unregister(out.ctypes.data))
+    assert np.array_equal(out, want) and want.any()
