@@ -53,8 +53,11 @@ N_AGENTS, NV, RAD, T_STEPS = 50, 500, 0.1, 64
 CPU_ROW_STRIDE = 64            # reference arm: every 64th roadmap edge as a row of (B)
 
 # algorithmic work per unit (DESIGN.md "Kernels"), FP64 flops with add/mul/cmp = 1 each
-FLOPS_BROAD = 17               # capsule bound per tested pair (2-D): w 2, |w|^2 3, w.u 3, perp^2 2,
-                               # excess 2, d^2 2, reach 2, compare 1
+FLOPS_BROAD32 = 20             # FP32 capsule bound per tested pair (2-D, FMA = 2): w 2, |w|^2 3, w.u 3,
+                               # excess 2, d^2 4, relative slack 2, reach 1, reach^2 + slack 2, compare 1
+FLOPS_FILTER = 91              # FP64 verdict filter per surviving pair (2-D, FMA = 2): differences 10,
+                               # three cross products 9, conditioning 5, crossing test 6, four clamped
+                               # point-segment distances 52, minimum 3, band compare 6
 FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
 FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
 NCU_DRAM_BYTES_PER_LAUNCH = 16.12e6   # profiles/r1_i_ncu_full_summary.md, last table (read 16.13 MB, written 16 KB)
@@ -103,7 +106,7 @@ class CpuArm:
         from oracle import oracle as O
         O.build()
         self.O = O
-        self.threads = O.max_threads()
+        self.threads = O.host_cores()      # not OMP_NUM_THREADS: torchrun sets it to 1
         self.inst = inst
         self.orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
 
@@ -435,10 +438,12 @@ def run_b200(args):
     ctx.stats(reset=True)
     ms_table = timed(k_table, reps=10)
     st_ = ctx.stats()
-    survivors = int(st_[0]) / 11.0        # pairs that ran the exact reference arithmetic
-    tested = int(st_[2]) / 11.0           # pairs that ran the midpoint bound (rest: tile boxes)
+    exact = int(st_[0]) / 11.0            # pairs that ran the reference's own arithmetic
+    tested = int(st_[2]) / 11.0           # pairs that ran the FP32 bound (rest: tile boxes)
+    survivors = int(st_[3]) / 11.0        # pairs that ran the FP64 verdict filter
     n_pairs = nnz_total * n_cols
-    flops = tested * FLOPS_BROAD + survivors * FLOPS_EXACT
+    flops = survivors * FLOPS_FILTER + exact * FLOPS_EXACT      # FP64 work only
+    flops32 = tested * FLOPS_BROAD32
     achieved = flops / (ms_table * 1e-3) / 1e12
     pk, pk_kind = peaks()
     roofline = {
@@ -451,13 +456,14 @@ def run_b200(args):
         "peak_source": "un-fused DADD/DMUL issue peak measured with tools/fp64_peak.cu on this "
                        "pool (profiles/r1_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure "
                        "and bit parity forbids FMA",
-        "algorithmic_flops": {"pairs": n_pairs, "pairs_bound_tested": tested,
-                              "per_tested_pair": FLOPS_BROAD, "survivors": survivors,
-                              "per_survivor_exact": FLOPS_EXACT,
-                              "note": "work the kernel performs: pairs whose column tile "
-                                      "survives the box test x 17 + pairs on the exact reference "
-                                      "path x 170 (SURVEY 8d); the reference itself spends 170 "
-                                      "per pair"},
+        "algorithmic_flops": {"pairs": n_pairs, "pairs_bound_tested_fp32": tested,
+                              "fp32_per_tested_pair": FLOPS_BROAD32, "fp32_tflops": flops32 / (ms_table * 1e-3) / 1e12,
+                              "pairs_filtered_fp64": survivors, "fp64_per_filtered_pair": FLOPS_FILTER,
+                              "pairs_reference_arithmetic": exact, "fp64_per_exact_pair": FLOPS_EXACT,
+                              "note": "work the kernel performs: `achieved` counts the FP64 part "
+                                      "(verdict filter x 91 + reference arithmetic x 170, FMA = 2); "
+                                      "the FP32 broad phase (20 per tested pair) is listed beside it; "
+                                      "the reference itself spends 170 FP64 per pair"},
         "reference_equivalent_tflops": n_pairs * FLOPS_EXACT / (ms_table * 1e-3) / 1e12,
         "pair_checks_per_s": n_pairs / (ms_table * 1e-3),
         "kernel_ms": {"conflict_table": ms_table, "roadmap_build": ms_build},
@@ -637,13 +643,14 @@ def extra_arm22(device, dev, st, timed):
     g_con = out[:n_con].cpu().numpy().copy()
     sl = slice(0, None, 16)
     t0 = time.perf_counter()
-    o_col = orc.collide_pairs(ai[sl], aj[sl], *[x[sl] for x in q], nthreads=0)
+    nt = O.host_cores()
+    o_col = orc.collide_pairs(ai[sl], aj[sl], *[x[sl] for x in q], nthreads=nt)
     t1 = time.perf_counter()
-    o_con = orc.connect_edges(ag[sl], cf[sl], ct[sl], nthreads=0)
+    o_con = orc.connect_edges(ag[sl], cf[sl], ct[sl], nthreads=nt)
     t2 = time.perf_counter()
     return {"n_agents": N, "n_obstacles": M,
             "collide_pairs": {"n": n_col, "gpu_ms": ms_col, "gpu_checks_per_s": n_col / ms_col * 1e3,
-                              "cpu_checks_per_s": o_col.size / (t1 - t0), "cpu_threads": O.max_threads(),
+                              "cpu_checks_per_s": o_col.size / (t1 - t0), "cpu_threads": nt,
                               "mismatches_on_sample": int((g_col[sl] != o_col).sum()),
                               "hit_rate": float(g_col.mean())},
             "connect_edges": {"n": n_con, "gpu_ms": ms_con, "gpu_checks_per_s": n_con / ms_con * 1e3,

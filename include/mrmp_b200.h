@@ -88,7 +88,8 @@ int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
 /* diagnostics since the last reset: out4[0] = point-model pairs that survived the cross
  * kernel's broad phase (ran the exact reference arithmetic); out4[1] = arm22 link pairs that ran
  * the exact test; out4[2] = point-model pairs whose column tile survived the box test (ran the
- * midpoint bound); out4[3] reserved */
+ * broad-phase bound); out4[3] = point-model pairs evaluated by the verdict filter (out4[0] of them
+ * undecided -> reference arithmetic) */
 int mrmp_ctx_stats(mrmp_ctx *ctx, int64_t *out4, int reset);
 
 /* ---- connect -------------------------------------------------------------------- */
@@ -247,6 +248,37 @@ int mrmp_collide_cross_dev(mrmp_ctx *ctx, int64_t n_rows, const int32_t *row_age
                            const int32_t *col_agent, const double *col_from,
                            const double *col_to, int group_size, uint32_t *out_bits,
                            void *stream);
+/* Reductions of the same cross product (out: int32 [n_rows][n_groups]), for the callers that
+ * need more than a bit per pair:
+ *  MRMP_CROSS_COUNT  out[r][g] = number of colliding columns of group g.  With MRMP_CROSS_FLAG_CBS
+ *    the pair test is the one of CBS's soft conflict count g_func_i (cbs.jl:336-347) and of
+ *    get_num_collisions (cbs.jl:449-457 via :391-401):
+ *      collide(col_to, row_to, j, i) || collide(col_from, col_to, row_from, row_to, j, i)
+ *    (vertex conflict OR edge conflict, the column's agent j first, as written at :345-346).
+ *    Rows = candidate edges of agent i, columns = the other agents' path edges, group = time step.
+ *  MRMP_CROSS_FIRST  out[r][g] = smallest column index (caller's order) of group g that collides
+ *    with row r, -1 if none: the type-2 dependency scan of get_temporal_plan_graph
+ *    (smoother.jl:78-106: per action_self and other agent j the FIRST later action_other that
+ *    collides).  row_key / col_key (both NULL, or both given): only pairs with
+ *    col_key[c] > row_key[r] are tested (`filter(a -> a.t > action_self.t, TPG[j])`, :88).
+ * Groups: col_group[c] in [0, n_groups) if non-NULL, else c / group_size (group_size > 0,
+ * n_groups >= ceil(n_cols / group_size)).  Same-agent pairs never count. */
+#define MRMP_CROSS_COUNT 2
+#define MRMP_CROSS_FIRST 3
+#define MRMP_CROSS_FLAG_CBS 1
+int mrmp_collide_cross_reduce(mrmp_ctx *ctx, int64_t n_rows, const int32_t *row_agent,
+                              const double *row_from, const double *row_to,
+                              const int32_t *row_key, int64_t n_cols, const int32_t *col_agent,
+                              const double *col_from, const double *col_to,
+                              const int32_t *col_group, const int32_t *col_key, int group_size,
+                              int n_groups, int mode, int flags, int32_t *out);
+int mrmp_collide_cross_reduce_dev(mrmp_ctx *ctx, int64_t n_rows, const int32_t *row_agent,
+                                  const double *row_from, const double *row_to,
+                                  const int32_t *row_key, int64_t n_cols,
+                                  const int32_t *col_agent, const double *col_from,
+                                  const double *col_to, const int32_t *col_group,
+                                  const int32_t *col_key, int group_size, int n_groups, int mode,
+                                  int flags, int32_t *out, void *stream);
 /* rows = every edge of the (built) roadmap set in packed CSR order (row e <-> col_idx[e]);
  * columns = roadmap edges given by ids (col_agent, col_vfrom -> col_vto) into rm_cols (NULL:
  * the same set; a shard passes the all-gathered full set here).  out_bits

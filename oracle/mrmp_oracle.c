@@ -631,6 +631,46 @@ void orc_collide_cross(const orc_ctx *c, int64_t n_rows, const int32_t *ra, cons
     }
 }
 
+/* Reductions of the same cross product that the reference's callers compute one collide call at
+ * a time (mode 2 = count, 3 = first; out int32 [n_rows][n_groups]):
+ *  - CBS soft conflict count, cbs.jl:336-347 (cbs != 0):  per candidate edge of agent i (row) and
+ *    time step (group), count(j -> collide(q_j_to, q_i_to, j, i) || collide(q_j_from, q_j_to,
+ *    q_i_from, q_i_to, j, i)) over the other agents' path edges (columns of that group) -- the
+ *    COLUMN agent is the first argument of both calls, as written at :345-346.
+ *  - TPG type-2 dependency scan, smoother.jl:78-106 (keys): per action_self (row) and other
+ *    agent j (group): the FIRST action_other of j, in list order, with a.t > action_self.t
+ *    (col_key > row_key) that collides (:86-103, `break` at the first hit).
+ * group of column k = col_group[k] if given, else k / group_size. */
+void orc_collide_cross_reduce(const orc_ctx *c, int64_t n_rows, const int32_t *ra, const double *rf,
+                              const double *rt, const int32_t *row_key, int64_t n_cols,
+                              const int32_t *ca, const double *cf, const double *ct,
+                              const int32_t *col_group, const int32_t *col_key, int group_size,
+                              int n_groups, int mode, int cbs, int32_t *out, int nthreads) {
+    int d = c->d, nt = pick_threads(nthreads);
+#pragma omp parallel for num_threads(nt) schedule(dynamic, 8)
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int32_t *o = out + r * (int64_t)n_groups;
+        for (int g = 0; g < n_groups; ++g) o[g] = mode == 3 ? -1 : 0;
+        for (int64_t k = 0; k < n_cols; ++k) {
+            if (ra[r] == ca[k]) continue;                       /* j != i */
+            if (row_key && !(col_key[k] > row_key[r])) continue; /* smoother.jl:88 a.t > t */
+            int64_t g = col_group ? col_group[k] : k / group_size;
+            if (mode == 3 && o[g] >= 0) continue;               /* `break` after the first hit */
+            int hit;
+            if (cbs)
+                hit = orc_collide_static(c, ct + d * k, rt + d * r, ca[k], ra[r]) ||
+                      orc_collide_pair(c, cf + d * k, ct + d * k, rf + d * r, rt + d * r, ca[k], ra[r]);
+            else
+                hit = orc_collide_pair(c, rf + d * r, rt + d * r, cf + d * k, ct + d * k, ra[r], ca[k]);
+            if (!hit) continue;
+            if (mode == 3)
+                o[g] = (int32_t)k;
+            else
+                o[g] += 1;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* sampler: counter-based Philox4x32-10 (Salmon et al., SC'11)               */
 /* ------------------------------------------------------------------------ */

@@ -115,6 +115,12 @@ void orc_collide_edges_indexed_batch(const orc_ctx *c, int64_t n, const int32_t 
 void orc_collide_cross(const orc_ctx *c, int64_t n_rows, const int32_t *ra, const double *rf,
                        const double *rt, int64_t n_cols, const int32_t *ca, const double *cf,
                        const double *ct, int group_size, uint32_t *out, int nthreads);
+/* count / first reductions of the cross product: cbs.jl:336-347, smoother.jl:78-106 */
+void orc_collide_cross_reduce(const orc_ctx *c, int64_t n_rows, const int32_t *ra, const double *rf,
+                              const double *rt, const int32_t *row_key, int64_t n_cols,
+                              const int32_t *ca, const double *cf, const double *ct,
+                              const int32_t *col_group, const int32_t *col_key, int group_size,
+                              int n_groups, int mode, int cbs, int32_t *out, int nthreads);
 
 /* counter-based sampler (Philox4x32-10), replaces Julia's task-local RNG:
  * gen_uniform_sampling, point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218 */

@@ -78,6 +78,10 @@ def _load(name: str) -> C.CDLL:
                                                     _ip, _ip, _dp, C.c_int64, _bp, C.c_int]
     lib.orc_collide_cross.argtypes = [C.c_void_p, C.c_int64, _ip, _dp, _dp, C.c_int64, _ip, _dp, _dp,
                                       C.c_int, C.c_void_p, C.c_int]
+    lib.orc_collide_cross_reduce.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_int]
     lib.orc_philox4x32.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     lib.orc_sample_state.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, _dp]
     lib.orc_sample_free.restype = C.c_int64
@@ -121,6 +125,16 @@ def _p(a: np.ndarray, t):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def host_cores() -> int:
+    """Cores this process may run on.  The batch drivers take an explicit thread count
+    (`num_threads` clause), so this is what the reference arm passes: OMP_NUM_THREADS -- which
+    torchrun sets to 1 in every worker -- must not decide how many host cores the CPU arm uses."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ----------------------------------------------------------------- primitives
@@ -299,6 +313,24 @@ class Oracle:
         self._lib.orc_collide_cross(self._h, ra.size, _p(ra, _ip), _p(rf, _dp), _p(rt, _dp),
                                     ca.size, _p(ca, _ip), _p(cf, _dp), _p(ct, _dp),
                                     int(group_size), out.ctypes.data_as(C.c_void_p), nthreads)
+        return out
+
+    def collide_cross_reduce(self, ra, rf, rt, ca, cf, ct, mode, group_size=0, col_group=None,
+                             n_groups=None, row_key=None, col_key=None, cbs=False, nthreads=1):
+        """mode "count" (cbs.jl:336-347) / "first" (smoother.jl:78-106) -> int32 [n_rows][n_groups]."""
+        ra, ca = _i32(ra), _i32(ca)
+        rf, rt, cf, ct = _f64(rf), _f64(rt), _f64(cf), _f64(ct)
+        cg = _i32(col_group) if col_group is not None else None
+        rk = _i32(row_key) if row_key is not None else None
+        ck = _i32(col_key) if col_key is not None else None
+        if n_groups is None:
+            n_groups = int(cg.max()) + 1 if cg is not None else -(-ca.size // group_size)
+        out = np.zeros((ra.size, n_groups), np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        self._lib.orc_collide_cross_reduce(self._h, ra.size, vp(ra), vp(rf), vp(rt), vp(rk), ca.size,
+                                           vp(ca), vp(cf), vp(ct), vp(cg), vp(ck), int(group_size),
+                                           int(n_groups), {"count": 2, "first": 3}[mode], int(bool(cbs)),
+                                           vp(out), nthreads)
         return out
 
     # sampler / roadmap

@@ -249,6 +249,30 @@ class Context:
                                              L.ptr(out, L._vp)))
         return out
 
+    def collide_cross_reduce(self, row_agent, row_from, row_to, col_agent, col_from, col_to, mode,
+                             group_size: int = 0, col_group=None, n_groups=None, row_key=None,
+                             col_key=None, cbs: bool = False) -> np.ndarray:
+        """Reductions of the cross product -> int32 [n_rows][n_groups].
+        mode "count": colliding columns per (row, group); with cbs=True the pair test of CBS's soft
+        conflict count (cbs.jl:336-347: vertex conflict OR edge conflict, column agent first).
+        mode "first": smallest colliding column index per (row, group), -1 if none; row_key /
+        col_key restrict to col_key > row_key (TPG type-2 dependencies, smoother.jl:78-106)."""
+        ra, ca = L.i32(row_agent).ravel(), L.i32(col_agent).ravel()
+        rf, rt = _states(row_from, self.d), _states(row_to, self.d)
+        cf, ct = _states(col_from, self.d), _states(col_to, self.d)
+        cg = L.i32(col_group).ravel() if col_group is not None else None
+        rk = L.i32(row_key).ravel() if row_key is not None else None
+        ck = L.i32(col_key).ravel() if col_key is not None else None
+        if n_groups is None:
+            n_groups = (int(cg.max()) + 1 if cg.size else 1) if cg is not None else max(1, -(-ca.size // group_size))
+        out = np.zeros((ra.size, n_groups), np.int32)
+        vp = lambda a: a.ctypes.data_as(L._vp) if a is not None else None
+        L.check(self._lib.mrmp_collide_cross_reduce(
+            self._h, ra.size, vp(ra), vp(rf), vp(rt), vp(rk), ca.size, vp(ca), vp(cf), vp(ct), vp(cg),
+            vp(ck), int(group_size), int(n_groups), {"count": L.CROSS_COUNT, "first": L.CROSS_FIRST}[mode],
+            L.CROSS_FLAG_CBS if cbs else 0, vp(out)))
+        return out
+
     def sample_states(self, agent: int, seed: int, t0: int, n: int) -> np.ndarray:
         out = np.empty((n, self.d))
         L.check(self._lib.mrmp_sample_states(self._h, int(agent), int(seed), int(t0), int(n),

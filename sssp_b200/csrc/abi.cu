@@ -1394,28 +1394,39 @@ static int cross_words(int64_t n_cols, int group_size) {
 // rows / cols / out are device pointers.  rows_sorted: Morton-sorted row records prepared
 // earlier (roadmap edges cache them) or NULL (sorted here into scratch slot 4).  Column tiles,
 // their headers and the sort workspace live in scratch slot 0.
+// rq.mode: bits / or -> `out` is uint32 [n_rows][wpr]; count / first -> int32 [n_rows][n_groups].
 static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                          const double *row_from, const double *row_to, const void *rows_sorted,
                          int64_t n_cols, const int32_t *col_agent, const double *col_from,
                          const double *col_to, const int32_t *col_vf, const int32_t *col_vt,
-                         const double *nodes, int agent0, int nv_stride, int group_size,
+                         const double *nodes, int agent0, int nv_stride, const CrossReq &rq,
                          uint32_t *out, cudaStream_t s) {
-    const int wpr = cross_words(n_cols, group_size);
+    const int group_size = rq.group_size;
+    const bool table = rq.mode == kCrossBits || rq.mode == kCrossOr;
+    const int wpr = table ? cross_words(n_cols, group_size) : rq.n_groups;
+    LaunchCfg lc = lcfg(c, s);
+    if (rq.mode == kCrossFirst)
+        CU(launch_fill_i32(lc, (int32_t *)out, n_rows * (int64_t)wpr, 0x7fffffff));
+    else if (rq.mode != kCrossOr || c->model >= MRMP_MODEL_ARM22)
+        // bits / count: hits are OR-ed / added into a zeroed output (the OR mode of the point
+        // models writes every word itself)
+        CU(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * wpr, s));
     if (c->model >= MRMP_MODEL_ARM22) {  // discretised models: warp per (row, column) check
         if (c->model == MRMP_MODEL_ARM22)
-            CU(launch_arm_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to,
-                                        n_cols, col_agent, col_from, col_to, col_vf, col_vt, nodes,
-                                        agent0, nv_stride, group_size, wpr, out, c->stats_d + 1));
+            CU(launch_arm_collide_cross(c->cv, lc, n_rows, row_agent, row_from, row_to, n_cols,
+                                        col_agent, col_from, col_to, col_vf, col_vt, nodes, agent0,
+                                        nv_stride, rq, wpr, out, c->stats_d + 1));
         else
-            CU(launch_chain_collide_cross(c->cv, lcfg(c, s), n_rows, row_agent, row_from, row_to,
-                                          n_cols, col_agent, col_from, col_to, col_vf, col_vt,
-                                          nodes, agent0, nv_stride, group_size, wpr, out,
-                                          c->stats_d + 1));
+            CU(launch_chain_collide_cross(c->cv, lc, n_rows, row_agent, row_from, row_to, n_cols,
+                                          col_agent, col_from, col_to, col_vf, col_vt, nodes,
+                                          agent0, nv_stride, rq, wpr, out, c->stats_d + 1));
+        if (rq.mode == kCrossFirst)
+            CU(launch_cross_first_finalize(lc, (int32_t *)out, n_rows * (int64_t)wpr));
         return MRMP_OK;
     }
-    LaunchCfg lc = lcfg(c, s);
     // columns per launch: everything, or kCrossMaxGroups groups in OR-reduced mode
-    const int64_t chunk_cols = group_size > 0 ? (int64_t)kCrossMaxGroups * group_size : n_cols;
+    const int64_t chunk_cols =
+        rq.mode == kCrossOr ? (int64_t)kCrossMaxGroups * group_size : n_cols;
     const int64_t max_cols = n_cols < chunk_cols ? n_cols : chunk_cols;
     const int64_t max_tiles = (max_cols + kCrossCols - 1) / kCrossCols;
     const size_t o_cells = 0, o_work = o_cells + 4096 * 4, o_order = o_work + 16,
@@ -1432,24 +1443,44 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                                   (int32_t *)(b + o_cells), c->scratch[4]));
         rows_sorted = c->scratch[4];
     }
-    if (group_size <= 0)  // full matrix: hits are OR-ed into a zeroed output
-        CU(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * wpr, s));
     const int d = c->d;
     for (int64_t c0 = 0; c0 < n_cols; c0 += chunk_cols) {
         const int64_t nc = n_cols - c0 < chunk_cols ? n_cols - c0 : chunk_cols;
+        CrossCols cc;
+        cc.group_size = rq.mode == kCrossBits ? 0 : group_size;
+        cc.col_group = rq.col_group ? rq.col_group + c0 : nullptr;
+        cc.col_key = rq.col_key ? rq.col_key + c0 : nullptr;
+        cc.orig_base = c0;
         CU(launch_cross_prep_cols(c->cv, lc, nc, col_agent + c0,
                                   col_from ? col_from + c0 * d : nullptr,
                                   col_to ? col_to + c0 * d : nullptr, col_vf ? col_vf + c0 : nullptr,
-                                  col_vt ? col_vt + c0 : nullptr, nodes, agent0, nv_stride,
-                                  group_size, (int32_t *)(b + o_cells), (int32_t *)(b + o_order),
-                                  b + o_tiles, b + o_hdr));
-        const int64_t g0 = group_size > 0 ? c0 / group_size : 0;
-        const int w = group_size > 0 ? cross_words(nc, group_size) : wpr;
-        CU(launch_cross_collide(c->cv, lc, n_rows, rows_sorted, nc, b + o_tiles, b + o_hdr,
-                                group_size, w, wpr, out + g0 / 32, c->max_rad, c->stats_d,
-                                (unsigned int *)(b + o_work)));
+                                  col_vt ? col_vt + c0 : nullptr, nodes, agent0, nv_stride, cc,
+                                  (int32_t *)(b + o_cells), (int32_t *)(b + o_order), b + o_tiles,
+                                  b + o_hdr));
+        const int64_t g0 = rq.mode == kCrossOr ? c0 / group_size : 0;
+        CrossOut co;
+        co.mode = rq.mode;
+        co.words_per_row = rq.mode == kCrossOr ? cross_words(nc, group_size) : wpr;
+        co.out_stride = wpr;
+        co.out = out + g0 / 32;
+        co.row_key = rq.row_key;
+        co.cbs = rq.cbs;
+        CU(launch_cross_collide(c->cv, lc, n_rows, rows_sorted, nc, b + o_tiles, b + o_hdr, co,
+                                c->stats_d, (unsigned int *)(b + o_work)));
     }
+    if (rq.mode == kCrossFirst)
+        CU(launch_cross_first_finalize(lc, (int32_t *)out, n_rows * (int64_t)wpr));
     return MRMP_OK;
+}
+
+static CrossReq table_req(int group_size) {
+    CrossReq rq;
+    rq.mode = group_size > 0 ? kCrossOr : kCrossBits;
+    rq.group_size = group_size;
+    rq.n_groups = 0;
+    rq.col_group = rq.col_key = rq.row_key = nullptr;
+    rq.cbs = 0;
+    return rq;
 }
 
 extern "C" int mrmp_collide_cross_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
@@ -1464,8 +1495,8 @@ extern "C" int mrmp_collide_cross_dev(mrmp_ctx *c, int64_t n_rows, const int32_t
         need_aligned(c, col_to))
         return MRMP_ERR_INVALID;
     return cross_run_dev(c, n_rows, row_agent, row_from, row_to, nullptr, n_cols, col_agent,
-                         col_from, col_to, nullptr, nullptr, nullptr, 0, 0, group_size, out_bits,
-                         (cudaStream_t)stream);
+                         col_from, col_to, nullptr, nullptr, nullptr, 0, 0, table_req(group_size),
+                         out_bits, (cudaStream_t)stream);
 }
 
 extern "C" int mrmp_collide_cross(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
@@ -1503,10 +1534,119 @@ extern "C" int mrmp_collide_cross(mrmp_ctx *c, int64_t n_rows, const int32_t *ro
     rc = cross_run_dev(c, n_rows, (const int32_t *)(b + o_ra), (const double *)(b + o_rf),
                        (const double *)(b + o_rt), nullptr, n_cols, (const int32_t *)(b + o_ca),
                        (const double *)(b + o_cf), (const double *)(b + o_ct), nullptr, nullptr,
-                       nullptr, 0, 0, group_size, (uint32_t *)c->scratch[2], s);
+                       nullptr, 0, 0, table_req(group_size), (uint32_t *)c->scratch[2], s);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out_bits, c->scratch[2], sizeof(uint32_t) * (size_t)n_rows * wpr,
                        cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MRMP_OK;
+}
+
+// ---- count / first reductions (cbs.jl:336-347, smoother.jl:78-106) ---------------------------
+static int reduce_req(mrmp_ctx *c, int64_t n_cols, const int32_t *col_group, const int32_t *col_key,
+                      const int32_t *row_key, int group_size, int n_groups, int mode, int flags,
+                      CrossReq &rq) {
+    NEED(mode == MRMP_CROSS_COUNT || mode == MRMP_CROSS_FIRST, "mode must be COUNT or FIRST");
+    NEED((row_key == nullptr) == (col_key == nullptr), "row_key and col_key go together");
+    NEED(n_groups >= 1 && n_groups <= (1 << 24), "n_groups out of range");
+    NEED(col_group || (group_size > 0 && (n_cols + group_size - 1) / group_size <= n_groups),
+         "group_size / n_groups do not cover the columns");
+    NEED((flags & ~MRMP_CROSS_FLAG_CBS) == 0, "unknown flags");
+    (void)c;
+    rq.mode = mode == MRMP_CROSS_COUNT ? kCrossCount : kCrossFirst;
+    rq.group_size = col_group ? 0 : group_size;
+    rq.n_groups = n_groups;
+    rq.col_group = col_group;
+    rq.col_key = col_key;
+    rq.row_key = row_key;
+    rq.cbs = (flags & MRMP_CROSS_FLAG_CBS) ? 1 : 0;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_collide_cross_reduce_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
+                                             const double *row_from, const double *row_to,
+                                             const int32_t *row_key, int64_t n_cols,
+                                             const int32_t *col_agent, const double *col_from,
+                                             const double *col_to, const int32_t *col_group,
+                                             const int32_t *col_key, int group_size, int n_groups,
+                                             int mode, int flags, int32_t *out, void *stream) {
+    NEED(c && n_rows >= 0 && n_cols >= 0 && out, "bad arguments");
+    CrossReq rq;
+    int rc = reduce_req(c, n_cols, col_group, col_key, row_key, group_size, n_groups, mode, flags, rq);
+    if (rc) return rc;
+    if (n_rows == 0) return MRMP_OK;
+    CU(cudaSetDevice(c->device));
+    if (n_cols == 0) {  // nothing collides: 0 counts / -1 first hits
+        CU(launch_fill_i32(lcfg(c, (cudaStream_t)stream), out, n_rows * (int64_t)n_groups,
+                           mode == MRMP_CROSS_FIRST ? -1 : 0));
+        return MRMP_OK;
+    }
+    if (need_aligned(c, row_from) || need_aligned(c, row_to) || need_aligned(c, col_from) ||
+        need_aligned(c, col_to))
+        return MRMP_ERR_INVALID;
+    return cross_run_dev(c, n_rows, row_agent, row_from, row_to, nullptr, n_cols, col_agent,
+                         col_from, col_to, nullptr, nullptr, nullptr, 0, 0, rq, (uint32_t *)out,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int mrmp_collide_cross_reduce(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
+                                         const double *row_from, const double *row_to,
+                                         const int32_t *row_key, int64_t n_cols,
+                                         const int32_t *col_agent, const double *col_from,
+                                         const double *col_to, const int32_t *col_group,
+                                         const int32_t *col_key, int group_size, int n_groups,
+                                         int mode, int flags, int32_t *out) {
+    NEED(c && n_rows >= 0 && n_cols >= 0, "bad arguments");
+    if (n_rows == 0) return MRMP_OK;
+    NEED(out && row_agent && row_from && row_to, "NULL buffer");
+    NEED(n_cols == 0 || (col_agent && col_from && col_to), "NULL buffer");
+    CrossReq rq;
+    int rc = reduce_req(c, n_cols, col_group, col_key, row_key, group_size, n_groups, mode, flags, rq);
+    if (rc) return rc;
+    rc = check_agents_host(c, n_rows, row_agent);
+    if (!rc) rc = check_agents_host(c, n_cols, col_agent);
+    if (rc) return rc;
+    if (col_group)
+        for (int64_t k = 0; k < n_cols; ++k)
+            NEED(col_group[k] >= 0 && col_group[k] < n_groups, "col_group out of range");
+    CU(cudaSetDevice(c->device));
+    const size_t sb = sizeof(double) * c->d;
+    const size_t o_ra = 0, o_rf = align16(o_ra + 4 * (size_t)n_rows),
+                 o_rt = align16(o_rf + sb * (size_t)n_rows),
+                 o_rk = align16(o_rt + sb * (size_t)n_rows),
+                 o_ca = align16(o_rk + 4 * (size_t)n_rows),
+                 o_cf = align16(o_ca + 4 * (size_t)n_cols),
+                 o_ct = align16(o_cf + sb * (size_t)n_cols),
+                 o_cg = align16(o_ct + sb * (size_t)n_cols),
+                 o_ck = align16(o_cg + 4 * (size_t)n_cols),
+                 tot = align16(o_ck + 4 * (size_t)n_cols);
+    const size_t ob = sizeof(int32_t) * (size_t)n_rows * n_groups;
+    rc = ensure_scratch(c, 1, tot);
+    if (!rc) rc = ensure_scratch(c, 2, ob);
+    if (rc) return rc;
+    unsigned char *b = c->scratch[1];
+    cudaStream_t s = c->s_k;
+    const auto up = [&](size_t off, const void *src, size_t bytes) {
+        return bytes ? cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyHostToDevice, s) : cudaSuccess;
+    };
+    CU(up(o_ra, row_agent, 4 * (size_t)n_rows));
+    CU(up(o_rf, row_from, sb * (size_t)n_rows));
+    CU(up(o_rt, row_to, sb * (size_t)n_rows));
+    if (row_key) CU(up(o_rk, row_key, 4 * (size_t)n_rows));
+    CU(up(o_ca, col_agent, 4 * (size_t)n_cols));
+    CU(up(o_cf, col_from, sb * (size_t)n_cols));
+    CU(up(o_ct, col_to, sb * (size_t)n_cols));
+    if (col_group) CU(up(o_cg, col_group, 4 * (size_t)n_cols));
+    if (col_key) CU(up(o_ck, col_key, 4 * (size_t)n_cols));
+    rc = mrmp_collide_cross_reduce_dev(
+        c, n_rows, (const int32_t *)(b + o_ra), (const double *)(b + o_rf),
+        (const double *)(b + o_rt), row_key ? (const int32_t *)(b + o_rk) : nullptr, n_cols,
+        (const int32_t *)(b + o_ca), (const double *)(b + o_cf), (const double *)(b + o_ct),
+        col_group ? (const int32_t *)(b + o_cg) : nullptr,
+        col_key ? (const int32_t *)(b + o_ck) : nullptr, group_size, n_groups, mode, flags,
+        (int32_t *)c->scratch[2], s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, c->scratch[2], ob, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     return MRMP_OK;
 }
@@ -1562,7 +1702,7 @@ extern "C" int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps
     if (rc) return rc;
     return cross_run_dev(c, rm->nnz, rm->e_agent, rm->e_from, rm->e_to, rm->e_rows, n_cols,
                          col_agent, nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes,
-                         rm_cols->agent0, rm_cols->nv, group_size, out_bits, s);
+                         rm_cols->agent0, rm_cols->nv, table_req(group_size), out_bits, s);
 }
 
 extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,

@@ -344,6 +344,7 @@ struct ListSrc {  // explicit list (mrmp_collide_pairs)
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const { out[k] = (ran && hit) ? 1 : 0; }
+    __device__ bool cbs() const { return false; }
 };
 
 struct IndexedSrc {  // roadmap edges by id (mrmp_collide_edges_indexed)
@@ -362,9 +363,10 @@ struct IndexedSrc {  // roadmap edges by id (mrmp_collide_edges_indexed)
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const { out[k] = (ran && hit) ? 1 : 0; }
+    __device__ bool cbs() const { return false; }
 };
 
-struct CrossSrc {  // rows x columns -> bit matrix (mrmp_collide_cross, edge_conflicts)
+struct CrossSrc {  // rows x columns -> bits / counts / first hits (mrmp_collide_cross*, edge_conflicts)
     const int32_t *row_agent;
     const double *row_from, *row_to;
     int64_t n_cols;
@@ -373,35 +375,48 @@ struct CrossSrc {  // rows x columns -> bit matrix (mrmp_collide_cross, edge_con
     const int32_t *col_vf, *col_vt;      // ids into nodes
     const double *nodes;
     int agent0, nv_stride;
-    int group_size;
+    CrossReq rq;
     int64_t out_stride;
-    uint32_t *out;  // zeroed by the launcher
-    __device__ int64_t bit_of(int64_t c) const { return group_size > 0 ? c / group_size : c; }
+    uint32_t *out;  // initialised by the caller (abi.cu: cross_run_dev)
+    __device__ int64_t slot_of(int64_t c) const {
+        return rq.col_group ? __ldg(rq.col_group + c) : (rq.group_size > 0 ? c / rq.group_size : c);
+    }
+    // cbs.jl:343-346: the COLUMN agent j is the first argument of both tests
+    __device__ bool cbs() const { return rq.cbs != 0; }
     __device__ bool fetch(int64_t k, PairCheck &p) const {
         const int64_t r = k / n_cols, c = k - r * n_cols;
-        p.i = __ldg(row_agent + r);
-        p.j = __ldg(col_agent + c);
-        if (p.i == p.j) return false;
-        if (group_size > 0) {  // OR-reduced: a set bit cannot change any more
-            const int64_t b = bit_of(c);
+        const int ri = __ldg(row_agent + r), cj = __ldg(col_agent + c);
+        if (ri == cj) return false;
+        if (rq.row_key && !(__ldg(rq.col_key + c) > __ldg(rq.row_key + r))) return false;
+        if (rq.mode == kCrossOr) {  // OR-reduced: a set bit cannot change any more
+            const int64_t b = slot_of(c);
             if ((*(volatile uint32_t *)(out + r * out_stride + (b >> 5)) >> (b & 31)) & 1u) return false;
         }
-        load_state<2>(row_from, r, p.qif);
-        load_state<2>(row_to, r, p.qit);
+        double *rf = rq.cbs ? p.qjf : p.qif, *rt = rq.cbs ? p.qjt : p.qit;
+        double *cf = rq.cbs ? p.qif : p.qjf, *ct = rq.cbs ? p.qit : p.qjt;
+        p.i = rq.cbs ? cj : ri;
+        p.j = rq.cbs ? ri : cj;
+        load_state<2>(row_from, r, rf);
+        load_state<2>(row_to, r, rt);
         if (col_from) {
-            load_state<2>(col_from, c, p.qjf);
-            load_state<2>(col_to, c, p.qjt);
+            load_state<2>(col_from, c, cf);
+            load_state<2>(col_to, c, ct);
         } else {
-            const int64_t bj = (int64_t)(p.j - agent0) * nv_stride;
-            load_state<2>(nodes, bj + __ldg(col_vf + c), p.qjf);
-            load_state<2>(nodes, bj + __ldg(col_vt + c), p.qjt);
+            const int64_t bj = (int64_t)(cj - agent0) * nv_stride;
+            load_state<2>(nodes, bj + __ldg(col_vf + c), cf);
+            load_state<2>(nodes, bj + __ldg(col_vt + c), ct);
         }
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const {
         if (!(ran && hit)) return;
-        const int64_t r = k / n_cols, b = bit_of(k - r * n_cols);
-        atomicOr(out + r * out_stride + (b >> 5), 1u << (b & 31));
+        const int64_t r = k / n_cols, c = k - r * n_cols, b = slot_of(c);
+        if (rq.mode == kCrossCount)
+            atomicAdd(reinterpret_cast<int *>(out) + r * out_stride + b, 1);
+        else if (rq.mode == kCrossFirst)
+            atomicMin(reinterpret_cast<int *>(out) + r * out_stride + b, (int)c);
+        else
+            atomicOr(out + r * out_stride + (b >> 5), 1u << (b & 31));
     }
 };
 
@@ -442,6 +457,7 @@ struct ConfigSrc {  // collide(Q_from, Q_to): arm22.jl:164-171, pairs i < j in r
             atomicMin(first + cfg, (unsigned long long)(i * N + i + 1 + (int)r));
         }
     }
+    __device__ bool cbs() const { return false; }
 };
 
 template <class Src>
@@ -466,7 +482,10 @@ k_arm_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
         PairCheck p;
         const bool run = src.fetch(k, p);  // warp-uniform
         bool hit = false;
-        if (run)
+        if (run && src.cbs())  // collide(q_j_to, q_i_to, j, i), cbs.jl:345 / arm22.jl:148-162
+            hit = arm_collide_static(ac, p.qit, p.qjt, sg.bx(p.i), sg.by(p.i), sg.rad(p.i),
+                                     sg.bx(p.j), sg.by(p.j), sg.rad(p.j));
+        if (run && !hit)
             hit = warp_arm_collide_pair(ac, sg, p.qif, p.qit, p.qjf, p.qjt, p.i, p.j, I, J, queue,
                                         cap, lane, n_exact);
         if (lane == 0) src.emit(k, run, hit);
@@ -639,13 +658,10 @@ cudaError_t launch_arm_collide_cross(const CtxView &cv, const LaunchCfg &lc, int
                                      const int32_t *col_agent, const double *col_from,
                                      const double *col_to, const int32_t *col_vf,
                                      const int32_t *col_vt, const double *nodes, int agent0,
-                                     int nv_stride, int group_size, int words_per_row,
+                                     int nv_stride, const CrossReq &rq, int out_stride,
                                      uint32_t *out, unsigned long long *stats) {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * words_per_row,
-                                    lc.stream);
-    if (e != cudaSuccess) return e;
     CrossSrc s{row_agent, row_from, row_to, n_cols, col_agent, col_from, col_to, col_vf, col_vt,
-               nodes, agent0, nv_stride, group_size, (int64_t)words_per_row, out};
+               nodes, agent0, nv_stride, rq, (int64_t)out_stride, out};
     return launch_arm_collide_src(cv, lc, n_rows * n_cols, s, stats);
 }
 

@@ -394,6 +394,7 @@ struct ListSrcN {
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const { out[k] = (ran && hit) ? 1 : 0; }
+    __device__ bool cbs() const { return false; }
 };
 
 template <int SD>
@@ -413,6 +414,7 @@ struct IndexedSrcN {
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const { out[k] = (ran && hit) ? 1 : 0; }
+    __device__ bool cbs() const { return false; }
 };
 
 template <int SD>
@@ -425,35 +427,47 @@ struct CrossSrcN {
     const int32_t *col_vf, *col_vt;
     const double *nodes;
     int agent0, nv_stride;
-    int group_size;
+    CrossReq rq;
     int64_t out_stride;
-    uint32_t *out;
-    __device__ int64_t bit_of(int64_t c) const { return group_size > 0 ? c / group_size : c; }
+    uint32_t *out;  // initialised by the caller (abi.cu: cross_run_dev)
+    __device__ int64_t slot_of(int64_t c) const {
+        return rq.col_group ? __ldg(rq.col_group + c) : (rq.group_size > 0 ? c / rq.group_size : c);
+    }
+    __device__ bool cbs() const { return rq.cbs != 0; }  // cbs.jl:343-346: column agent first
     __device__ bool fetch(int64_t k, PairCheckN<SD> &p) const {
         const int64_t r = k / n_cols, c = k - r * n_cols;
-        p.i = __ldg(row_agent + r);
-        p.j = __ldg(col_agent + c);
-        if (p.i == p.j) return false;
-        if (group_size > 0) {
-            const int64_t b = bit_of(c);
+        const int ri = __ldg(row_agent + r), cj = __ldg(col_agent + c);
+        if (ri == cj) return false;
+        if (rq.row_key && !(__ldg(rq.col_key + c) > __ldg(rq.row_key + r))) return false;
+        if (rq.mode == kCrossOr) {
+            const int64_t b = slot_of(c);
             if ((*(volatile uint32_t *)(out + r * out_stride + (b >> 5)) >> (b & 31)) & 1u) return false;
         }
-        load_state<SD>(row_from, r, p.qif);
-        load_state<SD>(row_to, r, p.qit);
+        double *rf = rq.cbs ? p.qjf : p.qif, *rt = rq.cbs ? p.qjt : p.qit;
+        double *cf = rq.cbs ? p.qif : p.qjf, *ct = rq.cbs ? p.qit : p.qjt;
+        p.i = rq.cbs ? cj : ri;
+        p.j = rq.cbs ? ri : cj;
+        load_state<SD>(row_from, r, rf);
+        load_state<SD>(row_to, r, rt);
         if (col_from) {
-            load_state<SD>(col_from, c, p.qjf);
-            load_state<SD>(col_to, c, p.qjt);
+            load_state<SD>(col_from, c, cf);
+            load_state<SD>(col_to, c, ct);
         } else {
-            const int64_t bj = (int64_t)(p.j - agent0) * nv_stride;
-            load_state<SD>(nodes, bj + __ldg(col_vf + c), p.qjf);
-            load_state<SD>(nodes, bj + __ldg(col_vt + c), p.qjt);
+            const int64_t bj = (int64_t)(cj - agent0) * nv_stride;
+            load_state<SD>(nodes, bj + __ldg(col_vf + c), cf);
+            load_state<SD>(nodes, bj + __ldg(col_vt + c), ct);
         }
         return true;
     }
     __device__ void emit(int64_t k, bool ran, bool hit) const {
         if (!(ran && hit)) return;
-        const int64_t r = k / n_cols, b = bit_of(k - r * n_cols);
-        atomicOr(out + r * out_stride + (b >> 5), 1u << (b & 31));
+        const int64_t r = k / n_cols, c = k - r * n_cols, b = slot_of(c);
+        if (rq.mode == kCrossCount)
+            atomicAdd(reinterpret_cast<int *>(out) + r * out_stride + b, 1);
+        else if (rq.mode == kCrossFirst)
+            atomicMin(reinterpret_cast<int *>(out) + r * out_stride + b, (int)c);
+        else
+            atomicOr(out + r * out_stride + (b >> 5), 1u << (b & 31));
     }
 };
 
@@ -493,6 +507,7 @@ struct ConfigSrcN {
             atomicMin(first + cfg, (unsigned long long)(i * N + j));
         }
     }
+    __device__ bool cbs() const { return false; }
 };
 
 template <int MODEL, class Src>
@@ -519,7 +534,13 @@ k_chain_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
         PairCheckN<SD> p;
         const bool run = src.fetch(k, p);
         bool hit = false;
-        if (run)
+        if (run && src.cbs()) {  // collide(q_j_to, q_i_to, j, i), cbs.jl:345
+            const ChainGeom gi = chain_geom<MODEL>(cv, col, false, p.i), gj = chain_geom<MODEL>(cv, col, false, p.j);
+            double thr, T2;
+            pair_threshold<MODEL>(cv, col, p.i, p.j, gi.rad, gj.rad, thr, T2);
+            hit = chain_collide_static<MODEL>(gi, gj, p.qit, p.qjt, thr, T2);
+        }
+        if (run && !hit)
             hit = warp_chain_collide_pair<MODEL>(cv, cp, col, p.qif, p.qit, p.qjf, p.qjt, p.i, p.j, I,
                                                  J, queue, lane, n_exact);
         if (lane == 0) src.emit(k, run, hit);
@@ -707,15 +728,12 @@ cudaError_t launch_chain_collide_cross(const CtxView &cv, const LaunchCfg &lc, i
                                        const int32_t *col_agent, const double *col_from,
                                        const double *col_to, const int32_t *col_vf,
                                        const int32_t *col_vt, const double *nodes, int agent0,
-                                       int nv_stride, int group_size, int words_per_row,
+                                       int nv_stride, const CrossReq &rq, int out_stride,
                                        uint32_t *out, unsigned long long *stats) {
-    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * words_per_row,
-                                    lc.stream);
-    if (e != cudaSuccess) return e;
     MRMP_CHAIN_SWITCH(cv, {
         CrossSrcN<Chain<MODEL>::SD> s{row_agent, row_from, row_to, n_cols, col_agent, col_from, col_to,
-                                      col_vf, col_vt, nodes, agent0, nv_stride, group_size,
-                                      (int64_t)words_per_row, out};
+                                      col_vf, col_vt, nodes, agent0, nv_stride, rq,
+                                      (int64_t)out_stride, out};
         return launch_chain_collide_src<MODEL>(cv, lc, n_rows * n_cols, s, stats);
     });
     return cudaErrorNotSupported;

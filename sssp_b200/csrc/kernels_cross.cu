@@ -1,42 +1,48 @@
-// kernels_cross.cu -- cross-product collide: every row edge x every column edge -> bits.
+// kernels_cross.cu -- cross-product collide: every row edge x every column edge -> bits / counts.
 //
 // This is the batched form of the reference's inter-agent check
 //   collide(qi_from, qi_to, qj_from, qj_to, i, j) = dist(seg_i, seg_j) < rads[i] + rads[j]
 // (src/models/point.jl:9-12) for the call shapes that issue it in bulk: PP's `invalid`
 // (pp.jl:179-189: candidate edge x planned agents' path edges), CBS's soft conflict count
-// (cbs.jl:336-347), the TPG construction (smoother.jl:86-103), SSSP's successor filter
+// (cbs.jl:336-347), the TPG construction (smoother.jl:78-106), SSSP's successor filter
 // (sssp.jl:196-223: candidate successor edges x other agents' current edges).
 //
-// Design (second version; the measurements that led here are in profiles/):
-//  * Both sides are sorted by the Morton cell of their midpoint (one-pass radix / counting
-//    sort over 4096 cells: histogram -> scan -> scatter).  32 consecutive rows then form a
-//    spatially compact WARP TILE, 64 consecutive columns a compact COLUMN TILE with a stored
-//    bounding box.
-//  * A warp owns a warp tile (one row per lane, in registers).  For every column tile it first
-//    tests box against box (lanes test 32 tile headers at once, one ballot): a column tile
-//    whose box is farther from the warp's box than the largest possible reach is skipped
-//    without being read.  Surviving tiles are read through L1/L2 with warp-uniform
-//    (broadcast) loads -- all column tiles of a launch are a few hundred KB and shared by
-//    every warp, so they stay cache resident.
-//  * Broad phase per pair (8 FP64 ops): every point of a segment lies within h = L/2 of its
-//    midpoint m, so dist(seg1, seg2) >= |m1 - m2| - h1 - h2; a pair with
-//    |m1 - m2|^2 > (thr_max + 2^-20 + h1 + h2)^2 cannot collide.  2^-20 dwarfs the rounding of
-//    both this bound and the exact path (coordinates up to 1e6), so culled pairs are pairs the
-//    reference arithmetic also calls "no collision".  NaN/inf never pass the `>` test and
-//    fall through to the exact path.
-//  * Survivors are compacted into a per-warp shared-memory queue (popc + warp prefix), then
-//    the exact reference arithmetic (geom.cuh: segseg_lt) runs on dense lanes.  No block-wide
-//    barrier anywhere: warps are autonomous and pull warp tiles from an atomic counter.
-// Output: full bit matrix (bit = original column index), or OR-reduced over consecutive
-// column groups (e.g. all agents' path edges of one time step).
+// Design (third version; the measurements that led here are in profiles/):
+//  * Both sides are sorted by the Morton cell of their midpoint (counting sort over 4096 cells:
+//    histogram -> scan -> scatter).  32 (or 64) consecutive rows form a spatially compact WARP
+//    TILE, 32 consecutive columns a COLUMN TILE with a stored bounding box.
+//  * A warp owns a warp tile (rows in registers).  Column tiles are first tested box against box
+//    (32 tile headers per ballot, FP64); a tile farther from the warp's box than the largest
+//    possible reach is skipped without being read.
+//  * Broad phase per pair in SINGLE precision (geom.cuh: bound32_far, 14 FP32 instructions, one
+//    16-byte warp-uniform load per column): capsule bound dist(seg_r, seg_c) >= dist(m_c, seg_r)
+//    - h_c against r_i + r_j + 2^-20 with a one-sided error budget, so a rejected pair is a pair
+//    the reference arithmetic calls "no collision".  The FP64 pipe is left to the pairs that
+//    matter.
+//  * Survivors are compacted into a per-warp shared-memory queue (popc + warp prefix) and
+//    evaluated on dense lanes by the verdict filter (geom.cuh: segseg_filter, FP64 with FMA and
+//    per-segment reciprocals, ~100 instructions instead of ~380): it decides every pair outside a
+//    2^-20 band around contact; the rest (parallel segments, contact within the band, coordinates
+//    outside [-2, 2]) runs the reference's own sequence of roundings (segseg_lt), so every verdict
+//    is the reference's bit for bit.  No block-wide barrier: warps are autonomous and pull warp
+//    tiles from an atomic counter.
+// Output modes: full bit matrix; OR over column groups (e.g. all agents' path edges of one time
+// step); COUNT per (row, group) (CBS soft conflicts); FIRST = smallest column index per
+// (row, group) (TPG dependency scan), optionally restricted to col_key > row_key.
+#include <stdlib.h>
+
 #include "point_model.cuh"
+
+#ifndef MRMP_CROSS_RPL_DEFAULT
+#define MRMP_CROSS_RPL_DEFAULT 1
+#endif
 
 namespace mrmp {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
 constexpr int kCols = 32;        // column edges per tile (must equal kCrossCols)
-constexpr int kRedWords = 8;     // reduced mode: up to 256 groups per launch
+constexpr int kRedWords = 8;     // OR mode: up to 256 groups per launch
 constexpr int kWarpsPerCta = 8;
 constexpr int kSortCells = 4096;  // Morton grid: 64 x 64 (2-D), 16^3 (3-D)
 
@@ -46,16 +52,24 @@ struct RowRec {  // one row edge, in Morton order
     int agent, orig;  // orig = row index in the caller's order
 };
 
-template <int D>
-struct ColTile {                 // 64 column edges in Morton order; sizeof is a multiple of 16
-    double mm[kCols][D];         // midpoints
-    struct SA { double h; int agent; int bit; } sa[kCols];  // half length (rounded up), agent
-                                 // id (-1 = padding), output bit (group or original column)
-    double ab[kCols][2 * D];     // q_from, q_to (exact path operands)
+struct ColB {  // broad-phase record of a column (16 bytes, one warp-uniform load)
+    float m[3];  // midpoint (z = 0 in 2-D)
+    float h;     // half length + agent radius, rounded up; +inf outside the FP32 domain
 };
 
 template <int D>
-struct TileHdr {  // bounding box of the tile's midpoints and its largest half length
+struct ColX {  // exact-stage record of a column (64 bytes in 2-D, 80 in 3-D)
+    double a[D], b[D];  // q_from, q_to
+    double inv;         // geom.cuh: seg_filter_inv
+    double rad;         // rads[agent]
+    int agent;          // -1 = padding
+    int bit;            // output slot: column index (bits), group (or / count / first)
+    int orig;           // column index in the caller's order (first mode)
+    int key;            // col_key (0 without keys)
+};
+
+template <int D>
+struct TileHdr {  // bounding box of the tile's midpoints and its largest reach
     double lo[D], hi[D], hmax, pad;
 };
 
@@ -181,60 +195,78 @@ k_cols_scatter(EdgeList<D> el, int64_t n, int32_t *__restrict__ cursor,
     }
 }
 
-// ---- column tiles: one warp builds one tile (2 columns per lane) and its header ------------
+// ---- column tiles: one warp builds one tile (one column per lane) and its header -----------
 template <int D>
-__global__ void __launch_bounds__(256)
-k_cross_prep_cols(EdgeList<D> el, int64_t n_cols, const int32_t *__restrict__ order,
-                  int group_size, ColTile<D> *__restrict__ tiles, TileHdr<D> *__restrict__ hdrs,
-                  int64_t n_tiles, const double *__restrict__ rads, int n_agents) {
+struct ColPrep {
+    EdgeList<D> el;
+    int64_t n_cols;
+    const int32_t *order;      // Morton order -> source index
+    int group_size;            // > 0: bit = src / group_size (unless col_group)
+    const int32_t *col_group;  // explicit group ids (may be NULL)
+    const int32_t *col_key;    // may be NULL
+    int64_t orig_base;         // added to src for ColX::orig
+    ColB *cb;
+    ColX<D> *cx;
+    TileHdr<D> *hdrs;
+    int64_t n_tiles;
+    const double *rads;
+    int n_agents;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
     const int lane = threadIdx.x & 31;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tiles;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < P.n_tiles;
          t += n_warps) {
-        ColTile<D> &T = tiles[t];
+        const int64_t c = t * kCols + lane;
+        ColB B;
+        ColX<D> X;
         double lo[D], hi[D], hmax = 0.0;
-#pragma unroll
-        for (int x = 0; x < D; ++x) {
-            lo[x] = 1e300;
-            hi[x] = -1e300;
-        }
         bool poison = false;  // a NaN midpoint must never be culled by the box test
-#pragma unroll
-        for (int half = 0; half < kCols / 32; ++half) {
-            const int k = half * 32 + lane;
-            const int64_t c = t * kCols + k;
-            if (c >= n_cols) {  // padding column: infinitely far, never selected
-#pragma unroll
-                for (int x = 0; x < D; ++x) T.mm[k][x] = 1e300;
-                T.sa[k].h = 0.0;
-                T.sa[k].agent = -1;
-                T.sa[k].bit = 0;
-#pragma unroll
-                for (int x = 0; x < 2 * D; ++x) T.ab[k][x] = 0.0;
-                continue;
-            }
-            const int64_t src = order[c];
-            double a[D], b[D];
-            const int j = el.get(src, a, b);
-            // reach of the column: half length + its agent's radius (an id outside the ctx is
-            // rejected by the exact stage; it must not be culled here)
-            const double h = half_len_up<D>(a, b) + (j >= 0 && j < n_agents ? __ldg(rads + j) : 1e300);
+        if (c >= P.n_cols) {  // padding column: far away, never selected
+            B.m[0] = B.m[1] = 1e15f;
+            B.m[2] = 0.0f;
+            B.h = 0.0f;
 #pragma unroll
             for (int x = 0; x < D; ++x) {
-                const double m = dmul(dadd(a[x], b[x]), 0.5);
-                T.mm[k][x] = m;
-                T.ab[k][x] = a[x];
-                T.ab[k][D + x] = b[x];
-                lo[x] = fmin(lo[x], m);
-                hi[x] = fmax(hi[x], m);
+                X.a[x] = X.b[x] = 0.0;
+                lo[x] = 1e300;
+                hi[x] = -1e300;
+            }
+            X.inv = -1.0;
+            X.rad = 0.0;
+            X.agent = -1;
+            X.bit = X.orig = X.key = 0;
+        } else {
+            const int64_t src = P.order[c];
+            const int j = P.el.get(src, X.a, X.b);
+            const bool known = j >= 0 && j < P.n_agents;
+            // reach of the column: half length + its agent's radius (an id outside the ctx is
+            // rejected by the exact stage; it must not be culled here)
+            const double rj = known ? __ldg(P.rads + j) : 1e300;
+            const double h = half_len_up<D>(X.a, X.b) + rj;
+            X.inv = seg_filter_inv<D>(X.a, X.b);
+            X.rad = known ? rj : 0.0;
+            X.agent = j;
+            X.bit = (int)(P.col_group ? __ldg(P.col_group + src)
+                                      : (P.group_size > 0 ? src / P.group_size : src));
+            X.orig = (int)(src + P.orig_base);
+            X.key = P.col_key ? __ldg(P.col_key + src) : 0;
+            B.m[2] = 0.0f;
+#pragma unroll
+            for (int x = 0; x < D; ++x) {
+                const double m = dmul(dadd(X.a[x], X.b[x]), 0.5);
+                B.m[x] = (float)m;
+                lo[x] = hi[x] = m;
                 poison |= !(m == m);
             }
+            B.h = (X.inv >= 0.0 && known) ? f32_up(h) : INFINITY;
             poison |= !(h == h);
-            hmax = fmax(hmax, h);
-            T.sa[k].h = h;
-            T.sa[k].agent = j;
-            T.sa[k].bit = (int)(group_size > 0 ? src / group_size : src);
+            hmax = h;
         }
+        P.cb[c] = B;
+        P.cx[c] = X;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -254,7 +286,7 @@ k_cross_prep_cols(EdgeList<D> el, int64_t n_cols, const int32_t *__restrict__ or
             }
             H.hmax = poison ? 1e300 : hmax;
             H.pad = 0.0;
-            hdrs[t] = H;
+            P.hdrs[t] = H;
         }
     }
 }
@@ -288,91 +320,156 @@ k_csr_expand_edges(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
 }
 
 // ---- the cross kernel -------------------------------------------------------------------------
-template <int D>
+enum { kModeBits = kCrossBits, kModeOr = kCrossOr, kModeCount = kCrossCount, kModeFirst = kCrossFirst };
+
+template <int D, int R>
 struct WarpSmem {
-    double row_ab[32][2 * D];
-    int row_agent[32];
-    int row_orig[32];
-    uint32_t obits[32][kRedWords];
-    uint16_t queue[32 * kCols];
+    double rab[R][2 * D];  // q_from, q_to of the warp tile's rows
+    double inv[R];         // seg_filter_inv
+    double rad[R];         // rads[agent]
+    int agent[R];
+    int orig[R];
+    int key[R];
+    uint32_t obits[R][kRedWords];
+    uint16_t queue[R * kCols];
+};
+
+template <int D>
+struct CrossArgs {
+    int64_t n_rows;
+    const RowRec<D> *rows;
+    int n_tiles;
+    const ColB *cb;
+    const ColX<D> *cx;
+    const TileHdr<D> *hdrs;
+    int words_per_row;   // or mode: words written per row
+    int64_t out_stride;  // 32-bit words (bits / or) or ints (count / first) per row
+    uint32_t *out;
+    const int32_t *row_key;  // NULL: every pair is admitted; else col_key > row_key[row]
+    int cbs;                 // cbs.jl:343-346: vertex test OR edge test with the column first
+    unsigned long long *stats;
+    unsigned int *work;
 };
 
 #ifndef MRMP_CROSS_MINB
 #define MRMP_CROSS_MINB 3
 #endif
 
-template <int D, bool REDUCED>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, MRMP_CROSS_MINB)
-k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, int n_tiles,
-                const ColTile<D> *__restrict__ tiles, const TileHdr<D> *__restrict__ hdrs,
-                int words_per_row, int64_t out_stride, uint32_t *__restrict__ out, double max_rad,
-                unsigned long long *__restrict__ stats, unsigned int *__restrict__ work) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem<D> &S = reinterpret_cast<WarpSmem<D> *>(smem_raw)[warp];
-    const double *rads = cv.blob + cv.crads_off;
+// The reference's own sequence of roundings for one pair (utils.jl:59-94): rare -- the filter
+// decides all but the pairs within 2^-20 of contact, near-parallel pairs and coordinates outside
+// [-2, 2].
+template <int D>
+__device__ __forceinline__ bool cross_exact(const double *p11, const double *p12,
+                                            const double *p21, const double *p22, double thr,
+                                            double t2, int has_tab) {
+    return has_tab ? segseg_lt<D, true>(p11, p12, p21, p22, thr, t2)
+                   : segseg_lt<D, false>(p11, p12, p21, p22, thr, 0.0);
+}
+
+// verdict of one (row, column) pair: filter first, reference arithmetic when undecided
+template <int D>
+__device__ __forceinline__ bool cross_pair_verdict(const CtxView &cv, const double *ra,
+                                                   const double *rb, double rinv, double rrad,
+                                                   int ri, const double *ca, const double *cb,
+                                                   double cinv, double crad, int cj, int cbs,
+                                                   bool &ran_exact) {
     const double *t2tab = cv.blob + cv.t2_pair_off;
-    const int N = cv.n_agents;
-    const int64_t n_wt = (n_rows + 31) >> 5;
-    unsigned long long n_tiles_read = 0, n_exact = 0;  // warp-uniform counters
+    const double thr = dadd(rrad, crad);  // rads[i] + rads[j], point.jl:11 (commutative)
+    ran_exact = false;
+    if (cbs) {
+        // collide(q_j_to, q_i_to, j, i)  cbs.jl:345 / point.jl:14-16
+        double v[D];
+#pragma unroll
+        for (int x = 0; x < D; ++x) v[x] = dsub(cb[x], rb[x]);
+        const double s = sumsq<D>(v);
+        const bool vertex = cv.has_pair_tab
+                                ? norm_lt<D, true>(v, s, thr, __ldg(t2tab + cj * cv.n_agents + ri))
+                                : norm_lt<D, false>(v, s, thr, 0.0);
+        if (vertex) return true;
+        // collide(q_j_from, q_j_to, q_i_from, q_i_to, j, i)  cbs.jl:346: the column is segment 1
+        const int f = segseg_filter<D>(ca, cb, ra, rb, cinv, rinv, thr);
+        if (f >= 0) return f != 0;
+        ran_exact = true;
+        return cross_exact<D>(ca, cb, ra, rb, thr,
+                              cv.has_pair_tab ? __ldg(t2tab + cj * cv.n_agents + ri) : 0.0,
+                              cv.has_pair_tab);
+    }
+    const int f = segseg_filter<D>(ra, rb, ca, cb, rinv, cinv, thr);
+    if (f >= 0) return f != 0;
+    ran_exact = true;
+    return cross_exact<D>(ra, rb, ca, cb, thr,
+                          cv.has_pair_tab ? __ldg(t2tab + ri * cv.n_agents + cj) : 0.0,
+                          cv.has_pair_tab);
+}
+
+template <int D, int MODE, int RPL>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, RPL == 1 ? MRMP_CROSS_MINB : 2)
+k_cross_collide(CtxView cv, CrossArgs<D> A) {
+    constexpr int R = 32 * RPL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem<D, R> &S = reinterpret_cast<WarpSmem<D, R> *>(smem_raw)[warp];
+    const double *rads = cv.blob + cv.crads_off;
+    const int64_t n_wt = (A.n_rows + R - 1) / R;
+    unsigned long long n_tiles_read = 0, n_filter = 0, n_exact = 0;  // per-warp / per-lane counters
 
     for (;;) {
         unsigned wt = 0;
-        if (lane == 0) wt = atomicAdd(work, 1u);
+        if (lane == 0) wt = atomicAdd(A.work, 1u);
         wt = __shfl_sync(0xffffffffu, wt, 0);
         if ((int64_t)wt >= n_wt) break;
-        const int64_t r = (int64_t)wt * 32 + lane;
-        const bool live = r < n_rows;
-        int i = -2, orig = 0;
-        double m1[D], R = 0.0;
-        double u1[D], h1 = 0.0, Rc = 0.0;  // unit direction, half length, reach without h1
-        double lo[D], hi[D];
+        RowB32 rb[RPL];
+        bool live[RPL];
+        double lo[D], hi[D], Rmax = 0.0;
+        bool poison = false;
 #pragma unroll
-        for (int x = 0; x < D; ++x) u1[x] = 0.0;
-        if (live) {
-            const RowRec<D> rec = rows[r];
-            i = rec.agent;
-            orig = rec.orig;
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                m1[x] = dmul(dadd(rec.a[x], rec.b[x]), 0.5);
-                S.row_ab[lane][x] = rec.a[x];
-                S.row_ab[lane][D + x] = rec.b[x];
-                lo[x] = hi[x] = m1[x];
-            }
-            // reach of this row: its radius + slack + its own half length (the column's
-            // radius and half length are in T.sa[c].h)
-            h1 = half_len_up<D>(rec.a, rec.b);
-            Rc = __ldg(rads + i) + kPad;
-            R = Rc + h1;
-            // direction of the row edge for the capsule bound (a zero-length edge keeps u1 = 0:
-            // its capsule is the disc of the midpoint bound)
-            double len2 = 0.0;
-#pragma unroll
-            for (int x = 0; x < D; ++x) len2 += (rec.b[x] - rec.a[x]) * (rec.b[x] - rec.a[x]);
-            if (len2 > 0.0 && len2 < 1e300) {
-                const double inv = 1.0 / sqrt(len2);
-#pragma unroll
-                for (int x = 0; x < D; ++x) u1[x] = (rec.b[x] - rec.a[x]) * inv;
-            }
-        } else {
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                m1[x] = 0.0;
-                lo[x] = 1e300;
-                hi[x] = -1e300;
-            }
+        for (int x = 0; x < D; ++x) {
+            lo[x] = 1e300;
+            hi[x] = -1e300;
         }
-        S.row_agent[lane] = i;
-        S.row_orig[lane] = orig;
-        if (REDUCED) {
 #pragma unroll
-            for (int w = 0; w < kRedWords; ++w) S.obits[lane][w] = 0u;
+        for (int k = 0; k < RPL; ++k) {
+            const int slot = k * 32 + lane;
+            const int64_t r = (int64_t)wt * R + slot;
+            live[k] = r < A.n_rows;
+            if (live[k]) {
+                const RowRec<D> rec = A.rows[r];
+                const bool known = rec.agent >= 0 && rec.agent < cv.n_agents;
+                const double ri = known ? __ldg(rads + rec.agent) : 1e300;
+                const double inv = seg_filter_inv<D>(rec.a, rec.b);
+                // reach of this row: its radius + slack (+ its own half length in the box test);
+                // the column's radius and half length are in its record
+                const double Rc = ri + kPad;
+                rb[k] = bound32_row<D>(rec.a, rec.b, Rc, inv >= 0.0 && known);
+                const double R64 = Rc + half_len_up<D>(rec.a, rec.b);
+                Rmax = fmax(Rmax, R64);
+                poison |= !(R64 == R64);
+#pragma unroll
+                for (int x = 0; x < D; ++x) {
+                    const double m = dmul(dadd(rec.a[x], rec.b[x]), 0.5);
+                    S.rab[slot][x] = rec.a[x];
+                    S.rab[slot][D + x] = rec.b[x];
+                    lo[x] = fmin(lo[x], m);
+                    hi[x] = fmax(hi[x], m);
+                    poison |= !(m == m);
+                }
+                S.inv[slot] = inv;
+                S.rad[slot] = known ? ri : 0.0;
+                S.agent[slot] = rec.agent;
+                S.orig[slot] = rec.orig;
+                S.key[slot] = A.row_key ? __ldg(A.row_key + rec.orig) : 0;
+            } else {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) rb[k].m[x] = rb[k].u[x] = 0.0f;
+                rb[k].h = rb[k].rc = 0.0f;
+                S.agent[slot] = -2;
+                S.orig[slot] = 0;
+            }
+            if (MODE == kModeOr) {
+#pragma unroll
+                for (int w = 0; w < kRedWords; ++w) S.obits[slot][w] = 0u;
+            }
         }
         // warp box and largest reach; a NaN row disables the box test for the whole warp tile
-        double Rmax = R;
-        bool poison = live && !(R == R);
-#pragma unroll
-        for (int x = 0; x < D; ++x) poison |= live && !(m1[x] == m1[x]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -385,11 +482,11 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
         poison = __any_sync(0xffffffffu, poison);
         __syncwarp();
 
-        for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+        for (int t0 = 0; t0 < A.n_tiles; t0 += 32) {
             // box-vs-box test of 32 column tiles at once
             bool near = false;
-            if (t0 + lane < n_tiles) {
-                const TileHdr<D> H = hdrs[t0 + lane];
+            if (t0 + lane < A.n_tiles) {
+                const TileHdr<D> H = A.hdrs[t0 + lane];
                 double d2 = 0.0;
 #pragma unroll
                 for (int x = 0; x < D; ++x) {
@@ -403,52 +500,40 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
             while (tmask) {
                 const int t = t0 + __ffs(tmask) - 1;
                 tmask &= tmask - 1;
-                const ColTile<D> &T = tiles[t];
-                // ---- broad phase: this lane's row against the 64 columns of the tile
-                unsigned long long mask = 0ull;
+                const float4 *cbp = reinterpret_cast<const float4 *>(A.cb + (int64_t)t * kCols);
+                const ColX<D> *cxp = A.cx + (int64_t)t * kCols;
+                // ---- broad phase (FP32): this lane's rows against the 32 columns of the tile
+                uint32_t mask[RPL];
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) mask[k] = 0u;
 #pragma unroll 8
                 for (int c = 0; c < kCols; ++c) {
-                    // capsule bound: the column's midpoint against the row SEGMENT --
-                    // dist(seg_r, seg_c) >= dist(m_c, seg_r) - h_c, and
-                    // dist(m_c, seg_r)^2 = |w_perp|^2 + max(|w_par| - h_r, 0)^2 with w = m_c - m_r
-                    double w2, par;
-                    if constexpr (D == 2) {
-                        const double2 mm = __ldg(reinterpret_cast<const double2 *>(&T.mm[c][0]));
-                        const double wx = mm.x - m1[0], wy = mm.y - m1[1];
-                        w2 = wx * wx + wy * wy;
-                        par = wx * u1[0] + wy * u1[1];
-                    } else {
-                        w2 = 0.0;
-                        par = 0.0;
+                    const float4 q = __ldg(cbp + c);
 #pragma unroll
-                        for (int x = 0; x < D; ++x) {
-                            const double w = __ldg(&T.mm[c][x]) - m1[x];
-                            w2 += w * w;
-                            par += w * u1[x];
-                        }
-                    }
-                    const double ex = fmax(fabs(par) - h1, 0.0);
-                    const double d2 = (w2 - par * par) + ex * ex;
-                    const double reach = Rc + __ldg(&T.sa[c].h);
-                    const bool far = d2 > reach * reach;
-                    mask |= (unsigned long long)(far ? 0 : 1) << c;
-                }
-                if (!live) mask = 0ull;
-                if (REDUCED) {
-                    // the output is an OR over each column group: a pair whose bit this row
-                    // has already set (by an earlier tile) cannot change it -- drop it here,
-                    // before the compaction, so the exact stage stays dense
-                    unsigned long long m2 = mask;
-                    while (m2) {
-                        const int c = __ffsll((long long)m2) - 1;
-                        m2 &= m2 - 1;
-                        const int bit = __ldg(&T.sa[c].bit);
-                        if ((S.obits[lane][bit >> 5] >> (bit & 31)) & 1u) mask &= ~(1ull << c);
-                    }
+                    for (int k = 0; k < RPL; ++k)
+                        mask[k] |= (bound32_far<D>(rb[k], q.x, q.y, q.z, q.w) ? 0u : 1u) << c;
                 }
                 ++n_tiles_read;
+                int cnt = 0;
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) {
+                    if (!live[k]) mask[k] = 0u;
+                    if (MODE == kModeOr) {
+                        // the output is an OR over each column group: a pair whose bit this row
+                        // has already set (by an earlier tile) cannot change it -- drop it here,
+                        // before the compaction, so the exact stage stays dense
+                        const int slot = k * 32 + lane;
+                        uint32_t m2 = mask[k];
+                        while (m2) {
+                            const int c = __ffs(m2) - 1;
+                            m2 &= m2 - 1;
+                            const int bit = __ldg(&cxp[c].bit);
+                            if ((S.obits[slot][bit >> 5] >> (bit & 31)) & 1u) mask[k] &= ~(1u << c);
+                        }
+                    }
+                    cnt += __popc(mask[k]);
+                }
                 // ---- compaction into the warp queue
-                const int cnt = __popcll(mask);
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -458,66 +543,114 @@ k_cross_collide(CtxView cv, int64_t n_rows, const RowRec<D> *__restrict__ rows, 
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total == 0) continue;
                 int base = incl - cnt;
-                while (mask) {
-                    const int c = __ffsll((long long)mask) - 1;
-                    mask &= mask - 1;
-                    S.queue[base++] = (uint16_t)((lane << 6) | c);
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) {
+                    uint32_t m2 = mask[k];
+                    while (m2) {
+                        const int c = __ffs(m2) - 1;
+                        m2 &= m2 - 1;
+                        S.queue[base++] = (uint16_t)(((k * 32 + lane) << 5) | c);
+                    }
                 }
                 __syncwarp();
-                n_exact += total;
-                // ---- exact reference arithmetic on dense lanes
+                // ---- verdict filter / reference arithmetic on dense lanes
                 for (int e = lane; e < total; e += 32) {
                     const int ent = S.queue[e];
-                    const int rr = ent >> 6, cc = ent & 63;
-                    const int ri = S.row_agent[rr], cj = __ldg(&T.sa[cc].agent);
+                    const int rr = ent >> 5, cc = ent & 31;
+                    const ColX<D> &X = cxp[cc];
+                    const int4 ids = __ldg(reinterpret_cast<const int4 *>(&X.agent));
+                    const int ri = S.agent[rr], cj = ids.x;
                     if (cj < 0 || cj == ri) continue;  // padding / same agent: never a conflict
+                    if (ri < 0 || ri >= cv.n_agents || cj >= cv.n_agents) continue;
+                    if (A.row_key && !(ids.w > S.key[rr])) continue;
                     double ca[D], cb[D];
+                    if constexpr (D == 2) {
+                        const double2 a2 = __ldg(reinterpret_cast<const double2 *>(&X.a[0]));
+                        const double2 b2 = __ldg(reinterpret_cast<const double2 *>(&X.b[0]));
+                        ca[0] = a2.x, ca[1] = a2.y, cb[0] = b2.x, cb[1] = b2.y;
+                    } else {
 #pragma unroll
-                    for (int x = 0; x < D; ++x) {
-                        ca[x] = __ldg(&T.ab[cc][x]);
-                        cb[x] = __ldg(&T.ab[cc][D + x]);
+                        for (int x = 0; x < D; ++x) {
+                            ca[x] = __ldg(&X.a[x]);
+                            cb[x] = __ldg(&X.b[x]);
+                        }
                     }
-                    const double thr = dadd(__ldg(rads + ri), __ldg(rads + cj));  // point.jl:11
-                    bool hit;
-                    if (cv.has_pair_tab)
-                        hit = segseg_lt<D, true>(&S.row_ab[rr][0], &S.row_ab[rr][D], ca, cb, thr,
-                                                 __ldg(t2tab + ri * N + cj));
-                    else
-                        hit = segseg_lt<D, false>(&S.row_ab[rr][0], &S.row_ab[rr][D], ca, cb, thr,
-                                                  0.0);
+                    const double2 ir = __ldg(reinterpret_cast<const double2 *>(&X.inv));
+                    bool ran_exact;
+                    const bool hit = cross_pair_verdict<D>(cv, &S.rab[rr][0], &S.rab[rr][D],
+                                                           S.inv[rr], S.rad[rr], ri, ca, cb, ir.x,
+                                                           ir.y, cj, A.cbs, ran_exact);
+                    ++n_filter;
+                    n_exact += ran_exact ? 1 : 0;
                     if (hit) {
-                        const int bit = __ldg(&T.sa[cc].bit);
-                        if (REDUCED)
+                        const int bit = ids.y;
+                        if (MODE == kModeOr)
                             atomicOr(&S.obits[rr][bit >> 5], 1u << (bit & 31));
-                        else
-                            atomicOr(out + (int64_t)S.row_orig[rr] * out_stride + (bit >> 5),
+                        else if (MODE == kModeBits)
+                            atomicOr(A.out + (int64_t)S.orig[rr] * A.out_stride + (bit >> 5),
                                      1u << (bit & 31));
+                        else if (MODE == kModeCount)
+                            atomicAdd(reinterpret_cast<int *>(A.out) +
+                                          (int64_t)S.orig[rr] * A.out_stride + bit, 1);
+                        else
+                            atomicMin(reinterpret_cast<int *>(A.out) +
+                                          (int64_t)S.orig[rr] * A.out_stride + bit, ids.z);
                     }
                 }
                 __syncwarp();
             }
         }
-        if (REDUCED && live) {
+        if (MODE == kModeOr) {
             // every word of the row is written exactly once (the output may be mapped host
             // memory: plain stores, two words per transaction where the layout allows)
-            uint32_t *dst = out + (int64_t)orig * out_stride;
-            if ((words_per_row & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-                for (int w = 0; w < words_per_row; w += 2)
-                    *reinterpret_cast<uint2 *>(dst + w) = make_uint2(S.obits[lane][w], S.obits[lane][w + 1]);
-            } else {
-                for (int w = 0; w < words_per_row; ++w) dst[w] = S.obits[lane][w];
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+                if (!live[k]) continue;
+                const int slot = k * 32 + lane;
+                uint32_t *dst = A.out + (int64_t)S.orig[slot] * A.out_stride;
+                if ((A.words_per_row & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                    for (int w = 0; w < A.words_per_row; w += 2)
+                        *reinterpret_cast<uint2 *>(dst + w) =
+                            make_uint2(S.obits[slot][w], S.obits[slot][w + 1]);
+                } else {
+                    for (int w = 0; w < A.words_per_row; ++w) dst[w] = S.obits[slot][w];
+                }
             }
         }
         __syncwarp();
     }
-    if (stats && lane == 0) {
-        if (n_exact) atomicAdd(stats, n_exact);                          // pairs on the exact path
-        if (n_tiles_read) atomicAdd(stats + 2, n_tiles_read * 32ull * kCols);  // pairs bound-tested
+    if (A.stats) {
+        // [0] pairs that ran the reference arithmetic, [2] pairs bound-tested, [3] pairs that ran
+        // the verdict filter
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_filter += __shfl_xor_sync(0xffffffffu, n_filter, o);
+            n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+        }
+        if (lane == 0) {
+            if (n_exact) atomicAdd(A.stats, n_exact);
+            if (n_tiles_read) atomicAdd(A.stats + 2, n_tiles_read * (unsigned long long)(R * kCols));
+            if (n_filter) atomicAdd(A.stats + 3, n_filter);
+        }
     }
 }
 
+// first mode: rows without a hit hold INT_MAX after the kernel -> -1
+__global__ void __launch_bounds__(256) k_first_finalize(int32_t *__restrict__ out, int64_t n) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x)
+        if (out[k] == 0x7fffffff) out[k] = -1;
+}
+__global__ void __launch_bounds__(256) k_fill_i32(int32_t *__restrict__ out, int64_t n, int32_t v) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = v;
+}
+
 // ---- launchers --------------------------------------------------------------------------------
-size_t cross_tile_bytes(int d) { return d == 2 ? sizeof(ColTile<2>) : sizeof(ColTile<3>); }
+size_t cross_tile_bytes(int d) {
+    return kCols * (sizeof(ColB) + (d == 2 ? sizeof(ColX<2>) : sizeof(ColX<3>)));
+}
 size_t cross_hdr_bytes(int d) { return d == 2 ? sizeof(TileHdr<2>) : sizeof(TileHdr<3>); }
 size_t cross_row_bytes(int d) { return d == 2 ? sizeof(RowRec<2>) : sizeof(RowRec<3>); }
 
@@ -558,8 +691,8 @@ cudaError_t launch_cross_sort_rows(const CtxView &cv, const LaunchCfg &lc, int64
 
 template <int D>
 static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const EdgeList<D> &el,
-                               int64_t n_cols, int group_size, int32_t *cells, int32_t *order,
-                               void *tiles, void *hdrs) {
+                               int64_t n_cols, const CrossCols &cc, int32_t *cells,
+                               int32_t *order, void *tiles, void *hdrs) {
     const int64_t n_tiles = (n_cols + kCols - 1) / kCols;
     cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * kSortCells, lc.stream);
     if (e != cudaSuccess) return e;
@@ -567,9 +700,21 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
     k_cell_hist<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells);
     k_cell_scan<<<1, 1024, 0, lc.stream>>>(cells);
     k_cols_scatter<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells, order);
-    k_cross_prep_cols<D><<<grid_for_n(lc, n_tiles * 32, 256), 256, 0, lc.stream>>>(
-        el, n_cols, order, group_size, (ColTile<D> *)tiles, (TileHdr<D> *)hdrs, n_tiles,
-        cv.blob + cv.crads_off, cv.n_agents);
+    ColPrep<D> P;
+    P.el = el;
+    P.n_cols = n_cols;
+    P.order = order;
+    P.group_size = cc.group_size;
+    P.col_group = cc.col_group;
+    P.col_key = cc.col_key;
+    P.orig_base = cc.orig_base;
+    P.cb = (ColB *)tiles;
+    P.cx = (ColX<D> *)((unsigned char *)tiles + sizeof(ColB) * kCols * (size_t)n_tiles);
+    P.hdrs = (TileHdr<D> *)hdrs;
+    P.n_tiles = n_tiles;
+    P.rads = cv.blob + cv.crads_off;
+    P.n_agents = cv.n_agents;
+    k_cross_prep_cols<D><<<grid_for_n(lc, n_tiles * 32, 256), 256, 0, lc.stream>>>(P);
     count_launch(4);
     return cudaGetLastError();
 }
@@ -578,16 +723,16 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
 cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64_t n_cols,
                                    const int32_t *agent, const double *qf, const double *qt,
                                    const int32_t *vf, const int32_t *vt, const double *nodes,
-                                   int agent0, int nv_stride, int group_size, int32_t *cells,
+                                   int agent0, int nv_stride, const CrossCols &cc, int32_t *cells,
                                    int32_t *order, void *tiles, void *hdrs) {
     if (n_cols <= 0) return cudaSuccess;
     if (n_cols >= ((int64_t)1 << 31)) return cudaErrorInvalidValue;
     if (cv.model == 0)
         return prep_cols_t<2>(cv, lc, EdgeList<2>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
-                              n_cols, group_size, cells, order, tiles, hdrs);
+                              n_cols, cc, cells, order, tiles, hdrs);
     if (cv.model == 1)
         return prep_cols_t<3>(cv, lc, EdgeList<3>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
-                              n_cols, group_size, cells, order, tiles, hdrs);
+                              n_cols, cc, cells, order, tiles, hdrs);
     return cudaErrorNotSupported;
 }
 
@@ -614,59 +759,96 @@ cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int6
     return cudaGetLastError();
 }
 
-template <int D>
-static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
-                                  const void *rows, int64_t n_cols, const void *tiles,
-                                  const void *hdrs, int group_size, int words_per_row,
-                                  int64_t out_stride, uint32_t *out, double max_rad,
-                                  unsigned long long *stats, unsigned int *work) {
-    const int n_tiles = (int)((n_cols + kCols - 1) / kCols);
-    const int smem = (int)sizeof(WarpSmem<D>) * kWarpsPerCta;
+// rows per lane of the OR-mode kernel (the bench shape): 1 or 2; MRMP_CROSS_RPL overrides
+static int cross_rpl() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("MRMP_CROSS_RPL");
+        v = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : MRMP_CROSS_RPL_DEFAULT;
+    }
+    return v;
+}
+
+template <int D, int MODE, int RPL>
+static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const CrossArgs<D> &A) {
+    constexpr int R = 32 * RPL;
+    const int smem = (int)sizeof(WarpSmem<D, R>) * kWarpsPerCta;
     int per_sm = (220 * 1024) / smem;
-    if (per_sm > MRMP_CROSS_MINB) per_sm = MRMP_CROSS_MINB;  // register-limited residency
+    const int minb = RPL == 1 ? MRMP_CROSS_MINB : 2;
+    if (per_sm > minb) per_sm = minb;  // register-limited residency
     if (per_sm < 1) per_sm = 1;
-    const int64_t n_wt = (n_rows + 31) / 32;
+    const int64_t n_wt = (A.n_rows + R - 1) / R;
     int64_t want = (n_wt + kWarpsPerCta - 1) / kWarpsPerCta;
     const int64_t cap = (int64_t)lc.sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned int), lc.stream);
+    cudaError_t e = cudaFuncSetAttribute(k_cross_collide<D, MODE, RPL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    if (group_size > 0) {
-        e = cudaFuncSetAttribute(k_cross_collide<D, true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        k_cross_collide<D, true><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(
-            cv, n_rows, (const RowRec<D> *)rows, n_tiles, (const ColTile<D> *)tiles,
-            (const TileHdr<D> *)hdrs, words_per_row, out_stride, out, max_rad, stats, work);
-    } else {
-        e = cudaFuncSetAttribute(k_cross_collide<D, false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        k_cross_collide<D, false><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(
-            cv, n_rows, (const RowRec<D> *)rows, n_tiles, (const ColTile<D> *)tiles,
-            (const TileHdr<D> *)hdrs, words_per_row, out_stride, out, max_rad, stats, work);
-    }
+    k_cross_collide<D, MODE, RPL><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(cv, A);
     count_launch();
     return cudaGetLastError();
 }
 
-// group_size == 0: full bit matrix (words_per_row = ceil(n_cols/32), `out` must be zeroed by the
-// caller: hits are OR-ed in); otherwise OR-reduced over consecutive groups of group_size
-// columns (at most 32*kRedWords groups per launch, every word of a row is written).
+template <int D>
+static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
+                                  const void *rows, int64_t n_cols, const void *tiles,
+                                  const void *hdrs, const CrossOut &co, unsigned long long *stats,
+                                  unsigned int *work) {
+    const int n_tiles = (int)((n_cols + kCols - 1) / kCols);
+    CrossArgs<D> A;
+    A.n_rows = n_rows;
+    A.rows = (const RowRec<D> *)rows;
+    A.n_tiles = n_tiles;
+    A.cb = (const ColB *)tiles;
+    A.cx = (const ColX<D> *)((const unsigned char *)tiles + sizeof(ColB) * kCols * (size_t)n_tiles);
+    A.hdrs = (const TileHdr<D> *)hdrs;
+    A.words_per_row = co.words_per_row;
+    A.out_stride = co.out_stride;
+    A.out = co.out;
+    A.row_key = co.row_key;
+    A.cbs = co.cbs;
+    A.stats = stats;
+    A.work = work;
+    cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned int), lc.stream);
+    if (e != cudaSuccess) return e;
+    switch (co.mode) {
+    case kModeOr:
+        return cross_rpl() == 2 ? launch_cross_v<D, kModeOr, 2>(cv, lc, A)
+                                : launch_cross_v<D, kModeOr, 1>(cv, lc, A);
+    case kModeBits: return launch_cross_v<D, kModeBits, 1>(cv, lc, A);
+    case kModeCount: return launch_cross_v<D, kModeCount, 1>(cv, lc, A);
+    case kModeFirst: return launch_cross_v<D, kModeFirst, 1>(cv, lc, A);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// mode bits: `out` must be zeroed by the caller (hits are OR-ed in); or: at most 32*kRedWords
+// groups per launch, every word of a row is written; count: zeroed int32 [n_rows][out_stride];
+// first: int32 [n_rows][out_stride] filled with INT_MAX (launch_cross_first_init / _finalize).
 cudaError_t launch_cross_collide(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
                                  const void *rows, int64_t n_cols, const void *tiles,
-                                 const void *hdrs, int group_size, int words_per_row,
-                                 int64_t out_stride, uint32_t *out, double max_rad,
-                                 unsigned long long *stats, unsigned int *work) {
+                                 const void *hdrs, const CrossOut &co, unsigned long long *stats,
+                                 unsigned int *work) {
     if (n_rows <= 0 || n_cols <= 0) return cudaSuccess;
-    if (group_size > 0 && words_per_row > kRedWords) return cudaErrorInvalidValue;
+    if (co.mode == kModeOr && co.words_per_row > kRedWords) return cudaErrorInvalidValue;
     if (cv.model == 0)
-        return launch_cross_t<2>(cv, lc, n_rows, rows, n_cols, tiles, hdrs, group_size,
-                                 words_per_row, out_stride, out, max_rad, stats, work);
+        return launch_cross_t<2>(cv, lc, n_rows, rows, n_cols, tiles, hdrs, co, stats, work);
     if (cv.model == 1)
-        return launch_cross_t<3>(cv, lc, n_rows, rows, n_cols, tiles, hdrs, group_size,
-                                 words_per_row, out_stride, out, max_rad, stats, work);
+        return launch_cross_t<3>(cv, lc, n_rows, rows, n_cols, tiles, hdrs, co, stats, work);
     return cudaErrorNotSupported;
+}
+
+cudaError_t launch_fill_i32(const LaunchCfg &lc, int32_t *out, int64_t n, int32_t v) {
+    if (n <= 0) return cudaSuccess;
+    k_fill_i32<<<grid_for_n(lc, n, 256 * 4), 256, 0, lc.stream>>>(out, n, v);
+    count_launch();
+    return cudaGetLastError();
+}
+cudaError_t launch_cross_first_finalize(const LaunchCfg &lc, int32_t *out, int64_t n) {
+    if (n <= 0) return cudaSuccess;
+    k_first_finalize<<<grid_for_n(lc, n, 256 * 4), 256, 0, lc.stream>>>(out, n);
+    count_launch();
+    return cudaGetLastError();
 }
 
 }  // namespace mrmp

@@ -102,6 +102,21 @@ struct LaunchCfg {
 
 void count_launch(int n = 1);
 
+// one cross-product request (abi.cu: cross_run_dev): output mode and how columns map to slots
+struct CrossReq {
+    int mode;                  // kCrossBits / kCrossOr / kCrossCount / kCrossFirst
+    int group_size;            // > 0: group = column / group_size (unless col_group)
+    int n_groups;              // count / first: output slots per row
+    const int32_t *col_group;  // device arrays or NULL
+    const int32_t *col_key;
+    const int32_t *row_key;    // only pairs with col_key[c] > row_key[r] are tested
+    int cbs;                   // cbs.jl:343-346: vertex test OR edge test, column agent first
+};
+constexpr int kCrossBits = 0;   // full bit matrix (hits OR-ed into a zeroed output)
+constexpr int kCrossOr = 1;     // OR over column groups, one bit per (row, group)
+constexpr int kCrossCount = 2;  // int32 count per (row, group)
+constexpr int kCrossFirst = 3;  // int32 smallest colliding column index per (row, group), -1 = none
+
 // kernels_point.cu
 cudaError_t launch_connect_points(const CtxView &cv, const LaunchCfg &lc, int64_t n,
                                   const int32_t *agent, const double *q, uint8_t *out);
@@ -153,7 +168,7 @@ cudaError_t launch_arm_collide_cross(const CtxView &cv, const LaunchCfg &lc, int
                                      const int32_t *col_agent, const double *col_from,
                                      const double *col_to, const int32_t *col_vf,
                                      const int32_t *col_vt, const double *nodes, int agent0,
-                                     int nv_stride, int group_size, int words_per_row,
+                                     int nv_stride, const CrossReq &rq, int out_stride,
                                      uint32_t *out, unsigned long long *stats);
 // first_scratch: n_cfg words of device scratch
 cudaError_t launch_arm_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64_t n_cfg,
@@ -189,7 +204,7 @@ cudaError_t launch_chain_collide_cross(const CtxView &cv, const LaunchCfg &lc, i
                                      const int32_t *col_agent, const double *col_from,
                                      const double *col_to, const int32_t *col_vf,
                                      const int32_t *col_vt, const double *nodes, int agent0,
-                                     int nv_stride, int group_size, int words_per_row,
+                                     int nv_stride, const CrossReq &rq, int out_stride,
                                      uint32_t *out, unsigned long long *stats);
 // first_scratch: n_cfg words of device scratch
 cudaError_t launch_chain_collide_configs(const CtxView &cv, const LaunchCfg &lc, int64_t n_cfg,
@@ -301,7 +316,21 @@ cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, cons
 
 // kernels_cross.cu
 constexpr int kCrossCols = 32;        // columns per tile
-constexpr int kCrossMaxGroups = 256;  // reduced mode: groups per launch
+constexpr int kCrossMaxGroups = 256;  // OR mode: groups per launch
+struct CrossCols {              // how the columns map to output slots
+    int group_size;             // > 0: group = column / group_size (unless col_group)
+    const int32_t *col_group;   // explicit group id per column (device) or NULL
+    const int32_t *col_key;     // per-column key (device) or NULL
+    int64_t orig_base;          // index of the first column of this launch in the caller's order
+};
+struct CrossOut {
+    int mode;
+    int words_per_row;        // OR mode: words written per row
+    int64_t out_stride;       // 32-bit words (bits / or) or ints (count / first) per row
+    uint32_t *out;
+    const int32_t *row_key;   // NULL, or: only pairs with col_key > row_key[row] are tested
+    int cbs;                  // cbs.jl:343-346 pair test (vertex OR edge, column first)
+};
 size_t cross_tile_bytes(int d);
 size_t cross_hdr_bytes(int d);
 size_t cross_row_bytes(int d);
@@ -313,7 +342,7 @@ cudaError_t launch_cross_sort_rows(const CtxView &cv, const LaunchCfg &lc, int64
 cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64_t n_cols,
                                    const int32_t *agent, const double *qf, const double *qt,
                                    const int32_t *vf, const int32_t *vt, const double *nodes,
-                                   int agent0, int nv_stride, int group_size, int32_t *cells,
+                                   int agent0, int nv_stride, const CrossCols &cc, int32_t *cells,
                                    int32_t *order, void *tiles, void *hdrs);
 cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                     int nv, int agent0, const int32_t *row_ptr,
@@ -321,8 +350,9 @@ cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int6
                                     double *e_from, double *e_to);
 cudaError_t launch_cross_collide(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows,
                                  const void *rows, int64_t n_cols, const void *tiles,
-                                 const void *hdrs, int group_size, int words_per_row,
-                                 int64_t out_stride, uint32_t *out, double max_rad,
-                                 unsigned long long *stats, unsigned int *work);
+                                 const void *hdrs, const CrossOut &co, unsigned long long *stats,
+                                 unsigned int *work);
+cudaError_t launch_fill_i32(const LaunchCfg &lc, int32_t *out, int64_t n, int32_t v);
+cudaError_t launch_cross_first_finalize(const LaunchCfg &lc, int32_t *out, int64_t n);
 
 }  // namespace mrmp

@@ -52,18 +52,6 @@ struct ColSeg {
 constexpr double kPad = 9.5367431640625e-07;  // 2^-20
 constexpr double kCullCoordMax = 1048576.0;   // 2^20
 
-// half length of an edge, rounded up
-template <int D>
-__device__ __forceinline__ double half_len_up(const double *a, const double *b) {
-    double v[D];
-#pragma unroll
-    for (int x = 0; x < D; ++x) v[x] = b[x] - a[x];
-    double s = v[0] * v[0];
-#pragma unroll
-    for (int x = 1; x < D; ++x) s += v[x] * v[x];
-    return 0.5 * sqrt(s) * (1.0 + 1e-9);
-}
-
 template <int D>
 __device__ __forceinline__ void load_state(const double *__restrict__ base, int64_t k, double *q) {
     if constexpr (D == 2) {

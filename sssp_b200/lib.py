@@ -15,6 +15,7 @@ from . import build as _build
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 MODEL_POINT2D, MODEL_POINT3D, MODEL_ARM22 = 0, 1, 2
 MODEL_LINE2D, MODEL_SNAKE2D, MODEL_ARM33, MODEL_CAPSULE3D = 3, 4, 5, 6
+CROSS_COUNT, CROSS_FIRST, CROSS_FLAG_CBS = 2, 3, 1
 STATE_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2, MODEL_LINE2D: 3, MODEL_SNAKE2D: 6,
              MODEL_ARM33: 6, MODEL_CAPSULE3D: 6}
 WORK_DIM = {MODEL_POINT2D: 2, MODEL_POINT3D: 3, MODEL_ARM22: 2, MODEL_LINE2D: 2, MODEL_SNAKE2D: 2,
@@ -88,6 +89,11 @@ _SIGS = {
                                      _vp]),
     "mrmp_collide_cross_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp,
                                          C.c_int, _vp, _vp]),
+    "mrmp_collide_cross_reduce": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp,
+                                            _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "mrmp_collide_cross_reduce_dev": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp,
+                                                _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                _vp, _vp]),
     "mrmp_roadmaps_edge_conflicts": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
                                                C.c_int64]),
     "mrmp_roadmaps_edge_conflicts_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
@@ -129,11 +135,14 @@ def load(path: str | None = None) -> C.CDLL:
         return _LIB
     p = path or os.environ.get("MRMP_B200_LIB") or _build.LIB_PATH
     if path is None and "MRMP_B200_LIB" not in os.environ:
-        try:
-            p = _build.build()
-        except Exception as e:  # nvcc missing on the GPU box: use the shipped .so
-            if not os.path.exists(p):
-                raise MRMPError(ERR_CUDA, f"libmrmp_b200.so missing and cannot be built: {e}")
+        if _build._stale():
+            # Sources differ from what the shipped .so was built from: rebuild or fail loudly.
+            # A stale library would be called through argtypes it does not have.
+            try:
+                p = _build.build()
+            except Exception as e:
+                raise MRMPError(ERR_CUDA, "libmrmp_b200.so is missing or older than csrc/ and "
+                                          f"cannot be rebuilt: {e}")
     lib = C.CDLL(p)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)

@@ -62,6 +62,49 @@ void probe_segpt_batch(int64_t n, int d, const double *a, const double *b, const
     }
 }
 
+// verdict filter of the conflict-table kernel (geom.cuh: segseg_filter): out[k] = 1 / 0 / -1
+// (undecided); exact[k] = segseg_lt.  thr per pair.
+void probe_segseg_filter_batch(int64_t n, int d, const double *a, const double *b, const double *c,
+                               const double *e, const double *thr, const double *T2, int8_t *out,
+                               uint8_t *exact) {
+    for (int64_t k = 0; k < n; ++k) {
+        if (d == 2) {
+            const double i1 = seg_filter_inv<2>(a + 2 * k, b + 2 * k),
+                         i2 = seg_filter_inv<2>(c + 2 * k, e + 2 * k);
+            out[k] = (int8_t)segseg_filter<2>(a + 2 * k, b + 2 * k, c + 2 * k, e + 2 * k, i1, i2, thr[k]);
+            exact[k] = segseg_lt<2, true>(a + 2 * k, b + 2 * k, c + 2 * k, e + 2 * k, thr[k], T2[k]);
+        } else {
+            const double i1 = seg_filter_inv<3>(a + 3 * k, b + 3 * k),
+                         i2 = seg_filter_inv<3>(c + 3 * k, e + 3 * k);
+            out[k] = (int8_t)segseg_filter<3>(a + 3 * k, b + 3 * k, c + 3 * k, e + 3 * k, i1, i2, thr[k]);
+            exact[k] = segseg_lt<3, true>(a + 3 * k, b + 3 * k, c + 3 * k, e + 3 * k, thr[k], T2[k]);
+        }
+    }
+}
+
+// FP32 broad phase of the conflict-table kernel (geom.cuh: bound32_far) exactly as the kernel
+// feeds it: out[k] = 1 when the pair is rejected as "certainly no collision"
+void probe_bound32_batch(int64_t n, int d, const double *a, const double *b, const double *c,
+                         const double *e, const double *ri, const double *rj, uint8_t *out) {
+    const double pad = 9.5367431640625e-07;
+    for (int64_t k = 0; k < n; ++k) {
+        if (d == 2) {
+            const double *pa = a + 2 * k, *pb = b + 2 * k, *pc = c + 2 * k, *pe = e + 2 * k;
+            const RowB32 r = bound32_row<2>(pa, pb, ri[k] + pad, seg_filter_inv<2>(pa, pb) >= 0.0);
+            const bool cin = seg_filter_inv<2>(pc, pe) >= 0.0;
+            const float ch = cin ? f32_up(half_len_up<2>(pc, pe) + rj[k]) : INFINITY;
+            out[k] = bound32_far<2>(r, (float)((pc[0] + pe[0]) * 0.5), (float)((pc[1] + pe[1]) * 0.5), 0.0f, ch);
+        } else {
+            const double *pa = a + 3 * k, *pb = b + 3 * k, *pc = c + 3 * k, *pe = e + 3 * k;
+            const RowB32 r = bound32_row<3>(pa, pb, ri[k] + pad, seg_filter_inv<3>(pa, pb) >= 0.0);
+            const bool cin = seg_filter_inv<3>(pc, pe) >= 0.0;
+            const float ch = cin ? f32_up(half_len_up<3>(pc, pe) + rj[k]) : INFINITY;
+            out[k] = bound32_far<3>(r, (float)((pc[0] + pe[0]) * 0.5), (float)((pc[1] + pe[1]) * 0.5),
+                                    (float)((pc[2] + pe[2]) * 0.5), ch);
+        }
+    }
+}
+
 // vcat(collect(0:step:D)/D, 1.0): writes min(n, cap) values, returns n
 int64_t probe_step_schedule(double step, double D, double *out, int64_t cap) {
     const ArmSched s = arm_schedule(step_rat(step), step, D);

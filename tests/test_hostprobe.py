@@ -57,6 +57,8 @@ def probe():
     vp = C.c_void_p
     lib.probe_segseg_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
     lib.probe_segpt_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    lib.probe_segseg_filter_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.probe_bound32_batch.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.probe_step_schedule.restype = C.c_int64
     lib.probe_step_schedule.argtypes = [C.c_double, C.c_double, _dp, C.c_int64]
     P = C.POINTER(ProbeArm)
@@ -310,3 +312,158 @@ def test_chain_models_match_oracle(probe, model, max_dist):
     assert 0 < tally["free"] < n and 0 < tally["hit4"] < n and 0 < tally["hit6"] < 150, tally
     if math.isnan(max_dist):
         assert 0 < tally["edge"] < n, tally
+
+
+def _filter_cases(rng, d, n):
+    """Segment pairs that stress the verdict filter: plain near pairs, contact offsets around the
+    hand-over band, parallel / nearly parallel / collinear / identical / reversed segments,
+    zero-length segments (stay moves), crossings at every angle, tiny segments, coordinates at and
+    beyond the domain edge, non-finite values."""
+    from helpers import near_threshold_pairs
+    N = 12
+    rads = np.concatenate([[1e-6, 2e-6, 5e-4], rng.uniform(0.002, 0.1, N - 3)])
+    ai = rng.integers(0, N, n)
+    aj = (ai + 1 + rng.integers(0, N - 1, n)) % N
+    a, b, c, e = near_threshold_pairs(rng, n, rads, ai, aj, d)
+    k = n // 8
+    # plain near pairs
+    a[:k] = rng.random((k, d))
+    b[:k] = a[:k] + rng.normal(size=(k, d)) * 0.05
+    c[:k] = a[:k] + rng.normal(size=(k, d)) * 0.05
+    e[:k] = c[:k] + rng.normal(size=(k, d)) * 0.05
+    # nearly parallel at angles 1e-12 .. 1e-1, offset around the threshold
+    s = slice(k, 2 * k)
+    thr = (rads[ai] + rads[aj])[s]
+    u = rng.normal(size=(k, d)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    v = rng.normal(size=(k, d)); v -= (v * u).sum(1, keepdims=True) * u
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    ang = 10.0 ** rng.uniform(-12, -1, k) * rng.choice([0, 1, 1, 1], k)
+    u2 = u * np.cos(ang)[:, None] + v * np.sin(ang)[:, None]
+    a[s] = rng.uniform(0.2, 0.8, (k, d))
+    b[s] = a[s] + u * rng.uniform(0.01, 0.1, (k, 1))
+    off = v * (thr * (1 + rng.choice([0, 1e-9, -1e-9, 1e-3, -1e-3, 0.5, -0.5, -1.0], k)))[:, None]
+    c[s] = a[s] + off + u * rng.uniform(-0.05, 0.05, (k, 1))
+    e[s] = c[s] + u2 * rng.uniform(0.01, 0.1, (k, 1)) * rng.choice([1, -1], (k, 1))
+    # zero-length segments (either, both), identical and reversed segments
+    s = slice(2 * k, 3 * k)
+    a[s] = rng.random((k, d)); b[s] = a[s] + rng.normal(size=(k, d)) * 0.04
+    c[s] = a[s] + rng.normal(size=(k, d)) * 0.03; e[s] = c[s] + rng.normal(size=(k, d)) * 0.04
+    kind = rng.integers(0, 5, k)
+    b[s][kind == 0] = a[s][kind == 0]
+    e[s][kind == 1] = c[s][kind == 1]
+    m = kind == 2; b[s][m] = a[s][m]; e[s][m] = c[s][m]
+    m = kind == 3; c[s][m] = a[s][m]; e[s][m] = b[s][m]
+    m = kind == 4; c[s][m] = b[s][m]; e[s][m] = a[s][m]
+    # crossings and near-crossings: second segment through a point of the first
+    s = slice(3 * k, 4 * k)
+    a[s] = rng.uniform(0.2, 0.8, (k, d)); b[s] = a[s] + rng.normal(size=(k, d)) * 0.05
+    x = a[s] + (b[s] - a[s]) * rng.uniform(-0.1, 1.1, (k, 1))
+    w = rng.normal(size=(k, d)) * 0.05
+    lift = np.zeros((k, d))
+    if d == 3:
+        lift[:, 2] = rng.choice([0.0, 1e-12, 1e-3, 0.02, 0.05], k)
+    c[s] = x - w * rng.uniform(-0.1, 1.0, (k, 1)) + lift
+    e[s] = x + w * rng.uniform(-0.1, 1.0, (k, 1)) + lift
+    # tiny segments (subnormal squares), domain edge, out of domain, non-finite
+    s = slice(4 * k, 5 * k)
+    a[s] = rng.random((k, d)); c[s] = a[s] + rng.normal(size=(k, d)) * 0.03
+    b[s] = a[s] + rng.normal(size=(k, d)) * 10.0 ** rng.uniform(-320, -3, (k, 1))
+    e[s] = c[s] + rng.normal(size=(k, d)) * 10.0 ** rng.uniform(-320, -3, (k, 1))
+    s = slice(5 * k, 6 * k)
+    sc = rng.choice([1.9, 2.0, 2.1, 10.0, 1e6], (k, 1))
+    for arr in (a, b, c, e):
+        arr[s] = (arr[s] - 0.5) * 2 * sc / np.maximum(1, np.abs(arr[s] - 0.5).max(1, keepdims=True) * 2) * \
+            rng.uniform(0.9, 1.0, (k, 1))
+    sp = rng.integers(5 * k, 6 * k, 64)
+    a[sp[:16], 0] = np.nan; b[sp[16:32], 1] = np.inf; c[sp[32:48], 0] = -np.inf; e[sp[48:], 1] = np.nan
+    return rads, ai, aj, [np.ascontiguousarray(t) for t in (a, b, c, e)]
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_verdict_filter_never_contradicts_reference_arithmetic(probe, d):
+    """geom.cuh: segseg_filter (the conflict-table kernel's cheap exact-verdict filter) answers
+    1 / 0 only where segseg_lt -- the reference's own sequence of roundings -- says the same;
+    everything else must come back undecided.  Also: it decides nearly all ordinary pairs."""
+    rng = np.random.default_rng(100 + d)
+    n = 400_000
+    rads, ai, aj, (a, b, c, e) = _filter_cases(rng, d, n)
+    thr = rads[ai] + rads[aj]
+    T2 = np.array([sq_lt_threshold(t) for t in np.unique(thr)])
+    T2 = T2[np.searchsorted(np.unique(thr), thr)]
+    out = np.empty(n, np.int8)
+    exact = np.empty(n, np.uint8)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    probe.probe_segseg_filter_batch(n, d, vp(a), vp(b), vp(c), vp(e), vp(thr), vp(T2), vp(out), vp(exact))
+    decided = out >= 0
+    bad = decided & (out != exact.astype(np.int8))
+    assert not bad.any(), (int(bad.sum()), np.flatnonzero(bad)[:10])
+    # the exact path agrees with the oracle on a sample (pins `exact` itself)
+    for k in rng.integers(0, n, 3000):
+        assert bool(exact[k]) == (O.dist_ss(a[k], b[k], c[k], e[k]) < thr[k]), k
+    k8 = n // 8
+    plain = decided[:k8].mean()
+    # (1.5 % of the pairs combine the two sub-2^-18 radii, for which the filter is switched off)
+    print('decided: plain %.4f, all %.4f' % (plain, decided.mean()))
+    assert plain > (0.98 if d == 2 else 0.5), plain
+    # both verdicts and the undecided answer all occur
+    assert (out == 1).any() and (out == 0).any() and (out == -1).any()
+
+
+@pytest.mark.parametrize("d", [2, 3])
+def test_fp32_broad_phase_is_one_sided(probe, d):
+    """geom.cuh: bound32_far (single-precision capsule bound of the conflict-table kernel) may
+    only reject pairs whose true distance exceeds r_i + r_j by a margin: checked against a
+    float128 evaluation of the true segment distance on pairs placed around the rejection
+    boundary, at every segment length the domain allows, plus the filter's adversarial set."""
+    rng = np.random.default_rng(200 + d)
+    n = 300_000
+    ri, rj = rng.uniform(1e-4, 0.05, n), rng.uniform(1e-4, 0.05, n)
+    # segment 1 anywhere in [-2, 2]^d, random length; segment 2 placed so that the true distance
+    # is (r_i + r_j) * (1 + tiny .. 1) -- i.e. just beyond contact, where a sloppy bound errs
+    L1 = 10.0 ** rng.uniform(-4, 0.3, n) * rng.choice([0, 1, 1, 1], n)
+    L2 = 10.0 ** rng.uniform(-4, 0.3, n) * rng.choice([0, 1, 1, 1], n)
+    u = rng.normal(size=(n, d)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    v = rng.normal(size=(n, d)); v -= (v * u).sum(1, keepdims=True) * u
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    mid = rng.uniform(-1.0, 1.0, (n, d))
+    a = mid - u * (L1 / 2)[:, None]
+    b = mid + u * (L1 / 2)[:, None]
+    gap = (ri + rj) * (1 + 10.0 ** rng.uniform(-7, 0, n))
+    along = rng.uniform(-0.6, 0.6, n) * L1        # closest point somewhere along segment 1
+    foot = mid + u * along[:, None] + v * gap[:, None]
+    w = rng.normal(size=(n, d)); w -= (w * v).sum(1, keepdims=True) * v
+    nw = np.linalg.norm(w, axis=1, keepdims=True); w /= np.where(nw > 0, nw, 1)
+    s0 = rng.uniform(0, 1, n)
+    c = foot - w * (L2 * s0)[:, None]
+    e = foot + w * (L2 * (1 - s0))[:, None]
+    keep = (np.abs(a).max(1) <= 2) & (np.abs(b).max(1) <= 2) & (np.abs(c).max(1) <= 2) & (np.abs(e).max(1) <= 2)
+    a, b, c, e = (np.ascontiguousarray(x[keep]) for x in (a, b, c, e))
+    ri, rj = np.ascontiguousarray(ri[keep]), np.ascontiguousarray(rj[keep])
+    m = a.shape[0]
+    out = np.empty(m, np.uint8)
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    probe.probe_bound32_batch(m, d, vp(a), vp(b), vp(c), vp(e), vp(ri), vp(rj), vp(out))
+    assert out.any() and not out.all()
+    # every rejected pair must be a "no collision" of the reference arithmetic ...
+    rej = np.flatnonzero(out)
+    for k in rej[:: max(1, rej.size // 20000)]:
+        assert not (O.dist_ss(a[k], b[k], c[k], e[k]) < ri[k] + rj[k]), k
+    # ... with the promised margin (true distance by dense sampling in long double: an upper
+    # bound of the true distance, so `>=` here is implied by the claim)
+    ld = np.longdouble
+    ts = np.linspace(0, 1, 65).astype(ld)
+    for k in rej[:: max(1, rej.size // 3000)]:
+        P = a[k].astype(ld)[None, :] + ts[:, None] * (b[k] - a[k]).astype(ld)[None, :]
+        Q = c[k].astype(ld)[None, :] + ts[:, None] * (e[k] - c[k]).astype(ld)[None, :]
+        dmin = np.sqrt(((P[:, None, :] - Q[None, :, :]) ** 2).sum(-1)).min()
+        assert dmin > ri[k] + rj[k] + 9.0e-7, (k, float(dmin), ri[k] + rj[k])
+    # the filter's adversarial set: out-of-domain and non-finite segments are never rejected
+    rads, ai, aj, (a2, b2, c2, e2) = _filter_cases(rng, d, 80_000)
+    out2 = np.empty(80_000, np.uint8)
+    r_i, r_j = np.ascontiguousarray(rads[ai]), np.ascontiguousarray(rads[aj])
+    probe.probe_bound32_batch(80_000, d, vp(a2), vp(b2), vp(c2), vp(e2), vp(r_i), vp(r_j), vp(out2))
+    bad = [k for k in np.flatnonzero(out2) if O.dist_ss(a2[k], b2[k], c2[k], e2[k]) < r_i[k] + r_j[k]]
+    assert not bad, bad[:10]
+    fin = np.isfinite(a2).all(1) & np.isfinite(b2).all(1) & np.isfinite(c2).all(1) & np.isfinite(e2).all(1)
+    big = (np.abs(a2).max(1) > 2) | (np.abs(b2).max(1) > 2) | (np.abs(c2).max(1) > 2) | (np.abs(e2).max(1) > 2)
+    assert not out2[~fin | big].any()
