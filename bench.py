@@ -13,14 +13,17 @@ obstacles (scripts/config/eval/point2d_many.yaml).  One STEP is one pass of the 
       steps (max_makespan of point2d_many.yaml), OR-reduced per time step -> the conflict
       table the search consults.  collide checks counted: nnz * T * (N-1).
 
-Multi-GPU (weak scaling): every rank evaluates the full table against its OWN path scenario
-(e.g. PP's random-priority restarts, pp.jl:104-128): per-GPU work is fixed.  The roadmap build
-has two modes (--build): "sharded" = the neighbour pass is sharded by agent and the CSR shards
-are exchanged by one NCCL all-gather of fixed-size slots (vertices are re-drawn on every rank
-from the counter-based sampler instead of being communicated); "replicated" = every rank
-builds all roadmaps itself, no exchange.  "auto" (default) times both at start-up and takes
-the faster one; both timings are reported (`multi_gpu_build`).  The connect checks of the
-build are counted once per step in either mode.
+Multi-GPU (--gpus N > 1, default --scaling strong): ONE scenario is strong-scaled.  Agents are
+block-partitioned over the ranks (prm.jl:265-275: the roadmaps are independent).  Every rank draws
+all vertices (counter-based sampler: nothing to communicate), builds the roadmaps of ITS agents,
+writes its CSR shard straight into every peer's memory over NVLink (peer mappings, one flag per
+peer -- sssp_b200/peer.py; NCCL all-gather only as a fallback or with --exchange nccl), computes
+the table rows of ITS agents' edges against all agents' path edges with the output pointer aimed
+at rank 0's memory, and adopts the peers' shards.  The step ends -- inside the CUDA-event region --
+when every rank holds all roadmaps and rank 0 the whole table; both are checked byte for byte
+against the 1-GPU result before timing.  checks/step are those of the one scenario; `value` =
+checks / max-over-ranks step time.  --scaling weak keeps the round-1 shape (one scenario per
+rank on a sharded build) as an extra.
 
 `value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream.
 `e2e`    = same through the host-buffer C ABI: host init/goal and path ids in, roadmaps
@@ -60,7 +63,7 @@ FLOPS_FILTER = 91              # FP64 verdict filter per surviving pair (2-D, FM
                                # point-segment distances 52, minimum 3, band compare 6
 FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
 FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
-NCU_DRAM_BYTES_PER_LAUNCH = 16.12e6   # profiles/r1_i_ncu_full_summary.md, last table (read 16.13 MB, written 16 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 16.19e6   # profiles/r2_a_ncu_full_summary.md (read 16.19 MB, written 1 KB)
 BYTES_CONNECT = 2 * 16 + 4 + 1
 BYTES_COLLIDE = 4 * 16 + 8 + 1
 
@@ -73,10 +76,14 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--build", default="auto", choices=["auto", "sharded", "replicated"],
-                    help="multi-GPU roadmap build: neighbour pass sharded by agent + CSR "
-                         "all-gather, or every rank builds all roadmaps (no exchange); auto "
-                         "times both at start-up and takes the faster")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="multi-GPU: strong = ONE scenario, roadmaps and table rows sharded by agent "
+                         "(default); weak = one scenario per GPU on a sharded build")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: peer stores over NVLink from the producing kernels "
+                         "(falls back to nccl when the peer mapping cannot be opened), or NCCL all-gather")
+    ap.add_argument("--num-vertices", type=int, default=NV,
+                    help="vertices per roadmap (500 = point2d_many.yaml; larger sizes for scaling studies)")
     return ap.parse_args()
 
 
@@ -88,13 +95,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def config_dict(world):
-    return {"workload": "point2d_many N=50 M=10: PRMs(500, rad=0.1) + conflict table (all "
-                        "roadmap edges x other agents' path edges, T=64) per GPU",
-            "n_agents": N_AGENTS, "num_vertices": NV, "rad": RAD, "path_steps": T_STEPS,
-            "n_obstacles": 10, "path_scenarios": world,
-            "parallelism": "single GPU" if world == 1 else
-                           "weak scaling: one path scenario per GPU, roadmap build per --build",
+def config_dict(world, strong=True, nv=NV):
+    return {"workload": "point2d_many N=50 M=10: PRMs(%d, rad=0.1) + conflict table (all "
+                        "roadmap edges x other agents' path edges, T=64)" % nv,
+            "n_agents": N_AGENTS, "num_vertices": nv, "rad": RAD, "path_steps": T_STEPS,
+            "n_obstacles": 10, "path_scenarios": 1 if (strong or world == 1) else world,
+            "parallelism": "single GPU" if world == 1 else (
+                "strong scaling of ONE scenario: agents block-partitioned over the GPUs, each rank "
+                "builds its agents' roadmaps and computes their table rows; CSR shards and table "
+                "rows are exchanged inside the timed step" if strong else
+                "weak scaling: one path scenario per GPU, sharded roadmap build + exchange"),
             "l2": "L2 flushed between timed steps (256 MB memset); per-step inputs are KB-sized"}
 
 
@@ -102,11 +112,11 @@ def config_dict(world):
 # reference arm / cpu_baseline: the CPU oracle on the same workload
 # ------------------------------------------------------------------------------------------
 class CpuArm:
-    def __init__(self, inst):
+    def __init__(self, inst, threads=None):
         from oracle import oracle as O
         O.build()
         self.O = O
-        self.threads = O.host_cores()      # not OMP_NUM_THREADS: torchrun sets it to 1
+        self.threads = threads or O.host_cores()   # not OMP_NUM_THREADS: torchrun sets it to 1
         self.inst = inst
         self.orc = O.Oracle(O.POINT2D, inst.rads, inst.obstacles)
 
@@ -171,6 +181,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": config_dict(1),
+        "cores_available": os.cpu_count(),
         "roadmap_build_ms": 1e3 * float(np.mean(tb)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
                          "sample": "per step: full N=50 roadmap build + conflict table on every "
@@ -247,7 +258,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import sssp_b200 as S
-    from sssp_b200 import lib as L, sharding as SH, workload as W
+    from sssp_b200 import lib as L, peer as P, sharding as SH, workload as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,9 +269,10 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
     warmup = max(args.warmup, 3)
+    strong = args.scaling == "strong"
 
-    inst = W.point2d_many(N_AGENTS, seed=0, nv=NV, rad=RAD)
-    N, nv, d = N_AGENTS, NV, 2
+    N, nv, d = N_AGENTS, args.num_vertices, 2
+    inst = W.point2d_many(N, seed=0, nv=nv, rad=RAD)
     ctx = S.Context(inst.model, inst.rads, inst.obstacles, device=local)
     stream = torch.cuda.current_stream()
     st = stream.cuda_stream
@@ -268,7 +280,7 @@ def run_b200(args):
     a0, n_local, cap = SH.agent_block(N, world, rank)
 
     # Node tables: the sampler is counter-based (any try can be generated anywhere), so every
-    # rank draws ALL agents' vertices itself (one launch, ~8 us) instead of all-gathering them;
+    # rank draws ALL agents' vertices itself (one launch, ~8 us) instead of receiving them;
     # the O(nv^2) neighbour pass -- the expensive part -- is sharded by agent.
     nodes_all = torch.zeros((N, nv, d), dtype=torch.float64, device=dev)
     rm_all = S.Roadmaps(ctx, 0, N, nv)
@@ -279,74 +291,32 @@ def run_b200(args):
     else:
         rm_sh = rm_all
     radv = np.full(max(n_local, 1), inst.rad)
-    # CSR exchange: ONE all-gather of fixed-size slots (cnt[cap*nv] | col[cap_nnz]); cap_nnz is
-    # sized from a first build, with head room (a later overflow raises MRMP_ERR_CAPACITY)
-    state = {"cap_nnz": 0, "slots": None}
-
     radv_all = np.full(N, inst.rad)
-    build_mode = {"mode": "sharded" if world > 1 else "single"}
+    wpr = (T_STEPS + 31) // 32
 
-    def build_sharded():
-        """(A): sample + neighbour pass of this rank's agents + [all-gather CSR shards]."""
-        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
-        nnz = rm_sh.build(radv)
+    def max_over_ranks(x, op=None):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op or dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
         if world > 1:
-            if state["slots"] is None:
-                t = torch.tensor([nnz], dtype=torch.int64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                state["cap_nnz"] = int(t.item()) * 5 // 4 + 1024
-                state["slots"] = torch.zeros((world, cap * nv + state["cap_nnz"]),
-                                             dtype=torch.int32, device=dev)
-            slots = state["slots"]
-            L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(rm_sh._h, cap, state["cap_nnz"],
-                                                         slots[rank].data_ptr(), st))
-            dist.all_gather_into_tensor(slots.view(-1), slots[rank])
-            out = C.c_int64(0)
-            L.check(lib.mrmp_roadmaps_set_csr_shards_dev(rm_all._h, world, cap, state["cap_nnz"],
-                                                         slots.data_ptr(), st, C.byref(out)))
-            return int(out.value)
-        return nnz
-
-    def build_replicated():
-        """(A'): every rank builds all N roadmaps itself -- no exchange.  Cheaper than the
-        sharded build whenever the whole build takes less than the all-gather round trip."""
-        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
-        return rm_all.build(radv_all)
-
-    def build_roadmaps():
-        return build_replicated() if build_mode["mode"] == "replicated" else build_sharded()
-
-    # ---- setup: one build gives the CSR the synthetic paths walk on
-    nnz_total = build_roadmaps()
-    torch.cuda.synchronize()
-    build_modes_ms = None
-    if world > 1:
-        def wall_ms(fn, reps=10):
-            for _ in range(3):
-                fn()
             dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                fn()
-            torch.cuda.synchronize()
-            t = torch.tensor([(time.perf_counter() - t0) / reps * 1e3], dtype=torch.float64,
-                             device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        build_modes_ms = {"sharded": wall_ms(build_sharded), "replicated": wall_ms(build_replicated)}
-        if args.build == "auto":
-            build_mode["mode"] = min(build_modes_ms, key=build_modes_ms.get)
-        else:
-            build_mode["mode"] = args.build
-        assert build_roadmaps() == nnz_total   # both modes give the same roadmaps
+        torch.cuda.synchronize()
+
+    # ---- setup: a full build on every rank gives the reference CSR, the synthetic paths and (for
+    # the multi-GPU modes) the table that the sharded computation must reproduce byte for byte
+    rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+    nnz_total = rm_all.build(radv_all)
     nodes_h = rm_all.nodes()
     row_ptr_h, col_h = rm_all.csr()
     gate = W.gate_pass_count(nodes_h, RAD)
-    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr_h, col_h, T_STEPS, seed=4321 + rank)
+    scen = 4321 if strong else 4321 + rank        # strong: ONE scenario shared by all ranks
+    _, ca, vf, vt = W.random_walk_paths(inst, row_ptr_h, col_h, T_STEPS, seed=scen)
     n_cols = int(ca.size)
     pair_checks = nnz_total * T_STEPS * (N - 1)
-    wpr = (T_STEPS + 31) // 32
 
     def pin(a):
         return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -355,48 +325,125 @@ def run_b200(args):
     cols_d = [t.to(dev) for t in cols_h]
     bits_d = torch.zeros((nnz_total, wpr), dtype=torch.int32, device=dev)
     bits_h = torch.zeros((nnz_total, wpr), dtype=torch.int32).pin_memory()
-    # e2e returns the roadmaps this rank built to the host: its shard, or all of them
-    rm_ret = rm_all if build_mode["mode"] == "replicated" else rm_sh
-    n_ret = N if build_mode["mode"] == "replicated" else max(n_local, 1)
-    rows_sh = n_ret * nv
-    nodes_out_h = torch.empty((n_ret, nv, d), dtype=torch.float64).pin_memory()
-    rowptr_out_h = torch.empty(rows_sh + 1, dtype=torch.int32).pin_memory()
-    colidx_out_h = torch.empty(max(nnz_total, 1), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def k_table():
+    def k_table_full():
         L.check(lib.mrmp_roadmaps_edge_conflicts_dev(rm_all._h, None, n_cols,
                                                      cols_d[0].data_ptr(), cols_d[1].data_ptr(),
                                                      cols_d[2].data_ptr(), N, bits_d.data_ptr(), st))
 
-    def step_value():
-        build_roadmaps()
-        k_table()
+    # ---- multi-GPU plumbing
+    mg = None
+    if world > 1:
+        nnz_sh = rm_sh.build(radv)
+        nnz_max = int(max_over_ranks(float(nnz_sh)))
+        cap_nnz = P.csr_slot_words(cap, nv, nnz_max)
+        tab_words = (nnz_max + nnz_max // 4 + 1024) * wpr
+        tab_words += (-tab_words) % 4
+        ex = P.Exchange(ctx, world, rank, [4 * (cap * nv + cap_nnz), 4 * tab_words])
+        p2p = ex.connect() and args.exchange != "nccl"
+        slots = None if p2p else torch.zeros((world, cap * nv + cap_nnz), dtype=torch.int32, device=dev)
+        tab_slots = None if p2p else torch.zeros((world, tab_words), dtype=torch.int32, device=dev)
+        nnz_all = torch.zeros(world, dtype=torch.int64, device=dev)
+        nnz_all[rank] = nnz_sh
+        dist.all_reduce(nnz_all)
+        mg = dict(ex=ex, p2p=p2p, cap_nnz=cap_nnz, tab_words=tab_words, slots=slots,
+                  tab_slots=tab_slots, nnz_sh=[int(x) for x in nnz_all.tolist()],
+                  exchange="nvlink peer stores from the producing kernels (CUDA IPC mappings) + flags"
+                  if p2p else "nccl all-gather (%s)" % (getattr(ex, "connect_error", None) or args.exchange))
 
-    def step_e2e():
-        build_roadmaps()
-        # roadmaps back to the host (what PRMs() returns to the solver): on the copy stream,
-        # beside the conflict-table kernel
-        nnz = C.c_int64(0)
-        L.check(lib.mrmp_roadmaps_read_async(rm_ret._h, nodes_out_h.data_ptr(),
-                                             rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
-                                             colidx_out_h.numel(), C.byref(nnz)))
-        L.check(lib.mrmp_roadmaps_edge_conflicts(rm_all._h, None, n_cols, cols_h[0].data_ptr(),
-                                                 cols_h[1].data_ptr(), cols_h[2].data_ptr(), N,
-                                                 bits_h.data_ptr(), bits_h.numel()))
-        L.check(lib.mrmp_roadmaps_read_wait(rm_ret._h))
+    def exchange_csr():
+        """this rank's CSR shard -> every rank; afterwards rm_all holds all roadmaps"""
+        ex = mg["ex"]
+        if mg["p2p"]:
+            ex.push_csr_shard(rm_sh, 0, cap, mg["cap_nnz"], st)
+            return None
+        L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(rm_sh._h, cap, mg["cap_nnz"],
+                                                     mg["slots"][rank].data_ptr(), st))
+        dist.all_gather_into_tensor(mg["slots"].view(-1), mg["slots"][rank])
+        return None
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def adopt_csr():
+        ex = mg["ex"]
+        if mg["p2p"]:
+            n = ex.adopt_csr_shards(rm_all, 0, cap, mg["cap_nnz"], st)
+            ex.advance(0)
+            return n
+        out = C.c_int64(0)
+        L.check(lib.mrmp_roadmaps_set_csr_shards_dev(rm_all._h, world, cap, mg["cap_nnz"],
+                                                     mg["slots"].data_ptr(), st, C.byref(out)))
+        return int(out.value)
+
+    def step_strong(cols=cols_d):
+        """ONE scenario over all ranks: draw all vertices, build the roadmaps of this rank's agent
+        block, publish the CSR shard to every rank, evaluate the table rows of this rank's agents
+        against all agents' path edges (written straight into rank 0's memory), adopt the peers'
+        shards.  The timed region ends when every rank holds all roadmaps and rank 0 the table."""
+        ex = mg["ex"]
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm_sh.build(radv)
+        exchange_csr()
+        if mg["p2p"]:
+            rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
+                                     N, ex.ptr(1, 0), st, cols=rm_all)
+            ex.signal(1, st, dst_mask=1)
+            n = adopt_csr()
+            if rank == 0:
+                ex.wait(1, st)
+            ex.advance(1)
+        else:
+            rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
+                                     N, mg["tab_slots"][rank].data_ptr(), st, cols=rm_all)
+            n = adopt_csr()
+            dist.all_gather_into_tensor(mg["tab_slots"].view(-1), mg["tab_slots"][rank])
+        return n
+
+    def gathered_table():
+        """rank 0: the table rows of all ranks in packed CSR order (after a strong step)"""
+        if mg["p2p"]:
+            sl = torch.as_tensor(CudaArray(mg["ex"].slots(1), (world, mg["tab_words"]), "<i4"), device=dev)
+        else:
+            sl = mg["tab_slots"]
+        return torch.cat([sl[r, : mg["nnz_sh"][r] * wpr].view(-1, wpr) for r in range(world)])
+
+    def step_weak():
+        """every rank its own scenario on all roadmaps; the build is sharded and exchanged"""
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm_sh.build(radv)
+        exchange_csr()
+        adopt_csr()
+        k_table_full()
+
+    def step_single():
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm_all.build(radv_all)
+        k_table_full()
+
+    step_value = step_single if world == 1 else (step_strong if strong else step_weak)
+
+    # ---- correctness of the sharded path before anything is timed
+    strong_check = None
+    if world > 1:
+        k_table_full()                     # 1-GPU table of this rank's scenario (setup build)
         torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        ref_bits = bits_d.clone()
+        ref_rp, ref_col = row_ptr_h, col_h
+        if strong:
+            # keep a previous round's data out of the buffers the check reads
+            n = step_strong()
+            barrier()
+            assert n == nnz_total, "stitched roadmaps differ in size"
+            rp2, col2 = rm_all.csr()
+            ok = bool(np.array_equal(rp2, ref_rp) and np.array_equal(col2, ref_col))
+            if rank == 0:
+                ok = ok and bool(torch.equal(gathered_table(), ref_bits))
+            strong_check = {"roadmaps_identical": bool(max_over_ranks(0.0 if ok else 1.0) == 0.0),
+                            "table_identical_on_rank0": ok if rank == 0 else None}
+            assert strong_check["roadmaps_identical"], "sharded path differs from the 1-GPU result"
+        else:
+            step_weak()
+            torch.cuda.synchronize()
+            assert torch.equal(bits_d, ref_bits)
 
     # ---- value: device-resident, CUDA events per step on the launching stream, L2 flushed
     for _ in range(warmup):
@@ -410,16 +457,19 @@ def run_b200(args):
           for _ in range(args.steps)]
     for k in range(args.steps):
         flush.zero_()                      # evict L2 (outside the per-step event pair)
+        if world > 1 and strong:
+            dist.barrier()                 # ranks start a step together (outside the event pair)
         ev[k][0].record(stream)
         step_value()
         ev[k][1].record(stream)
     barrier()
     t_end = time.perf_counter()
     launches = L.kernel_launch_count() - launches0
-    ms_total = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    per_step = [a.elapsed_time(b) for a, b in ev]
+    ms_total = max_over_ranks(sum(per_step))
     clk = clocks.stop(t_begin, t_end)
     ms_step = ms_total / args.steps
-    checks_step = gate + world * pair_checks
+    checks_step = gate + (pair_checks if (strong or world == 1) else world * pair_checks)
     value = checks_step / (ms_step * 1e-3)
 
     # ---- per-kernel durations for the roofline (same stream, same inputs)
@@ -434,9 +484,18 @@ def run_b200(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    ms_build = timed(build_roadmaps, reps=5)
+    def build_local():
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm_sh.build(radv)
+
+    def build_full():
+        rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm_all.build(radv_all)
+
+    ms_build_local = timed(build_local, reps=5)
+    ms_build = timed(build_full, reps=5)       # all N roadmaps on one GPU (leaves rm_all complete)
     ctx.stats(reset=True)
-    ms_table = timed(k_table, reps=10)
+    ms_table = timed(k_table_full, reps=10)
     st_ = ctx.stats()
     exact = int(st_[0]) / 11.0            # pairs that ran the reference's own arithmetic
     tested = int(st_[2]) / 11.0           # pairs that ran the FP32 bound (rest: tile boxes)
@@ -447,15 +506,16 @@ def run_b200(args):
     achieved = flops / (ms_table * 1e-3) / 1e12
     pk, pk_kind = peaks()
     roofline = {
-        "bound": "fp64", "kernel": "k_cross_collide<2,true> (+ column sort/prep)",
+        "bound": "fp64", "kernel": "k_cross_collide<2,or,fast-drop> (+ column sort/prep), all %d "
+                                   "roadmap edges x %d columns on one GPU" % (nnz_total, n_cols),
         "achieved": achieved, "peak": FP64_UNFUSED_PEAK_TFLOPS, "unit": "TFLOP/s",
         "frac": achieved / FP64_UNFUSED_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
-                          "capture of this kernel on this workload (profiles/r1_i_ncu_full_summary.md); "
+                          "capture of this kernel on this workload (profiles/r2_a_ncu_full_summary.md); "
                           "algorithmic bytes per launch: 17.0e6",
         "peak_source": "un-fused DADD/DMUL issue peak measured with tools/fp64_peak.cu on this "
                        "pool (profiles/r1_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure "
-                       "and bit parity forbids FMA",
+                       "and bit parity forbids FMA in the reference arithmetic",
         "algorithmic_flops": {"pairs": n_pairs, "pairs_bound_tested_fp32": tested,
                               "fp32_per_tested_pair": FLOPS_BROAD32, "fp32_tflops": flops32 / (ms_table * 1e-3) / 1e12,
                               "pairs_filtered_fp64": survivors, "fp64_per_filtered_pair": FLOPS_FILTER,
@@ -464,12 +524,56 @@ def run_b200(args):
                                       "(verdict filter x 91 + reference arithmetic x 170, FMA = 2); "
                                       "the FP32 broad phase (20 per tested pair) is listed beside it; "
                                       "the reference itself spends 170 FP64 per pair"},
+        "issue_slot_note": "the kernel is issue-bound, not pipe-bound: see profiles/r2_* (issue "
+                           "active, pipe utilisation per pipe)",
         "reference_equivalent_tflops": n_pairs * FLOPS_EXACT / (ms_table * 1e-3) / 1e12,
         "pair_checks_per_s": n_pairs / (ms_table * 1e-3),
-        "kernel_ms": {"conflict_table": ms_table, "roadmap_build": ms_build},
+        "kernel_ms": {"conflict_table": ms_table, "roadmap_build": ms_build,
+                      "roadmap_build_this_rank_shard": ms_build_local},
     }
 
-    # ---- e2e: host buffers through the C ABI
+    # ---- e2e: host buffers through the C ABI (host -> device inputs, device -> host results)
+    e2e_roadmaps = rm_sh if world > 1 else rm_all
+    n_ret = max(n_local, 1) if world > 1 else N
+    rows_sh = n_ret * nv
+    nodes_out_h = torch.empty((n_ret, nv, d), dtype=torch.float64).pin_memory()
+    rowptr_out_h = torch.empty(rows_sh + 1, dtype=torch.int32).pin_memory()
+    colidx_out_h = torch.empty(max(nnz_total, 1), dtype=torch.int32).pin_memory()
+    cols_up = [torch.empty_like(t) for t in cols_d]
+
+    def step_e2e():
+        if world == 1:
+            build_full()
+            # roadmaps back to the host (what PRMs() returns to the solver): on the copy stream,
+            # beside the conflict-table kernel
+            nnz = C.c_int64(0)
+            L.check(lib.mrmp_roadmaps_read_async(rm_all._h, nodes_out_h.data_ptr(),
+                                                 rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
+                                                 colidx_out_h.numel(), C.byref(nnz)))
+            L.check(lib.mrmp_roadmaps_edge_conflicts(rm_all._h, None, n_cols, cols_h[0].data_ptr(),
+                                                     cols_h[1].data_ptr(), cols_h[2].data_ptr(), N,
+                                                     bits_h.data_ptr(), bits_h.numel()))
+            L.check(lib.mrmp_roadmaps_read_wait(rm_all._h))
+            return
+        # multi-GPU: path ids from pinned host memory on every rank, this rank's roadmaps back to
+        # its host, the gathered table back to rank 0's host
+        for up, h in zip(cols_up, cols_h):
+            up.copy_(h, non_blocking=True)
+        if strong:
+            step_strong(cols_up)
+        else:
+            step_weak()
+        nnz = C.c_int64(0)
+        L.check(lib.mrmp_roadmaps_read_async(rm_sh._h, nodes_out_h.data_ptr(), rowptr_out_h.data_ptr(),
+                                             colidx_out_h.data_ptr(), colidx_out_h.numel(), C.byref(nnz)))
+        if strong:
+            if rank == 0:
+                bits_h.copy_(gathered_table(), non_blocking=True)
+        else:
+            bits_h.copy_(bits_d, non_blocking=True)
+        L.check(lib.mrmp_roadmaps_read_wait(rm_sh._h))
+        torch.cuda.current_stream().synchronize()
+
     for _ in range(2):
         step_e2e()
     barrier()
@@ -480,14 +584,18 @@ def run_b200(args):
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     h2d = 2 * N * d * 8 + 3 * n_cols * 4
-    nnz_ret = nnz_total if build_mode["mode"] == "replicated" else nnz_total // world
-    d2h = n_ret * nv * d * 8 + (rows_sh + 1) * 4 + nnz_ret * 4 + nnz_total * wpr * 4
+    if world == 1:
+        d2h = N * nv * d * 8 + (N * nv + 1) * 4 + nnz_total * 4 + nnz_total * wpr * 4
+    else:     # rank 0, the busiest: its roadmaps + the whole table (strong) / its table (weak)
+        d2h = n_ret * nv * d * 8 + (rows_sh + 1) * 4 + (nnz_total // world) * 4 + nnz_total * wpr * 4
     e2e = {"value": checks_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+           "note": "per rank; rank 0 also reads the gathered table" if world > 1 else None}
 
-    # ---- extras: explicit-list kernels (HBM-side of the path), inputs resident in HBM
-    extras = None
+    # ---- explicit-list kernels (HBM side of the path), SSSP expansion, arm22: rank 0 only
+    lists = sssp_x = arm = None
     if rank == 0 and not args.no_extras:
+        build_full()
         n = 1 << 24
         con = W.connect_list(inst, n, seed=1234)
         con_d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in con]
@@ -499,49 +607,82 @@ def run_b200(args):
             out.data_ptr(), st)))
         ms_idx = timed(lambda: L.check(lib.mrmp_collide_edges_indexed_dev(
             rm_all._h, n, *[t.data_ptr() for t in cl_d], out.data_ptr(), st)))
-        extras = {"explicit_list_n": n,
-                  "connect_edges": {"ms": ms_con, "checks_per_s": n / ms_con * 1e3,
-                                    "hbm_gbs": n * BYTES_CONNECT / ms_con / 1e6,
-                                    "hbm_frac": n * BYTES_CONNECT / ms_con / 1e6 / pk["hbm_gbs"]},
-                  "collide_edges_indexed": {"ms": ms_idx, "checks_per_s": n / ms_idx * 1e3}}
-        del con_d, cl_d, out
-        extras["sssp_expansion"] = extra_sssp_expansion(inst, nodes_h, local)
-        extras["arm22"] = extra_arm22(local, dev, st, timed)
+        # collide(Q, q_to, i) (point.jl:27-33, the SSSP successor form): n_cand candidates against
+        # the N-1 static others
+        n_cand = 1 << 20
+        Qs = torch.from_numpy(np.ascontiguousarray(nodes_h[:, 0])).to(dev)
+        cand = torch.rand((n_cand, 2), dtype=torch.float64, device=dev)
+        outc = torch.empty(n_cand, dtype=torch.uint8, device=dev)
+        ms_mv = timed(lambda: L.check(lib.mrmp_collide_config_moves_dev(
+            ctx._h, 0, Qs.data_ptr(), n_cand, cand.data_ptr(), outc.data_ptr(), st)))
+        flops_con = 6 + 10 * (15 * 2 + 4)
+        flops_mv = (N - 1) * (15 * 2 + 4)
+        lists = {"n": n,
+                 "connect_edges": {"ms": ms_con, "checks_per_s": n / ms_con * 1e3,
+                                   "hbm_gbs": n * BYTES_CONNECT / ms_con / 1e6,
+                                   "hbm_frac": n * BYTES_CONNECT / ms_con / 1e6 / pk["hbm_gbs"],
+                                   "fp64_tflops": n * flops_con / ms_con / 1e9,
+                                   "fp64_frac": n * flops_con / ms_con / 1e9 / FP64_UNFUSED_PEAK_TFLOPS},
+                 "collide_edges_indexed": {"ms": ms_idx, "checks_per_s": n / ms_idx * 1e3,
+                                           "fp64_tflops": n * FLOPS_EXACT / ms_idx / 1e9,
+                                           "fp64_frac": n * FLOPS_EXACT / ms_idx / 1e9 / FP64_UNFUSED_PEAK_TFLOPS},
+                 "collide_config_moves": {"n_candidates": n_cand, "ms": ms_mv,
+                                          "candidates_per_s": n_cand / ms_mv * 1e3,
+                                          "segment_point_tests_per_s": n_cand * (N - 1) / ms_mv * 1e3,
+                                          "fp64_tflops": n_cand * flops_mv / ms_mv / 1e9,
+                                          "fp64_frac": n_cand * flops_mv / ms_mv / 1e9 / FP64_UNFUSED_PEAK_TFLOPS},
+                 "peak_hbm_gbs": pk["hbm_gbs"], "peak_source": pk_kind}
+        del con_d, cl_d, out, cand, outc
+        sssp_x = extra_sssp_expansion(inst, nodes_h[:, :500] if nv >= 500 else nodes_h, local)
+        arm = extra_arm22(local, dev, st, timed)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        arm = CpuArm(inst)
-        arm.step(ca, vf, vt, CPU_ROW_STRIDE)      # warm-up
+        arm_cpu = CpuArm(inst)
+        arm_cpu.step(ca, vf, vt, CPU_ROW_STRIDE)      # warm-up
         best = None
         for _ in range(3):
-            b, t, n_rows, *_ = arm.step(ca, vf, vt, CPU_ROW_STRIDE)
+            b, t, n_rows, *_ = arm_cpu.step(ca, vf, vt, CPU_ROW_STRIDE)
             if best is None or b + t < best[0] + best[1]:
                 best = (b, t, n_rows)
         cchecks = gate + best[2] * T_STEPS * (N - 1)
-        cpu = {"value": cchecks / (best[0] + best[1]), "unit": UNIT, "cores": arm.threads,
+        # one host thread (a single reference solver call is single-threaded)
+        arm1 = CpuArm(inst, threads=1)
+        b1, t1, n1, *_ = arm1.step(ca, vf, vt, CPU_ROW_STRIDE * 8)
+        cpu = {"value": cchecks / (best[0] + best[1]), "unit": UNIT, "cores": arm_cpu.threads,
                "kind": "port",
                "sample": "full N=50 roadmap build + conflict table on every %dth roadmap edge "
                          "(%d rows x %d columns), best of 3; C oracle, OpenMP %d threads"
-                         % (CPU_ROW_STRIDE, best[2], n_cols, arm.threads),
+                         % (CPU_ROW_STRIDE, best[2], n_cols, arm_cpu.threads),
                "roadmap_build_ms": 1e3 * best[0],
-               "collide_pair_checks_per_s": best[2] * T_STEPS * (N - 1) / best[1]}
+               "collide_pair_checks_per_s": best[2] * T_STEPS * (N - 1) / best[1],
+               "one_thread": {"value": (gate + n1 * T_STEPS * (N - 1)) / (b1 + t1),
+                              "roadmap_build_ms": 1e3 * b1,
+                              "collide_pair_checks_per_s": n1 * T_STEPS * (N - 1) / t1,
+                              "sample": "every %dth roadmap edge" % (CPU_ROW_STRIDE * 8)}}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world),
-            "checks_per_step": {"connect": gate, "collide": world * pair_checks},
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(world, strong, nv),
+            "checks_per_step": {"connect": gate, "collide": checks_step - gate},
             "roadmap_build_ms": ms_build, "roadmap_nnz": nnz_total,
-            "multi_gpu_build": None if world == 1 else dict(mode=build_mode["mode"],
-                                                            wall_ms=build_modes_ms),
+            "multi_gpu": None if world == 1 else {
+                "mode": "strong: one scenario, agents' roadmaps and table rows sharded over the ranks"
+                        if strong else "weak: one scenario per rank, sharded build",
+                "exchange": mg["exchange"], "csr_slot_bytes": 4 * (cap * nv + mg["cap_nnz"]),
+                "table_bytes_to_rank0": int(nnz_total * wpr * 4) if strong else 0,
+                "check": strong_check, "ms_per_step_each": per_step[:8]},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "explicit_lists": lists, "sssp_expansion": sssp_x, "arm22": arm,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 

@@ -193,6 +193,50 @@ int mrmp_roadmaps_read_wait(mrmp_roadmaps *rm);
 int mrmp_host_register(void *ptr, size_t bytes);
 int mrmp_host_unregister(void *ptr);
 
+/* ---- peer-memory exchange between the GPUs of one box (one process per GPU) -------------------
+ * What shards is the agent axis (prm.jl:265-275: roadmaps are built per agent; pp.jl:179-189: one
+ * agent's candidate edges against the others' paths).  What must move is (1) the CSR of each
+ * rank's agent block, so that every GPU holds all roadmaps, and (2) the conflict-table rows a rank
+ * computed.  Both are written by the producing kernels STRAIGHT INTO THE PEERS' MEMORY over NVLink
+ * (peer mappings from CUDA IPC handles), followed by one flag per peer; consumers wait on their
+ * local flags.  No collective call and nothing on the host between producer and consumer.
+ *
+ * An exchange has n_chan channels; per channel every rank owns one slot of slot_bytes[ch] (double
+ * buffered by epoch) in every rank's buffer.  Per round and channel, in stream order:
+ *   producer: write own slot at mrmp_exchange_ptr(x, ch, dst) for each destination,
+ *             mrmp_exchange_signal(x, ch, dst_mask, stream)
+ *   consumer: mrmp_exchange_wait(x, ch, src_mask, stream), read mrmp_exchange_slots(x, ch)
+ *   both:     mrmp_exchange_advance(x, ch) once the round's launches are enqueued
+ * handle_out (mrmp_exchange_handle_bytes() bytes, may be NULL) is this rank's IPC handle; the host
+ * framework all-gathers the handles (sssp_b200/peer.py uses torch.distributed) and passes the
+ * [world][handle_bytes] array to mrmp_exchange_connect.  MRMP_ERR_UNSUPPORTED when the peer
+ * mapping cannot be opened (the caller falls back to a collective).  A wait gives up after a few
+ * seconds instead of hanging the GPU; mrmp_exchange_error() then names the missing rank. */
+typedef struct mrmp_exchange mrmp_exchange;
+int mrmp_exchange_handle_bytes(void);
+int mrmp_exchange_create(mrmp_ctx *ctx, int world, int rank, int n_chan, const int64_t *slot_bytes,
+                         mrmp_exchange **out, unsigned char *handle_out);
+void mrmp_exchange_destroy(mrmp_exchange *x);
+int mrmp_exchange_connect(mrmp_exchange *x, const unsigned char *handles);
+/* one process driving several ranks (tests: emulated ranks on one device) */
+int mrmp_exchange_connect_ptrs(mrmp_exchange *x, void *const *bufs);
+void *mrmp_exchange_local_buffer(mrmp_exchange *x);
+void *mrmp_exchange_ptr(mrmp_exchange *x, int ch, int dst);
+void *mrmp_exchange_slots(mrmp_exchange *x, int ch);
+int64_t mrmp_exchange_slot_bytes(mrmp_exchange *x, int ch);
+int mrmp_exchange_signal(mrmp_exchange *x, int ch, unsigned int dst_mask, void *stream);
+int mrmp_exchange_wait(mrmp_exchange *x, int ch, unsigned int src_mask, void *stream);
+int mrmp_exchange_advance(mrmp_exchange *x, int ch);
+int mrmp_exchange_error(mrmp_exchange *x);
+/* Multi-GPU roadmap build without a collective: pack the CSR of this rank's agent block (slot
+ * layout of mrmp_roadmaps_pack_csr_shard_dev; 4*(cap_agents*nv + cap_nnz) must equal the channel's
+ * slot size and be a multiple of 16) into the slot of this rank in EVERY rank's buffer and
+ * signal; adopt = wait for all ranks, then stitch the slots into the CSR of the full set. */
+int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
+                                 int cap_agents, int64_t cap_nnz, void *stream);
+int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
+                                   int cap_agents, int64_t cap_nnz, void *stream, int64_t *nnz_out);
+
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
                               int32_t **row_ptr_dev, int32_t **col_idx_dev, int64_t *nnz_out);

@@ -474,6 +474,18 @@ class Roadmaps:
                                                        out.size))
         return out
 
+    def edge_conflicts_dev(self, n_cols: int, col_agent_ptr: int, col_vfrom_ptr: int,
+                           col_vto_ptr: int, group_size: int, out_ptr: int, stream: int,
+                           cols: "Roadmaps | None" = None) -> None:
+        """The same table with device-resident column ids and a device (or peer-mapped) output
+        buffer, asynchronous on `stream`: a rank of a multi-GPU job computes the rows of its agents
+        against all agents' path edges (cols = the full set) and writes them straight into the
+        memory of the rank that gathers the table (sssp_b200/peer.py)."""
+        L.check(self._lib.mrmp_roadmaps_edge_conflicts_dev(self._h, cols._h if cols else None,
+                                                           int(n_cols), col_agent_ptr,
+                                                           col_vfrom_ptr, col_vto_ptr,
+                                                           int(group_size), out_ptr, stream))
+
     def to_nodes(self) -> List[List[Node]]:
         """Vector{Vector{Node}} as the reference's PRMs returns it (0-based ids)."""
         tabs = self.nodes()

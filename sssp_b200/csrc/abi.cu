@@ -1194,6 +1194,54 @@ extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, in
     return roadmaps_settle(rm, false);  // a deferred sampling verdict of this set, if any
 }
 
+// ---- the same exchange without a collective: shards pushed into the peers' memory ------------
+extern "C" int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x, int ch,
+                                            int world, int cap_agents, int64_t cap_nnz,
+                                            void *stream) {
+    NEED(rm && x && world >= 1 && world <= 32 && cap_agents >= rm->n_agents && cap_nnz >= 0,
+         "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    if (rm->nnz > cap_nnz)
+        return fail(MRMP_ERR_CAPACITY, "shard holds %lld edges, slot only %lld", (long long)rm->nnz,
+                    (long long)cap_nnz);
+    const int64_t rows_cap = (int64_t)cap_agents * rm->nv;
+    NEED(mrmp_exchange_slot_bytes(x, ch) >= (int64_t)sizeof(int32_t) * (rows_cap + cap_nnz),
+         "exchange slot too small for the shard");
+    mrmp_ctx *c = rm->ctx;
+    CU(cudaSetDevice(c->device));
+    LaunchCfg lc = lcfg(c, (cudaStream_t)stream);
+    for (int d0 = 0; d0 < world; d0 += 8) {
+        CsrPushDst dst;
+        dst.n = world - d0 < 8 ? world - d0 : 8;
+        for (int k = 0; k < 8; ++k) {
+            dst.slot[k] = k < dst.n ? (int32_t *)mrmp_exchange_ptr(x, ch, d0 + k) : nullptr;
+            NEED(k >= dst.n || dst.slot[k], "exchange is not connected to every rank");
+        }
+        CU(launch_csr_pack_push(lc, (int64_t)rm->n_agents * rm->nv, rows_cap, rm->row_ptr,
+                                rm->col_idx, dst));
+    }
+    return mrmp_exchange_signal(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
+}
+
+extern "C" int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *x, int ch,
+                                              int world, int cap_agents, int64_t cap_nnz,
+                                              void *stream, int64_t *nnz_out) {
+    NEED(rm && x && world >= 1 && world <= 32, "bad arguments");
+    int rc = mrmp_exchange_wait(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
+    if (rc) return rc;
+    NEED(((int64_t)cap_agents * rm->nv + cap_nnz) % 4 == 0 &&
+             mrmp_exchange_slot_bytes(x, ch) ==
+                 (int64_t)sizeof(int32_t) * ((int64_t)cap_agents * rm->nv + cap_nnz),
+         "exchange slot must be exactly 4 * (cap_agents * nv + cap_nnz) bytes, a multiple of 16");
+    rc = mrmp_roadmaps_set_csr_shards_dev(rm, world, cap_agents, cap_nnz,
+                                          (const int32_t *)mrmp_exchange_slots(x, ch), stream,
+                                          nnz_out);
+    if (rc) return rc;
+    const int bad = mrmp_exchange_error(x);  // the stream has been synchronised by the stitch
+    if (bad) return fail(MRMP_ERR_CUDA, "exchange: rank %d never published its shard", bad - 1);
+    return MRMP_OK;
+}
+
 extern "C" int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out) {
     NEED(rm && nnz_total_out, "bad arguments");
     NEED(rm->built, "roadmaps not built");

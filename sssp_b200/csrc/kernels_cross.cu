@@ -9,7 +9,7 @@
 //
 // Design (third version; the measurements that led here are in profiles/):
 //  * Both sides are sorted by the Morton cell of their midpoint (counting sort over 4096 cells:
-//    histogram -> scan -> scatter).  32 (or 64) consecutive rows form a spatially compact WARP
+//    histogram -> scan -> scatter).  32 consecutive rows form a spatially compact WARP
 //    TILE, 32 consecutive columns a COLUMN TILE with a stored bounding box.
 //  * A warp owns a warp tile (rows in registers).  Column tiles are first tested box against box
 //    (32 tile headers per ballot, FP64); a tile farther from the warp's box than the largest
@@ -32,10 +32,6 @@
 #include <stdlib.h>
 
 #include "point_model.cuh"
-
-#ifndef MRMP_CROSS_RPL_DEFAULT
-#define MRMP_CROSS_RPL_DEFAULT 1
-#endif
 
 namespace mrmp {
 
@@ -253,7 +249,8 @@ __global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
                                       : (P.group_size > 0 ? src / P.group_size : src));
             X.orig = (int)(src + P.orig_base);
             X.key = P.col_key ? __ldg(P.col_key + src) : 0;
-            B.m[2] = 0.0f;
+            // 2-D: the z slot carries the output slot for the kernel's in-loop "already set" test
+            B.m[2] = D == 2 ? __int_as_float(X.bit) : 0.0f;
 #pragma unroll
             for (int x = 0; x < D; ++x) {
                 const double m = dmul(dadd(X.a[x], X.b[x]), 0.5);
@@ -402,10 +399,13 @@ __device__ __forceinline__ bool cross_pair_verdict(const CtxView &cv, const doub
                           cv.has_pair_tab);
 }
 
-template <int D, int MODE, int RPL>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, RPL == 1 ? MRMP_CROSS_MINB : 2)
+// FD ("fast drop", 2-D OR mode with at most 64 groups): the group id of a column travels in the
+// unused z slot of its broad-phase record and the row's output words live in registers, so the
+// "bit already set" test is part of the broad phase instead of a loop over the survivors.
+template <int D, int MODE, bool FD>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, MRMP_CROSS_MINB)
 k_cross_collide(CtxView cv, CrossArgs<D> A) {
-    constexpr int R = 32 * RPL;
+    constexpr int R = 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem<D, R> &S = reinterpret_cast<WarpSmem<D, R> *>(smem_raw)[warp];
     const double *rads = cv.blob + cv.crads_off;
@@ -417,8 +417,7 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
         if (lane == 0) wt = atomicAdd(A.work, 1u);
         wt = __shfl_sync(0xffffffffu, wt, 0);
         if ((int64_t)wt >= n_wt) break;
-        RowB32 rb[RPL];
-        bool live[RPL];
+        RowB32 rb;
         double lo[D], hi[D], Rmax = 0.0;
         bool poison = false;
 #pragma unroll
@@ -426,49 +425,44 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
             lo[x] = 1e300;
             hi[x] = -1e300;
         }
+        const int64_t r = (int64_t)wt * R + lane;
+        const bool live = r < A.n_rows;
+        if (live) {
+            const RowRec<D> rec = A.rows[r];
+            const bool known = rec.agent >= 0 && rec.agent < cv.n_agents;
+            const double ri = known ? __ldg(rads + rec.agent) : 1e300;
+            const double inv = seg_filter_inv<D>(rec.a, rec.b);
+            // reach of this row: its radius + slack (+ its own half length in the box test);
+            // the column's radius and half length are in its record
+            const double Rc = ri + kPad;
+            rb = bound32_row<D>(rec.a, rec.b, Rc, inv >= 0.0 && known);
+            Rmax = Rc + half_len_up<D>(rec.a, rec.b);
+            poison |= !(Rmax == Rmax);
 #pragma unroll
-        for (int k = 0; k < RPL; ++k) {
-            const int slot = k * 32 + lane;
-            const int64_t r = (int64_t)wt * R + slot;
-            live[k] = r < A.n_rows;
-            if (live[k]) {
-                const RowRec<D> rec = A.rows[r];
-                const bool known = rec.agent >= 0 && rec.agent < cv.n_agents;
-                const double ri = known ? __ldg(rads + rec.agent) : 1e300;
-                const double inv = seg_filter_inv<D>(rec.a, rec.b);
-                // reach of this row: its radius + slack (+ its own half length in the box test);
-                // the column's radius and half length are in its record
-                const double Rc = ri + kPad;
-                rb[k] = bound32_row<D>(rec.a, rec.b, Rc, inv >= 0.0 && known);
-                const double R64 = Rc + half_len_up<D>(rec.a, rec.b);
-                Rmax = fmax(Rmax, R64);
-                poison |= !(R64 == R64);
-#pragma unroll
-                for (int x = 0; x < D; ++x) {
-                    const double m = dmul(dadd(rec.a[x], rec.b[x]), 0.5);
-                    S.rab[slot][x] = rec.a[x];
-                    S.rab[slot][D + x] = rec.b[x];
-                    lo[x] = fmin(lo[x], m);
-                    hi[x] = fmax(hi[x], m);
-                    poison |= !(m == m);
-                }
-                S.inv[slot] = inv;
-                S.rad[slot] = known ? ri : 0.0;
-                S.agent[slot] = rec.agent;
-                S.orig[slot] = rec.orig;
-                S.key[slot] = A.row_key ? __ldg(A.row_key + rec.orig) : 0;
-            } else {
-#pragma unroll
-                for (int x = 0; x < 3; ++x) rb[k].m[x] = rb[k].u[x] = 0.0f;
-                rb[k].h = rb[k].rc = 0.0f;
-                S.agent[slot] = -2;
-                S.orig[slot] = 0;
+            for (int x = 0; x < D; ++x) {
+                const double m = dmul(dadd(rec.a[x], rec.b[x]), 0.5);
+                S.rab[lane][x] = rec.a[x];
+                S.rab[lane][D + x] = rec.b[x];
+                lo[x] = hi[x] = m;
+                poison |= !(m == m);
             }
-            if (MODE == kModeOr) {
+            S.inv[lane] = inv;
+            S.rad[lane] = known ? ri : 0.0;
+            S.agent[lane] = known ? rec.agent : -2;
+            S.orig[lane] = rec.orig;
+            S.key[lane] = A.row_key ? __ldg(A.row_key + rec.orig) : 0;
+        } else {
 #pragma unroll
-                for (int w = 0; w < kRedWords; ++w) S.obits[slot][w] = 0u;
-            }
+            for (int x = 0; x < 3; ++x) rb.m[x] = rb.u[x] = 0.0f;
+            rb.h = rb.rc = 0.0f;
+            S.agent[lane] = -2;
+            S.orig[lane] = 0;
         }
+        if (MODE == kModeOr) {
+#pragma unroll
+            for (int w = 0; w < kRedWords; ++w) S.obits[lane][w] = 0u;
+        }
+        uint32_t ob0 = 0u, ob1 = 0u;  // FD: this row's output words
         // warp box and largest reach; a NaN row disables the box test for the whole warp tile
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -502,38 +496,35 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                 tmask &= tmask - 1;
                 const float4 *cbp = reinterpret_cast<const float4 *>(A.cb + (int64_t)t * kCols);
                 const ColX<D> *cxp = A.cx + (int64_t)t * kCols;
-                // ---- broad phase (FP32): this lane's rows against the 32 columns of the tile
-                uint32_t mask[RPL];
+                // ---- broad phase (FP32): this lane's row against the 32 columns of the tile
+                uint32_t mask = 0u;
 #pragma unroll
-                for (int k = 0; k < RPL; ++k) mask[k] = 0u;
-#pragma unroll 8
                 for (int c = 0; c < kCols; ++c) {
                     const float4 q = __ldg(cbp + c);
-#pragma unroll
-                    for (int k = 0; k < RPL; ++k)
-                        mask[k] |= (bound32_far<D>(rb[k], q.x, q.y, q.z, q.w) ? 0u : 1u) << c;
+                    bool keep = !bound32_far<D>(rb, q.x, q.y, FD ? 0.0f : q.z, q.w);
+                    if (FD) {
+                        // the output is an OR over each column group: a pair whose bit this row
+                        // has already set (by an earlier tile) cannot change it
+                        const int bit = __float_as_int(q.z);  // warp-uniform
+                        keep &= !(((bit & 32 ? ob1 : ob0) >> (bit & 31)) & 1u);
+                    }
+                    mask |= (keep ? 1u : 0u) << c;
                 }
                 ++n_tiles_read;
-                int cnt = 0;
-#pragma unroll
-                for (int k = 0; k < RPL; ++k) {
-                    if (!live[k]) mask[k] = 0u;
-                    if (MODE == kModeOr) {
-                        // the output is an OR over each column group: a pair whose bit this row
-                        // has already set (by an earlier tile) cannot change it -- drop it here,
-                        // before the compaction, so the exact stage stays dense
-                        const int slot = k * 32 + lane;
-                        uint32_t m2 = mask[k];
-                        while (m2) {
-                            const int c = __ffs(m2) - 1;
-                            m2 &= m2 - 1;
-                            const int bit = __ldg(&cxp[c].bit);
-                            if ((S.obits[slot][bit >> 5] >> (bit & 31)) & 1u) mask[k] &= ~(1u << c);
-                        }
+                if (!live) mask = 0u;
+                if (MODE == kModeOr && !FD) {
+                    // same drop for the general layout (3-D, more than 64 groups): walk the
+                    // survivors, before the compaction, so that the exact stage stays dense
+                    uint32_t m2 = mask;
+                    while (m2) {
+                        const int c = __ffs(m2) - 1;
+                        m2 &= m2 - 1;
+                        const int bit = __ldg(&cxp[c].bit);
+                        if ((S.obits[lane][bit >> 5] >> (bit & 31)) & 1u) mask &= ~(1u << c);
                     }
-                    cnt += __popc(mask[k]);
                 }
                 // ---- compaction into the warp queue
+                const int cnt = __popc(mask);
                 int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -543,14 +534,10 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total == 0) continue;
                 int base = incl - cnt;
-#pragma unroll
-                for (int k = 0; k < RPL; ++k) {
-                    uint32_t m2 = mask[k];
-                    while (m2) {
-                        const int c = __ffs(m2) - 1;
-                        m2 &= m2 - 1;
-                        S.queue[base++] = (uint16_t)(((k * 32 + lane) << 5) | c);
-                    }
+                while (mask) {
+                    const int c = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    S.queue[base++] = (uint16_t)((lane << 5) | c);
                 }
                 __syncwarp();
                 // ---- verdict filter / reference arithmetic on dense lanes
@@ -560,8 +547,8 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                     const ColX<D> &X = cxp[cc];
                     const int4 ids = __ldg(reinterpret_cast<const int4 *>(&X.agent));
                     const int ri = S.agent[rr], cj = ids.x;
-                    if (cj < 0 || cj == ri) continue;  // padding / same agent: never a conflict
-                    if (ri < 0 || ri >= cv.n_agents || cj >= cv.n_agents) continue;
+                    // padding / unknown agent / same agent: never a conflict
+                    if (cj < 0 || ri < 0 || cj == ri) continue;
                     if (A.row_key && !(ids.w > S.key[rr])) continue;
                     double ca[D], cb[D];
                     if constexpr (D == 2) {
@@ -598,23 +585,22 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                     }
                 }
                 __syncwarp();
+                if (FD) {
+                    ob0 = S.obits[lane][0];
+                    ob1 = S.obits[lane][1];
+                }
             }
         }
-        if (MODE == kModeOr) {
-            // every word of the row is written exactly once (the output may be mapped host
-            // memory: plain stores, two words per transaction where the layout allows)
-#pragma unroll
-            for (int k = 0; k < RPL; ++k) {
-                if (!live[k]) continue;
-                const int slot = k * 32 + lane;
-                uint32_t *dst = A.out + (int64_t)S.orig[slot] * A.out_stride;
-                if ((A.words_per_row & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-                    for (int w = 0; w < A.words_per_row; w += 2)
-                        *reinterpret_cast<uint2 *>(dst + w) =
-                            make_uint2(S.obits[slot][w], S.obits[slot][w + 1]);
-                } else {
-                    for (int w = 0; w < A.words_per_row; ++w) dst[w] = S.obits[slot][w];
-                }
+        if (MODE == kModeOr && live) {
+            // every word of the row is written exactly once (the output may be mapped host or
+            // peer memory: plain stores, two words per transaction where the layout allows)
+            uint32_t *dst = A.out + (int64_t)S.orig[lane] * A.out_stride;
+            if ((A.words_per_row & 1) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+                for (int w = 0; w < A.words_per_row; w += 2)
+                    *reinterpret_cast<uint2 *>(dst + w) =
+                        make_uint2(S.obits[lane][w], S.obits[lane][w + 1]);
+            } else {
+                for (int w = 0; w < A.words_per_row; ++w) dst[w] = S.obits[lane][w];
             }
         }
         __syncwarp();
@@ -759,32 +745,21 @@ cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int6
     return cudaGetLastError();
 }
 
-// rows per lane of the OR-mode kernel (the bench shape): 1 or 2; MRMP_CROSS_RPL overrides
-static int cross_rpl() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("MRMP_CROSS_RPL");
-        v = (e && e[0] == '2') ? 2 : (e && e[0] == '1') ? 1 : MRMP_CROSS_RPL_DEFAULT;
-    }
-    return v;
-}
-
-template <int D, int MODE, int RPL>
+template <int D, int MODE, bool FD>
 static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const CrossArgs<D> &A) {
-    constexpr int R = 32 * RPL;
+    constexpr int R = 32;
     const int smem = (int)sizeof(WarpSmem<D, R>) * kWarpsPerCta;
     int per_sm = (220 * 1024) / smem;
-    const int minb = RPL == 1 ? MRMP_CROSS_MINB : 2;
-    if (per_sm > minb) per_sm = minb;  // register-limited residency
+    if (per_sm > MRMP_CROSS_MINB) per_sm = MRMP_CROSS_MINB;  // register-limited residency
     if (per_sm < 1) per_sm = 1;
     const int64_t n_wt = (A.n_rows + R - 1) / R;
     int64_t want = (n_wt + kWarpsPerCta - 1) / kWarpsPerCta;
     const int64_t cap = (int64_t)lc.sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    cudaError_t e = cudaFuncSetAttribute(k_cross_collide<D, MODE, RPL>,
+    cudaError_t e = cudaFuncSetAttribute(k_cross_collide<D, MODE, FD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k_cross_collide<D, MODE, RPL><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(cv, A);
+    k_cross_collide<D, MODE, FD><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(cv, A);
     count_launch();
     return cudaGetLastError();
 }
@@ -813,11 +788,12 @@ static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_
     if (e != cudaSuccess) return e;
     switch (co.mode) {
     case kModeOr:
-        return cross_rpl() == 2 ? launch_cross_v<D, kModeOr, 2>(cv, lc, A)
-                                : launch_cross_v<D, kModeOr, 1>(cv, lc, A);
-    case kModeBits: return launch_cross_v<D, kModeBits, 1>(cv, lc, A);
-    case kModeCount: return launch_cross_v<D, kModeCount, 1>(cv, lc, A);
-    case kModeFirst: return launch_cross_v<D, kModeFirst, 1>(cv, lc, A);
+        if constexpr (D == 2)
+            if (co.words_per_row <= 2) return launch_cross_v<D, kModeOr, true>(cv, lc, A);
+        return launch_cross_v<D, kModeOr, false>(cv, lc, A);
+    case kModeBits: return launch_cross_v<D, kModeBits, false>(cv, lc, A);
+    case kModeCount: return launch_cross_v<D, kModeCount, false>(cv, lc, A);
+    case kModeFirst: return launch_cross_v<D, kModeFirst, false>(cv, lc, A);
     default: return cudaErrorInvalidValue;
     }
 }

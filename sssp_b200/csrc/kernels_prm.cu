@@ -857,6 +857,29 @@ k_csr_pack_shard(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ r
     for (int64_t e = tid; e < nnz; e += stride) slot[rows_cap + e] = col_idx[e];
 }
 
+// the same pack, written to the slot of this rank in the buffers of up to 8 ranks at once (peer
+// mappings over NVLink; consecutive threads write consecutive words, so every warp store is one
+// 128-byte transaction per destination)
+__global__ void __launch_bounds__(kThreads)
+k_csr_pack_push(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ row_ptr,
+                const int32_t *__restrict__ col_idx, CsrPushDst dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t r = tid; r < rows_cap; r += stride) {
+        const int32_t v = r < n_rows ? row_ptr[r + 1] - row_ptr[r] : 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < dst.n) dst.slot[k][r] = v;
+    }
+    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    for (int64_t e = tid; e < nnz; e += stride) {
+        const int32_t v = col_idx[e];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < dst.n) dst.slot[k][rows_cap + e] = v;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_csr_shard_counts(int64_t n_rows, int64_t rows_cap, int64_t slot_stride,
                    const int32_t *__restrict__ slots, int32_t *__restrict__ row_cnt) {
@@ -971,6 +994,15 @@ cudaError_t launch_csr_pack_shard(const LaunchCfg &lc, int64_t n_rows, int64_t r
                                   const int32_t *row_ptr, const int32_t *col_idx, int32_t *slot) {
     k_csr_pack_shard<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, row_ptr, col_idx,
                                                                  slot);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_csr_pack_push(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                 const int32_t *row_ptr, const int32_t *col_idx,
+                                 const CsrPushDst &dst) {
+    k_csr_pack_push<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, row_ptr, col_idx,
+                                                                 dst);
     count_launch();
     return cudaGetLastError();
 }

@@ -242,6 +242,13 @@ cudaError_t launch_grid_gather_rows(const LaunchCfg &lc, int64_t n_rows, const i
 // CSR shards of a multi-GPU build: slot = int32 cnt[rows_cap] | int32 col[cap_nnz]
 cudaError_t launch_csr_pack_shard(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
                                   const int32_t *row_ptr, const int32_t *col_idx, int32_t *slot);
+struct CsrPushDst {  // destinations of one shard push (own buffer and peer mappings)
+    int n;
+    int32_t *slot[8];
+};
+cudaError_t launch_csr_pack_push(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
+                                 const int32_t *row_ptr, const int32_t *col_idx,
+                                 const CsrPushDst &dst);
 cudaError_t launch_csr_shard_counts(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
                                     int64_t slot_stride, const int32_t *slots, int32_t *row_cnt);
 cudaError_t launch_csr_stitch(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,

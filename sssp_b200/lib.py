@@ -101,6 +101,22 @@ _SIGS = {
     "mrmp_roadmaps_set_csr_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "mrmp_roadmaps_pack_csr_shard_dev": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp]),
     "mrmp_roadmaps_set_csr_shards_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _lp]),
+    "mrmp_exchange_handle_bytes": (C.c_int, []),
+    "mrmp_exchange_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp), _vp]),
+    "mrmp_exchange_destroy": (None, [_vp]),
+    "mrmp_exchange_connect": (C.c_int, [_vp, _vp]),
+    "mrmp_exchange_connect_ptrs": (C.c_int, [_vp, _vp]),
+    "mrmp_exchange_local_buffer": (_vp, [_vp]),
+    "mrmp_exchange_ptr": (_vp, [_vp, C.c_int, C.c_int]),
+    "mrmp_exchange_slots": (_vp, [_vp, C.c_int]),
+    "mrmp_exchange_slot_bytes": (C.c_int64, [_vp, C.c_int]),
+    "mrmp_exchange_signal": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
+    "mrmp_exchange_wait": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
+    "mrmp_exchange_advance": (C.c_int, [_vp, C.c_int]),
+    "mrmp_exchange_error": (C.c_int, [_vp]),
+    "mrmp_roadmaps_push_csr_shard": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64, _vp]),
+    "mrmp_roadmaps_adopt_csr_shards": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64, _vp,
+                                                 _lp]),
     "mrmp_ctx_stats": (C.c_int, [_vp, _vp, C.c_int]),
     "mrmp_sample_states": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _dp]),
     "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),

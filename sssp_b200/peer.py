@@ -1,0 +1,131 @@
+"""Peer-memory exchange between the GPUs of one box (include/mrmp_b200.h, "peer-memory exchange").
+
+One process per GPU; torch.distributed only carries the 64-byte CUDA IPC handles at set-up.
+After that the roadmap shards (CSR of each rank's agent block, prm.jl:265-275) and the
+conflict-table rows (pp.jl:179-189) are written by the producing kernels straight into the
+peers' memory over NVLink, followed by one flag per peer -- no collective call in the data path.
+
+`Exchange.connect()` returns False when the peer mapping cannot be opened on this machine
+(cudaIpcOpenMemHandle refused): callers then fall back to the NCCL all-gather path of
+sssp_b200.sharding / mrmp_roadmaps_pack_csr_shard_dev.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import lib as L
+
+
+class Exchange:
+    """n_chan channels of fixed-size per-rank slots, double buffered by epoch."""
+
+    def __init__(self, ctx, world: int, rank: int, slot_bytes: Sequence[int]):
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        self.n_chan = len(slot_bytes)
+        self._lib = ctx._lib
+        sb = (C.c_int64 * self.n_chan)(*[int(b) for b in slot_bytes])
+        self.handle = np.zeros(int(self._lib.mrmp_exchange_handle_bytes()), np.uint8)
+        h = C.c_void_p()
+        L.check(self._lib.mrmp_exchange_create(ctx._h, self.world, self.rank, self.n_chan, sb,
+                                               C.byref(h), self.handle.ctypes.data_as(L._vp)))
+        self._h = h
+        self.all_mask = (1 << self.world) - 1
+        self.connected = self.world == 1
+        if self.world == 1:   # a single rank is its own peer
+            bufs = (C.c_void_p * 1)(self._lib.mrmp_exchange_local_buffer(self._h))
+            L.check(self._lib.mrmp_exchange_connect_ptrs(self._h, bufs))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mrmp_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- set-up -----------------------------------------------------------------------------
+    def connect(self, group=None) -> bool:
+        """All-gather the IPC handles over torch.distributed (any backend) and open the peers'
+        buffers.  Returns True when EVERY rank succeeded, False otherwise (nobody uses it then)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return True
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", self.ctx.device) if backend == "nccl" else torch.device("cpu")
+        mine = torch.from_numpy(self.handle.copy()).to(dev)
+        allh = torch.empty(self.world * mine.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        handles = np.ascontiguousarray(allh.cpu().numpy())
+        rc = self._lib.mrmp_exchange_connect(self._h, handles.ctypes.data_as(L._vp))
+        ok = torch.tensor([1 if rc == L.OK else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        self.connected = bool(int(ok.item()))
+        self.connect_error = None if rc == L.OK else self._lib.mrmp_last_error().decode("utf-8", "replace")
+        return self.connected
+
+    @staticmethod
+    def connect_local(xs: List["Exchange"]) -> None:
+        """Several ranks driven by one process on one device (tests): raw pointers."""
+        bufs = (C.c_void_p * len(xs))(*[x._lib.mrmp_exchange_local_buffer(x._h) for x in xs])
+        for x in xs:
+            L.check(x._lib.mrmp_exchange_connect_ptrs(x._h, bufs))
+            x.connected = True
+
+    # ---- one round --------------------------------------------------------------------------
+    def ptr(self, ch: int, dst: int) -> int:
+        """Device address (in rank dst's buffer) where THIS rank writes its slot of channel ch."""
+        p = self._lib.mrmp_exchange_ptr(self._h, int(ch), int(dst))
+        if not p:
+            raise L.MRMPError(L.ERR_INVALID, "exchange not connected to rank %d" % dst)
+        return int(p)
+
+    def slots(self, ch: int) -> int:
+        """Base of the local [world][slot] block of channel ch (valid after wait)."""
+        return int(self._lib.mrmp_exchange_slots(self._h, int(ch)))
+
+    def slot_bytes(self, ch: int) -> int:
+        return int(self._lib.mrmp_exchange_slot_bytes(self._h, int(ch)))
+
+    def signal(self, ch: int, stream: int, dst_mask: Optional[int] = None) -> None:
+        L.check(self._lib.mrmp_exchange_signal(self._h, int(ch),
+                                               self.all_mask if dst_mask is None else int(dst_mask),
+                                               stream))
+
+    def wait(self, ch: int, stream: int, src_mask: Optional[int] = None) -> None:
+        L.check(self._lib.mrmp_exchange_wait(self._h, int(ch),
+                                             self.all_mask if src_mask is None else int(src_mask),
+                                             stream))
+
+    def advance(self, ch: int) -> None:
+        L.check(self._lib.mrmp_exchange_advance(self._h, int(ch)))
+
+    def error(self) -> int:
+        return int(self._lib.mrmp_exchange_error(self._h))
+
+    # ---- roadmap shards -------------------------------------------------------------------------
+    def push_csr_shard(self, rm_shard, ch: int, cap_agents: int, cap_nnz: int, stream: int) -> None:
+        L.check(self._lib.mrmp_roadmaps_push_csr_shard(rm_shard._h, self._h, int(ch), self.world,
+                                                       int(cap_agents), int(cap_nnz), stream))
+
+    def adopt_csr_shards(self, rm_all, ch: int, cap_agents: int, cap_nnz: int, stream: int) -> int:
+        out = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_adopt_csr_shards(rm_all._h, self._h, int(ch), self.world,
+                                                         int(cap_agents), int(cap_nnz), stream,
+                                                         C.byref(out)))
+        return int(out.value)
+
+
+def csr_slot_words(cap_agents: int, nv: int, nnz_max: int) -> int:
+    """cap_nnz for a shard slot: head room over the largest shard, and the slot
+    (cap_agents*nv + cap_nnz words) a multiple of 16 bytes."""
+    cap_nnz = int(nnz_max) * 5 // 4 + 1024
+    rows_cap = int(cap_agents) * int(nv)
+    cap_nnz += (-(rows_cap + cap_nnz)) % 4
+    return cap_nnz

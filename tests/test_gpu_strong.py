@@ -1,0 +1,106 @@
+"""One conflict table strong-scaled over several ranks (emulated on one GPU): every rank draws
+all vertices, builds the roadmaps of its agent block (prm.jl:265-275), pushes its CSR shard into
+every rank's exchange buffer, evaluates the table rows of ITS agents against all agents' path
+edges (pp.jl:179-189) and writes them into rank 0's buffer.  The stitched roadmaps and the
+gathered table must equal the single-GPU results byte for byte."""
+import numpy as np
+import pytest
+
+import sssp_b200 as S
+from sssp_b200 import peer as P, sharding as SH, workload as W
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_row_sharded_table_equals_single_gpu_table(world):
+    import torch
+    N, nv, T = 10, 160, 17
+    inst = W.point2d_many(N=N, seed=3, nv=nv, rad=0.17)
+    st = torch.cuda.current_stream().cuda_stream
+    # ---- single GPU
+    ctx0 = S.Context(inst.model, inst.rads, inst.obstacles)
+    ctx0.set_stream(st)
+    full = S.Roadmaps(ctx0, 0, N, nv)
+    full.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+    nnz = full.build(inst.rad)
+    rp_ref, col_ref = full.csr()
+    _, ca, vf, vt = W.random_walk_paths(inst, rp_ref, col_ref, T, seed=5)
+    bits_ref = full.edge_conflicts(ca, vf, vt, N)
+    wpr = bits_ref.shape[1]
+    assert bits_ref.any() and nnz == bits_ref.shape[0]
+    # the oracle agrees with the single-GPU table (so the sharded one is pinned to it as well)
+    nodes = full.nodes()
+    rows = np.repeat(np.arange(N * nv), np.diff(rp_ref))
+    ra = (rows // nv).astype(np.int32)
+    sel = slice(0, None, 9)
+    obits = O.Oracle(O.POINT2D, inst.rads, inst.obstacles).collide_cross(
+        ra[sel], nodes[ra, rows % nv][sel], nodes[ra, col_ref][sel], ca, nodes[ca, vf], nodes[ca, vt], N)
+    assert np.array_equal(bits_ref[sel], obits)
+
+    # ---- `world` ranks on this GPU, each with its own context
+    cols_d = [torch.from_numpy(x).cuda() for x in (ca, vf, vt)]
+    ranks = []
+    nnz_sh = []
+    for r in range(world):
+        a0, n_local, cap = SH.agent_block(N, world, r)
+        ctx = S.Context(inst.model, inst.rads, inst.obstacles)
+        ctx.set_stream(st)
+        allrm = S.Roadmaps(ctx, 0, N, nv)
+        allrm.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+        sh = None
+        if n_local > 0:
+            sh = S.Roadmaps(ctx, a0, n_local, nv)
+            sh.bind_nodes(nv, allrm.device_ptrs()["nodes"] + a0 * nv * 2 * 8)
+            nnz_sh.append(sh.build(inst.rad))
+        else:
+            nnz_sh.append(0)
+        ranks.append((ctx, allrm, sh, a0, n_local, cap))
+    cap = ranks[0][5]
+    cap_nnz = P.csr_slot_words(cap, nv, max(nnz_sh))
+    tab_words = (max(nnz_sh) + 64) * wpr
+    tab_words += (-tab_words) % 4
+    xs = [P.Exchange(ranks[r][0], world, r, [4 * (cap * nv + cap_nnz), 4 * tab_words])
+          for r in range(world)]
+    P.Exchange.connect_local(xs)
+    for round_ in range(3):            # several rounds: epochs and double buffering
+        for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
+            xs[r].push_csr_shard(sh, 0, cap, cap_nnz, st)
+            sh.edge_conflicts_dev(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                  cols_d[2].data_ptr(), N, xs[r].ptr(1, 0), st, cols=allrm)
+            xs[r].signal(1, st, dst_mask=1)
+        for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
+            assert xs[r].adopt_csr_shards(allrm, 0, cap, cap_nnz, st) == nnz
+            rp, col = allrm.csr()
+            assert np.array_equal(rp, rp_ref) and np.array_equal(col, col_ref)
+        xs[0].wait(1, st)
+        torch.cuda.synchronize()
+        assert xs[0].error() == 0
+        slots = torch.as_tensor(_CudaArray(xs[0].slots(1), (world, xs[0].slot_bytes(1) // 4), "<i4"),
+                                device="cuda").cpu().numpy().view(np.uint32)
+        got = np.concatenate([slots[r, : nnz_sh[r] * wpr].reshape(-1, wpr) for r in range(world)])
+        assert got.shape == bits_ref.shape and np.array_equal(got, bits_ref)
+        for x in xs:
+            x.advance(0)
+            x.advance(1)
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3}
+
+
+def test_exchange_wait_gives_up_instead_of_hanging():
+    """A rank that never publishes must not hang the stream: the wait times out and reports."""
+    import torch
+    rads = np.array([0.02, 0.03])
+    ctx = S.Context(O.POINT2D, rads, np.zeros((0, 3)))
+    st = torch.cuda.current_stream().cuda_stream
+    xs = [P.Exchange(ctx, 2, r, [64]) for r in range(2)]
+    P.Exchange.connect_local(xs)
+    xs[0].signal(0, st)                  # rank 0 publishes to both, rank 1 never does
+    xs[0].wait(0, st)
+    torch.cuda.synchronize()
+    assert xs[0].error() == 2            # 1 + the missing rank
