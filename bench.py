@@ -347,7 +347,7 @@ def run_b200(args):
         nnz_all = torch.zeros(world, dtype=torch.int64, device=dev)
         nnz_all[rank] = nnz_sh
         dist.all_reduce(nnz_all)
-        mg = dict(ex=ex, p2p=p2p, cap_nnz=cap_nnz, tab_words=tab_words, slots=slots,
+        mg = dict(ex=ex, p2p=p2p, round=0, cap_nnz=cap_nnz, tab_words=tab_words, slots=slots,
                   tab_slots=tab_slots, nnz_sh=[int(x) for x in nnz_all.tolist()],
                   exchange="nvlink peer stores from the producing kernels (CUDA IPC mappings) + flags"
                   if p2p else "nccl all-gather (%s)" % (getattr(ex, "connect_error", None) or args.exchange))
@@ -356,6 +356,10 @@ def run_b200(args):
         """this rank's CSR shard -> every rank; afterwards rm_all holds all roadmaps"""
         ex = mg["ex"]
         if mg["p2p"]:
+            if mg["round"] > 0:      # next epoch of both channels (slots are double buffered)
+                ex.advance(0)
+                ex.advance(1)
+            mg["round"] += 1
             ex.push_csr_shard(rm_sh, 0, cap, mg["cap_nnz"], st)
             return None
         L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(rm_sh._h, cap, mg["cap_nnz"],
@@ -366,37 +370,70 @@ def run_b200(args):
     def adopt_csr():
         ex = mg["ex"]
         if mg["p2p"]:
-            n = ex.adopt_csr_shards(rm_all, 0, cap, mg["cap_nnz"], st)
-            ex.advance(0)
-            return n
+            return ex.adopt_csr_shards(rm_all, 0, cap, mg["cap_nnz"], st)
         out = C.c_int64(0)
         L.check(lib.mrmp_roadmaps_set_csr_shards_dev(rm_all._h, world, cap, mg["cap_nnz"],
                                                      mg["slots"].data_ptr(), st, C.byref(out)))
         return int(out.value)
 
-    def step_strong(cols=cols_d):
+    def step_strong(cols=cols_d, marks=None):
         """ONE scenario over all ranks: draw all vertices, build the roadmaps of this rank's agent
         block, publish the CSR shard to every rank, evaluate the table rows of this rank's agents
         against all agents' path edges (written straight into rank 0's memory), adopt the peers'
-        shards.  The timed region ends when every rank holds all roadmaps and rank 0 the table."""
+        shards.  The timed region ends when every rank holds all roadmaps and rank 0 the table.
+        marks: optional list that receives a CUDA event after every stage (timeline)."""
         ex = mg["ex"]
+
+        def mark():
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                marks.append(e)
+
+        mark()
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
         rm_sh.build(radv)
+        mark()                                   # 0: sample + neighbour pass of this rank's agents
         exchange_csr()
+        mark()                                   # 1: shard packed and pushed / all-gathered
         if mg["p2p"]:
             rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
                                      N, ex.ptr(1, 0), st, cols=rm_all)
             ex.signal(1, st, dst_mask=1)
+            mark()                               # 2: table rows of this rank (written to rank 0)
             n = adopt_csr()
+            mark()                               # 3: peers' shards arrived and stitched
             if rank == 0:
                 ex.wait(1, st)
-            ex.advance(1)
+            mark()                               # 4: rank 0: all table rows arrived
         else:
             rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
                                      N, mg["tab_slots"][rank].data_ptr(), st, cols=rm_all)
+            mark()
             n = adopt_csr()
+            mark()
             dist.all_gather_into_tensor(mg["tab_slots"].view(-1), mg["tab_slots"][rank])
+            mark()
         return n
+
+    def stage_timeline(reps=10):
+        """per-stage CUDA-event durations of the strong step on this rank, mean over reps, gathered
+        from every rank (there is no nsys in this image: the events are the timeline)"""
+        names = ["build_own_agents", "publish_csr_shard", "table_rows_own_agents",
+                 "adopt_peer_shards", "wait_table_rows"]
+        acc = np.zeros(len(names))
+        for _ in range(reps):
+            flush.zero_()
+            dist.barrier()
+            marks = []
+            step_strong(marks=marks)
+            torch.cuda.synchronize()
+            acc += np.array([marks[k].elapsed_time(marks[k + 1]) for k in range(len(names))])
+        t = torch.tensor(acc / reps, dtype=torch.float64, device=dev)
+        allt = torch.empty((world, len(names)), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt.view(-1), t)
+        return {"stages": names, "ms_by_rank": [[round(float(x), 4) for x in row] for row in allt.tolist()],
+                "rows_by_rank": mg["nnz_sh"]}
 
     def gathered_table():
         """rank 0: the table rows of all ranks in packed CSR order (after a strong step)"""
@@ -492,6 +529,7 @@ def run_b200(args):
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
         rm_all.build(radv_all)
 
+    timeline = stage_timeline() if (world > 1 and strong) else None
     ms_build_local = timed(build_local, reps=5)
     ms_build = timed(build_full, reps=5)       # all N roadmaps on one GPU (leaves rm_all complete)
     ctx.stats(reset=True)
@@ -675,7 +713,7 @@ def run_b200(args):
                         if strong else "weak: one scenario per rank, sharded build",
                 "exchange": mg["exchange"], "csr_slot_bytes": 4 * (cap * nv + mg["cap_nnz"]),
                 "table_bytes_to_rank0": int(nnz_total * wpr * 4) if strong else 0,
-                "check": strong_check, "ms_per_step_each": per_step[:8]},
+                "check": strong_check, "ms_per_step_each": per_step[:8], "timeline": timeline},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "explicit_lists": lists, "sssp_expansion": sssp_x, "arm22": arm,

@@ -46,14 +46,20 @@ function make_ctx(q::State, obstacles, rads::Vector{Float64};
                   safety_dist = SAFETY_DIST_LINE, max_dist = nothing,
                   device = 0) where {State<:AbsState}
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    base = isnothing(positions) ? C_NULL : pointer(reduce(vcat, positions))
-    aux = isnothing(axises) ? C_NULL : pointer(axises)          # capsule3d.jl:65
-    check(ccall((:mrmp_ctx_create, LIB), Cint,
-                (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
-                 Ptr{Cvoid}, Float64, Float64, Float64, Cint),
-                h, MODEL[State], length(rads), rads, base, aux, length(obstacles),
-                isempty(obstacles) ? C_NULL : pointer(obstacles), step_dist, safety_dist,
-                isnothing(max_dist) ? NaN : max_dist, device))
+    # positions::Vector{Vector{Float64}} (arm22.jl:32) -> one flat rooted array; every array whose
+    # raw pointer crosses the ccall is kept alive by GC.@preserve (the library copies them)
+    flat = isnothing(positions) ? Float64[] : reduce(vcat, positions)
+    ax = isnothing(axises) ? Float64[] : axises                   # capsule3d.jl:65
+    GC.@preserve flat ax obstacles begin
+        base = isnothing(positions) ? Ptr{Float64}(C_NULL) : pointer(flat)
+        aux = isnothing(axises) ? Ptr{Float64}(C_NULL) : pointer(ax)
+        check(ccall((:mrmp_ctx_create, LIB), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
+                     Ptr{Cvoid}, Float64, Float64, Float64, Cint),
+                    h, MODEL[State], length(rads), rads, base, aux, length(obstacles),
+                    isempty(obstacles) ? C_NULL : pointer(obstacles), step_dist, safety_dist,
+                    isnothing(max_dist) ? NaN : max_dist, device))
+    end
     return Ctx(h[])
 end
 

@@ -146,6 +146,8 @@ class Context:
         if step_dist is None:
             step_dist = _DEFAULT_STEP.get(self.model, STEP_DIST)
         self.device = int(device)
+        self.step_dist, self.safety_dist = float(step_dist), float(safety_dist)
+        self.max_dist = None if max_dist is None else float(max_dist)
         self._lib = L.load()
         h = C.c_void_p()
         L.check(self._lib.mrmp_ctx_create(
@@ -365,6 +367,17 @@ class Context:
                 continue
             L.check(rc)
             return row_ptr, col[: nnz.value].copy()
+
+
+def collide_params_agree(a: "Context", b: "Context") -> bool:
+    """True when two contexts give the same collide verdicts: same model, radii, base positions,
+    capsule axes, step_dist and safety_dist (the parameters gen_collide captures: point.jl:5-8,
+    arm22.jl:90-99, ...).  Obstacles and max_dist only matter to connect."""
+    def same(x, y):
+        return (x is None and y is None) or (x is not None and y is not None and np.array_equal(x, y))
+    return (a.model == b.model and a.N == b.N and np.array_equal(a.rads, b.rads)
+            and same(a.base_pos, b.base_pos) and same(a.aux, b.aux)
+            and a.step_dist == b.step_dist and a.safety_dist == b.safety_dist)
 
 
 class Roadmaps:
@@ -647,16 +660,26 @@ def gen_collide(q, *ins_params, step_dist: Optional[float] = None,
 
 
 def gen_check_goal(config_goal: Sequence, goal_rad: float = 0.0,
-                   goal_rads: Optional[Sequence[float]] = None, dist=None):
+                   goal_rads: Optional[Sequence[float]] = None, dist=None,
+                   ctx: Optional["Context"] = None):
     """utils.jl:117-138.  O(N) host logic (stays on the host in the reference design too:
-    SURVEY 8(b)); `dist` is the model's state distance (defaults to Euclidean, exact for the
-    default goal_rad = 0 equality test of every model)."""
+    SURVEY 8(b)).  The reference tests `dist(q, goal) <= goal_rads[i]` with the MODEL's dist
+    (utils.jl:126-134: arm22 wraps angles, line2d / snake2d / capsule3d weigh their components):
+    pass `dist`, or `ctx` to use the model metric of the library (mrmp_state_dist).  Without
+    either the test is the exact equality `q == goal` that goal_rad = 0 means for every model;
+    a positive goal radius on a non-point model then needs `dist` or `ctx` and raises otherwise."""
     N = len(config_goal)
     rads = list(goal_rads) if goal_rads is not None else [goal_rad] * N
+    point = isinstance(config_goal[0], (StatePoint2D, StatePoint3D)) if N else True
+    if dist is None and ctx is None and not point and any(r > 0 for r in rads):
+        raise ValueError("gen_check_goal: goal_rad > 0 on a non-point model needs the model's dist "
+                         "(pass dist=... or ctx=connect.ctx)")
 
     def _d(a, b):
         if dist is not None:
             return dist(a, b)
+        if ctx is not None:
+            return float(ctx.state_dist([a], [b])[0])
         return math.sqrt(sum((x - y) * (x - y) for x, y in zip(a, b)))
 
     def _q(v):

@@ -1704,6 +1704,7 @@ extern "C" int mrmp_collide_cross_reduce(mrmp_ctx *c, int64_t n_rows, const int3
 static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
     if (rm->e_valid) return MRMP_OK;
     mrmp_ctx *c = rm->ctx;
+    const bool point = c->model <= MRMP_MODEL_POINT3D;
     if (rm->nnz > rm->e_cap) {
         CU(cudaStreamSynchronize(s));
         cudaFree(rm->e_agent);
@@ -1714,20 +1715,25 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
         rm->e_from = rm->e_to = nullptr;
         rm->e_rows = nullptr;
         rm->e_cap = rm->nnz + rm->nnz / 8 + 64;
-        if (c->model <= MRMP_MODEL_POINT3D)
+        if (point) {
+            // point models: the cross kernel reads Morton-sorted row records only
             CU(cudaMalloc(&rm->e_rows, cross_row_bytes(c->d) * (size_t)rm->e_cap));
-        CU(cudaMalloc((void **)&rm->e_agent, sizeof(int32_t) * rm->e_cap));
-        CU(cudaMalloc((void **)&rm->e_from, sizeof(double) * c->d * rm->e_cap));
-        CU(cudaMalloc((void **)&rm->e_to, sizeof(double) * c->d * rm->e_cap));
+        } else {
+            CU(cudaMalloc((void **)&rm->e_agent, sizeof(int32_t) * rm->e_cap));
+            CU(cudaMalloc((void **)&rm->e_from, sizeof(double) * c->d * rm->e_cap));
+            CU(cudaMalloc((void **)&rm->e_to, sizeof(double) * c->d * rm->e_cap));
+        }
     }
-    CU(launch_csr_expand_edges(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
-                               rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes, rm->e_agent,
-                               rm->e_from, rm->e_to));
-    if (rm->e_rows) {
-        int rc = ensure_scratch(c, 0, 4096 * 4 + 64);
+    if (point) {
+        int rc = ensure_scratch(c, 6, 2 * 4096 * 4 + 64);
         if (rc) return rc;
-        CU(launch_cross_sort_rows(c->cv, lcfg(c, s), rm->nnz, rm->e_agent, rm->e_from, rm->e_to,
-                                  (int32_t *)c->scratch[0], rm->e_rows));
+        CU(launch_cross_sort_csr_rows(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
+                                      rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes,
+                                      (int32_t *)c->scratch[6], rm->e_rows));
+    } else {
+        CU(launch_csr_expand_edges(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
+                                   rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes, rm->e_agent,
+                                   rm->e_from, rm->e_to));
     }
     rm->e_valid = true;
     return MRMP_OK;

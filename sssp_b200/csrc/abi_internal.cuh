@@ -81,7 +81,7 @@ struct mrmp_ctx {
     unsigned char *small_h = nullptr, *small_d = nullptr;
     size_t small_bytes = 0;
     // named device scratch buffers (column tiles, staged rows/cols, output bits)
-    static const int kScratch = 6;
+    static const int kScratch = 8;
     unsigned char *scratch[kScratch]{};
     size_t scratch_bytes[kScratch]{};
     double max_rad = 0.0;

@@ -323,7 +323,9 @@ extern "C" int mrmp_distance_tables_g(mrmp_ctx *c, int n_graphs, const int32_t *
                                       const int32_t *col_idx, const int32_t *goal,
                                       double stay_penalty, double *tables_out) {
     NEED(c && n_graphs >= 0, "bad ctx / n_graphs");
-    NEED(stay_penalty == stay_penalty, "stay_penalty is NaN");
+    // the relaxation orders distances by their bit patterns (non-negative doubles) and a negative
+    // cost on a self loop would decrease forever: gen_g_func's penalty is a non-negative number
+    NEED(stay_penalty >= 0.0 && stay_penalty < INFINITY, "stay_penalty must be finite and >= 0");
     if (n_graphs == 0) return MRMP_OK;
     NEED(v_off && nodes && row_ptr && goal && tables_out, "NULL buffer");
     const int64_t V = v_off[n_graphs];

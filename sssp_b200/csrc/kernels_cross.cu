@@ -209,12 +209,9 @@ struct ColPrep {
     int n_agents;
 };
 
+// one warp builds tile t (one column per lane) and its header
 template <int D>
-__global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < P.n_tiles;
-         t += n_warps) {
+__device__ __forceinline__ void prep_tile(const ColPrep<D> &P, int64_t t, int lane) {
         const int64_t c = t * kCols + lane;
         ColB B;
         ColX<D> X;
@@ -285,7 +282,63 @@ __global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
             H.pad = 0.0;
             P.hdrs[t] = H;
         }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < P.n_tiles;
+         t += n_warps)
+        prep_tile<D>(P, t, lane);
+}
+
+// The whole column side in ONE launch for the usual case of a few thousand columns (a conflict
+// table has N x T of them): one CTA counts the Morton cells in shared memory, scans, scatters the
+// order and builds the tiles -- instead of histogram / scan / scatter / tile kernels whose launch
+// latencies exceed their work.
+constexpr int kPrepSmallMax = 32768;
+template <int D>
+__global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P, int32_t *order) {
+    __shared__ int h[kSortCells];
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    for (int c = tid; c < kSortCells; c += 1024) h[c] = 0;
+    __syncthreads();
+    for (int64_t k = tid; k < P.n_cols; k += 1024) {
+        double a[D], b[D];
+        P.el.get(k, a, b);
+        atomicAdd(&h[morton_cell<D>(a, b)], 1);
     }
+    __syncthreads();
+    int v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = h[4 * tid + k];
+        sum += v[k];
+    }
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int tv = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += tv;
+        __syncthreads();
+    }
+    int base = tid == 0 ? 0 : part[tid - 1];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[4 * tid + k] = base;
+        base += v[k];
+    }
+    __syncthreads();
+    for (int64_t k = tid; k < P.n_cols; k += 1024) {
+        double a[D], b[D];
+        P.el.get(k, a, b);
+        order[atomicAdd(&h[morton_cell<D>(a, b)], 1)] = (int)k;
+    }
+    __syncthreads();  // the order array (global) is complete and visible to the whole CTA
+    for (int64_t t = tid >> 5; t < P.n_tiles; t += 32) prep_tile<D>(P, t, tid & 31);
 }
 
 // ---- rows from the CSR of a roadmap set: edge e of row (agent a, vertex v) -----------------
@@ -312,6 +365,87 @@ k_csr_expand_edges(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
                 e_from[(int64_t)e * D + x] = qv[x];
                 e_to[(int64_t)e * D + x] = qk[x];
             }
+        }
+    }
+}
+
+// ---- CSR of a roadmap set -> Morton-sorted row records in two launches (point models) ------------
+// warp per CSR row (the source vertex is loaded once), lane per edge: count the cells, then -- with
+// the exclusive scan of the 4096 counts redone by every CTA in shared memory instead of a launch of
+// its own -- scatter the records.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
+                const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
+                int32_t *__restrict__ counts) {
+    __shared__ int h[kSortCells];
+    for (int c = threadIdx.x; c < kSortCells; c += blockDim.x) h[c] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows_csr;
+         row += n_warps) {
+        const int a = (int)(row / nv), v = (int)(row - (int64_t)a * nv);
+        const double *tab = nodes + (int64_t)a * nv * D;
+        double qv[D];
+        load_state<D>(tab, v, qv);
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) {
+            double qk[D];
+            load_state<D>(tab, col_idx[e], qk);
+            atomicAdd(&h[morton_cell<D>(qv, qk)], 1);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < kSortCells; c += blockDim.x)
+        if (h[c]) atomicAdd(counts + c, h[c]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__restrict__ row_ptr,
+                   const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
+                   const int32_t *__restrict__ counts, int32_t *__restrict__ cursor,
+                   RowRec<D> *__restrict__ rows) {
+    __shared__ int off[kSortCells];
+    __shared__ int part[256];
+    {   // exclusive scan of the 4096 cell counts (16 per thread)
+        const int tid = threadIdx.x;
+        int v[16], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            v[k] = counts[16 * tid + k];
+            sum += v[k];
+        }
+        part[tid] = sum;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {
+            const int tv = tid >= o ? part[tid - o] : 0;
+            __syncthreads();
+            part[tid] += tv;
+            __syncthreads();
+        }
+        int base = tid == 0 ? 0 : part[tid - 1];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            off[16 * tid + k] = base;
+            base += v[k];
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows_csr;
+         row += n_warps) {
+        const int a = (int)(row / nv), v = (int)(row - (int64_t)a * nv);
+        const double *tab = nodes + (int64_t)a * nv * D;
+        RowRec<D> r;
+        load_state<D>(tab, v, r.a);
+        r.agent = agent0 + a;
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) {
+            load_state<D>(tab, col_idx[e], r.b);
+            r.orig = e;
+            const int cell = morton_cell<D>(r.a, r.b);
+            rows[off[cell] + atomicAdd(cursor + cell, 1)] = r;
         }
     }
 }
@@ -680,12 +814,6 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
                                int64_t n_cols, const CrossCols &cc, int32_t *cells,
                                int32_t *order, void *tiles, void *hdrs) {
     const int64_t n_tiles = (n_cols + kCols - 1) / kCols;
-    cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * kSortCells, lc.stream);
-    if (e != cudaSuccess) return e;
-    const int grid = grid_for_n(lc, n_cols, 256 * 4);
-    k_cell_hist<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells);
-    k_cell_scan<<<1, 1024, 0, lc.stream>>>(cells);
-    k_cols_scatter<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells, order);
     ColPrep<D> P;
     P.el = el;
     P.n_cols = n_cols;
@@ -700,6 +828,17 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
     P.n_tiles = n_tiles;
     P.rads = cv.blob + cv.crads_off;
     P.n_agents = cv.n_agents;
+    if (n_cols <= kPrepSmallMax) {
+        k_cross_prep_cols_small<D><<<1, 1024, 0, lc.stream>>>(P, order);
+        count_launch();
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * kSortCells, lc.stream);
+    if (e != cudaSuccess) return e;
+    const int grid = grid_for_n(lc, n_cols, 256 * 4);
+    k_cell_hist<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells);
+    k_cell_scan<<<1, 1024, 0, lc.stream>>>(cells);
+    k_cols_scatter<D><<<grid, 256, 0, lc.stream>>>(el, n_cols, cells, order);
     k_cross_prep_cols<D><<<grid_for_n(lc, n_tiles * 32, 256), 256, 0, lc.stream>>>(P);
     count_launch(4);
     return cudaGetLastError();
@@ -720,6 +859,34 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
         return prep_cols_t<3>(cv, lc, EdgeList<3>{agent, qf, qt, vf, vt, nodes, agent0, nv_stride},
                               n_cols, cc, cells, order, tiles, hdrs);
     return cudaErrorNotSupported;
+}
+
+// CSR edges of a point-model roadmap set -> Morton-sorted RowRec array (row e <-> col_idx[e]);
+// cells = 2 * 4096 ints of device scratch (counts | cursors)
+cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
+                                       int nv, int agent0, const int32_t *row_ptr,
+                                       const int32_t *col_idx, const double *nodes, int32_t *cells,
+                                       void *rows_out) {
+    if (n_rows_csr <= 0) return cudaSuccess;
+    if (cv.model > 1) return cudaErrorNotSupported;
+    cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * 2 * kSortCells, lc.stream);
+    if (e != cudaSuccess) return e;
+    int64_t want = (n_rows_csr + 7) / 8;
+    const int64_t cap = (int64_t)lc.sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    if (cv.model == 0) {
+        k_csr_cell_hist<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells);
+        k_csr_rows_scatter<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
+                                                          nodes, cells, cells + kSortCells,
+                                                          (RowRec<2> *)rows_out);
+    } else {
+        k_csr_cell_hist<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells);
+        k_csr_rows_scatter<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
+                                                          nodes, cells, cells + kSortCells,
+                                                          (RowRec<3> *)rows_out);
+    }
+    count_launch(2);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,

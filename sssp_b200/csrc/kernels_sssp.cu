@@ -596,7 +596,9 @@ k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *
     for (int v = threadIdx.x; v < nv; v += blockDim.x)
         T[v] = v == goal[g] ? 0ull : 0x7ff0000000000000ull;  // typemax(Float64) == Inf
     __syncthreads();
-    for (;;) {
+    // non-negative edge costs: the fixed point is reached after at most nv rounds; the cap keeps a
+    // corrupted input (negative cost on a cycle) from spinning for ever
+    for (int round = 0; round <= nv; ++round) {
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         bool changed = false;

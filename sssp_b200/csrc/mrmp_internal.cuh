@@ -351,6 +351,10 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
                                    const int32_t *vf, const int32_t *vt, const double *nodes,
                                    int agent0, int nv_stride, const CrossCols &cc, int32_t *cells,
                                    int32_t *order, void *tiles, void *hdrs);
+cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
+                                       int nv, int agent0, const int32_t *row_ptr,
+                                       const int32_t *col_idx, const double *nodes, int32_t *cells,
+                                       void *rows_out);
 cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                     int nv, int agent0, const int32_t *row_ptr,
                                     const int32_t *col_idx, const double *nodes, int32_t *e_agent,

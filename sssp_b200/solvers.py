@@ -27,7 +27,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import lib as L
-from .closures import Context, Node, SsspRoadmaps, _STATE_OF, _states
+from .closures import Context, Node, SsspRoadmaps, _STATE_OF, _states, collide_params_agree
 
 
 class PriorityQueue:
@@ -90,6 +90,9 @@ class PriorityQueue:
 
 def gen_g_func(greedy: bool = False, stay_penalty: float = 0.0, ctx: Optional[Context] = None):
     """solvers/utils.jl:29-39.  The non-greedy form needs the model's dist: pass the ctx."""
+    if not greedy and ctx is None:
+        raise ValueError("gen_g_func(greedy=False) needs ctx (the model's dist runs in the library)")
+
     def f(Q_from, Q_to) -> float:
         if greedy:
             return 0.0
@@ -188,8 +191,12 @@ def SSSP(config_init: Sequence, config_goal: Sequence, connect: Callable, collid
     (solution | None, roadmaps): sssp.jl:49-73.  `connect` / `collide` come from gen_connect /
     gen_collide (built from the same rads); `seed` selects the sampler streams."""
     ctx: Context = connect.ctx
-    if collide.ctx.N != ctx.N or not np.array_equal(collide.ctx.rads, ctx.rads):
-        raise ValueError("connect and collide must be built from the same ins_params")
+    # The fused expansion runs the steering (connect) and the successor filter (collide) of one
+    # popped node in ONE launch on connect's context: that is only the reference's computation
+    # when the collide closure was built from the same parameters.
+    if not collide_params_agree(collide.ctx, ctx):
+        raise ValueError("SSSP: connect and collide must be built from the same ins_params, "
+                         "step_dist and safety_dist (the node expansion evaluates both on one context)")
     t_s = time.monotonic()
     deadline = None if TIME_LIMIT is None else t_s + TIME_LIMIT
 

@@ -4,7 +4,6 @@ Same signatures and return values as the reference; `validate` additionally expo
 failing check (`validate.last_failure`) that the reference only prints as a warning."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Sequence
 
 import numpy as np
@@ -27,14 +26,24 @@ def validate(config_init: Sequence, connect, collide, check_goal, solution) -> b
     if not check_goal(solution[-1]):                               # :339-343
         validate.last_failure = ("last configuration",)
         return False
-    ok, kind, i, j = C.c_int32(1), C.c_int32(0), C.c_int32(-1), C.c_int32(-1)
-    t = C.c_int64(-1)
-    L.check(ctx._lib.mrmp_validate_solution(ctx._h, T, L.ptr(sol, L._dp), C.byref(ok), C.byref(t),
-                                            C.byref(kind), C.byref(i), C.byref(j)))
-    if not ok.value:
-        validate.last_failure = ("not connected", int(t.value), int(i.value)) if kind.value == 1 \
-            else ("colliding", int(t.value), int(i.value), int(j.value))
-        return False
+    if T < 2:
+        return True
+    # Transition checks (:345-363), each through the closure that owns it: the connect tests run
+    # on connect's context (obstacles, max_dist), the collide tests on COLLIDE's context -- a
+    # collide closure built with its own step_dist / safety_dist / base positions decides, exactly
+    # as in the reference where the two closures are independent (arm22.jl:29-37 vs :93-99).
+    ag = np.tile(np.arange(N, dtype=np.int32), T - 1)
+    con = connect.ctx.connect_edges(ag, sol[:-1].reshape(-1, d), sol[1:].reshape(-1, d)).reshape(T - 1, N)
+    hit, first = collide.ctx.collide_configs(sol[:-1], sol[1:])
+    for t in range(1, T):                      # the reference's order: connect (i ascending), then collide
+        bad = np.flatnonzero(con[t - 1] == 0)
+        if bad.size:
+            validate.last_failure = ("not connected", t, int(bad[0]))
+            return False
+        if hit[t - 1]:
+            fp = int(first[t - 1])
+            validate.last_failure = ("colliding", t, fp // N, fp % N)
+            return False
     return True
 
 

@@ -16,8 +16,13 @@ pytestmark = pytest.mark.gpu
 TWO_PI = 2 * math.pi
 
 
-def _pair(N, M, seed, **kw):
-    rads, obs, base = make_arm_instance(N, M, seed)
+# BASELINE configs[3] / scripts/config/eval/arm22.yaml:11-20: link length 0.15-0.25, up to 3
+# obstacles of radius 0.05-0.10 (the instance bench.py measures)
+LINK = (0.15, 0.25)
+
+
+def _pair(N, M, seed, link=LINK, **kw):
+    rads, obs, base = make_arm_instance(N, M, seed, link=link)
     ctx = S.Context(L.MODEL_ARM22, rads, obs, base_pos=base, **kw)
     okw = dict(kw)
     if okw.get("max_dist") is None:
@@ -93,7 +98,7 @@ def test_connect_parity_fine_steps_and_single_calls():
 
 def test_collide_pairs_parity():
     N = 10
-    ctx, orc, rads, obs, base = _pair(N, 0, seed=13)
+    ctx, orc, rads, obs, base = _pair(N, 3, seed=13)
     rng = np.random.default_rng(23)
     n = 3000
     ai = rng.integers(0, N, n).astype(np.int32)
@@ -151,7 +156,7 @@ def test_collide_configs_and_moves_parity():
 def test_roadmaps_and_cross_parity():
     # arm22.yaml: PRM num_vertices 100, rad 0.3 (scripts/config/eval/arm22.yaml:26-30)
     N, M, nv, rad = 6, 2, 100, 0.3
-    ctx, orc, rads, obs, base = _pair(N, M, seed=17)   # every agent has free postures
+    ctx, orc, rads, obs, base = _pair(N, M, seed=17, link=(0.1, 0.15))   # every agent has free postures
     rng = np.random.default_rng(26)
     init = np.stack([orc.sample_free(a, 900, 1)[0][0] for a in range(N)])
     goal = np.stack([orc.sample_free(a, 901, 1)[0][0] for a in range(N)])
@@ -197,3 +202,29 @@ def test_roadmaps_and_cross_parity():
     o = orc.collide_cross((rows // nv).astype(np.int32)[::50], rows_f[::50], rows_t[::50], ca, cf, ct, 8,
                           nthreads=0)
     assert np.array_equal(g[::50], o)
+
+
+def test_config4_conflict_table_full_parity():
+    """The whole conflict table of the BASELINE configs[3] instance (N=10, M=3, links 0.15-0.25):
+    every roadmap edge (PP's num_vertices / rad of arm22.yaml:26-30, smaller vertex count) against
+    the path edges of the other agents over T steps, OR-reduced per step -- every row, not a sample."""
+    N, M, nv, rad, T = 10, 3, 40, 0.3, 3
+    ctx, orc, rads, obs, base = _pair(N, M, seed=41)
+    nodes = np.stack([orc.sample_free(a, 77, nv)[0] for a in range(N)])
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.set_nodes(nodes)
+    nnz = rm.build(rad)
+    row_ptr, col = rm.csr()
+    orp, ocol, onnz = orc.prm_build(0, nodes, rad, nthreads=0)
+    assert nnz == int(onnz.sum()) and nnz > 500
+    rng = np.random.default_rng(1)
+    ca = np.tile(np.arange(N, dtype=np.int32), T)
+    vf = rng.integers(0, nv, N * T).astype(np.int32)
+    vt = rng.integers(0, nv, N * T).astype(np.int32)
+    rows = np.repeat(np.arange(N * nv), np.diff(row_ptr))
+    ra = (rows // nv).astype(np.int32)
+    g = rm.edge_conflicts(ca, vf, vt, group_size=N)
+    o = orc.collide_cross(ra, nodes[ra, rows % nv], nodes[ra, col], ca, nodes[ca, vf], nodes[ca, vt], N,
+                          nthreads=0)
+    assert g.shape == o.shape == (nnz, 1) and np.array_equal(g, o)
+    assert 0 < (o != 0).sum() and (o != 7).any()

@@ -3,6 +3,7 @@ oracle's expand! / successor filter, and whole SSSP runs (sssp_b200.solvers.SSSP
 path) against the committed golden solutions and the live oracle -- identical solutions,
 identical roadmaps (vertices bit for bit, neighbour lists in the same order)."""
 import glob
+import math
 import json
 import os
 
@@ -298,3 +299,30 @@ def test_distance_tables_with_stay_penalty_edge_cost():
             assert np.array_equal(got[a].view(np.uint64), want.view(np.uint64)), (pen, a)
     twin = ctx.distance_tables(graphs, goal=1, stay_penalty=0.1)[0][41]
     assert twin == 0.1                           # one hop goal -> its twin costs the penalty
+
+
+def test_validate_runs_collide_checks_on_the_collide_closure():
+    """connect and collide are independent closures in the reference (arm22.jl:29-37 vs :93-99):
+    a collide built with its own safety_dist must be the one that decides, and SSSP refuses a
+    pair of closures it cannot evaluate on one context."""
+    A = S.StateArm22
+    base, rads = [[0.35, 0.5], [0.65, 0.5]], [0.1, 0.1]
+    connect = S.gen_connect(A(0, 0), [], base, rads)
+    loose = S.gen_collide(A(0, 0), base, rads)                       # safety_dist 0.01
+    strict = S.gen_collide(A(0, 0), base, rads, safety_dist=0.2)
+    # arm 0 points right (tip at x = 0.55), arm 1 points up: closest approach 0.10
+    q0, q1 = A(0.0, 0.0), A(math.pi / 2, 0.0)
+    sol = [[S.Node(q0, 0), S.Node(q1, 0)], [S.Node(q0, 0), S.Node(q1, 0)]]
+    ok = lambda Q: True
+    assert loose(q0, q1, 0, 1) is False and strict(q0, q1, 0, 1) is True
+    assert S.validate([q0, q1], connect, loose, ok, sol) is True
+    assert S.validate([q0, q1], connect, strict, ok, sol) is False
+    assert S.validate.last_failure == ("colliding", 1, 0, 1)
+    with pytest.raises(ValueError):
+        S.SSSP([q0, q1], [q0, q1], connect, strict, S.gen_check_goal([q0, q1]), TIME_LIMIT=1)
+    # goal radius on a non-point model: needs the model's metric
+    with pytest.raises(ValueError):
+        S.gen_check_goal([q0, q1], goal_rad=0.1)
+    near = S.gen_check_goal([q0, q1], goal_rad=0.1, ctx=connect.ctx)
+    assert near(A(2 * math.pi - 0.05, 0.0), 0) is True     # wraps around: dist = 0.05 / pi
+    assert near(A(1.0, 0.0), 0) is False
