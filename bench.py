@@ -347,7 +347,8 @@ def run_b200(args):
         nnz_all = torch.zeros(world, dtype=torch.int64, device=dev)
         nnz_all[rank] = nnz_sh
         dist.all_reduce(nnz_all)
-        mg = dict(ex=ex, p2p=p2p, round=0, cap_nnz=cap_nnz, tab_words=tab_words, slots=slots,
+        mg = dict(ex=ex, p2p=p2p, round=0, cap_nnz=cap_nnz,
+                  tab_local=torch.zeros(tab_words, dtype=torch.int32, device=dev), tab_words=tab_words, slots=slots,
                   tab_slots=tab_slots, nnz_sh=[int(x) for x in nnz_all.tolist()],
                   exchange="nvlink peer stores from the producing kernels (CUDA IPC mappings) + flags"
                   if p2p else "nccl all-gather (%s)" % (getattr(ex, "connect_error", None) or args.exchange))
@@ -397,8 +398,13 @@ def run_b200(args):
         exchange_csr()
         mark()                                   # 1: shard packed and pushed / all-gathered
         if mg["p2p"]:
+            # rows of this rank's agents: into local memory (a rank's share of the table is small,
+            # the kernel cuts it into finer work items that OR into local memory), then one
+            # coalesced copy kernel into rank 0's buffer over NVLink + a flag
             rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
-                                     N, ex.ptr(1, 0), st, cols=rm_all)
+                                     N, mg["tab_local"].data_ptr(), st, cols=rm_all)
+            nb = mg["nnz_sh"][rank] * wpr * 4
+            ex.push(1, 0, mg["tab_local"].data_ptr(), nb + (-nb) % 16, st)
             ex.signal(1, st, dst_mask=1)
             mark()                               # 2: table rows of this rank (written to rank 0)
             n = adopt_csr()

@@ -224,6 +224,9 @@ void *mrmp_exchange_local_buffer(mrmp_exchange *x);
 void *mrmp_exchange_ptr(mrmp_exchange *x, int ch, int dst);
 void *mrmp_exchange_slots(mrmp_exchange *x, int ch);
 int64_t mrmp_exchange_slot_bytes(mrmp_exchange *x, int ch);
+/* copy kernel: `bytes` (multiple of 16) of this rank's device memory -> its slot in rank dst */
+int mrmp_exchange_push(mrmp_exchange *x, int ch, int dst, const void *src_dev, int64_t bytes,
+                       void *stream);
 int mrmp_exchange_signal(mrmp_exchange *x, int ch, unsigned int dst_mask, void *stream);
 int mrmp_exchange_wait(mrmp_exchange *x, int ch, unsigned int src_mask, void *stream);
 int mrmp_exchange_advance(mrmp_exchange *x, int ch);

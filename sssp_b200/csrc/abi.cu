@@ -1453,11 +1453,25 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
     const bool table = rq.mode == kCrossBits || rq.mode == kCrossOr;
     const int wpr = table ? cross_words(n_cols, group_size) : rq.n_groups;
     LaunchCfg lc = lcfg(c, s);
+    // An OR table may be written with plain stores straight into mapped host memory or a peer's
+    // memory (one work item per row).  When the output is ordinary memory of this GPU, a small
+    // table is cut into finer work items that OR into it (kernels_cross.cu: cross_split).
+    bool local_out = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess)
+            local_out = at.type == cudaMemoryTypeDevice && at.device == c->device;
+        else
+            cudaGetLastError();
+    }
+    const int n_tiles_all = (int)((n_cols + kCrossCols - 1) / kCrossCols);
+    const bool split_or = rq.mode == kCrossOr && c->model <= MRMP_MODEL_POINT3D && local_out &&
+                          cross_split(lc, n_rows, n_tiles_all, 1) > 1;
     if (rq.mode == kCrossFirst)
         CU(launch_fill_i32(lc, (int32_t *)out, n_rows * (int64_t)wpr, 0x7fffffff));
-    else if (rq.mode != kCrossOr || c->model >= MRMP_MODEL_ARM22)
-        // bits / count: hits are OR-ed / added into a zeroed output (the OR mode of the point
-        // models writes every word itself)
+    else if (rq.mode != kCrossOr || c->model >= MRMP_MODEL_ARM22 || split_or)
+        // bits / count: hits are OR-ed / added into a zeroed output (the un-split OR mode of the
+        // point models writes every word itself)
         CU(cudaMemsetAsync(out, 0, sizeof(uint32_t) * (size_t)n_rows * wpr, s));
     if (c->model >= MRMP_MODEL_ARM22) {  // discretised models: warp per (row, column) check
         if (c->model == MRMP_MODEL_ARM22)
@@ -1513,6 +1527,7 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
         co.out = out + g0 / 32;
         co.row_key = rq.row_key;
         co.cbs = rq.cbs;
+        co.may_split = rq.mode == kCrossOr ? (split_or ? 1 : 0) : (local_out ? 1 : 0);
         CU(launch_cross_collide(c->cv, lc, n_rows, rows_sorted, nc, b + o_tiles, b + o_hdr, co,
                                 c->stats_d, (unsigned int *)(b + o_work)));
     }

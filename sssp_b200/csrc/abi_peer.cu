@@ -74,6 +74,14 @@ __global__ void k_exchange_wait(const unsigned int *flags, unsigned int mask, un
     }
 }
 
+// coalesced 16-byte copy of a finished block into a peer's slot (NVLink stores)
+__global__ void __launch_bounds__(256) k_exchange_push(int4 *__restrict__ dst,
+                                                       const int4 *__restrict__ src, int64_t n16) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n16;
+         k += (int64_t)gridDim.x * blockDim.x)
+        dst[k] = src[k];
+}
+
 }  // namespace
 
 extern "C" int mrmp_exchange_create(mrmp_ctx *c, int world, int rank, int n_chan,
@@ -239,3 +247,24 @@ extern "C" int mrmp_exchange_advance(mrmp_exchange *x, int ch) {
 
 /* 0, or 1 + rank of a peer a wait gave up on (after the stream has been synchronised) */
 extern "C" int mrmp_exchange_error(mrmp_exchange *x) { return x ? *x->err_h : -1; }
+
+/* copy `bytes` (a multiple of 16, at most the slot size) of device memory of this rank into its
+ * slot of channel ch in rank dst's buffer; follow with mrmp_exchange_signal */
+extern "C" int mrmp_exchange_push(mrmp_exchange *x, int ch, int dst, const void *src_dev,
+                                  int64_t bytes, void *stream) {
+    NEED(x && ch >= 0 && ch < x->n_chan && dst >= 0 && dst < x->world && src_dev, "bad arguments");
+    NEED(bytes >= 0 && bytes % 16 == 0 && bytes <= x->slot_bytes[ch] && aligned16(src_dev),
+         "bytes must be a multiple of 16 within the slot, src 16-byte aligned");
+    void *p = mrmp_exchange_ptr(x, ch, dst);
+    NEED(p, "exchange is not connected to the destination rank");
+    if (bytes == 0) return MRMP_OK;
+    CU(cudaSetDevice(x->ctx->device));
+    const int64_t n16 = bytes / 16;
+    int64_t grid = (n16 + 255) / 256;
+    const int64_t cap = (int64_t)x->ctx->sm_count * 4;
+    if (grid > cap) grid = cap;
+    k_exchange_push<<<(int)grid, 256, 0, (cudaStream_t)stream>>>((int4 *)p, (const int4 *)src_dev, n16);
+    count_launch();
+    CU(cudaGetLastError());
+    return MRMP_OK;
+}

@@ -478,6 +478,7 @@ struct CrossArgs {
     uint32_t *out;
     const int32_t *row_key;  // NULL: every pair is admitted; else col_key > row_key[row]
     int cbs;                 // cbs.jl:343-346: vertex test OR edge test with the column first
+    int split;               // work items per warp tile (column tiles divided into `split` ranges)
     unsigned long long *stats;
     unsigned int *work;
 };
@@ -544,13 +545,20 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
     WarpSmem<D, R> &S = reinterpret_cast<WarpSmem<D, R> *>(smem_raw)[warp];
     const double *rads = cv.blob + cv.crads_off;
     const int64_t n_wt = (A.n_rows + R - 1) / R;
+    const int64_t n_items = n_wt * A.split;
     unsigned long long n_tiles_read = 0, n_filter = 0, n_exact = 0;  // per-warp / per-lane counters
 
     for (;;) {
-        unsigned wt = 0;
-        if (lane == 0) wt = atomicAdd(A.work, 1u);
-        wt = __shfl_sync(0xffffffffu, wt, 0);
-        if ((int64_t)wt >= n_wt) break;
+        // work item = (warp tile, range of column tiles).  A large table has several warp tiles
+        // per resident warp and split == 1; a small one (a rank's share of a strong-scaled
+        // table) is cut finer so that the dynamic distribution can balance the SMs.
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(A.work, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((int64_t)item >= n_items) break;
+        const unsigned wt = item / (unsigned)A.split, chunk = item - wt * (unsigned)A.split;
+        const int t_begin = (int)((int64_t)chunk * A.n_tiles / A.split);
+        const int t_end = (int)((int64_t)(chunk + 1) * A.n_tiles / A.split);
         RowB32 rb;
         double lo[D], hi[D], Rmax = 0.0;
         bool poison = false;
@@ -610,10 +618,10 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
         poison = __any_sync(0xffffffffu, poison);
         __syncwarp();
 
-        for (int t0 = 0; t0 < A.n_tiles; t0 += 32) {
+        for (int t0 = t_begin; t0 < t_end; t0 += 32) {
             // box-vs-box test of 32 column tiles at once
             bool near = false;
-            if (t0 + lane < A.n_tiles) {
+            if (t0 + lane < t_end) {
                 const TileHdr<D> H = A.hdrs[t0 + lane];
                 double d2 = 0.0;
 #pragma unroll
@@ -725,7 +733,12 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                 }
             }
         }
-        if (MODE == kModeOr && live) {
+        if (MODE == kModeOr && live && A.split > 1) {
+            // several work items share the row: OR into the (zeroed, device-local) output
+            uint32_t *dst = A.out + (int64_t)S.orig[lane] * A.out_stride;
+            for (int w = 0; w < A.words_per_row; ++w)
+                if (S.obits[lane][w]) atomicOr(dst + w, S.obits[lane][w]);
+        } else if (MODE == kModeOr && live) {
             // every word of the row is written exactly once (the output may be mapped host or
             // peer memory: plain stores, two words per transaction where the layout allows)
             uint32_t *dst = A.out + (int64_t)S.orig[lane] * A.out_stride;
@@ -919,7 +932,7 @@ static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const 
     int per_sm = (220 * 1024) / smem;
     if (per_sm > MRMP_CROSS_MINB) per_sm = MRMP_CROSS_MINB;  // register-limited residency
     if (per_sm < 1) per_sm = 1;
-    const int64_t n_wt = (A.n_rows + R - 1) / R;
+    const int64_t n_wt = (A.n_rows + R - 1) / R * A.split;
     int64_t want = (n_wt + kWarpsPerCta - 1) / kWarpsPerCta;
     const int64_t cap = (int64_t)lc.sm_count * per_sm;
     const int grid = (int)(want < cap ? want : cap);
@@ -929,6 +942,20 @@ static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const 
     k_cross_collide<D, MODE, FD><<<grid, 32 * kWarpsPerCta, smem, lc.stream>>>(cv, A);
     count_launch();
     return cudaGetLastError();
+}
+
+// Work items per warp tile.  With >= 3 warp tiles per resident warp the dynamic distribution
+// balances by itself (and one item per row keeps the OR mode's plain stores); below that the
+// column tiles of a warp tile are divided so that there are ~4 items per resident warp.
+int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split) {
+    if (!may_split || n_tiles <= 1) return 1;
+    const int64_t n_wt = (n_rows + 31) / 32;
+    const int64_t warps = (int64_t)lc.sm_count * MRMP_CROSS_MINB * kWarpsPerCta;
+    if (n_wt >= 3 * warps) return 1;
+    int64_t s = (4 * warps + n_wt - 1) / n_wt;
+    if (s > 16) s = 16;
+    if (s > n_tiles) s = n_tiles;
+    return (int)(s < 1 ? 1 : s);
 }
 
 template <int D>
@@ -949,6 +976,7 @@ static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_
     A.out = co.out;
     A.row_key = co.row_key;
     A.cbs = co.cbs;
+    A.split = cross_split(lc, n_rows, n_tiles, co.may_split);
     A.stats = stats;
     A.work = work;
     cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned int), lc.stream);

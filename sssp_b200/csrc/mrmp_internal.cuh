@@ -337,7 +337,10 @@ struct CrossOut {
     uint32_t *out;
     const int32_t *row_key;   // NULL, or: only pairs with col_key > row_key[row] are tested
     int cbs;                  // cbs.jl:343-346 pair test (vertex OR edge, column first)
+    int may_split;            // `out` is zeroed memory of this GPU: a warp tile's columns may be
+                              // divided over several work items that OR / add into it
 };
+int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split);
 size_t cross_tile_bytes(int d);
 size_t cross_hdr_bytes(int d);
 size_t cross_row_bytes(int d);

@@ -8,9 +8,13 @@ Lets the reference's experiment configs drive the GPU path unchanged: the same Y
 What differs, by necessity: instances are drawn with numpy's PCG64 instead of Julia's RNG
 (the procedure is gen_random_instance, utils.jl:204-245, without its wall-clock retry); only
 solvers built on this path are run (`MRMP.SSSP`) -- other `_target_`s produce a row with
-`solved = false` and `elapsed_planning = 0` so that the table keeps the reference's shape;
-`smoothing` is out of scope, so the `*_refined` columns repeat the original
-costs and `elapsed_refinement` is 0.
+`solved = false` and `elapsed_planning = 0` so that the table keeps the reference's shape.
+`smoothing` (src/smoother.jl, eval.jl:64) runs on the batched path (sssp_b200/smoother.py) and
+fills the `*_refined` columns and `elapsed_refinement`.
+
+`planning(req)` answers one request of the reference's planning server (scripts/server.jl:84-122)
+in its JSON format -- {"status": "success", "instructions": [...]} -- without the WebSocket
+transport, which is not part of the path.
 """
 from __future__ import annotations
 
@@ -25,7 +29,8 @@ import numpy as np
 from . import closures as CL
 from . import lib as L
 from .solvers import SSSP
-from .validation import validate
+from .smoother import get_instructions, smoothing
+from .validation import is_valid_instance, validate
 
 RESULT_COLUMNS = ["instance", "N", "num_obs", "solver", "solver_index", "solved", "elapsed_planning",
                   "elapsed_refinement", "elapsed_total", "sum_of_cost_original", "makespan_original",
@@ -165,13 +170,18 @@ def run(config: dict, *, out_dir: Optional[str] = None, device: int = 0) -> List
                     raise RuntimeError(f"{name} yields invalid solution for instance-{k}, "
                                        f"seed={seed_offset}: {validate.last_failure}")
             cost = get_solution_cost(connect.ctx, solution)
+            # refinement (eval.jl:62-66): temporal plan graph + greedy re-timing
+            t0 = time.perf_counter()
+            refined = smoothing(solution, connect, collide)
+            t_ref = time.perf_counter() - t0 if solution is not None else 0.0
+            cost_ref = None if refined is None else refined[2]
             rows.append(dict(instance=k, N=len(init), num_obs=len(obstacles), solver=name, solver_index=l,
-                             solved=solution is not None, elapsed_planning=t_plan, elapsed_refinement=0.0,
-                             elapsed_total=t_plan,
+                             solved=solution is not None, elapsed_planning=t_plan,
+                             elapsed_refinement=t_ref, elapsed_total=t_plan + t_ref,
                              sum_of_cost_original=0 if cost is None else cost["sum_of_cost"],
                              makespan_original=0 if cost is None else cost["makespan"],
-                             sum_of_cost_refined=0 if cost is None else cost["sum_of_cost"],
-                             makespan_refined=0 if cost is None else cost["makespan"]))
+                             sum_of_cost_refined=0 if cost_ref is None else cost_ref["sum_of_cost"],
+                             makespan_refined=0 if cost_ref is None else cost_ref["makespan"]))
     if out_dir is not None:
         date_str = datetime.datetime.now().isoformat()
         root = os.path.join(out_dir, date_str)
@@ -188,6 +198,35 @@ def run(config: dict, *, out_dir: Optional[str] = None, device: int = 0) -> List
 
 
 run.last_dir = None
+
+
+def planning(req: dict, device: int = 0) -> dict:
+    """One request of the planning server (scripts/server.jl:84-122) -> its reply as a dict in the
+    reference's JSON format.  req = {"field": {"x", "y", "size"}, "agents": [{"x_init", "y_init",
+    "x_goal", "y_goal", "rad"}, ...], "obstacles": [{"x", "y", "rad"}, ...] | null,
+    "solver": {"_target_": "MRMP.Solvers.SSSP", <keyword arguments>}}; coordinates are scaled into
+    the unit square by the field (server.jl:20-27) and the instructions scaled back (:29-52)."""
+    fx, fy, fs = float(req["field"]["x"]), float(req["field"]["y"]), float(req["field"]["size"])
+    P = CL.StatePoint2D
+    init = [P((float(a["x_init"]) - fx) / fs, (float(a["y_init"]) - fy) / fs) for a in req["agents"]]
+    goal = [P((float(a["x_goal"]) - fx) / fs, (float(a["y_goal"]) - fy) / fs) for a in req["agents"]]
+    obstacles = np.array([[(float(o["x"]) - fx) / fs, (float(o["y"]) - fy) / fs, float(o["rad"]) / fs]
+                          for o in (req.get("obstacles") or [])]).reshape(-1, 3)
+    rads = [float(a["rad"]) / fs for a in req["agents"]]
+    connect = CL.gen_connect(init[0], obstacles, rads, device=device)
+    collide = CL.gen_collide(init[0], rads, device=device)
+    check_goal = CL.gen_check_goal(goal)
+    if not is_valid_instance(init, goal, connect, collide):            # server.jl:100-101
+        return {"status": "failure"}
+    solver = req["solver"]["_target_"].split(".")[-1]
+    params = {k: v for k, v in req["solver"].items() if k != "_target_"}
+    if solver != "SSSP":
+        raise ValueError(f"solver {req['solver']['_target_']} is not built on this path")
+    solution, _ = SSSP(init, goal, connect, collide, check_goal, **params)
+    if solution is None:                                               # server.jl:110
+        return {"status": "failure"}
+    TPG, solution, cost = smoothing(solution, connect, collide)
+    return {"status": "success", "instructions": get_instructions(TPG, fx, fy, fs)}
 
 
 def main(argv: Sequence[str]) -> None:

@@ -110,6 +110,7 @@ _SIGS = {
     "mrmp_exchange_ptr": (_vp, [_vp, C.c_int, C.c_int]),
     "mrmp_exchange_slots": (_vp, [_vp, C.c_int]),
     "mrmp_exchange_slot_bytes": (C.c_int64, [_vp, C.c_int]),
+    "mrmp_exchange_push": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.c_int64, _vp]),
     "mrmp_exchange_signal": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
     "mrmp_exchange_wait": (C.c_int, [_vp, C.c_int, C.c_uint, _vp]),
     "mrmp_exchange_advance": (C.c_int, [_vp, C.c_int]),

@@ -93,6 +93,10 @@ class Exchange:
     def slot_bytes(self, ch: int) -> int:
         return int(self._lib.mrmp_exchange_slot_bytes(self._h, int(ch)))
 
+    def push(self, ch: int, dst: int, src_ptr: int, nbytes: int, stream: int) -> None:
+        """Copy kernel: nbytes (multiple of 16) of this rank's device memory -> its slot in rank dst."""
+        L.check(self._lib.mrmp_exchange_push(self._h, int(ch), int(dst), src_ptr, int(nbytes), stream))
+
     def signal(self, ch: int, stream: int, dst_mask: Optional[int] = None) -> None:
         L.check(self._lib.mrmp_exchange_signal(self._h, int(ch),
                                                self.all_mask if dst_mask is None else int(dst_mask),

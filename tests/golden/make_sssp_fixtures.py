@@ -61,6 +61,13 @@ CASES = {
     "sssp_point2d_many_n10_seed0": dict(model=O.POINT2D, N=10, num_obs=10,
                                         rad=(0.015625, 0.0234375), rad_obs=(0.025, 0.04), seed=0,
                                         params=dict(epsilon=0.2, init_min_dist_thread=0.05)),
+    # configs[1] at the sizes north_star names (N = 30 and the target N = 50; 472 / 7811 expansions)
+    "sssp_point2d_many_n30_seed0": dict(model=O.POINT2D, N=30, num_obs=10,
+                                        rad=(0.015625, 0.0234375), rad_obs=(0.025, 0.04), seed=0,
+                                        params=dict(epsilon=0.2, init_min_dist_thread=0.05)),
+    "sssp_point2d_many_n50_seed0": dict(model=O.POINT2D, N=50, num_obs=10,
+                                        rad=(0.015625, 0.0234375), rad_obs=(0.025, 0.04), seed=0,
+                                        params=dict(epsilon=0.2, init_min_dist_thread=0.05)),
     # configs[2]: point3d.yaml solver parameters, radii reduced so that N agents fit
     "sssp_point3d_n6_seed1": dict(model=O.POINT3D, N=6, num_obs=6, rad=(0.05, 0.05),
                                   rad_obs=(0.05, 0.1), seed=1,
@@ -89,7 +96,10 @@ CASES = {
 
 
 def main():
+    only = set(sys.argv[1:])     # optional: names of the cases to (re)generate
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         inst = gen_instance(c["model"], c["N"], c["num_obs"], c["rad"], c["rad_obs"], c["seed"])
         orc = O.Oracle(c["model"], inst["rads"], np.array(inst["obstacles"]),
                        base=None if inst["base"] is None else np.array(inst["base"]),

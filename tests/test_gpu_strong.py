@@ -13,8 +13,8 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world", [1, 3, 4])
-def test_row_sharded_table_equals_single_gpu_table(world):
+@pytest.mark.parametrize("world,via", [(1, "direct"), (3, "direct"), (4, "direct"), (3, "push"), (8, "push")])
+def test_row_sharded_table_equals_single_gpu_table(world, via):
     import torch
     N, nv, T = 10, 160, 17
     inst = W.point2d_many(N=N, seed=3, nv=nv, rad=0.17)
@@ -67,8 +67,15 @@ def test_row_sharded_table_equals_single_gpu_table(world):
     for round_ in range(3):            # several rounds: epochs and double buffering
         for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
             xs[r].push_csr_shard(sh, 0, cap, cap_nnz, st)
-            sh.edge_conflicts_dev(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
-                                  cols_d[2].data_ptr(), N, xs[r].ptr(1, 0), st, cols=allrm)
+            if via == "direct":    # the table kernel stores straight into rank 0's buffer
+                sh.edge_conflicts_dev(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                      cols_d[2].data_ptr(), N, xs[r].ptr(1, 0), st, cols=allrm)
+            else:                  # rows into local memory (finer work items), then a copy kernel
+                local = torch.full((tab_words,), -1, dtype=torch.int32, device="cuda")
+                sh.edge_conflicts_dev(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                      cols_d[2].data_ptr(), N, local.data_ptr(), st, cols=allrm)
+                nb = nnz_sh[r] * wpr * 4
+                xs[r].push(1, 0, local.data_ptr(), nb + (-nb) % 16, st)
             xs[r].signal(1, st, dst_mask=1)
         for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
             assert xs[r].adopt_csr_shards(allrm, 0, cap, cap_nnz, st) == nnz
