@@ -323,7 +323,7 @@ def run_b200(args):
 
     cols_h = [pin(x) for x in (ca, vf, vt)]
     cols_d = [t.to(dev) for t in cols_h]
-    bits_d = torch.zeros((nnz_total, wpr), dtype=torch.int32, device=dev)
+    bits_d = torch.zeros((nnz_total + 4096, wpr), dtype=torch.int32, device=dev)[:nnz_total]
     bits_h = torch.zeros((nnz_total, wpr), dtype=torch.int32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -353,6 +353,8 @@ def run_b200(args):
                   exchange="nvlink peer stores from the producing kernels (CUDA IPC mappings) + flags"
                   if p2p else "nccl all-gather (%s)" % (getattr(ex, "connect_error", None) or args.exchange))
 
+    tab_rows_cap = 0 if mg is None else mg["tab_words"] // wpr
+
     def exchange_csr():
         """this rank's CSR shard -> every rank; afterwards rm_all holds all roadmaps"""
         ex = mg["ex"]
@@ -363,6 +365,7 @@ def run_b200(args):
             mg["round"] += 1
             ex.push_csr_shard(rm_sh, 0, cap, mg["cap_nnz"], st)
             return None
+        rm_sh.finish()
         L.check(lib.mrmp_roadmaps_pack_csr_shard_dev(rm_sh._h, cap, mg["cap_nnz"],
                                                      mg["slots"][rank].data_ptr(), st))
         dist.all_gather_into_tensor(mg["slots"].view(-1), mg["slots"][rank])
@@ -371,7 +374,8 @@ def run_b200(args):
     def adopt_csr():
         ex = mg["ex"]
         if mg["p2p"]:
-            return ex.adopt_csr_shards(rm_all, 0, cap, mg["cap_nnz"], st)
+            ex.adopt_csr_shards_async(rm_all, 0, cap, mg["cap_nnz"], st)
+            return None
         out = C.c_int64(0)
         L.check(lib.mrmp_roadmaps_set_csr_shards_dev(rm_all._h, world, cap, mg["cap_nnz"],
                                                      mg["slots"].data_ptr(), st, C.byref(out)))
@@ -380,9 +384,10 @@ def run_b200(args):
     def step_strong(cols=cols_d, marks=None):
         """ONE scenario over all ranks: draw all vertices, build the roadmaps of this rank's agent
         block, publish the CSR shard to every rank, evaluate the table rows of this rank's agents
-        against all agents' path edges (written straight into rank 0's memory), adopt the peers'
-        shards.  The timed region ends when every rank holds all roadmaps and rank 0 the table.
-        marks: optional list that receives a CUDA event after every stage (timeline)."""
+        against all agents' path edges and send them to rank 0, adopt the peers' shards.  With the
+        peer exchange nothing waits on the host until the end of the step (asynchronous build: the
+        edge count stays on the device).  The timed region ends when every rank holds all roadmaps
+        and rank 0 the table.  marks: optional list that receives a CUDA event after every stage."""
         ex = mg["ex"]
 
         def mark():
@@ -393,7 +398,7 @@ def run_b200(args):
 
         mark()
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
-        rm_sh.build(radv)
+        rm_sh.build_async(radv)
         mark()                                   # 0: sample + neighbour pass of this rank's agents
         exchange_csr()
         mark()                                   # 1: shard packed and pushed / all-gathered
@@ -401,17 +406,20 @@ def run_b200(args):
             # rows of this rank's agents: into local memory (a rank's share of the table is small,
             # the kernel cuts it into finer work items that OR into local memory), then one
             # coalesced copy kernel into rank 0's buffer over NVLink + a flag
-            rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
-                                     N, mg["tab_local"].data_ptr(), st, cols=rm_all)
-            nb = mg["nnz_sh"][rank] * wpr * 4
-            ex.push(1, 0, mg["tab_local"].data_ptr(), nb + (-nb) % 16, st)
+            rm_sh.edge_conflicts_async(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
+                                       N, mg["tab_local"].data_ptr(), tab_rows_cap, st, cols=rm_all)
+            ex.push_table_rows(rm_sh, 1, 0, mg["tab_local"].data_ptr(), wpr, tab_rows_cap, st)
             ex.signal(1, st, dst_mask=1)
-            mark()                               # 2: table rows of this rank (written to rank 0)
-            n = adopt_csr()
+            mark()                               # 2: table rows of this rank (sent to rank 0)
+            adopt_csr()
             mark()                               # 3: peers' shards arrived and stitched
             if rank == 0:
                 ex.wait(1, st)
             mark()                               # 4: rank 0: all table rows arrived
+            rm_sh.finish()                       # the only host waits of the step
+            n = rm_all.finish()
+            if ex.error():
+                raise RuntimeError("exchange: rank %d never published" % (ex.error() - 1))
         else:
             rm_sh.edge_conflicts_dev(n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(),
                                      N, mg["tab_slots"][rank].data_ptr(), st, cols=rm_all)
@@ -452,15 +460,20 @@ def run_b200(args):
     def step_weak():
         """every rank its own scenario on all roadmaps; the build is sharded and exchanged"""
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
-        rm_sh.build(radv)
+        rm_sh.build_async(radv)
         exchange_csr()
         adopt_csr()
+        rm_sh.finish()
+        rm_all.finish()
         k_table_full()
 
     def step_single():
+        """sample -> neighbour pass -> conflict table without a host round trip in between"""
         rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
-        rm_all.build(radv_all)
-        k_table_full()
+        rm_all.build_async(radv_all)
+        rm_all.edge_conflicts_async(n_cols, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                    cols_d[2].data_ptr(), N, bits_d.data_ptr(), nnz_total + 4096, st)
+        rm_all.finish()
 
     step_value = step_single if world == 1 else (step_strong if strong else step_weak)
 
@@ -487,6 +500,13 @@ def run_b200(args):
             step_weak()
             torch.cuda.synchronize()
             assert torch.equal(bits_d, ref_bits)
+    if world == 1:     # the asynchronous pipeline gives the table of the synchronous calls
+        k_table_full()
+        torch.cuda.synchronize()
+        ref_bits = bits_d.clone()
+        bits_d.zero_()
+        step_single()
+        assert torch.equal(bits_d, ref_bits), "asynchronous step differs from the synchronous one"
 
     # ---- value: device-resident, CUDA events per step on the launching stream, L2 flushed
     for _ in range(warmup):

@@ -158,6 +158,16 @@ int mrmp_roadmaps_sample(mrmp_roadmaps *rm, int nv, uint64_t seed, const double 
  * j != k, (rad is NaN || dist(q_j,q_k) <= rad) && connect(q_j,q_k,i); rows ascending in k.
  * rad[n_agents].  Also covers the all-pairs pass of sssp.jl:388-395 (rad = epsilon). */
 int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad);
+/* Asynchronous pipeline (no host round trip between the kernels of one step): build_async
+ * launches the same kernels and returns; the edge count stays on the device.  Until
+ * mrmp_roadmaps_finish() the set may only be passed to the calls that take the count from the
+ * device: mrmp_roadmaps_edge_conflicts_async (as the row set), mrmp_roadmaps_push_csr_shard,
+ * mrmp_roadmaps_push_table_rows.  finish() waits for the ctx's stream, publishes nnz and checks
+ * that the CSR buffer, a pushed shard slot and a table's row capacity were large enough
+ * (MRMP_ERR_CAPACITY otherwise: those results are truncated, the buffers have been grown, build
+ * again).  Large point roadmaps (uniform-grid path) build synchronously. */
+int mrmp_roadmaps_build_async(mrmp_roadmaps *rm, const double *rad);
+int mrmp_roadmaps_finish(mrmp_roadmaps *rm, int64_t *nnz_out);
 /* diagnostics: 1 when the last build searched neighbours through the uniform-grid spatial hash
  * (point models, nv >= 2048, finite rad), 0 when it tested all ordered pairs */
 int mrmp_roadmaps_used_grid(mrmp_roadmaps *rm);
@@ -227,6 +237,10 @@ int64_t mrmp_exchange_slot_bytes(mrmp_exchange *x, int ch);
 /* copy kernel: `bytes` (multiple of 16) of this rank's device memory -> its slot in rank dst */
 int mrmp_exchange_push(mrmp_exchange *x, int ch, int dst, const void *src_dev, int64_t bytes,
                        void *stream);
+/* the same with the length on the device: min(*count_dev * unit_bytes, max_bytes), rounded up to 16 */
+int mrmp_exchange_push_counted(mrmp_exchange *x, int ch, int dst, const void *src_dev,
+                               const long long *count_dev, int64_t unit_bytes, int64_t max_bytes,
+                               void *stream);
 int mrmp_exchange_signal(mrmp_exchange *x, int ch, unsigned int dst_mask, void *stream);
 int mrmp_exchange_wait(mrmp_exchange *x, int ch, unsigned int src_mask, void *stream);
 int mrmp_exchange_advance(mrmp_exchange *x, int ch);
@@ -239,6 +253,16 @@ int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, in
                                  int cap_agents, int64_t cap_nnz, void *stream);
 int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
                                    int cap_agents, int64_t cap_nnz, void *stream, int64_t *nnz_out);
+/* no wait: the stitched set stays pending (see mrmp_roadmaps_build_async) until
+ * mrmp_roadmaps_finish; `stream` must be the ctx's stream */
+int mrmp_roadmaps_adopt_csr_shards_async(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
+                                         int cap_agents, int64_t cap_nnz, void *stream);
+/* conflict-table rows of this set (words_per_row words each, device memory of this rank) -> this
+ * rank's slot of channel ch in rank dst's buffer (copy kernel over NVLink); the row count is the
+ * set's edge count, read on the device while a build is pending; max_rows = room of the source */
+int mrmp_roadmaps_push_table_rows(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int dst,
+                                  const uint32_t *bits_dev, int words_per_row, int64_t max_rows,
+                                  void *stream);
 
 /* raw device pointers (for NCCL all-gather of shards / zero-copy consumers) */
 int mrmp_roadmaps_device_ptrs(mrmp_roadmaps *rm, int *nv_out, double **nodes_dev,
@@ -338,6 +362,11 @@ int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, 
                                      const int32_t *col_agent, const int32_t *col_vfrom,
                                      const int32_t *col_vto, int group_size, uint32_t *out_bits,
                                      void *stream);
+/* the same behind mrmp_roadmaps_build_async: out_bits has room for out_cap_rows rows */
+int mrmp_roadmaps_edge_conflicts_async(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_t n_cols,
+                                       const int32_t *col_agent, const int32_t *col_vfrom,
+                                       const int32_t *col_vto, int group_size, uint32_t *out_bits,
+                                       int64_t out_cap_rows, void *stream);
 
 /* sampler: gen_uniform_sampling (point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218)
  * restated on a counter-based generator; writes try t0..t0+n-1 of (seed, agent) */

@@ -435,6 +435,18 @@ class Roadmaps:
         L.check(self._lib.mrmp_roadmaps_nnz(self._h, C.byref(nnz)))
         return int(nnz.value)
 
+    def build_async(self, rad) -> None:
+        """Launch the neighbour pass without waiting for the edge count (mrmp_roadmaps_build_async);
+        until finish() the set may only feed edge_conflicts_async / the exchange pushes."""
+        radv = np.broadcast_to(L.f64(math.nan if rad is None else rad), (self.n,)).copy()
+        L.check(self._lib.mrmp_roadmaps_build_async(self._h, L.ptr(radv, L._dp)))
+
+    def finish(self) -> int:
+        """Wait for an asynchronous build / adoption, validate capacities, return nnz."""
+        nnz = C.c_int64(0)
+        L.check(self._lib.mrmp_roadmaps_finish(self._h, C.byref(nnz)))
+        return int(nnz.value)
+
     def used_grid(self) -> bool:
         """True when the last build() searched neighbours through the uniform-grid hash."""
         return bool(self._lib.mrmp_roadmaps_used_grid(self._h))
@@ -498,6 +510,17 @@ class Roadmaps:
                                                            int(n_cols), col_agent_ptr,
                                                            col_vfrom_ptr, col_vto_ptr,
                                                            int(group_size), out_ptr, stream))
+
+    def edge_conflicts_async(self, n_cols: int, col_agent_ptr: int, col_vfrom_ptr: int,
+                             col_vto_ptr: int, group_size: int, out_ptr: int, out_cap_rows: int,
+                             stream: int, cols: "Roadmaps | None" = None) -> None:
+        """edge_conflicts_dev behind build_async: the row count stays on the device; `out` has
+        room for out_cap_rows rows (checked by finish())."""
+        L.check(self._lib.mrmp_roadmaps_edge_conflicts_async(self._h, cols._h if cols else None,
+                                                             int(n_cols), col_agent_ptr,
+                                                             col_vfrom_ptr, col_vto_ptr,
+                                                             int(group_size), out_ptr,
+                                                             int(out_cap_rows), stream))
 
     def to_nodes(self) -> List[List[Node]]:
         """Vector{Vector{Node}} as the reference's PRMs returns it (0-based ids)."""

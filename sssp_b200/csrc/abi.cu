@@ -779,6 +779,11 @@ struct mrmp_roadmaps {
     double *rad_d = nullptr;     // [2][n_agents]: rad, r2
     int64_t nnz = -1;            // host copy after build
     bool built = false;
+    // asynchronous build (mrmp_roadmaps_build_async): launched, nnz still on the device (nnz_d and
+    // its mapped mirror); mrmp_roadmaps_finish() waits and validates the capacities used meanwhile
+    bool pending = false;
+    int64_t pend_slot_nnz = -1;  // cap_nnz of a shard pushed while pending (-1: none)
+    int64_t pend_rows_cap = -1;  // row capacity of a table computed while pending (-1: none)
     // CSR edges expanded to explicit (agent, from, to) rows for the cross kernels
     int32_t *e_agent = nullptr;
     double *e_from = nullptr, *e_to = nullptr;
@@ -1029,9 +1034,11 @@ static int roadmaps_build_grid(mrmp_roadmaps *rm, int g, cudaStream_t s) {
     return fail(MRMP_ERR_CUDA, "grid neighbour pass did not converge");
 }
 
-extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
+static int roadmaps_build_impl(mrmp_roadmaps *rm, const double *rad, bool async) {
     NEED(rm && rad, "bad roadmaps / rad");
     NEED(rm->nv >= 1, "no nodes set");
+    rm->pending = false;
+    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     const int n = rm->n_agents, nv = rm->nv;
@@ -1094,6 +1101,13 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
                        rm->chunk_ws, rm->chunk_ws_len, rm->dev(h_nnz)));
     rc = roadmaps_emit(rm, c->s_k);
     if (rc) return rc;
+    if (async) {  // no wait: nnz is examined by mrmp_roadmaps_finish()
+        rm->pending = true;
+        rm->built = true;
+        rm->nnz = -1;
+        rm->e_valid = false;
+        return MRMP_OK;
+    }
     CU(cudaStreamSynchronize(c->s_k));
     rc = roadmaps_settle(rm, true);
     if (rc) return rc;
@@ -1110,6 +1124,59 @@ extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
     }
     rm->built = true;
     rm->e_valid = false;
+    return MRMP_OK;
+}
+
+extern "C" int mrmp_roadmaps_build(mrmp_roadmaps *rm, const double *rad) {
+    return roadmaps_build_impl(rm, rad, false);
+}
+
+/* The same launches without the wait for nnz (the uniform-grid path of large roadmaps needs nnz on
+ * the host to size its gather and builds synchronously). */
+extern "C" int mrmp_roadmaps_build_async(mrmp_roadmaps *rm, const double *rad) {
+    return roadmaps_build_impl(rm, rad, true);
+}
+
+/* Wait for an asynchronous build (or adoption) and for everything launched on it since, then
+ * validate: the CSR fitted its buffer, a shard pushed meanwhile fitted its slot, a table computed
+ * meanwhile had room for every row.  MRMP_ERR_CAPACITY means those consumers worked on a truncated
+ * edge list: the buffers have been grown, build again. */
+extern "C" int mrmp_roadmaps_finish(mrmp_roadmaps *rm, int64_t *nnz_out) {
+    NEED(rm, "bad roadmaps");
+    mrmp_ctx *c = rm->ctx;
+    if (!rm->pending) {
+        NEED(rm->built, "roadmaps not built");
+        if (nnz_out) *nnz_out = rm->nnz;
+        return MRMP_OK;
+    }
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_k));
+    rm->pending = false;
+    int rc = roadmaps_settle(rm, true);
+    if (rc) {
+        rm->built = false;
+        return rc;
+    }
+    rm->nnz = *rm->st_nnz();
+    if (nnz_out) *nnz_out = rm->nnz;
+    const int64_t slot = rm->pend_slot_nnz, rows_cap = rm->pend_rows_cap;
+    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
+    if (rm->nnz >= ((int64_t)1 << 31)) return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
+    if (rm->nnz > rm->col_cap) {
+        CU(cudaFree(rm->col_idx));
+        rm->col_idx = nullptr;
+        rm->col_cap = rm->nnz + rm->nnz / 4;
+        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+        rm->built = false;
+        return fail(MRMP_ERR_CAPACITY, "asynchronous build: %lld edges overflowed the CSR buffer "
+                    "(grown now); build again", (long long)rm->nnz);
+    }
+    if (slot >= 0 && rm->nnz > slot)
+        return fail(MRMP_ERR_CAPACITY, "asynchronous build: shard of %lld edges pushed into a slot "
+                    "of %lld", (long long)rm->nnz, (long long)slot);
+    if (rows_cap >= 0 && rm->nnz > rows_cap)
+        return fail(MRMP_ERR_CAPACITY, "asynchronous build: table of %lld rows computed into room "
+                    "for %lld", (long long)rm->nnz, (long long)rows_cap);
     return MRMP_OK;
 }
 
@@ -1149,6 +1216,7 @@ extern "C" int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agent
                                                 int32_t *slot_dev, void *stream) {
     NEED(rm && slot_dev && cap_agents >= rm->n_agents && cap_nnz >= 0, "bad arguments");
     NEED(rm->built, "roadmaps not built");
+    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     if (rm->nnz > cap_nnz)
         return fail(MRMP_ERR_CAPACITY, "shard holds %lld edges, slot only %lld", (long long)rm->nnz,
                     (long long)cap_nnz);
@@ -1159,9 +1227,17 @@ extern "C" int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agent
     return MRMP_OK;
 }
 
+static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int64_t cap_nnz,
+                               const int32_t *slots_dev, void *stream, int64_t *nnz_out, bool async);
+
 extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agents,
                                                 int64_t cap_nnz, const int32_t *slots_dev,
                                                 void *stream, int64_t *nnz_out) {
+    return set_csr_shards_impl(rm, world, cap_agents, cap_nnz, slots_dev, stream, nnz_out, false);
+}
+
+static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int64_t cap_nnz,
+                               const int32_t *slots_dev, void *stream, int64_t *nnz_out, bool async) {
     NEED(rm && slots_dev && world >= 1 && cap_agents >= 1 && cap_nnz >= 0, "bad arguments");
     NEED(rm->nv >= 1, "no nodes set");
     NEED((int64_t)world * cap_agents >= rm->n_agents, "shards do not cover the agents of this set");
@@ -1172,8 +1248,10 @@ extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, in
     const int64_t stride = rows_cap + cap_nnz;
     LaunchCfg lc = lcfg(c, s);
     CU(launch_csr_shard_counts(lc, rows, rows_cap, stride, slots_dev, rm->row_cnt));
+    rm->pending = false;
+    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
     CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
-                           rm->chunk_ws, rm->chunk_ws_len));
+                           rm->chunk_ws, rm->chunk_ws_len, async ? rm->dev(rm->st_nnz()) : nullptr));
     if ((int64_t)world * cap_nnz > rm->col_cap) {  // upper bound of the stitched size
         CU(cudaStreamSynchronize(s));
         if (rm->col_idx) CU(cudaFree(rm->col_idx));
@@ -1183,6 +1261,15 @@ extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, in
     }
     CU(launch_csr_stitch(lc, rows, rows_cap, stride, slots_dev, rm->row_ptr, rm->col_idx,
                          rm->col_cap));
+    if (async) {  // nnz stays on the device (and in the mapped mirror) until mrmp_roadmaps_finish
+        NEED(s == c->s_k, "asynchronous adoption runs on the ctx's stream (mrmp_ctx_set_stream)");
+        rm->pending = true;
+        rm->built = true;
+        rm->nnz = -1;
+        rm->e_valid = false;
+        if (nnz_out) *nnz_out = -1;
+        return MRMP_OK;
+    }
     int rc = ensure_small(c, 64);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->small_h, rm->nnz_d, 8, cudaMemcpyDeviceToHost, s));
@@ -1201,7 +1288,9 @@ extern "C" int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x,
     NEED(rm && x && world >= 1 && world <= 32 && cap_agents >= rm->n_agents && cap_nnz >= 0,
          "bad arguments");
     NEED(rm->built, "roadmaps not built");
-    if (rm->nnz > cap_nnz)
+    if (rm->pending)
+        rm->pend_slot_nnz = cap_nnz;  // validated by mrmp_roadmaps_finish (the kernel truncates)
+    else if (rm->nnz > cap_nnz)
         return fail(MRMP_ERR_CAPACITY, "shard holds %lld edges, slot only %lld", (long long)rm->nnz,
                     (long long)cap_nnz);
     const int64_t rows_cap = (int64_t)cap_agents * rm->nv;
@@ -1217,15 +1306,31 @@ extern "C" int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x,
             dst.slot[k] = k < dst.n ? (int32_t *)mrmp_exchange_ptr(x, ch, d0 + k) : nullptr;
             NEED(k >= dst.n || dst.slot[k], "exchange is not connected to every rank");
         }
-        CU(launch_csr_pack_push(lc, (int64_t)rm->n_agents * rm->nv, rows_cap, rm->row_ptr,
+        CU(launch_csr_pack_push(lc, (int64_t)rm->n_agents * rm->nv, rows_cap, cap_nnz, rm->row_ptr,
                                 rm->col_idx, dst));
     }
     return mrmp_exchange_signal(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
 }
 
+static int adopt_impl(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world, int cap_agents,
+                      int64_t cap_nnz, void *stream, int64_t *nnz_out, bool async);
+
 extern "C" int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *x, int ch,
                                               int world, int cap_agents, int64_t cap_nnz,
                                               void *stream, int64_t *nnz_out) {
+    return adopt_impl(rm, x, ch, world, cap_agents, cap_nnz, stream, nnz_out, false);
+}
+
+/* no wait: the stitched set stays pending until mrmp_roadmaps_finish (which also reports a peer
+ * that never published, through mrmp_exchange_error) */
+extern "C" int mrmp_roadmaps_adopt_csr_shards_async(mrmp_roadmaps *rm, mrmp_exchange *x, int ch,
+                                                    int world, int cap_agents, int64_t cap_nnz,
+                                                    void *stream) {
+    return adopt_impl(rm, x, ch, world, cap_agents, cap_nnz, stream, nullptr, true);
+}
+
+static int adopt_impl(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world, int cap_agents,
+                      int64_t cap_nnz, void *stream, int64_t *nnz_out, bool async) {
     NEED(rm && x && world >= 1 && world <= 32, "bad arguments");
     int rc = mrmp_exchange_wait(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
     if (rc) return rc;
@@ -1233,18 +1338,41 @@ extern "C" int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *
              mrmp_exchange_slot_bytes(x, ch) ==
                  (int64_t)sizeof(int32_t) * ((int64_t)cap_agents * rm->nv + cap_nnz),
          "exchange slot must be exactly 4 * (cap_agents * nv + cap_nnz) bytes, a multiple of 16");
-    rc = mrmp_roadmaps_set_csr_shards_dev(rm, world, cap_agents, cap_nnz,
-                                          (const int32_t *)mrmp_exchange_slots(x, ch), stream,
-                                          nnz_out);
-    if (rc) return rc;
+    rc = set_csr_shards_impl(rm, world, cap_agents, cap_nnz,
+                             (const int32_t *)mrmp_exchange_slots(x, ch), stream, nnz_out, async);
+    if (rc || async) return rc;
     const int bad = mrmp_exchange_error(x);  // the stream has been synchronised by the stitch
     if (bad) return fail(MRMP_ERR_CUDA, "exchange: rank %d never published its shard", bad - 1);
     return MRMP_OK;
 }
 
+/* table rows of this set (out_bits of mrmp_roadmaps_edge_conflicts_dev / _async, words_per_row
+ * words each, in device memory of this rank) -> this rank's slot of channel ch in rank dst's
+ * buffer; the number of rows is the set's edge count, taken on the device while a build is
+ * pending.  max_rows = room of the source buffer (and of the slot) in rows. */
+extern "C" int mrmp_roadmaps_push_table_rows(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int dst,
+                                             const uint32_t *bits_dev, int words_per_row,
+                                             int64_t max_rows, void *stream) {
+    NEED(rm && x && bits_dev && words_per_row >= 1 && max_rows >= 0, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    int64_t max_bytes = max_rows * words_per_row * 4;
+    max_bytes -= max_bytes % 16;
+    if (!rm->pending) {
+        NEED(rm->nnz <= max_rows, "more rows than the source buffer holds");
+        int64_t bytes = rm->nnz * words_per_row * 4;
+        bytes += (16 - bytes % 16) % 16;
+        if (bytes > max_bytes) bytes = max_bytes;
+        return mrmp_exchange_push(x, ch, dst, bits_dev, bytes, stream);
+    }
+    if (rm->pend_rows_cap < 0 || rm->pend_rows_cap > max_rows) rm->pend_rows_cap = max_rows;
+    return mrmp_exchange_push_counted(x, ch, dst, bits_dev, (const long long *)rm->nnz_d,
+                                      (int64_t)words_per_row * 4, max_bytes, stream);
+}
+
 extern "C" int mrmp_roadmaps_nnz(mrmp_roadmaps *rm, int64_t *nnz_total_out) {
     NEED(rm && nnz_total_out, "bad arguments");
     NEED(rm->built, "roadmaps not built");
+    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     *nnz_total_out = rm->nnz;
     return MRMP_OK;
 }
@@ -1264,6 +1392,7 @@ extern "C" int mrmp_roadmaps_get_csr(mrmp_roadmaps *rm, int32_t *row_ptr, int32_
                                      int64_t col_cap, int64_t *nnz_out) {
     NEED(rm && row_ptr && nnz_out, "bad arguments");
     NEED(rm->built, "roadmaps not built");
+    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     *nnz_out = rm->nnz;
@@ -1303,6 +1432,7 @@ extern "C" int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, in
                                         int32_t *col_idx, int64_t col_cap, int64_t *nnz_out) {
     NEED(rm && nodes_out && row_ptr && nnz_out, "bad arguments");
     NEED(rm->built, "roadmaps not built");
+    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     *nnz_out = rm->nnz;
@@ -1448,7 +1578,7 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                          int64_t n_cols, const int32_t *col_agent, const double *col_from,
                          const double *col_to, const int32_t *col_vf, const int32_t *col_vt,
                          const double *nodes, int agent0, int nv_stride, const CrossReq &rq,
-                         uint32_t *out, cudaStream_t s) {
+                         uint32_t *out, cudaStream_t s, const long long *n_rows_dev = nullptr) {
     const int group_size = rq.group_size;
     const bool table = rq.mode == kCrossBits || rq.mode == kCrossOr;
     const int wpr = table ? cross_words(n_cols, group_size) : rq.n_groups;
@@ -1528,6 +1658,7 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
         co.row_key = rq.row_key;
         co.cbs = rq.cbs;
         co.may_split = rq.mode == kCrossOr ? (split_or ? 1 : 0) : (local_out ? 1 : 0);
+        co.n_rows_dev = n_rows_dev;
         CU(launch_cross_collide(c->cv, lc, n_rows, rows_sorted, nc, b + o_tiles, b + o_hdr, co,
                                 c->stats_d, (unsigned int *)(b + o_work)));
     }
@@ -1720,7 +1851,9 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
     if (rm->e_valid) return MRMP_OK;
     mrmp_ctx *c = rm->ctx;
     const bool point = c->model <= MRMP_MODEL_POINT3D;
-    if (rm->nnz > rm->e_cap) {
+    if (rm->pending) NEED(point, "an asynchronous build of this model must be finished first");
+    const int64_t need = rm->pending ? rm->col_cap : rm->nnz;  // pending: bounded by the CSR buffer
+    if (need > rm->e_cap) {
         CU(cudaStreamSynchronize(s));
         cudaFree(rm->e_agent);
         cudaFree(rm->e_from);
@@ -1729,7 +1862,7 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
         rm->e_agent = nullptr;
         rm->e_from = rm->e_to = nullptr;
         rm->e_rows = nullptr;
-        rm->e_cap = rm->nnz + rm->nnz / 8 + 64;
+        rm->e_cap = need + need / 8 + 64;
         if (point) {
             // point models: the cross kernel reads Morton-sorted row records only
             CU(cudaMalloc(&rm->e_rows, cross_row_bytes(c->d) * (size_t)rm->e_cap));
@@ -1744,7 +1877,8 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
         if (rc) return rc;
         CU(launch_cross_sort_csr_rows(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
                                       rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes,
-                                      (int32_t *)c->scratch[6], rm->e_rows));
+                                      (int32_t *)c->scratch[6], rm->e_rows,
+                                      rm->col_cap < rm->e_cap ? rm->col_cap : rm->e_cap));
     } else {
         CU(launch_csr_expand_edges(c->cv, lcfg(c, s), (int64_t)rm->n_agents * rm->nv, rm->nv,
                                    rm->agent0, rm->row_ptr, rm->col_idx, rm->nodes, rm->e_agent,
@@ -1754,24 +1888,58 @@ static int roadmaps_expand_edges(mrmp_roadmaps *rm, cudaStream_t s) {
     return MRMP_OK;
 }
 
+// out_cap_rows < 0: the set is built (nnz known); >= 0: room of `out` in rows, the set may be pending
+static int edge_conflicts_core(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_t n_cols,
+                               const int32_t *col_agent, const int32_t *col_vfrom,
+                               const int32_t *col_vto, int group_size, uint32_t *out_bits,
+                               int64_t out_cap_rows, cudaStream_t s) {
+    NEED(rm && n_cols >= 0 && group_size >= 0, "bad arguments");
+    NEED(rm->built, "roadmaps not built");
+    if (!rm_cols) rm_cols = rm;
+    NEED(rm_cols->ctx == rm->ctx && rm_cols->nv >= 1, "rm_cols must belong to the same ctx");
+    mrmp_ctx *c = rm->ctx;
+    int64_t n_rows = rm->nnz;
+    const long long *n_rows_dev = nullptr;
+    if (rm->pending) {
+        NEED(out_cap_rows >= 0, "the set has a pending asynchronous build: finish it first");
+        NEED(c->model <= MRMP_MODEL_POINT3D, "asynchronous tables are built for the point models");
+        n_rows = out_cap_rows < rm->col_cap ? out_cap_rows : rm->col_cap;
+        n_rows_dev = (const long long *)rm->nnz_d;
+        rm->pend_rows_cap = out_cap_rows;
+    } else if (out_cap_rows >= 0 && rm->nnz > out_cap_rows) {
+        return fail(MRMP_ERR_CAPACITY, "out_bits has room for %lld rows, the set has %lld edges",
+                    (long long)out_cap_rows, (long long)rm->nnz);
+    }
+    if (n_cols == 0 || n_rows == 0) return MRMP_OK;
+    CU(cudaSetDevice(c->device));
+    int rc = roadmaps_expand_edges(rm, s);
+    if (rc) return rc;
+    return cross_run_dev(c, n_rows, rm->e_agent, rm->e_from, rm->e_to, rm->e_rows, n_cols,
+                         col_agent, nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes,
+                         rm_cols->agent0, rm_cols->nv, table_req(group_size), out_bits, s,
+                         n_rows_dev);
+}
+
 extern "C" int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,
                                                 int64_t n_cols, const int32_t *col_agent,
                                                 const int32_t *col_vfrom, const int32_t *col_vto,
                                                 int group_size, uint32_t *out_bits,
                                                 void *stream) {
-    NEED(rm && n_cols >= 0 && group_size >= 0, "bad arguments");
-    NEED(rm->built, "roadmaps not built");
-    if (!rm_cols) rm_cols = rm;
-    NEED(rm_cols->ctx == rm->ctx && rm_cols->nv >= 1, "rm_cols must belong to the same ctx");
-    if (n_cols == 0 || rm->nnz == 0) return MRMP_OK;
-    mrmp_ctx *c = rm->ctx;
-    CU(cudaSetDevice(c->device));
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = roadmaps_expand_edges(rm, s);
-    if (rc) return rc;
-    return cross_run_dev(c, rm->nnz, rm->e_agent, rm->e_from, rm->e_to, rm->e_rows, n_cols,
-                         col_agent, nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes,
-                         rm_cols->agent0, rm_cols->nv, table_req(group_size), out_bits, s);
+    return edge_conflicts_core(rm, rm_cols, n_cols, col_agent, col_vfrom, col_vto, group_size,
+                               out_bits, -1, (cudaStream_t)stream);
+}
+
+/* the same behind an asynchronous build: the row count stays on the device; out_bits has room for
+ * out_cap_rows rows (checked by mrmp_roadmaps_finish) */
+extern "C" int mrmp_roadmaps_edge_conflicts_async(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,
+                                                  int64_t n_cols, const int32_t *col_agent,
+                                                  const int32_t *col_vfrom,
+                                                  const int32_t *col_vto, int group_size,
+                                                  uint32_t *out_bits, int64_t out_cap_rows,
+                                                  void *stream) {
+    NEED(out_cap_rows >= 0, "out_cap_rows must be >= 0");
+    return edge_conflicts_core(rm, rm_cols, n_cols, col_agent, col_vfrom, col_vto, group_size,
+                               out_bits, out_cap_rows, (cudaStream_t)stream);
 }
 
 extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,
@@ -1781,6 +1949,7 @@ extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm
                                             uint32_t *out_bits, int64_t out_cap_words) {
     NEED(rm && n_cols >= 0 && group_size >= 0, "bad arguments");
     NEED(rm->built, "roadmaps not built");
+    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     if (n_cols == 0 || rm->nnz == 0) return MRMP_OK;
     NEED(col_agent && col_vfrom && col_vto && out_bits, "NULL buffer");
     if (!rm_cols) rm_cols = rm;

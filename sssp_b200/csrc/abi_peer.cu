@@ -82,6 +82,19 @@ __global__ void __launch_bounds__(256) k_exchange_push(int4 *__restrict__ dst,
         dst[k] = src[k];
 }
 
+// the same with the length on the device: n16 = ceil(min(*count * unit, max_bytes) / 16)
+__global__ void __launch_bounds__(256) k_exchange_push_n(int4 *__restrict__ dst,
+                                                         const int4 *__restrict__ src,
+                                                         const long long *__restrict__ count,
+                                                         long long unit, long long max_bytes) {
+    long long bytes = *count * unit;
+    if (bytes > max_bytes) bytes = max_bytes;
+    const int64_t n16 = (bytes + 15) / 16;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n16;
+         k += (int64_t)gridDim.x * blockDim.x)
+        dst[k] = src[k];
+}
+
 }  // namespace
 
 extern "C" int mrmp_exchange_create(mrmp_ctx *c, int world, int rank, int n_chan,
@@ -264,6 +277,31 @@ extern "C" int mrmp_exchange_push(mrmp_exchange *x, int ch, int dst, const void 
     const int64_t cap = (int64_t)x->ctx->sm_count * 4;
     if (grid > cap) grid = cap;
     k_exchange_push<<<(int)grid, 256, 0, (cudaStream_t)stream>>>((int4 *)p, (const int4 *)src_dev, n16);
+    count_launch();
+    CU(cudaGetLastError());
+    return MRMP_OK;
+}
+
+/* as mrmp_exchange_push with the length taken from device memory at run time:
+ * min(*count_dev * unit_bytes, max_bytes) bytes, rounded up to 16 (max_bytes a multiple of 16
+ * within the slot; the source buffer must be readable up to that rounding) */
+extern "C" int mrmp_exchange_push_counted(mrmp_exchange *x, int ch, int dst, const void *src_dev,
+                                          const long long *count_dev, int64_t unit_bytes,
+                                          int64_t max_bytes, void *stream) {
+    NEED(x && ch >= 0 && ch < x->n_chan && dst >= 0 && dst < x->world && src_dev && count_dev,
+         "bad arguments");
+    NEED(unit_bytes > 0 && max_bytes >= 0 && max_bytes % 16 == 0 && max_bytes <= x->slot_bytes[ch] &&
+             aligned16(src_dev),
+         "max_bytes must be a multiple of 16 within the slot, src 16-byte aligned");
+    void *p = mrmp_exchange_ptr(x, ch, dst);
+    NEED(p, "exchange is not connected to the destination rank");
+    if (max_bytes == 0) return MRMP_OK;
+    CU(cudaSetDevice(x->ctx->device));
+    int64_t grid = (max_bytes / 16 + 255) / 256;
+    const int64_t cap = (int64_t)x->ctx->sm_count * 4;
+    if (grid > cap) grid = cap;
+    k_exchange_push_n<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(
+        (int4 *)p, (const int4 *)src_dev, count_dev, (long long)unit_bytes, (long long)max_bytes);
     count_launch();
     CU(cudaGetLastError());
     return MRMP_OK;

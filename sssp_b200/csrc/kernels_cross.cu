@@ -209,79 +209,105 @@ struct ColPrep {
     int n_agents;
 };
 
+// broad-phase and exact-stage records of one column; m / h = its midpoint and reach in FP64
+// (inputs of the tile header)
+template <int D>
+__device__ __forceinline__ void make_col(const ColPrep<D> &P, int64_t src, int j, const double *a,
+                                         const double *b, ColB &B, ColX<D> &X, double *m,
+                                         double &h) {
+    const bool known = j >= 0 && j < P.n_agents;
+    // reach of the column: half length + its agent's radius (an id outside the ctx is rejected
+    // by the exact stage; it must not be culled here)
+    const double rj = known ? __ldg(P.rads + j) : 1e300;
+    h = half_len_up<D>(a, b) + rj;
+    X.inv = seg_filter_inv<D>(a, b);
+    X.rad = known ? rj : 0.0;
+    X.agent = known ? j : -1;
+    X.bit = (int)(P.col_group ? __ldg(P.col_group + src)
+                              : (P.group_size > 0 ? src / P.group_size : src));
+    X.orig = (int)(src + P.orig_base);
+    X.key = P.col_key ? __ldg(P.col_key + src) : 0;
+    // 2-D: the z slot carries the output slot for the kernel's in-loop "already set" test
+    B.m[2] = D == 2 ? __int_as_float(X.bit) : 0.0f;
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+        X.a[x] = a[x];
+        X.b[x] = b[x];
+        m[x] = dmul(dadd(a[x], b[x]), 0.5);
+        B.m[x] = (float)m[x];
+    }
+    B.h = (X.inv >= 0.0 && known) ? f32_up(h) : INFINITY;
+}
+
+template <int D>
+__device__ __forceinline__ void make_pad(ColB &B, ColX<D> &X) {  // far away, never selected
+    B.m[0] = B.m[1] = 1e15f;
+    B.m[2] = 0.0f;
+    B.h = 0.0f;
+#pragma unroll
+    for (int x = 0; x < D; ++x) X.a[x] = X.b[x] = 0.0;
+    X.inv = -1.0;
+    X.rad = 0.0;
+    X.agent = -1;
+    X.bit = X.orig = X.key = 0;
+}
+
+// header of tile t from this lane's column (m, h; `real` false for padding): warp reduction
+template <int D>
+__device__ __forceinline__ void tile_header(const ColPrep<D> &P, int64_t t, int lane, bool real,
+                                            const double *m, double h) {
+    double lo[D], hi[D], hmax = real ? h : 0.0;
+    bool poison = real && !(h == h);  // a NaN midpoint must never be culled by the box test
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+        lo[x] = real ? m[x] : 1e300;
+        hi[x] = real ? m[x] : -1e300;
+        poison |= real && !(m[x] == m[x]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            lo[x] = fmin(lo[x], __shfl_xor_sync(0xffffffffu, lo[x], o));
+            hi[x] = fmax(hi[x], __shfl_xor_sync(0xffffffffu, hi[x], o));
+        }
+        hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    }
+    poison = __any_sync(0xffffffffu, poison);
+    if (lane == 0) {
+        TileHdr<D> H;
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            H.lo[x] = poison ? -1e300 : lo[x];
+            H.hi[x] = poison ? 1e300 : hi[x];
+        }
+        H.hmax = poison ? 1e300 : hmax;
+        H.pad = 0.0;
+        P.hdrs[t] = H;
+    }
+}
+
 // one warp builds tile t (one column per lane) and its header
 template <int D>
 __device__ __forceinline__ void prep_tile(const ColPrep<D> &P, int64_t t, int lane) {
-        const int64_t c = t * kCols + lane;
-        ColB B;
-        ColX<D> X;
-        double lo[D], hi[D], hmax = 0.0;
-        bool poison = false;  // a NaN midpoint must never be culled by the box test
-        if (c >= P.n_cols) {  // padding column: far away, never selected
-            B.m[0] = B.m[1] = 1e15f;
-            B.m[2] = 0.0f;
-            B.h = 0.0f;
+    const int64_t c = t * kCols + lane;
+    ColB B;
+    ColX<D> X;
+    double m[D], h = 0.0;
+    const bool real = c < P.n_cols;
+    if (real) {
+        const int64_t src = P.order[c];
+        double a[D], b[D];
+        const int j = P.el.get(src, a, b);
+        make_col<D>(P, src, j, a, b, B, X, m, h);
+    } else {
+        make_pad<D>(B, X);
 #pragma unroll
-            for (int x = 0; x < D; ++x) {
-                X.a[x] = X.b[x] = 0.0;
-                lo[x] = 1e300;
-                hi[x] = -1e300;
-            }
-            X.inv = -1.0;
-            X.rad = 0.0;
-            X.agent = -1;
-            X.bit = X.orig = X.key = 0;
-        } else {
-            const int64_t src = P.order[c];
-            const int j = P.el.get(src, X.a, X.b);
-            const bool known = j >= 0 && j < P.n_agents;
-            // reach of the column: half length + its agent's radius (an id outside the ctx is
-            // rejected by the exact stage; it must not be culled here)
-            const double rj = known ? __ldg(P.rads + j) : 1e300;
-            const double h = half_len_up<D>(X.a, X.b) + rj;
-            X.inv = seg_filter_inv<D>(X.a, X.b);
-            X.rad = known ? rj : 0.0;
-            X.agent = j;
-            X.bit = (int)(P.col_group ? __ldg(P.col_group + src)
-                                      : (P.group_size > 0 ? src / P.group_size : src));
-            X.orig = (int)(src + P.orig_base);
-            X.key = P.col_key ? __ldg(P.col_key + src) : 0;
-            // 2-D: the z slot carries the output slot for the kernel's in-loop "already set" test
-            B.m[2] = D == 2 ? __int_as_float(X.bit) : 0.0f;
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                const double m = dmul(dadd(X.a[x], X.b[x]), 0.5);
-                B.m[x] = (float)m;
-                lo[x] = hi[x] = m;
-                poison |= !(m == m);
-            }
-            B.h = (X.inv >= 0.0 && known) ? f32_up(h) : INFINITY;
-            poison |= !(h == h);
-            hmax = h;
-        }
-        P.cb[c] = B;
-        P.cx[c] = X;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                lo[x] = fmin(lo[x], __shfl_xor_sync(0xffffffffu, lo[x], o));
-                hi[x] = fmax(hi[x], __shfl_xor_sync(0xffffffffu, hi[x], o));
-            }
-            hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
-        }
-        poison = __any_sync(0xffffffffu, poison);
-        if (lane == 0) {
-            TileHdr<D> H;
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                H.lo[x] = poison ? -1e300 : lo[x];
-                H.hi[x] = poison ? 1e300 : hi[x];
-            }
-            H.hmax = poison ? 1e300 : hmax;
-            H.pad = 0.0;
-            P.hdrs[t] = H;
-        }
+        for (int x = 0; x < D; ++x) m[x] = 0.0;
+    }
+    P.cb[c] = B;
+    P.cx[c] = X;
+    tile_header<D>(P, t, lane, real, m, h);
 }
 
 template <int D>
@@ -294,21 +320,30 @@ __global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
 }
 
 // The whole column side in ONE launch for the usual case of a few thousand columns (a conflict
-// table has N x T of them): one CTA counts the Morton cells in shared memory, scans, scatters the
-// order and builds the tiles -- instead of histogram / scan / scatter / tile kernels whose launch
-// latencies exceed their work.
-constexpr int kPrepSmallMax = 32768;
+// table has N x T of them): one CTA, every thread keeps its (up to 4) columns in registers,
+// counts the Morton cells in shared memory, scans, and writes the finished records straight to
+// their sorted position; the headers are reduced from the records afterwards -- instead of
+// histogram / scan / scatter / tile kernels whose launch latencies exceed their work.
+constexpr int kPrepSmallCpt = 4;
+constexpr int kPrepSmallMax = 1024 * kPrepSmallCpt;
 template <int D>
-__global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P, int32_t *order) {
+__global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
     __shared__ int h[kSortCells];
     __shared__ int part[1024];
     const int tid = threadIdx.x;
     for (int c = tid; c < kSortCells; c += 1024) h[c] = 0;
     __syncthreads();
-    for (int64_t k = tid; k < P.n_cols; k += 1024) {
-        double a[D], b[D];
-        P.el.get(k, a, b);
-        atomicAdd(&h[morton_cell<D>(a, b)], 1);
+    double a[kPrepSmallCpt][D], b[kPrepSmallCpt][D];
+    int ag[kPrepSmallCpt], cell[kPrepSmallCpt];
+#pragma unroll
+    for (int i = 0; i < kPrepSmallCpt; ++i) {
+        const int64_t k = tid + 1024 * i;
+        cell[i] = -1;
+        if (k < P.n_cols) {
+            ag[i] = P.el.get(k, a[i], b[i]);
+            cell[i] = morton_cell<D>(a[i], b[i]);
+            atomicAdd(&h[cell[i]], 1);
+        }
     }
     __syncthreads();
     int v[4], sum = 0;
@@ -332,13 +367,45 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P, in
         base += v[k];
     }
     __syncthreads();
-    for (int64_t k = tid; k < P.n_cols; k += 1024) {
-        double a[D], b[D];
-        P.el.get(k, a, b);
-        order[atomicAdd(&h[morton_cell<D>(a, b)], 1)] = (int)k;
+#pragma unroll
+    for (int i = 0; i < kPrepSmallCpt; ++i) {
+        if (cell[i] < 0) continue;
+        const int pos = atomicAdd(&h[cell[i]], 1);
+        ColB B;
+        ColX<D> X;
+        double m[D], hh;
+        make_col<D>(P, tid + 1024 * i, ag[i], a[i], b[i], B, X, m, hh);
+        P.cb[pos] = B;
+        P.cx[pos] = X;
     }
-    __syncthreads();  // the order array (global) is complete and visible to the whole CTA
-    for (int64_t t = tid >> 5; t < P.n_tiles; t += 32) prep_tile<D>(P, t, tid & 31);
+    for (int64_t p = P.n_cols + tid; p < P.n_tiles * kCols; p += 1024) {
+        ColB B;
+        ColX<D> X;
+        make_pad<D>(B, X);
+        P.cb[p] = B;
+        P.cx[p] = X;
+    }
+    __syncthreads();  // the records (global) are complete and visible to the whole CTA
+    for (int64_t t = tid >> 5; t < P.n_tiles; t += 32) {
+        const int lane = tid & 31;
+        const int64_t c = t * kCols + lane;
+        const bool real = c < P.n_cols;
+        double m[D], hh = 0.0;
+#pragma unroll
+        for (int x = 0; x < D; ++x) m[x] = 0.0;
+        if (real) {
+            const ColX<D> &X = P.cx[c];
+            double xa[D], xb[D];
+#pragma unroll
+            for (int x = 0; x < D; ++x) {
+                xa[x] = X.a[x];
+                xb[x] = X.b[x];
+                m[x] = dmul(dadd(xa[x], xb[x]), 0.5);
+            }
+            hh = half_len_up<D>(xa, xb) + (X.agent >= 0 ? X.rad : 1e300);
+        }
+        tile_header<D>(P, t, lane, real, m, hh);
+    }
 }
 
 // ---- rows from the CSR of a roadmap set: edge e of row (agent a, vertex v) -----------------
@@ -377,7 +444,7 @@ template <int D>
 __global__ void __launch_bounds__(256)
 k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
                 const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
-                int32_t *__restrict__ counts) {
+                int32_t *__restrict__ counts, int64_t e_cap) {
     __shared__ int h[kSortCells];
     for (int c = threadIdx.x; c < kSortCells; c += blockDim.x) h[c] = 0;
     __syncthreads();
@@ -389,7 +456,9 @@ k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
         const double *tab = nodes + (int64_t)a * nv * D;
         double qv[D];
         load_state<D>(tab, v, qv);
-        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) {
+        // (e_cap: capacity of col_idx / the row records; only an overflowing asynchronous build
+        // ever reaches it, and that build is rejected by mrmp_roadmaps_finish)
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += 32) {
             double qk[D];
             load_state<D>(tab, col_idx[e], qk);
             atomicAdd(&h[morton_cell<D>(qv, qk)], 1);
@@ -405,7 +474,7 @@ __global__ void __launch_bounds__(256)
 k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__restrict__ row_ptr,
                    const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
                    const int32_t *__restrict__ counts, int32_t *__restrict__ cursor,
-                   RowRec<D> *__restrict__ rows) {
+                   RowRec<D> *__restrict__ rows, int64_t e_cap) {
     __shared__ int off[kSortCells];
     __shared__ int part[256];
     {   // exclusive scan of the 4096 cell counts (16 per thread)
@@ -441,7 +510,7 @@ k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
         RowRec<D> r;
         load_state<D>(tab, v, r.a);
         r.agent = agent0 + a;
-        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) {
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += 32) {
             load_state<D>(tab, col_idx[e], r.b);
             r.orig = e;
             const int cell = morton_cell<D>(r.a, r.b);
@@ -479,6 +548,7 @@ struct CrossArgs {
     const int32_t *row_key;  // NULL: every pair is admitted; else col_key > row_key[row]
     int cbs;                 // cbs.jl:343-346: vertex test OR edge test with the column first
     int split;               // work items per warp tile (column tiles divided into `split` ranges)
+    const long long *n_rows_dev;  // NULL, or the actual row count (<= n_rows) on the device
     unsigned long long *stats;
     unsigned int *work;
 };
@@ -544,7 +614,12 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem<D, R> &S = reinterpret_cast<WarpSmem<D, R> *>(smem_raw)[warp];
     const double *rads = cv.blob + cv.crads_off;
-    const int64_t n_wt = (A.n_rows + R - 1) / R;
+    int64_t n_rows_k = A.n_rows;
+    if (A.n_rows_dev) {  // launched behind an asynchronous build: the count is only known here
+        const long long nd = *A.n_rows_dev;
+        if (nd < n_rows_k) n_rows_k = nd;
+    }
+    const int64_t n_wt = (n_rows_k + R - 1) / R;
     const int64_t n_items = n_wt * A.split;
     unsigned long long n_tiles_read = 0, n_filter = 0, n_exact = 0;  // per-warp / per-lane counters
 
@@ -556,9 +631,9 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
         if (lane == 0) item = atomicAdd(A.work, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if ((int64_t)item >= n_items) break;
+        // (column tiles are dealt to the items round robin: the tiles near a warp tile are
+        // neighbours in Morton order, a contiguous range would give one item all the work)
         const unsigned wt = item / (unsigned)A.split, chunk = item - wt * (unsigned)A.split;
-        const int t_begin = (int)((int64_t)chunk * A.n_tiles / A.split);
-        const int t_end = (int)((int64_t)(chunk + 1) * A.n_tiles / A.split);
         RowB32 rb;
         double lo[D], hi[D], Rmax = 0.0;
         bool poison = false;
@@ -568,7 +643,7 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
             hi[x] = -1e300;
         }
         const int64_t r = (int64_t)wt * R + lane;
-        const bool live = r < A.n_rows;
+        const bool live = r < n_rows_k;
         if (live) {
             const RowRec<D> rec = A.rows[r];
             const bool known = rec.agent >= 0 && rec.agent < cv.n_agents;
@@ -618,10 +693,11 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
         poison = __any_sync(0xffffffffu, poison);
         __syncwarp();
 
-        for (int t0 = t_begin; t0 < t_end; t0 += 32) {
+        for (int t0 = 0; t0 < A.n_tiles; t0 += 32) {
             // box-vs-box test of 32 column tiles at once
             bool near = false;
-            if (t0 + lane < t_end) {
+            if (t0 + lane < A.n_tiles &&
+                (A.split == 1 || (unsigned)(t0 + lane) % (unsigned)A.split == chunk)) {
                 const TileHdr<D> H = A.hdrs[t0 + lane];
                 double d2 = 0.0;
 #pragma unroll
@@ -842,7 +918,7 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
     P.rads = cv.blob + cv.crads_off;
     P.n_agents = cv.n_agents;
     if (n_cols <= kPrepSmallMax) {
-        k_cross_prep_cols_small<D><<<1, 1024, 0, lc.stream>>>(P, order);
+        k_cross_prep_cols_small<D><<<1, 1024, 0, lc.stream>>>(P);
         count_launch();
         return cudaGetLastError();
     }
@@ -879,7 +955,7 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
 cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                        int nv, int agent0, const int32_t *row_ptr,
                                        const int32_t *col_idx, const double *nodes, int32_t *cells,
-                                       void *rows_out) {
+                                       void *rows_out, int64_t e_cap) {
     if (n_rows_csr <= 0) return cudaSuccess;
     if (cv.model > 1) return cudaErrorNotSupported;
     cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * 2 * kSortCells, lc.stream);
@@ -888,15 +964,17 @@ cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, i
     const int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     if (cv.model == 0) {
-        k_csr_cell_hist<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells);
+        k_csr_cell_hist<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells,
+                                                       e_cap);
         k_csr_rows_scatter<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
                                                           nodes, cells, cells + kSortCells,
-                                                          (RowRec<2> *)rows_out);
+                                                          (RowRec<2> *)rows_out, e_cap);
     } else {
-        k_csr_cell_hist<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells);
+        k_csr_cell_hist<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells,
+                                                       e_cap);
         k_csr_rows_scatter<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
                                                           nodes, cells, cells + kSortCells,
-                                                          (RowRec<3> *)rows_out);
+                                                          (RowRec<3> *)rows_out, e_cap);
     }
     count_launch(2);
     return cudaGetLastError();
@@ -948,7 +1026,13 @@ static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const 
 // balances by itself (and one item per row keeps the OR mode's plain stores); below that the
 // column tiles of a warp tile are divided so that there are ~4 items per resident warp.
 int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split) {
+    static int forced = -1;  // MRMP_CROSS_SPLIT=<n> pins the factor (experiments)
+    if (forced < 0) {
+        const char *e = getenv("MRMP_CROSS_SPLIT");
+        forced = e ? atoi(e) : 0;
+    }
     if (!may_split || n_tiles <= 1) return 1;
+    if (forced > 0) return forced < n_tiles ? forced : n_tiles;
     const int64_t n_wt = (n_rows + 31) / 32;
     const int64_t warps = (int64_t)lc.sm_count * MRMP_CROSS_MINB * kWarpsPerCta;
     if (n_wt >= 3 * warps) return 1;
@@ -977,6 +1061,7 @@ static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_
     A.row_key = co.row_key;
     A.cbs = co.cbs;
     A.split = cross_split(lc, n_rows, n_tiles, co.may_split);
+    A.n_rows_dev = co.n_rows_dev;
     A.stats = stats;
     A.work = work;
     cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned int), lc.stream);

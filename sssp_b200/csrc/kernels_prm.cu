@@ -861,8 +861,9 @@ k_csr_pack_shard(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ r
 // mappings over NVLink; consecutive threads write consecutive words, so every warp store is one
 // 128-byte transaction per destination)
 __global__ void __launch_bounds__(kThreads)
-k_csr_pack_push(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ row_ptr,
-                const int32_t *__restrict__ col_idx, CsrPushDst dst) {
+k_csr_pack_push(int64_t n_rows, int64_t rows_cap, int64_t cap_nnz,
+                const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                CsrPushDst dst) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t r = tid; r < rows_cap; r += stride) {
@@ -871,7 +872,9 @@ k_csr_pack_push(int64_t n_rows, int64_t rows_cap, const int32_t *__restrict__ ro
         for (int k = 0; k < 8; ++k)
             if (k < dst.n) dst.slot[k][r] = v;
     }
-    const int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    // (a shard larger than its slot is truncated here; the host detects it from nnz)
+    int64_t nnz = n_rows > 0 ? row_ptr[n_rows] : 0;
+    if (nnz > cap_nnz) nnz = cap_nnz;
     for (int64_t e = tid; e < nnz; e += stride) {
         const int32_t v = col_idx[e];
 #pragma unroll
@@ -999,10 +1002,10 @@ cudaError_t launch_csr_pack_shard(const LaunchCfg &lc, int64_t n_rows, int64_t r
 }
 
 cudaError_t launch_csr_pack_push(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
-                                 const int32_t *row_ptr, const int32_t *col_idx,
+                                 int64_t cap_nnz, const int32_t *row_ptr, const int32_t *col_idx,
                                  const CsrPushDst &dst) {
-    k_csr_pack_push<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, row_ptr, col_idx,
-                                                                 dst);
+    k_csr_pack_push<<<lc.sm_count * 4, kThreads, 0, lc.stream>>>(n_rows, rows_cap, cap_nnz, row_ptr,
+                                                                 col_idx, dst);
     count_launch();
     return cudaGetLastError();
 }

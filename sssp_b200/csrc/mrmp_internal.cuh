@@ -247,7 +247,7 @@ struct CsrPushDst {  // destinations of one shard push (own buffer and peer mapp
     int32_t *slot[8];
 };
 cudaError_t launch_csr_pack_push(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
-                                 const int32_t *row_ptr, const int32_t *col_idx,
+                                 int64_t cap_nnz, const int32_t *row_ptr, const int32_t *col_idx,
                                  const CsrPushDst &dst);
 cudaError_t launch_csr_shard_counts(const LaunchCfg &lc, int64_t n_rows, int64_t rows_cap,
                                     int64_t slot_stride, const int32_t *slots, int32_t *row_cnt);
@@ -339,6 +339,8 @@ struct CrossOut {
     int cbs;                  // cbs.jl:343-346 pair test (vertex OR edge, column first)
     int may_split;            // `out` is zeroed memory of this GPU: a warp tile's columns may be
                               // divided over several work items that OR / add into it
+    const long long *n_rows_dev;  // NULL, or the row count on the device (<= the host bound
+                                  // passed as n_rows): a table launched behind an asynchronous build
 };
 int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split);
 size_t cross_tile_bytes(int d);
@@ -357,7 +359,7 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
 cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                        int nv, int agent0, const int32_t *row_ptr,
                                        const int32_t *col_idx, const double *nodes, int32_t *cells,
-                                       void *rows_out);
+                                       void *rows_out, int64_t e_cap);
 cudaError_t launch_csr_expand_edges(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                     int nv, int agent0, const int32_t *row_ptr,
                                     const int32_t *col_idx, const double *nodes, int32_t *e_agent,

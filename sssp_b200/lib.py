@@ -66,6 +66,8 @@ _SIGS = {
     "mrmp_roadmaps_set_nodes": (C.c_int, [_vp, C.c_int, _dp]),
     "mrmp_roadmaps_sample": (C.c_int, [_vp, C.c_int, C.c_uint64, _dp, _dp, _lp]),
     "mrmp_roadmaps_build": (C.c_int, [_vp, _dp]),
+    "mrmp_roadmaps_build_async": (C.c_int, [_vp, _dp]),
+    "mrmp_roadmaps_finish": (C.c_int, [_vp, _lp]),
     "mrmp_roadmaps_nnz": (C.c_int, [_vp, _lp]),
     "mrmp_roadmaps_used_grid": (C.c_int, [_vp]),
     "mrmp_roadmaps_get_nodes": (C.c_int, [_vp, _dp]),
@@ -98,6 +100,11 @@ _SIGS = {
                                                C.c_int64]),
     "mrmp_roadmaps_edge_conflicts_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
                                                    _vp, _vp]),
+    "mrmp_roadmaps_edge_conflicts_async": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int,
+                                                     _vp, C.c_int64, _vp]),
+    "mrmp_roadmaps_adopt_csr_shards_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64, _vp]),
+    "mrmp_roadmaps_push_table_rows": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int64, _vp]),
+    "mrmp_exchange_push_counted": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "mrmp_roadmaps_set_csr_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "mrmp_roadmaps_pack_csr_shard_dev": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp]),
     "mrmp_roadmaps_set_csr_shards_dev": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _lp]),

@@ -126,6 +126,18 @@ class Exchange:
         return int(out.value)
 
 
+    def adopt_csr_shards_async(self, rm_all, ch: int, cap_agents: int, cap_nnz: int, stream: int) -> None:
+        """No wait: rm_all stays pending until rm_all.finish()."""
+        L.check(self._lib.mrmp_roadmaps_adopt_csr_shards_async(rm_all._h, self._h, int(ch), self.world,
+                                                               int(cap_agents), int(cap_nnz), stream))
+
+    def push_table_rows(self, rm, ch: int, dst: int, bits_ptr: int, words_per_row: int,
+                        max_rows: int, stream: int) -> None:
+        """Table rows of `rm` (device memory of this rank) -> this rank's slot in rank dst."""
+        L.check(self._lib.mrmp_roadmaps_push_table_rows(rm._h, self._h, int(ch), int(dst), bits_ptr,
+                                                        int(words_per_row), int(max_rows), stream))
+
+
 def csr_slot_words(cap_agents: int, nv: int, nnz_max: int) -> int:
     """cap_nnz for a shard slot: head room over the largest shard, and the slot
     (cap_agents*nv + cap_nnz words) a multiple of 16 bytes."""

@@ -11,9 +11,11 @@ from sssp_b200 import peer as P, sharding as SH, workload as W
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
+L_ERR_CAPACITY = -3
 
 
-@pytest.mark.parametrize("world,via", [(1, "direct"), (3, "direct"), (4, "direct"), (3, "push"), (8, "push")])
+@pytest.mark.parametrize("world,via", [(1, "direct"), (3, "direct"), (4, "direct"), (3, "push"), (5, "push"),
+                                       (1, "async"), (4, "async")])
 def test_row_sharded_table_equals_single_gpu_table(world, via):
     import torch
     N, nv, T = 10, 160, 17
@@ -66,8 +68,17 @@ def test_row_sharded_table_equals_single_gpu_table(world, via):
     P.Exchange.connect_local(xs)
     for round_ in range(3):            # several rounds: epochs and double buffering
         for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
+            if via == "async":     # no host wait between the kernels: the edge count stays on the device
+                allrm.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+                sh.build_async(inst.rad)
             xs[r].push_csr_shard(sh, 0, cap, cap_nnz, st)
-            if via == "direct":    # the table kernel stores straight into rank 0's buffer
+            if via == "async":
+                local = torch.full((tab_words,), -1, dtype=torch.int32, device="cuda")
+                sh.edge_conflicts_async(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                                        cols_d[2].data_ptr(), N, local.data_ptr(), tab_words // wpr, st,
+                                        cols=allrm)
+                xs[r].push_table_rows(sh, 1, 0, local.data_ptr(), wpr, tab_words // wpr, st)
+            elif via == "direct":  # the table kernel stores straight into rank 0's buffer
                 sh.edge_conflicts_dev(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
                                       cols_d[2].data_ptr(), N, xs[r].ptr(1, 0), st, cols=allrm)
             else:                  # rows into local memory (finer work items), then a copy kernel
@@ -78,7 +89,11 @@ def test_row_sharded_table_equals_single_gpu_table(world, via):
                 xs[r].push(1, 0, local.data_ptr(), nb + (-nb) % 16, st)
             xs[r].signal(1, st, dst_mask=1)
         for r, (ctx, allrm, sh, a0, n_local, _) in enumerate(ranks):
-            assert xs[r].adopt_csr_shards(allrm, 0, cap, cap_nnz, st) == nnz
+            if via == "async":
+                xs[r].adopt_csr_shards_async(allrm, 0, cap, cap_nnz, st)
+                assert sh.finish() == nnz_sh[r] and allrm.finish() == nnz
+            else:
+                assert xs[r].adopt_csr_shards(allrm, 0, cap, cap_nnz, st) == nnz
             rp, col = allrm.csr()
             assert np.array_equal(rp, rp_ref) and np.array_equal(col, col_ref)
         xs[0].wait(1, st)
@@ -111,3 +126,36 @@ def test_exchange_wait_gives_up_instead_of_hanging():
     xs[0].wait(0, st)
     torch.cuda.synchronize()
     assert xs[0].error() == 2            # 1 + the missing rank
+
+
+def test_async_build_reports_capacity_overflow():
+    """A table computed behind an asynchronous build into too little room is truncated on the
+    device and rejected by finish(); host-side queries are refused while the build is pending."""
+    import torch
+    N, nv = 4, 120
+    inst = W.point2d_many(N=N, seed=1, nv=nv, rad=0.2)
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles)
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.set_stream(st)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+    nnz = rm.build(inst.rad)
+    rp, col = rm.csr()
+    _, ca, vf, vt = W.random_walk_paths(inst, rp, col, 5, seed=2)
+    ref = rm.edge_conflicts(ca, vf, vt, N)
+    cols_d = [torch.from_numpy(x).cuda() for x in (ca, vf, vt)]
+    out = torch.full((nnz + 64, ref.shape[1]), -1, dtype=torch.int32, device="cuda")
+    rm.build_async(inst.rad)
+    with pytest.raises(S.MRMPError):
+        rm.csr()                                      # pending: nnz is not on the host yet
+    rm.edge_conflicts_async(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(), cols_d[2].data_ptr(),
+                            N, out.data_ptr(), nnz + 64, st)
+    assert rm.finish() == nnz
+    assert np.array_equal(out[:nnz].cpu().numpy().view(np.uint32), ref)
+    rm.build_async(inst.rad)
+    rm.edge_conflicts_async(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(), cols_d[2].data_ptr(),
+                            N, out.data_ptr(), nnz // 2, st)
+    with pytest.raises(S.MRMPError) as e:
+        rm.finish()
+    assert e.value.code == L_ERR_CAPACITY
+    assert (out[nnz // 2 + 32:].cpu().numpy() == -1).all()    # nothing written beyond the room given
