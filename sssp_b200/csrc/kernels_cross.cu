@@ -549,6 +549,7 @@ struct CrossArgs {
     int cbs;                 // cbs.jl:343-346: vertex test OR edge test with the column first
     int split;               // work items per warp tile (column tiles divided into `split` ranges)
     const long long *n_rows_dev;  // NULL, or the actual row count (<= n_rows) on the device
+    int64_t out_rows;             // rows `out` has room for: a row whose index is beyond is dropped
     unsigned long long *stats;
     unsigned int *work;
 };
@@ -643,7 +644,9 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
             hi[x] = -1e300;
         }
         const int64_t r = (int64_t)wt * R + lane;
-        const bool live = r < n_rows_k;
+        // (orig beyond the output's room: only behind an asynchronous build whose edge count
+        // exceeded the room the caller gave -- rejected afterwards by mrmp_roadmaps_finish)
+        const bool live = r < n_rows_k && A.rows[r].orig < A.out_rows;
         if (live) {
             const RowRec<D> rec = A.rows[r];
             const bool known = rec.agent >= 0 && rec.agent < cv.n_agents;
@@ -1062,6 +1065,7 @@ static cudaError_t launch_cross_t(const CtxView &cv, const LaunchCfg &lc, int64_
     A.cbs = co.cbs;
     A.split = cross_split(lc, n_rows, n_tiles, co.may_split);
     A.n_rows_dev = co.n_rows_dev;
+    A.out_rows = n_rows;   // the host bound: room of `out` behind an asynchronous build
     A.stats = stats;
     A.work = work;
     cudaError_t e = cudaMemsetAsync(work, 0, sizeof(unsigned int), lc.stream);
