@@ -657,7 +657,7 @@ def run_b200(args):
            "note": "per rank; rank 0 also reads the gathered table" if world > 1 else None}
 
     # ---- explicit-list kernels (HBM side of the path), SSSP expansion, arm22: rank 0 only
-    lists = sssp_x = arm = None
+    lists = sssp_x = arm = sssp_solve = None
     if rank == 0 and not args.no_extras:
         build_full()
         n = 1 << 24
@@ -699,6 +699,7 @@ def run_b200(args):
         del con_d, cl_d, out, cand, outc
         sssp_x = extra_sssp_expansion(inst, nodes_h[:, :500] if nv >= 500 else nodes_h, local)
         arm = extra_arm22(local, dev, st, timed)
+        sssp_solve = extra_sssp_solve(local)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -742,7 +743,7 @@ def run_b200(args):
                 "check": strong_check, "ms_per_step_each": per_step[:8], "timeline": timeline},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "explicit_lists": lists, "sssp_expansion": sssp_x, "arm22": arm,
+            "explicit_lists": lists, "sssp_expansion": sssp_x, "sssp_solve": sssp_solve, "arm22": arm,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -813,6 +814,48 @@ def extra_sssp_expansion(inst, nodes_h, device):
             "gpu_ms_per_expansion": 1e3 * t_gpu / n, "cpu_c_1core_ms_per_expansion": 1e3 * t_cpu / n,
             "timed": "mrmp_sssp_expand through the C ABI (host buffers in, results out)",
             "accepted_vertices": n_new, "mismatching_calls": mism}
+
+
+def extra_sssp_solve(device):
+    """End-to-end SSSP (sssp.jl:49-232) on point2d_many instances with the solver parameters of
+    point2d_many.yaml:22-24: the GPU-backed host mirror (sssp_b200/solvers.py: one fused expansion
+    call per popped node) against the per-call restatement over the C oracle (oracle/sssp_ref.py).
+    Instances and the oracle's solutions are the committed golden fixtures; the solutions must be
+    identical.  The N=50 oracle run (34 s in the build container) is not repeated here."""
+    import sssp_b200 as S
+    from sssp_b200 import solvers
+    from oracle import oracle as O
+    from oracle import sssp_ref as R
+    out = {}
+    for name, live in (("sssp_point2d_many_n30_seed0", True), ("sssp_point2d_many_n50_seed0", False)):
+        path = os.path.join(ROOT, "tests", "golden", name + ".json")
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            fx = json.load(f)
+        inst = fx["instance"]
+        P = S.StatePoint2D
+        init, goal = [P(*q) for q in inst["config_init"]], [P(*q) for q in inst["config_goal"]]
+        obs = np.array(inst["obstacles"])
+        connect = S.gen_connect(init[0], obs, inst["rads"], device=device)
+        collide = S.gen_collide(init[0], inst["rads"], device=device)
+        st = {}
+        t0 = time.perf_counter()
+        sol, _ = solvers.SSSP(init, goal, connect, collide, S.gen_check_goal(goal), TIME_LIMIT=None,
+                              seed=fx["seed"], stats=st, **fx["params"])
+        t_gpu = time.perf_counter() - t0
+        row = {"n_agents": len(init), "expansions": st.get("expansions"),
+               "solution_steps": None if sol is None else len(sol),
+               "gpu_backed_s": t_gpu, "gpu_ms_per_expansion_incl_host_search": 1e3 * t_gpu / max(1, st.get("expansions", 1)),
+               "identical_to_oracle_solution": st.get("solution_ids") == fx["solution"]}
+        if live:
+            orc = O.Oracle(O.POINT2D, inst["rads"], obs)
+            t0 = time.perf_counter()
+            osol, _, ost = R.SSSP(orc, inst["config_init"], inst["config_goal"], seed=fx["seed"], **fx["params"])
+            row["oracle_per_call_s"] = time.perf_counter() - t0
+            row["identical_to_oracle_solution"] = row["identical_to_oracle_solution"] and osol == fx["solution"]
+        out[name] = row
+    return out
 
 
 def extra_arm22(device, dev, st, timed):

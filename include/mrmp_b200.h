@@ -254,7 +254,7 @@ int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, in
 int mrmp_roadmaps_adopt_csr_shards(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
                                    int cap_agents, int64_t cap_nnz, void *stream, int64_t *nnz_out);
 /* no wait: the stitched set stays pending (see mrmp_roadmaps_build_async) until
- * mrmp_roadmaps_finish; `stream` must be the ctx's stream */
+ * mrmp_roadmaps_finish (which waits on `stream` as well as on the ctx's stream) */
 int mrmp_roadmaps_adopt_csr_shards_async(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world,
                                          int cap_agents, int64_t cap_nnz, void *stream);
 /* conflict-table rows of this set (words_per_row words each, device memory of this rank) -> this

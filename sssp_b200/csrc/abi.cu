@@ -784,6 +784,7 @@ struct mrmp_roadmaps {
     bool pending = false;
     int64_t pend_slot_nnz = -1;  // cap_nnz of a shard pushed while pending (-1: none)
     int64_t pend_rows_cap = -1;  // row capacity of a table computed while pending (-1: none)
+    cudaStream_t pend_stream = nullptr;  // stream of an asynchronous adoption (finish waits on it)
     // CSR edges expanded to explicit (agent, from, to) rows for the cross kernels
     int32_t *e_agent = nullptr;
     double *e_from = nullptr, *e_to = nullptr;
@@ -1039,6 +1040,7 @@ static int roadmaps_build_impl(mrmp_roadmaps *rm, const double *rad, bool async)
     NEED(rm->nv >= 1, "no nodes set");
     rm->pending = false;
     rm->pend_slot_nnz = rm->pend_rows_cap = -1;
+    rm->pend_stream = nullptr;
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
     const int n = rm->n_agents, nv = rm->nv;
@@ -1151,6 +1153,8 @@ extern "C" int mrmp_roadmaps_finish(mrmp_roadmaps *rm, int64_t *nnz_out) {
     }
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->s_k));
+    if (rm->pend_stream && rm->pend_stream != c->s_k) CU(cudaStreamSynchronize(rm->pend_stream));
+    rm->pend_stream = nullptr;
     rm->pending = false;
     int rc = roadmaps_settle(rm, true);
     if (rc) {
@@ -1262,7 +1266,7 @@ static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int
     CU(launch_csr_stitch(lc, rows, rows_cap, stride, slots_dev, rm->row_ptr, rm->col_idx,
                          rm->col_cap));
     if (async) {  // nnz stays on the device (and in the mapped mirror) until mrmp_roadmaps_finish
-        NEED(s == c->s_k, "asynchronous adoption runs on the ctx's stream (mrmp_ctx_set_stream)");
+        rm->pend_stream = s;
         rm->pending = true;
         rm->built = true;
         rm->nnz = -1;

@@ -11,6 +11,7 @@ struct mrmp_sssp {
     std::vector<int32_t> nv_h;   // host mirror
     unsigned char *io_h = nullptr, *io_d = nullptr;  // pinned / device staging of one expansion
     size_t io_bytes = 0;
+    int seq = 0;                 // completion counter of the fused expansion (hdr[3])
 };
 
 static int sssp_io(mrmp_sssp *s, size_t bytes) {
@@ -224,9 +225,14 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
                        n_old_nbrs <= kFusedMaxOld &&
                        (int64_t)K * 2 * (nv0 + K) <= (1 << 16) &&
                        sssp_fused_smem(c->cv, a) <= 160 * 1024;
+    bool polled = false;
     if (fused) {
         unsigned char *hb = nullptr;
         CU(cudaHostGetDevicePointer((void **)&hb, s->io_h, 0));
+        a.seq = ++s->seq;
+        if (a.seq == 0) a.seq = s->seq = 1;
+        volatile int32_t *flag = (volatile int32_t *)(s->io_h + o_hdr) + 3;
+        *flag = 0;
         SsspFusedIn in;
         memcpy(in.q_ids, Q_ids, 4 * (size_t)N);
         if (n_old_nbrs) memcpy(in.old_nbrs, old_nbrs, 4 * (size_t)n_old_nbrs);
@@ -234,13 +240,25 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
         CU(launch_sssp_expand_fused(c->cv, lcfg(c, st), view, a, in, (int32_t *)(hb + o_hdr),
                                     (double *)(hb + o_qnew), (uint32_t *)(hb + o_bits),
                                     (int32_t *)(hb + o_succ), (uint8_t *)(hb + o_sout)));
+        // The kernel takes ~20 us and writes its results into this mapped block: poll its
+        // completion flag (a stream wait costs several microseconds of wake-up latency on top);
+        // after ~2 ms without it fall back to the stream wait, which also surfaces launch errors.
+        for (int spin = 0; spin < 400000; ++spin) {
+            if (*flag == a.seq) {
+                polled = true;
+                break;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
     } else {
         CU(cudaMemcpyAsync(s->io_d, s->io_h, in_end, cudaMemcpyHostToDevice, st));
         CU(launch_sssp_expand(c->cv, lcfg(c, st), view, a, ws, nv0));
         CU(cudaMemcpyAsync(s->io_h + in_end, s->io_d + in_end, out_end - in_end,
                            cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaStreamSynchronize(st));
+    if (!polled) CU(cudaStreamSynchronize(st));
 
     const int32_t *hdr = (const int32_t *)(s->io_h + o_hdr);
     const int n_new = hdr[0], n_succ = hdr[1];

@@ -1025,9 +1025,11 @@ static cudaError_t launch_cross_v(const CtxView &cv, const LaunchCfg &lc, const 
     return cudaGetLastError();
 }
 
-// Work items per warp tile.  With >= 3 warp tiles per resident warp the dynamic distribution
-// balances by itself (and one item per row keeps the OR mode's plain stores); below that the
-// column tiles of a warp tile are divided so that there are ~4 items per resident warp.
+// Work items per warp tile.  A warp tile (32 rows x all column tiles) is ~25 k dependent-latency
+// bound instructions, 60-140 us of one warp's time, and every finished item can drop the pairs
+// whose output bit it has already set -- so items are only cut finer (column tiles dealt round
+// robin) when there is less than one warp tile per resident warp, i.e. when SMs would idle
+// (measured on B200, profiles/r2_shard_split.md: a rank's 1/8 share gains 10 %, larger shares lose).
 int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split) {
     static int forced = -1;  // MRMP_CROSS_SPLIT=<n> pins the factor (experiments)
     if (forced < 0) {
@@ -1038,9 +1040,9 @@ int cross_split(const LaunchCfg &lc, int64_t n_rows, int n_tiles, int may_split)
     if (forced > 0) return forced < n_tiles ? forced : n_tiles;
     const int64_t n_wt = (n_rows + 31) / 32;
     const int64_t warps = (int64_t)lc.sm_count * MRMP_CROSS_MINB * kWarpsPerCta;
-    if (n_wt >= 3 * warps) return 1;
-    int64_t s = (4 * warps + n_wt - 1) / n_wt;
-    if (s > 16) s = 16;
+    if (n_wt >= warps) return 1;
+    int64_t s = (2 * warps + n_wt - 1) / n_wt;
+    if (s > 4) s = 4;
     if (s > n_tiles) s = n_tiles;
     return (int)(s < 1 ? 1 : s);
 }

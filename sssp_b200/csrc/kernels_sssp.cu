@@ -477,7 +477,13 @@ k_sssp_expand_fused(CtxView cv, SsspView view, SsspExpand a, const __grid_consta
         h_hdr[1] = n_succ;
         h_hdr[2] = nv0;
     }
+    // completion flag for the polling host: after every thread's results are visible system-wide
     __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        *reinterpret_cast<volatile int32_t *>(h_hdr + 3) = a.seq;
+        __threadfence_system();
+    }
 }
 
 // ---- small per-state helpers for the host search loops --------------------------------------

@@ -279,6 +279,8 @@ struct SsspExpand {             // scalar arguments of one expansion
     int words;                  // bitmap words per new vertex: ceil((nv_before + K) / 32)
     int n_old;                  // old neighbours of v_from
     int slow_collide;           // no_fast_collision_check: collide(S.Q, Q) instead of (S.Q, q, i)
+    int seq;                    // fused path: written to hdr[3] after every result has landed in
+                                // mapped host memory (the host polls it instead of a stream wait)
 };
 struct SsspWs {                 // device workspace of one expansion (laid out by abi_sssp.cu)
     const double *q_rand;       // [K][d]
