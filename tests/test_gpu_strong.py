@@ -152,6 +152,7 @@ def test_async_build_reports_capacity_overflow():
                             N, out.data_ptr(), nnz + 64, st)
     assert rm.finish() == nnz
     assert np.array_equal(out[:nnz].cpu().numpy().view(np.uint32), ref)
+    out.fill_(-1)
     rm.build_async(inst.rad)
     rm.edge_conflicts_async(ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(), cols_d[2].data_ptr(),
                             N, out.data_ptr(), nnz // 2, st)
