@@ -657,7 +657,7 @@ def run_b200(args):
            "note": "per rank; rank 0 also reads the gathered table" if world > 1 else None}
 
     # ---- explicit-list kernels (HBM side of the path), SSSP expansion, arm22: rank 0 only
-    lists = sssp_x = arm = sssp_solve = None
+    lists = sssp_x = arm = sssp_solve = p3d = None
     if rank == 0 and not args.no_extras:
         build_full()
         n = 1 << 24
@@ -700,6 +700,7 @@ def run_b200(args):
         sssp_x = extra_sssp_expansion(inst, nodes_h[:, :500] if nv >= 500 else nodes_h, local)
         arm = extra_arm22(local, dev, st, timed)
         sssp_solve = extra_sssp_solve(local)
+        p3d = extra_point3d(local, dev, st, timed)
 
     # ---- cpu_baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu = None
@@ -743,7 +744,7 @@ def run_b200(args):
                 "check": strong_check, "ms_per_step_each": per_step[:8], "timeline": timeline},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "explicit_lists": lists, "sssp_expansion": sssp_x, "sssp_solve": sssp_solve, "arm22": arm,
+            "explicit_lists": lists, "sssp_expansion": sssp_x, "sssp_solve": sssp_solve, "arm22": arm, "point3d": p3d,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -791,11 +792,16 @@ def extra_sssp_expansion(inst, nodes_h, device):
     call(*calls[0])
     tabs[calls[0][0]] = dev_rm.nodes(calls[0][0])
     t_gpu, t_cpu, mism, n_acc = 0.0, 0.0, 0, 0
+    t_lib = t_waitk = 0.0
+    tot_us, wait_us = C.c_double(0), C.c_double(0)
     for a, v, ids, old, qr in calls[1:]:
         Q = np.stack([tabs[j][ids[j]] for j in range(N)])
         t0 = time.perf_counter()
         call(a, v, ids, old, qr)
         t1 = time.perf_counter()
+        lib.mrmp_sssp_last_call_us(dev_rm._h, C.byref(tot_us), C.byref(wait_us))
+        t_lib += tot_us.value
+        t_waitk += wait_us.value
         after, ob, ib, osucc, ohit = orc.sssp_expand(a, tabs[a], v, qr, 2, 0.2, 0.02, Q, old)
         t2 = time.perf_counter()
         t_gpu += t1 - t0
@@ -812,6 +818,8 @@ def extra_sssp_expansion(inst, nodes_h, device):
     n = len(calls) - 1
     return {"calls": n, "K": K, "n_agents": int(N), "roadmap_vertices": nv0,
             "gpu_ms_per_expansion": 1e3 * t_gpu / n, "cpu_c_1core_ms_per_expansion": 1e3 * t_cpu / n,
+            "inside_library_ms_per_expansion": 1e-3 * t_lib / n,
+            "of_which_waiting_for_the_kernel_ms": 1e-3 * t_waitk / n,
             "timed": "mrmp_sssp_expand through the C ABI (host buffers in, results out)",
             "accepted_vertices": n_new, "mismatching_calls": mism}
 
@@ -858,6 +866,58 @@ def extra_sssp_solve(device):
     return out
 
 
+def extra_point3d(device, dev, st, timed):
+    """BASELINE configs[2]: StatePoint3D N=20 with sphere obstacles: PRMs(200, rad 0.3) + the
+    conflict table (all roadmap edges x the other agents' path edges, T=64) through the same
+    kernels (3-D instantiations), with the kernel counters and a sampled parity check."""
+    import torch
+    import sssp_b200 as S
+    from sssp_b200 import lib as L, workload as W
+    from oracle import oracle as O
+    lib = L.load()
+    inst = W.point3d_n20()
+    N, nv = inst.rads.size, inst.nv
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles, device=device)
+    ctx.set_stream(st)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+
+    def build():
+        rm.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        return rm.build(inst.rad)
+
+    nnz = build()
+    ms_build = timed(build, reps=5)
+    nodes = rm.nodes()
+    rp, col = rm.csr()
+    _, ca, vf, vt = W.random_walk_paths(inst, rp, col, T_STEPS, seed=77)
+    cols = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ca, vf, vt)]
+    wpr = (T_STEPS + 31) // 32
+    bits = torch.zeros((nnz, wpr), dtype=torch.int32, device=dev)
+    table = lambda: L.check(lib.mrmp_roadmaps_edge_conflicts_dev(
+        rm._h, None, ca.size, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(), N,
+        bits.data_ptr(), st))
+    ctx.stats(reset=True)
+    ms = timed(table, reps=10)
+    s4 = ctx.stats()
+    exact, tested, filt = int(s4[0]) / 11.0, int(s4[2]) / 11.0, int(s4[3]) / 11.0
+    flops = filt * 150 + exact * 243            # 3-D: verdict filter ~150 (FMA = 2), reference test 243
+    # parity on every 97th row against the oracle
+    rows = np.repeat(np.arange(N * nv), np.diff(rp))
+    sel = slice(0, None, 97)
+    ra = (rows // nv).astype(np.int32)
+    orc = O.Oracle(O.POINT3D, inst.rads, inst.obstacles)
+    obits = orc.collide_cross(ra[sel], nodes[ra, rows % nv][sel], nodes[ra, col][sel], ca,
+                              nodes[ca, vf], nodes[ca, vt], N, nthreads=O.host_cores())
+    g = bits.cpu().numpy().view(np.uint32)[sel]
+    return {"n_agents": int(N), "num_vertices": nv, "rad": inst.rad, "roadmap_nnz": int(nnz),
+            "roadmap_build_ms": ms_build, "table_ms": ms, "pair_checks_per_s": nnz * ca.size / ms * 1e3,
+            "pairs": int(nnz) * int(ca.size), "pairs_bound_tested_fp32": tested,
+            "pairs_filtered_fp64": filt, "pairs_reference_arithmetic": exact,
+            "roofline": {"bound": "fp64", "achieved": flops / ms / 1e9, "peak": FP64_UNFUSED_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": flops / ms / 1e9 / FP64_UNFUSED_PEAK_TFLOPS},
+            "mismatching_rows_on_sample": int((g != obits).any(axis=1).sum()), "sample_rows": int(g.shape[0])}
+
+
 def extra_arm22(device, dev, st, timed):
     """BASELINE configs[3]: StateArm22 N=10 (link 0.15-0.25, 3 obstacles): swept-link collide
     (6-arity, arm22.jl:100-146) and edge connect (arm22.jl:56-86) on uniformly random joint
@@ -883,8 +943,13 @@ def extra_arm22(device, dev, st, timed):
     d_ = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ai, aj, *q, ag, cf, ct)]
     out = torch.empty(max(n_col, n_con), dtype=torch.uint8, device=dev)
     ctx.set_stream(st)
-    ms_col = timed(lambda: L.check(lib.mrmp_collide_pairs_dev(
-        ctx._h, n_col, *[t.data_ptr() for t in d_[:6]], out.data_ptr(), st)), reps=3)
+    run_col = lambda: L.check(lib.mrmp_collide_pairs_dev(
+        ctx._h, n_col, *[t.data_ptr() for t in d_[:6]], out.data_ptr(), st))
+    ms_col = timed(run_col, reps=3)
+    ctx.stats8(reset=True)
+    run_col()
+    s8 = ctx.stats8()
+    bounds, exact_links = int(s8[4]), int(s8[1])
     g_col = out[:n_col].cpu().numpy().copy()
     ms_con = timed(lambda: L.check(lib.mrmp_connect_edges_dev(
         ctx._h, n_con, d_[6].data_ptr(), d_[7].data_ptr(), d_[8].data_ptr(), out.data_ptr(), st)), reps=3)
@@ -900,7 +965,16 @@ def extra_arm22(device, dev, st, timed):
             "collide_pairs": {"n": n_col, "gpu_ms": ms_col, "gpu_checks_per_s": n_col / ms_col * 1e3,
                               "cpu_checks_per_s": o_col.size / (t1 - t0), "cpu_threads": nt,
                               "mismatches_on_sample": int((g_col[sl] != o_col).sum()),
-                              "hit_rate": float(g_col.mean())},
+                              "hit_rate": float(g_col.mean()),
+                              # as-executed FP64 work of k_arm_collide<ListSrc> (kernel counters): 7 per
+                              # link-pair midpoint bound (2 sub, 2 mul, add, compare = 6, + 1 select),
+                              # 170 per link pair that ran the reference segment-segment test, against the
+                              # un-fused DADD/DMUL peak; trig of the posture tables not counted
+                              "roofline": {"bound": "fp64", "link_pair_bounds": bounds, "exact_link_pairs": exact_links,
+                                           "achieved": (bounds * 7 + exact_links * FLOPS_EXACT) / ms_col / 1e9,
+                                           "peak": FP64_UNFUSED_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                           "frac": (bounds * 7 + exact_links * FLOPS_EXACT) / ms_col / 1e9 / FP64_UNFUSED_PEAK_TFLOPS,
+                                           "reference_equivalent_link_pair_tests": None}},
             "connect_edges": {"n": n_con, "gpu_ms": ms_con, "gpu_checks_per_s": n_con / ms_con * 1e3,
                               "cpu_checks_per_s": o_con.size / (t2 - t1),
                               "mismatches_on_sample": int((g_con[sl] != o_con).sum()),

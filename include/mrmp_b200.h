@@ -91,6 +91,9 @@ int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
  * broad-phase bound); out4[3] = point-model pairs evaluated by the verdict filter (out4[0] of them
  * undecided -> reference arithmetic) */
 int mrmp_ctx_stats(mrmp_ctx *ctx, int64_t *out4, int reset);
+/* the same four, then out8[4] = arm22 link-pair midpoint bounds evaluated (4 per posture pair),
+ * out8[5..7] reserved */
+int mrmp_ctx_stats8(mrmp_ctx *ctx, int64_t *out8, int reset);
 
 /* ---- connect -------------------------------------------------------------------- */
 /* connect(q, i): point2d.jl:49-57, point3d.jl:54-64, arm22.jl:40-54 */
@@ -426,6 +429,10 @@ int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_samples, const d
                      double *q_new_out, int32_t *words_out, uint32_t *out_bits, uint32_t *in_bits,
                      int64_t bits_cap_words, int32_t *n_succ_out, int32_t *succ_ids,
                      uint8_t *succ_collide);
+
+/* diagnostics: host time of the last mrmp_sssp_expand spent inside the library (total / waiting
+ * for the kernel after the launch call returned), microseconds */
+int mrmp_sssp_last_call_us(mrmp_sssp *s, double *total_us, double *wait_us);
 
 /* ---- distance tables: get_distance_table(s) (src/solvers/utils.jl:146-236) ------------------ */
 /* n_graphs roadmaps at once (SSSP after every expansion that added a vertex, sssp.jl:193;

@@ -285,6 +285,57 @@ function pp_conflict_tables(ctx::Ctx, roadmaps::Vector{Vector{Node{State}}}, i::
     return blocked, stay_hits, planned
 end
 
+# ---- CBS (cbs.jl:336-347) and the smoother's TPG scan (smoother.jl:78-106) ---------------------
+const CROSS_COUNT, CROSS_FIRST, CROSS_FLAG_CBS = Cint(2), Cint(3), Cint(1)
+
+"""
+    cbs_collision_counts(ctx, roadmap_i, i, paths, T) -> counts[move, t-1]
+
+The soft conflict count of `g_func_i` (cbs.jl:336-347) for every candidate move of agent `i`
+(rows, `vcat(v.neighbors, v.id)` per vertex) and every time step `t = 2:T` in one launch:
+`count(j -> collide(q_j_to, q_i_to, j, i) || collide(q_j_from, q_j_to, q_i_from, q_i_to, j, i))`
+over the other agents' path edges.  The low-level search adds `counts[move, t-1] * collision_weight`.
+"""
+function cbs_collision_counts(ctx::Ctx, rm::Vector{Node{State}}, i::Int64,
+                              paths::Vector{Vector{Node{State}}}, T::Int64) where {State<:AbsState}
+    others = [j for j = 1:length(paths) if j != i]
+    rf = State[v.q for v in rm for _ in 1:(length(v.neighbors) + 1)]
+    rt = State[rm[k].q for v in rm for k in vcat(v.neighbors, v.id)]
+    ca = Int32[j - 1 for _ = 2:T for j in others]
+    cf = State[paths[j][min(t - 1, length(paths[j]))].q for t = 2:T for j in others]
+    ct = State[paths[j][min(t, length(paths[j]))].q for t = 2:T for j in others]
+    counts = zeros(Int32, T - 1, length(rf))                # column r = row r in C
+    check(ccall((:mrmp_collide_cross_reduce, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{State}, Ptr{State}, Ptr{Int32}, Int64,
+                 Ptr{Int32}, Ptr{State}, Ptr{State}, Ptr{Int32}, Ptr{Int32}, Cint, Cint, Cint, Cint,
+                 Ptr{Int32}),
+                ctx.h, length(rf), fill(Int32(i - 1), length(rf)), rf, rt, C_NULL, length(ca), ca,
+                cf, ct, C_NULL, C_NULL, length(others), T - 1, CROSS_COUNT, CROSS_FLAG_CBS, counts))
+    return permutedims(counts)
+end
+
+"""
+    tpg_first_hits(ctx, actions) -> first[action, agent]  (1-based index into `actions`, 0 = none)
+
+Type-2 dependencies of `get_temporal_plan_graph` (smoother.jl:78-106): for every action and every
+other agent the first LATER action of that agent that collides with it -- one launch instead of
+the triple loop of `collide` calls.  `actions` = all actions ordered by agent, then by time.
+"""
+function tpg_first_hits(ctx::Ctx, actions::Vector{Action{State}}, N::Int64) where {State<:AbsState}
+    ag = Int32[a.agent - 1 for a in actions]
+    key = Int32[a.t for a in actions]
+    qf = State[a.from.q for a in actions]
+    qt = State[a.to.q for a in actions]
+    first = fill(Int32(-1), N, length(actions))
+    check(ccall((:mrmp_collide_cross_reduce, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{State}, Ptr{State}, Ptr{Int32}, Int64,
+                 Ptr{Int32}, Ptr{State}, Ptr{State}, Ptr{Int32}, Ptr{Int32}, Cint, Cint, Cint, Cint,
+                 Ptr{Int32}),
+                ctx.h, length(actions), ag, qf, qt, key, length(actions), ag, qf, qt, ag, key, 0, N,
+                CROSS_FIRST, 0, first))
+    return permutedims(first) .+ Int32(1)
+end
+
 # ---- pinned host arrays: async read-back / in-place conflict tables ---------------------------
 """
     with_pinned(f, arrays...)

@@ -178,6 +178,12 @@ class Context:
         L.check(self._lib.mrmp_ctx_stats(self._h, L.ptr(out, L._vp), int(reset)))
         return out
 
+    def stats8(self, reset: bool = False) -> np.ndarray:
+        """the four counters of stats(), then [4] arm22 link-pair midpoint bounds evaluated"""
+        out = np.zeros(8, np.int64)
+        L.check(self._lib.mrmp_ctx_stats8(self._h, L.ptr(out, L._vp), int(reset)))
+        return out
+
     def set_stream(self, cuda_stream: int | None) -> None:
         """Run this ctx's kernels on a caller-owned CUDA stream (e.g. torch's current)."""
         L.check(self._lib.mrmp_ctx_set_stream(self._h, cuda_stream))

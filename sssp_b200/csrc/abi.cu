@@ -193,8 +193,8 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     cudaError_t e = cudaMalloc((void **)&c->blob, h.size() * sizeof(double));
     if (e == cudaSuccess)
         e = cudaMemcpy(c->blob, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->stats_d, 4 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(c->stats_d, 0, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->stats_d, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->stats_d, 0, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking);
     c->s_k_owned = c->s_k;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
@@ -244,6 +244,18 @@ extern "C" int mrmp_ctx_stats(mrmp_ctx *c, int64_t *out4, int reset) {
     unsigned long long h[4];
     CU(cudaMemcpy(h, c->stats_d, sizeof(h), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 4; ++k) out4[k] = (int64_t)h[k];
+    if (reset) CU(cudaMemset(c->stats_d, 0, sizeof(h)));
+    return MRMP_OK;
+}
+
+/* 8 counters: the four of mrmp_ctx_stats, then [4] arm22 link-pair midpoint bounds evaluated */
+extern "C" int mrmp_ctx_stats8(mrmp_ctx *c, int64_t *out8, int reset) {
+    if (!c || !out8) return fail(MRMP_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->s_k));
+    unsigned long long h[8];
+    CU(cudaMemcpy(h, c->stats_d, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out8[k] = (int64_t)h[k];
     if (reset) CU(cudaMemset(c->stats_d, 0, sizeof(h)));
     return MRMP_OK;
 }

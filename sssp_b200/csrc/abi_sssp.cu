@@ -3,6 +3,8 @@
 // (dist, get_mid_status, nearest vertex) the host-side search loops call.
 #include "abi_internal.cuh"
 
+#include <chrono>
+
 struct mrmp_sssp {
     mrmp_ctx *ctx = nullptr;
     int cap = 0;                 // vertices per agent the node table can hold
@@ -12,6 +14,7 @@ struct mrmp_sssp {
     unsigned char *io_h = nullptr, *io_d = nullptr;  // pinned / device staging of one expansion
     size_t io_bytes = 0;
     int seq = 0;                 // completion counter of the fused expansion (hdr[3])
+    double last_total_us = 0.0, last_wait_us = 0.0;  // host time of the last mrmp_sssp_expand
 };
 
 static int sssp_io(mrmp_sssp *s, size_t bytes) {
@@ -157,6 +160,7 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     *words_out = words;
     if (bits_cap_words < (int64_t)K * words || !out_bits || !in_bits)
         return fail(MRMP_ERR_CAPACITY, "out_bits / in_bits need %d x %d words each", K, words);
+    const auto t_call = std::chrono::steady_clock::now();
     CU(cudaSetDevice(c->device));
     int rc = sssp_reserve(s, nv0 + K);
     if (rc) return rc;
@@ -226,6 +230,7 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
                        (int64_t)K * 2 * (nv0 + K) <= (1 << 16) &&
                        sssp_fused_smem(c->cv, a) <= 160 * 1024;
     bool polled = false;
+    auto t_wait = std::chrono::steady_clock::now();
     if (fused) {
         unsigned char *hb = nullptr;
         CU(cudaHostGetDevicePointer((void **)&hb, s->io_h, 0));
@@ -240,6 +245,7 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
         CU(launch_sssp_expand_fused(c->cv, lcfg(c, st), view, a, in, (int32_t *)(hb + o_hdr),
                                     (double *)(hb + o_qnew), (uint32_t *)(hb + o_bits),
                                     (int32_t *)(hb + o_succ), (uint8_t *)(hb + o_sout)));
+        t_wait = std::chrono::steady_clock::now();
         // The kernel takes ~20 us and writes its results into this mapped block: poll its
         // completion flag (a stream wait costs several microseconds of wake-up latency on top);
         // after ~2 ms without it fall back to the stream wait, which also surfaces launch errors.
@@ -258,7 +264,10 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
         CU(cudaMemcpyAsync(s->io_h + in_end, s->io_d + in_end, out_end - in_end,
                            cudaMemcpyDeviceToHost, st));
     }
-    if (!polled) CU(cudaStreamSynchronize(st));
+    if (!polled) {
+        if (!fused) t_wait = std::chrono::steady_clock::now();
+        CU(cudaStreamSynchronize(st));
+    }
 
     const int32_t *hdr = (const int32_t *)(s->io_h + o_hdr);
     const int n_new = hdr[0], n_succ = hdr[1];
@@ -270,6 +279,18 @@ extern "C" int mrmp_sssp_expand(mrmp_sssp *s, int agent, int v_from, int n_sampl
     memcpy(in_bits, s->io_h + o_bits + 4 * (size_t)K * words, 4 * (size_t)K * words);
     memcpy(succ_ids, s->io_h + o_succ, 4 * (size_t)n_succ);
     memcpy(succ_collide, s->io_h + o_sout, (size_t)n_succ);
+    const auto t_end = std::chrono::steady_clock::now();
+    s->last_total_us = std::chrono::duration<double, std::micro>(t_end - t_call).count();
+    s->last_wait_us = std::chrono::duration<double, std::micro>(t_end - t_wait).count();
+    return MRMP_OK;
+}
+
+/* diagnostics: host time of the last mrmp_sssp_expand inside the library (total, and the part
+ * spent waiting for the kernel after the launch call returned), in microseconds */
+extern "C" int mrmp_sssp_last_call_us(mrmp_sssp *s, double *total_us, double *wait_us) {
+    NEED(s, "bad sssp");
+    if (total_us) *total_us = s->last_total_us;
+    if (wait_us) *wait_us = s->last_wait_us;
     return MRMP_OK;
 }
 

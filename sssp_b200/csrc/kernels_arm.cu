@@ -220,12 +220,14 @@ __device__ __forceinline__ bool queue_entry_hit(unsigned ent, const IEntry *I, d
 // Warp-synchronous; the tables must be visible to the warp (__syncwarp before the call).
 __device__ __forceinline__ bool warp_sweep(const IEntry *I, int nI, double aix, double aiy,
                                            const JEntry *J, int nJ, unsigned *queue,
-                                           const ArmCtx &ac, int lane, unsigned &n_exact) {
+                                           const ArmCtx &ac, int lane, unsigned &n_exact,
+                                           unsigned long long &n_bound) {
     int qlen = 0;
     const unsigned lt = (1u << lane) - 1u;
     for (int j0 = 0; j0 < nJ; j0 += 32) {
         const int jj = j0 + lane;
         const bool jv = jj < nJ;
+        const int live_j = nJ - j0 < 32 ? nJ - j0 : 32;
         const JEntry ej = J[jv ? jj : 0];
         const double n1x = dmul(dadd(ej.ax, ej.bx), 0.5), n1y = dmul(dadd(ej.ay, ej.by), 0.5);
         const double n2x = dmul(dadd(ej.bx, ej.cx), 0.5), n2y = dmul(dadd(ej.by, ej.cy), 0.5);
@@ -233,6 +235,7 @@ __device__ __forceinline__ bool warp_sweep(const IEntry *I, int nI, double aix, 
             const IEntry ei = I[ii];  // broadcast read
             double dx, dy;
             unsigned mask = 0;
+            n_bound += 4u * (unsigned)live_j;  // link-pair midpoint bounds of this round (diagnostics)
             dx = dsub(ei.m1x, n1x), dy = dsub(ei.m1y, n1y);
             mask |= !(dadd(dmul(dx, dx), dmul(dy, dy)) > ej.G) ? 1u : 0u;
             dx = dsub(ei.m1x, n2x), dy = dsub(ei.m1y, n2y);
@@ -296,7 +299,8 @@ __device__ __forceinline__ bool warp_arm_collide_pair(const ArmCtx &ac, const Ar
                                                       const double *qif, const double *qit,
                                                       const double *qjf, const double *qjt, int i,
                                                       int j, IEntry *I, JEntry *J, unsigned *queue,
-                                                      int cap, int lane, unsigned &n_exact) {
+                                                      int cap, int lane, unsigned &n_exact,
+                                                      unsigned long long &n_bound) {
     ArmMove mi, mj;
     warp_arm_moves(ac, lane, qif, qit, qjf, qjt, mi, mj, true);
     mi.ax = sg.bx(i), mi.ay = sg.by(i), mi.rad = sg.rad(i);
@@ -317,7 +321,7 @@ __device__ __forceinline__ bool warp_arm_collide_pair(const ArmCtx &ac, const Ar
             const int cj = (int)(nj - j0 < cap ? nj - j0 : cap);
             if (i0 == 0 || nj > cap) fill_J(J, mj, j0, cj, G, lane);
             __syncwarp();
-            if (warp_sweep(I, ci, mi.ax, mi.ay, J, cj, queue, ac, lane, n_exact)) return true;
+            if (warp_sweep(I, ci, mi.ax, mi.ay, J, cj, queue, ac, lane, n_exact, n_bound)) return true;
             __syncwarp();
         }
     }
@@ -472,6 +476,7 @@ k_arm_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
     JEntry *J = reinterpret_cast<JEntry *>(wb + cap * sizeof(IEntry));
     unsigned *queue = reinterpret_cast<unsigned *>(wb + cap * (sizeof(IEntry) + sizeof(JEntry)));
     unsigned n_exact = 0;
+    unsigned long long n_bound = 0;
     // checks differ in cost by orders of magnitude (S_i x S_j posture pairs, early exits):
     // warps pull the next check from a counter instead of striding
     for (;;) {
@@ -487,11 +492,12 @@ k_arm_collide(CtxView cv, int64_t n, Src src, unsigned long long *stats,
                                      sg.bx(p.j), sg.by(p.j), sg.rad(p.j));
         if (run && !hit)
             hit = warp_arm_collide_pair(ac, sg, p.qif, p.qit, p.qjf, p.qjt, p.i, p.j, I, J, queue,
-                                        cap, lane, n_exact);
+                                        cap, lane, n_exact, n_bound);
         if (lane == 0) src.emit(k, run, hit);
         __syncwarp();
     }
     if (lane == 0 && stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
+    if (lane == 0 && stats && n_bound) atomicAdd(stats + 3, n_bound);  // ctx stats slot 4
 }
 
 // ---- collide(C, q_to, i): arm22.jl:173-205, warp per candidate --------------------------------
@@ -525,6 +531,7 @@ k_arm_config_moves(CtxView cv, int agent_i, const double *__restrict__ Q, int64_
     double from[2];
     load_state<2>(Q, agent_i, from);
     unsigned n_exact = 0;
+    unsigned long long n_bound = 0;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_cand;
          k += n_warps) {
@@ -539,7 +546,7 @@ k_arm_config_moves(CtxView cv, int agent_i, const double *__restrict__ Q, int64_
             const int cnt = (int)(ns - s0 < kArmCap ? ns - s0 : kArmCap);
             fill_I(I, mv, s0, cnt, lane);
             __syncwarp();
-            hit = warp_sweep(I, cnt, aix, aiy, J, N - 1, queue, ac, lane, n_exact);
+            hit = warp_sweep(I, cnt, aix, aiy, J, N - 1, queue, ac, lane, n_exact, n_bound);
             __syncwarp();
         }
         if (lane == 0) out[k] = hit ? 1 : 0;

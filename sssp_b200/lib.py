@@ -126,6 +126,7 @@ _SIGS = {
     "mrmp_roadmaps_adopt_csr_shards": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64, _vp,
                                                  _lp]),
     "mrmp_ctx_stats": (C.c_int, [_vp, _vp, C.c_int]),
+    "mrmp_ctx_stats8": (C.c_int, [_vp, _vp, C.c_int]),
     "mrmp_sample_states": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _dp]),
     "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),
     "mrmp_state_dist": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
@@ -143,6 +144,7 @@ _SIGS = {
     "mrmp_sssp_set_roadmap": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
     "mrmp_sssp_nv": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "mrmp_sssp_get_nodes": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
+    "mrmp_sssp_last_call_us": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mrmp_sssp_expand": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_uint64, C.c_uint64,
                                    C.c_int, C.c_double, C.c_double, _ip, C.c_int, _ip, C.c_int,
                                    C.POINTER(C.c_int32), _dp, C.POINTER(C.c_int32), _vp, _vp,

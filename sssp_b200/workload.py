@@ -40,6 +40,20 @@ def point2d_many(N: int = 50, seed: int = 0, nv: int = 500, rad: float = 0.1) ->
     return Instance(POINT2D, rads, obstacles, q_init, q_goal, nv, rad, seed)
 
 
+def point3d_n20(N: int = 20, seed: int = 0, nv: int = 200, rad: float = 0.3) -> Instance:
+    """BASELINE configs[2]: StatePoint3D, N = 20, sphere obstacles.  point3d.yaml:11-20 draws radii
+    0.1-0.15 for at most 6 agents; 20 such spheres do not fit the unit cube, so the
+    agents get rad 0.05 and the 10 obstacles radii U[0.05, 0.1].  PRM: num_vertices 200, rad 0.3
+    (point3d.yaml:26-30)."""
+    rng = np.random.default_rng(seed)
+    M = 10
+    obstacles = np.concatenate([rng.random((M, 3)), rng.uniform(0.05, 0.1, (M, 1))], axis=1)
+    rads = np.full(N, 0.05)
+    q_init = rng.uniform(0.1, 0.9, (N, 3))
+    q_goal = rng.uniform(0.1, 0.9, (N, 3))
+    return Instance(1, rads, obstacles, q_init, q_goal, nv, rad, seed)
+
+
 def connect_list(inst: Instance, n: int, seed: int = 1234, max_len: float = 0.1):
     """n explicit connect(q_from, q_to, i) checks: endpoints U[0,1]^2, edge length <= max_len
     (PRM-like), agent ids U{0..N-1}  (SURVEY 8d, config 5)."""
