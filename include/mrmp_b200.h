@@ -79,6 +79,10 @@ int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const double *rads,
                     const double *base_pos, const double *aux, int n_obs,
                     const double *obstacles_aos, double step_dist, double safety_dist,
                     double max_dist, int device);
+/* Objects created on a ctx (mrmp_roadmaps, mrmp_sssp, mrmp_exchange) use it in their own destroy
+ * call: destroy them first.  (A binding whose finalisers run in no particular order -- Python's
+ * cyclic GC, Julia's finalizers -- must defer this call until its dependents are gone, as
+ * sssp_b200/closures.py: Context.close does.) */
 void mrmp_ctx_destroy(mrmp_ctx *ctx);
 int mrmp_ctx_state_dim(const mrmp_ctx *ctx);
 int mrmp_ctx_sync(mrmp_ctx *ctx);

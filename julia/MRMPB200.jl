@@ -25,13 +25,31 @@ default_step(::Type{StateSnake2D}) = STEP_DIST_SNAKE2D
 default_step(::Type{StateCapsule3D}) = STEP_DIST_CAPSULE3D
 default_step(::Type) = STEP_DIST
 
+# Objects created on a ctx use it in their own destroy call and Julia runs finalizers in no
+# particular order: the ctx is destroyed when its own finalizer has run AND its last dependent
+# (SsspRoadmaps, ...) is gone.
 mutable struct Ctx
     h::Ptr{Cvoid}
+    deps::Int
+    dead::Bool
     function Ctx(h)
-        c = new(h)
-        finalizer(x -> ccall((:mrmp_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), c)
+        c = new(h, 0, false)
+        finalizer(c) do x
+            x.dead = true
+            x.deps == 0 && destroy_ctx!(x)
+        end
         return c
     end
+end
+function destroy_ctx!(c::Ctx)
+    c.h == C_NULL && return
+    ccall((:mrmp_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.h)
+    c.h = C_NULL
+end
+adopt!(c::Ctx) = (c.deps += 1; c)
+function release!(c::Ctx)
+    c.deps -= 1
+    c.dead && c.deps == 0 && destroy_ctx!(c)
 end
 
 function check(rc::Cint)
@@ -187,12 +205,16 @@ end
 # itself (OPEN, VISITED, h_func, backtrack) is unchanged Julia.
 mutable struct SsspRoadmaps
     h::Ptr{Cvoid}
+    ctx::Ctx
     function SsspRoadmaps(ctx::Ctx, nv_cap::Int = 256)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:mrmp_sssp_create, LIB), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}),
                     ctx.h, nv_cap, h))
-        s = new(h[])
-        finalizer(x -> ccall((:mrmp_sssp_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), s)
+        s = new(h[], adopt!(ctx))
+        finalizer(s) do x
+            ccall((:mrmp_sssp_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h)
+            release!(x.ctx)
+        end
         return s
     end
 end

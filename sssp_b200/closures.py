@@ -157,8 +157,24 @@ class Context:
             L.ptr(obs, L._dp) if obs.size else None, float(step_dist), float(safety_dist),
             math.nan if max_dist is None else float(max_dist), self.device))
         self._h = h
+        # Objects created on this context (Roadmaps, SsspRoadmaps, peer.Exchange) use it in their
+        # own destroy call, and the cyclic garbage collector finalises in no particular order:
+        # the context is only destroyed once the last of them is gone.
+        self._dependents = 0
+        self._close_wanted = False
+
+    def _adopt(self) -> None:
+        self._dependents += 1
+
+    def _release(self) -> None:
+        self._dependents -= 1
+        if self._dependents <= 0 and self._close_wanted:
+            self.close()
 
     def close(self):
+        if getattr(self, "_dependents", 0) > 0:
+            self._close_wanted = True      # deferred until the dependents are destroyed
+            return
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.mrmp_ctx_destroy(h)
@@ -397,11 +413,13 @@ class Roadmaps:
                                                C.byref(h)))
         self._h = h
         self.nv = 0
+        ctx._adopt()
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.mrmp_roadmaps_destroy(h)
+            self.ctx._release()
 
     def __del__(self):
         # at interpreter shutdown the CUDA runtime may already be gone: leave the handle to the
@@ -552,11 +570,13 @@ class SsspRoadmaps:
         h = C.c_void_p()
         L.check(self._lib.mrmp_sssp_create(ctx._h, int(nv_cap), C.byref(h)))
         self._h = h
+        ctx._adopt()
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.mrmp_sssp_destroy(h)
+            self.ctx._release()
 
     def __del__(self):
         # at interpreter shutdown the CUDA runtime may already be gone: leave the handle to the

@@ -12,6 +12,7 @@ sssp_b200.sharding / mrmp_roadmaps_pack_csr_shard_dev.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -32,6 +33,7 @@ class Exchange:
         L.check(self._lib.mrmp_exchange_create(ctx._h, self.world, self.rank, self.n_chan, sb,
                                                C.byref(h), self.handle.ctypes.data_as(L._vp)))
         self._h = h
+        ctx._adopt()      # the context outlives this object (see Context.close)
         self.all_mask = (1 << self.world) - 1
         self.connected = self.world == 1
         if self.world == 1:   # a single rank is its own peer
@@ -39,11 +41,14 @@ class Exchange:
             L.check(self._lib.mrmp_exchange_connect_ptrs(self._h, bufs))
 
     def close(self):
-        if getattr(self, "_h", None):
-            self._lib.mrmp_exchange_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.mrmp_exchange_destroy(h)
+            self.ctx._release()
 
     def __del__(self):
+        if sys.is_finalizing():   # the CUDA runtime may already be gone at interpreter shutdown
+            return
         try:
             self.close()
         except Exception:
