@@ -1110,7 +1110,7 @@ static int roadmaps_build_impl(mrmp_roadmaps *rm, const double *rad, bool async)
     }
     // rad / r2 are read from, and nnz is written to, the mapped staging block
     CU(launch_prm_adjacency(c->cv, lcfg(c, c->s_k), rm->agent0, n, nv, rm->dev(hr) + n,
-                            rm->dev(hr), rm->nodes, rm->bitmap, rm->words, rm->row_cnt));
+                            rm->dev(hr), rm->nodes, rm->bitmap, rm->words, rm->row_cnt, hr, hr + n));
     CU(launch_row_scan(lcfg(c, c->s_k), rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
                        rm->chunk_ws, rm->chunk_ws_len, rm->dev(h_nnz)));
     rc = roadmaps_emit(rm, c->s_k);

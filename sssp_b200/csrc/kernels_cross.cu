@@ -322,16 +322,38 @@ __global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
 // The whole column side in ONE launch for the usual case of a few thousand columns (a conflict
 // table has N x T of them): one CTA, every thread keeps its (up to 4) columns in registers,
 // counts the Morton cells in shared memory, scans, and writes the finished records straight to
-// their sorted position; the headers are reduced from the records afterwards -- instead of
-// histogram / scan / scatter / tile kernels whose launch latencies exceed their work.
+// their sorted position.  The tile headers (box of the midpoints, largest reach) are reduced with
+// shared-memory integer atomics on order-preserving float keys, rounded outward -- a box that is
+// 1e-7 too large only culls that much less.
 constexpr int kPrepSmallCpt = 4;
 constexpr int kPrepSmallMax = 1024 * kPrepSmallCpt;
+constexpr int kPrepSmallTiles = kPrepSmallMax / kCols;
+
+__device__ __forceinline__ int fkey(float f) {  // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float fkey_inv(int k) {
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
 template <int D>
 __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
     __shared__ int h[kSortCells];
     __shared__ int part[1024];
+    __shared__ int t_lo[kPrepSmallTiles][D], t_hi[kPrepSmallTiles][D], t_h[kPrepSmallTiles];
+    __shared__ int t_poison[kPrepSmallTiles];
     const int tid = threadIdx.x;
     for (int c = tid; c < kSortCells; c += 1024) h[c] = 0;
+    for (int t = tid; t < kPrepSmallTiles; t += 1024) {
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            t_lo[t][x] = fkey(INFINITY);
+            t_hi[t][x] = fkey(-INFINITY);
+        }
+        t_h[t] = fkey(0.0f);
+        t_poison[t] = 0;
+    }
     __syncthreads();
     double a[kPrepSmallCpt][D], b[kPrepSmallCpt][D];
     int ag[kPrepSmallCpt], cell[kPrepSmallCpt];
@@ -377,6 +399,16 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
         make_col<D>(P, tid + 1024 * i, ag[i], a[i], b[i], B, X, m, hh);
         P.cb[pos] = B;
         P.cx[pos] = X;
+        const int t = pos / kCols;
+        bool bad = !(hh == hh);
+#pragma unroll
+        for (int x = 0; x < D; ++x) {
+            bad |= !(m[x] == m[x]);
+            atomicMin(&t_lo[t][x], fkey(__double2float_rd(m[x])));
+            atomicMax(&t_hi[t][x], fkey(__double2float_ru(m[x])));
+        }
+        atomicMax(&t_h[t], fkey(__double2float_ru(hh)));
+        if (bad) t_poison[t] = 1;  // a NaN midpoint / reach must never be culled by the box test
     }
     for (int64_t p = P.n_cols + tid; p < P.n_tiles * kCols; p += 1024) {
         ColB B;
@@ -385,26 +417,19 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
         P.cb[p] = B;
         P.cx[p] = X;
     }
-    __syncthreads();  // the records (global) are complete and visible to the whole CTA
-    for (int64_t t = tid >> 5; t < P.n_tiles; t += 32) {
-        const int lane = tid & 31;
-        const int64_t c = t * kCols + lane;
-        const bool real = c < P.n_cols;
-        double m[D], hh = 0.0;
+    __syncthreads();
+    for (int t = tid; t < P.n_tiles; t += 1024) {
+        TileHdr<D> H;
+        const bool poison = t_poison[t] != 0;
 #pragma unroll
-        for (int x = 0; x < D; ++x) m[x] = 0.0;
-        if (real) {
-            const ColX<D> &X = P.cx[c];
-            double xa[D], xb[D];
-#pragma unroll
-            for (int x = 0; x < D; ++x) {
-                xa[x] = X.a[x];
-                xb[x] = X.b[x];
-                m[x] = dmul(dadd(xa[x], xb[x]), 0.5);
-            }
-            hh = half_len_up<D>(xa, xb) + (X.agent >= 0 ? X.rad : 1e300);
+        for (int x = 0; x < D; ++x) {
+            H.lo[x] = poison ? -1e300 : (double)fkey_inv(t_lo[t][x]);
+            H.hi[x] = poison ? 1e300 : (double)fkey_inv(t_hi[t][x]);
         }
-        tile_header<D>(P, t, lane, real, m, hh);
+        const float hm = fkey_inv(t_h[t]);
+        H.hmax = (poison || !(hm < INFINITY)) ? 1e300 : (double)hm;
+        H.pad = 0.0;
+        P.hdrs[t] = H;
     }
 }
 

@@ -140,17 +140,25 @@ __device__ __forceinline__ int warp_offsets(int c, int lane, int &total) {
 
 // SMEM: the connect segment and the agent's vertex table (padded to 32 * words entries) are
 // staged in shared memory -- the normal case; the other instantiation reads both from global.
+// The per-agent radii of a build travel in the kernel parameters when there are at most 64 agents:
+// read from the mapped staging block (a PCIe round trip per CTA) they were 18 % of the kernel's
+// stall samples (profiles/r2_i_adj_ncu_summary.md).
+struct RadTab {
+    int n;  // 0: read rad / rad_r2 through the pointers
+    double rad[64], r2[64];
+};
+
 template <class M, bool SMEM, bool OPAD>
 __global__ void __launch_bounds__(kThreads, 3)
 k_prm_adjacency(CtxView cv, int agent0, int n_agents, int nv, int chunks,
                 const double *__restrict__ rad, const double *__restrict__ rad_r2,
                 const double *__restrict__ nodes, uint32_t *__restrict__ bitmap, int words,
-                int32_t *__restrict__ row_cnt, int seg_bytes, int obs_pad) {
+                int32_t *__restrict__ row_cnt, int seg_bytes, int obs_pad,
+                const __grid_constant__ RadTab rt) {
     constexpr int SD = M::SD;
     constexpr bool kCull = AdjTraits<M>::kCull;
     const int a = blockIdx.x / chunks, chunk = blockIdx.x - a * chunks;
-    // rad / r2 may live in mapped host memory: issue the reads before the staging waits
-    const double r = rad[a], r2 = rad_r2[a];
+    const double r = rt.n ? rt.rad[a] : rad[a], r2 = rt.n ? rt.r2[a] : rad_r2[a];
     const ConSeg cs(cv, stage_segment(cv, cv.con_off, cv.con_len, smem_raw, SMEM));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int agent = agent0 + a;
@@ -763,8 +771,18 @@ template <class M, bool SMEM, bool OPAD>
 static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                 int nv, const double *rad_r2, const double *rad,
                                 const double *nodes, uint32_t *bitmap, int words,
-                                int32_t *row_cnt, int seg, int sm, int obs_pad) {
+                                int32_t *row_cnt, int seg, int sm, int obs_pad,
+                                const double *rad_host, const double *r2_host) {
     auto kern = k_prm_adjacency<M, SMEM, OPAD>;
+    RadTab rt;
+    rt.n = 0;
+    if (rad_host && r2_host && n_agents <= 64) {
+        rt.n = n_agents;
+        for (int a = 0; a < n_agents; ++a) {
+            rt.rad[a] = rad_host[a];
+            rt.r2[a] = r2_host[a];
+        }
+    }
     cudaError_t e = set_smem(kern, sm);
     if (e != cudaSuccess) return e;
     const int slots = lc.sm_count * adj_occupancy(kern, 4 * cv.model + (SMEM ? 1 : 0) + (OPAD ? 2 : 0), sm);
@@ -774,14 +792,14 @@ static cudaError_t launch_adj_t(const CtxView &cv, const LaunchCfg &lc, int agen
     if (chunks < 1) chunks = 1;
     kern<<<n_agents * chunks, kThreads, sm, lc.stream>>>(cv, agent0, n_agents, nv, chunks, rad,
                                                          rad_r2, nodes, bitmap, words, row_cnt, seg,
-                                                         obs_pad);
+                                                         obs_pad, rt);
     return cudaSuccess;
 }
 
 cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                  int nv, const double *rad_r2, const double *rad,
                                  const double *nodes, uint32_t *bitmap, int words,
-                                 int32_t *row_cnt) {
+                                 int32_t *row_cnt, const double *rad_host, const double *r2_host) {
     if (n_agents <= 0 || nv <= 0) return cudaSuccess;
     const bool cull = cv.model <= 1;  // AdjTraits<PointModel<D>>::kCull: second ring
     if (cull && (cv.n_obs >= (1 << 24) || nv > (1 << 20)))
@@ -795,7 +813,7 @@ cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int age
         obs_pad = (cv.n_obs + kCullGroup - 1) / kCullGroup * kCullGroup;
     const int sm = rings + obs_pad * (cv.d + 1) * 8 + (smem_on ? seg + (int)tab : 0);
     cudaError_t e = cudaSuccess;
-#define ADJ_ARGS cv, lc, agent0, n_agents, nv, rad_r2, rad, nodes, bitmap, words, row_cnt, seg, sm, obs_pad
+#define ADJ_ARGS cv, lc, agent0, n_agents, nv, rad_r2, rad, nodes, bitmap, words, row_cnt, seg, sm, obs_pad, rad_host, r2_host
     if (obs_pad > 0) {  // point models with a re-packed obstacle copy
         if (smem_on) {
             if (cv.model == 0) e = launch_adj_t<PointModel<2>, true, true>(ADJ_ARGS);

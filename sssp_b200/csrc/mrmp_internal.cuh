@@ -220,7 +220,8 @@ cudaError_t launch_chain_collide_config_moves(const CtxView &cv, const LaunchCfg
 cudaError_t launch_prm_adjacency(const CtxView &cv, const LaunchCfg &lc, int agent0, int n_agents,
                                  int nv, const double *rad_le /*[n] R2 or NaN*/,
                                  const double *rad /*[n]*/, const double *nodes,
-                                 uint32_t *bitmap, int words, int32_t *row_cnt);
+                                 uint32_t *bitmap, int words, int32_t *row_cnt,
+                                 const double *rad_host = nullptr, const double *r2_host = nullptr);
 cudaError_t launch_row_scan(const LaunchCfg &lc, int64_t n_rows, const int32_t *row_cnt,
                             int32_t *row_ptr, int64_t *nnz_total, long long *chunk_ws,
                             int64_t chunk_ws_len, int64_t *nnz_mirror = nullptr);
