@@ -393,6 +393,17 @@ int mrmp_mid_status(mrmp_ctx *ctx, int64_t n, const double *p, const double *q, 
 int mrmp_nearest(mrmp_ctx *ctx, int n_v, const double *V, const double *q, int reversed,
                  int32_t *idx_out, double *dist_out);
 
+/* extend!(connect, q_rand, V, from_start, steering_depth) of RRT-Connect (sssp.jl:404-440), which
+ * builds SSSP's initial roadmaps (:325-401), in ONE call instead of one per closure call: nearest
+ * vertex of the tree V[n_v][d] (argmin dist(q, q_rand), or dist(q_rand, q) for the goal tree),
+ * the connection test towards q_rand -- connect(q_near, q) from the start tree, connect(q) &&
+ * connect(q, q_near) from the goal tree, with the epsilon gate of conn (:87-89; NaN = nothing) --
+ * and the bisection (get_mid_status) of steering_depth rounds.  flag_out: 0 = :trapped (q_new_out
+ * is then not to be pushed), 1 = :advanced, 2 = :reached; near_out (may be NULL) = index of q_near. */
+int mrmp_rrt_extend(mrmp_ctx *ctx, int agent, int n_v, const double *V, const double *q_rand,
+                    int from_start, int steering_depth, double epsilon, int32_t *flag_out,
+                    int32_t *near_out, double *q_new_out);
+
 /* ---- SSSP: device-resident growing roadmaps and the fused node expansion ------------------ */
 /* The reference's SSSP (src/solvers/sssp.jl:49-232) calls, for every search node it pops,
  * expand! (:235-267, K x [steering :269-291 + nearest-distance filter :250 + conn against the

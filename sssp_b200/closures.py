@@ -335,6 +335,20 @@ class Context:
                                        int(reversed), C.byref(idx), C.byref(dist)))
         return int(idx.value), float(dist.value)
 
+    def rrt_extend(self, agent: int, V, q_rand, from_start: bool, steering_depth: int,
+                   epsilon: Optional[float]):
+        """extend! of RRT-Connect (sssp.jl:404-440) in one call -> (flag, q_new, index of q_near);
+        flag in {"trapped", "advanced", "reached"}."""
+        V = _states(V, self.d)
+        q = L.f64(q_rand).ravel()
+        flag, near = C.c_int32(-1), C.c_int32(-1)
+        out = np.empty(self.d)
+        L.check(self._lib.mrmp_rrt_extend(self._h, int(agent), V.shape[0], L.ptr(V, L._dp),
+                                          L.ptr(q, L._dp), int(bool(from_start)), int(steering_depth),
+                                          math.nan if epsilon is None else float(epsilon),
+                                          C.byref(flag), C.byref(near), L.ptr(out, L._dp)))
+        return ("trapped", "advanced", "reached")[flag.value], out, int(near.value)
+
     def first_conflict(self, configs):
         """get_constraints' scan (cbs.jl:374-412) over configs [T][N][d]: None when conflict
         free, else (t, kind, i, j) with kind 'vertex' / 'edge' of the first conflict."""

@@ -348,6 +348,39 @@ extern "C" int mrmp_nearest(mrmp_ctx *c, int n_v, const double *V, const double 
     return MRMP_OK;
 }
 
+/* extend! of RRT-Connect (sssp.jl:404-440) in one launch: see include/mrmp_b200.h */
+extern "C" int mrmp_rrt_extend(mrmp_ctx *c, int agent, int n_v, const double *V,
+                               const double *q_rand, int from_start, int steering_depth,
+                               double epsilon, int32_t *flag_out, int32_t *near_out,
+                               double *q_new_out) {
+    NEED(c && n_v >= 1 && V && q_rand && flag_out && q_new_out, "bad arguments");
+    NEED(agent >= 0 && agent < c->n_agents && steering_depth >= 0, "agent / depth out of range");
+    CU(cudaSetDevice(c->device));
+    const size_t vb = sizeof(double) * c->d * (size_t)n_v, qb = sizeof(double) * c->d;
+    const size_t o_q = align16(vb), o_out = o_q + align16(qb);
+    int rc = ensure_small(c, o_out + align16(qb) + 32);
+    if (rc) return rc;
+    memcpy(c->small_h, V, vb);
+    memcpy(c->small_h + o_q, q_rand, qb);
+    CU(cudaMemcpyAsync(c->small_d, c->small_h, o_out, cudaMemcpyHostToDevice, c->s_k));
+    SsspExpand a{};
+    a.agent = agent;
+    a.depth = steering_depth;
+    a.eps = epsilon;
+    a.eps_r2 = sq_le_threshold(epsilon);
+    CU(launch_rrt_extend(c->cv, lcfg(c, c->s_k), a, n_v, (const double *)c->small_d,
+                         (const double *)(c->small_d + o_q), from_start ? 1 : 0,
+                         (int32_t *)(c->small_d + o_out), (int32_t *)(c->small_d + o_out + 4),
+                         (double *)(c->small_d + o_out + 16)));
+    CU(cudaMemcpyAsync(c->small_h + o_out, c->small_d + o_out, 16 + qb, cudaMemcpyDeviceToHost,
+                       c->s_k));
+    CU(cudaStreamSynchronize(c->s_k));
+    *flag_out = *(const int32_t *)(c->small_h + o_out);
+    if (near_out) *near_out = *(const int32_t *)(c->small_h + o_out + 4);
+    memcpy(q_new_out, c->small_h + o_out + 16, qb);
+    return MRMP_OK;
+}
+
 // ---- distance tables -----------------------------------------------------------------------------
 extern "C" int mrmp_distance_tables(mrmp_ctx *c, int n_graphs, const int32_t *v_off,
                                     const double *nodes, const int32_t *row_ptr,

@@ -311,7 +311,10 @@ MRMP_HD double seg_filter_inv(const double *a, const double *b) {
     return ddiv(1.0, V);
 }
 
-MRMP_HD double clamp01(double t) { return fmin(fmax(t, 0.0), 1.0); }
+// (plain selects: the filter's operands are finite inside its domain, and fmin / fmax would spend
+// instructions on NaN handling)
+MRMP_HD double clamp01(double t) { return t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
+MRMP_HD double min2(double a, double b) { return a < b ? a : b; }
 
 // squared distance of the point (origin + r) from the segment origin + t*v, t in [0,1]
 template <int D>
@@ -382,7 +385,8 @@ MRMP_HD int segseg_filter(const double *p11, const double *p12, const double *p2
     const double s1 = filt_ptseg_sq<D>(ng2, v1, inv1);  // p22 against segment 1
     const double s2 = filt_ptseg_sq<D>(nw, v2, inv2);   // p11 against segment 2
     const double s3 = filt_ptseg_sq<D>(g0, v2, inv2);   // p12 against segment 2
-    const double s = fmin(fmin(s0, s1), fmin(s2, s3));
+    const double s = min2(min2(s0, s1), min2(s2, s3));
+    if (!(s == s)) return -1;  // cannot happen inside the domain; never decide on a NaN
     const double lo = dsub(thr, kFilterBand), hi = dadd(thr, kFilterBand);
     if (s < dmul(lo, lo)) return 1;
     if (s > dmul(hi, hi)) return 0;

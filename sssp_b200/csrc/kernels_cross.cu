@@ -374,15 +374,29 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
         v[k] = h[4 * tid + k];
         sum += v[k];
     }
-    part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int tv = tid >= o ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += tv;
-        __syncthreads();
+    // exclusive scan of the 1024 partial sums: warp shuffles + one pass over the 32 warp totals
+    // (two barriers instead of twenty)
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int tv = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += tv;
     }
-    int base = tid == 0 ? 0 : part[tid - 1];
+    if (lane == 31) part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int wt = part[lane];
+        int wi = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tv = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += tv;
+        }
+        part[lane] = wi - wt;
+    }
+    __syncthreads();
+    int base = part[warp] + incl - sum;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         h[4 * tid + k] = base;
@@ -510,15 +524,18 @@ k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
             v[k] = counts[16 * tid + k];
             sum += v[k];
         }
-        part[tid] = sum;
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            const int tv = tid >= o ? part[tid - o] : 0;
-            __syncthreads();
-            part[tid] += tv;
-            __syncthreads();
+        const int ln = tid & 31, wp = tid >> 5;
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tv = __shfl_up_sync(0xffffffffu, incl, o);
+            if (ln >= o) incl += tv;
         }
-        int base = tid == 0 ? 0 : part[tid - 1];
+        if (ln == 31) part[wp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < wp; ++w) wbase += part[w];  // 8 warps
+        int base = wbase + incl - sum;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             off[16 * tid + k] = base;

@@ -631,6 +631,87 @@ k_distance_tables(CtxView cv, const int32_t *__restrict__ v_off, const int32_t *
     (void)e1;
 }
 
+// ---- extend! of RRT-Connect (sssp.jl:404-440) in one launch -------------------------------------
+// nearest vertex of the tree (first minimum, like Julia's argmin), the connection test towards the
+// sample and the bisection of `steering_depth` rounds: ~3 + 3*depth closure calls of the reference,
+// each of which used to be its own launch + wait.  One CTA; the sequential decisions run on
+// thread 0 (the reference's own order of calls).  flag: 0 trapped, 1 advanced, 2 reached.
+template <class M>
+__global__ void __launch_bounds__(256)
+k_rrt_extend(CtxView cv, SsspExpand a, int n_v, const double *__restrict__ V,
+             const double *__restrict__ q_rand, int from_start, int32_t *__restrict__ out_flag,
+             int32_t *__restrict__ out_near, double *__restrict__ out_q) {
+    constexpr int D = M::SD;
+    __shared__ double s_d[256];
+    __shared__ int s_i[256];
+    double qr[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) qr[c] = q_rand[c];
+    double best = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int v = threadIdx.x; v < n_v; v += blockDim.x) {
+        double qv[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) qv[c] = V[(int64_t)v * D + c];
+        // argmin(q -> dist(q, q_rand), V) from the start tree, dist(q_rand, q) from the goal tree
+        const double dd = from_start ? M::dist(cv, qv, qr) : M::dist(cv, qr, qv);
+        if (dd < best || (dd == best && v < bi)) {
+            best = dd;
+            bi = v;
+        }
+    }
+    s_d[threadIdx.x] = best;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double d2 = s_d[threadIdx.x + o];
+            const int i2 = s_i[threadIdx.x + o];
+            if (d2 < s_d[threadIdx.x] || (d2 == s_d[threadIdx.x] && i2 < s_i[threadIdx.x])) {
+                s_d[threadIdx.x] = d2;
+                s_i[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const int near = s_i[0] == 0x7fffffff ? 0 : s_i[0];  // all distances NaN: index 0
+    const ConSeg cs(cv, cv.blob + cv.con_off);
+    double q_near[D], q_l[D], q_h[D], q[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        q_near[c] = V[(int64_t)near * D + c];
+        q_l[c] = q_near[c];
+        q_h[c] = qr[c];
+    }
+    // from_start: connect(q_near, q);  else: connect(q) && connect(q, q_near)   (:424, :428)
+    const auto linked = [&](const double *x) {
+        if (from_start) return conn<M>(cv, cs, a, q_near, x);
+        return M::connect_point(cv, cs, x, a.agent) && conn<M>(cv, cs, a, x, q_near);
+    };
+    int flag = 2;
+    if (!linked(q_h)) {
+        flag = 0;
+        for (int st = 0; st < a.depth; ++st) {
+            if (from_start) M::mid(q_l, q_h, q);
+            else M::mid(q_h, q_l, q);
+            const bool ok = linked(q);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                if (ok) q_l[c] = q[c];
+                else q_h[c] = q[c];
+            }
+            if (ok) flag = 1;
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) q_h[c] = q_l[c];
+    }
+    *out_flag = flag;
+    *out_near = near;
+#pragma unroll
+    for (int c = 0; c < D; ++c) out_q[c] = q_h[c];
+}
+
 // ---- launchers ---------------------------------------------------------------------------------
 #define MRMP_MODEL_SWITCH(cv, EXPR)                      \
     switch ((cv).model) {                                \
@@ -745,6 +826,16 @@ cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int6
     const int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     MRMP_MODEL_SWITCH(cv, (k_state_op<M><<<grid, 256, 0, lc.stream>>>(cv, op, n, q1, q2, out)));
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rrt_extend(const CtxView &cv, const LaunchCfg &lc, const SsspExpand &a, int n_v,
+                              const double *V, const double *q_rand, int from_start,
+                              int32_t *out_flag, int32_t *out_near, double *out_q) {
+    if (n_v <= 0) return cudaErrorInvalidValue;
+    MRMP_MODEL_SWITCH(cv, (k_rrt_extend<M><<<1, 256, 0, lc.stream>>>(cv, a, n_v, V, q_rand, from_start,
+                                                                    out_flag, out_near, out_q)));
     count_launch();
     return cudaGetLastError();
 }

@@ -321,6 +321,9 @@ cudaError_t launch_distance_tables(const CtxView &cv, const LaunchCfg &lc, int n
                                    const int32_t *goal, double stay_penalty, double *w, double *table);
 cudaError_t launch_state_op(const CtxView &cv, const LaunchCfg &lc, int op, int64_t n,
                             const double *q1, const double *q2, double *out);
+cudaError_t launch_rrt_extend(const CtxView &cv, const LaunchCfg &lc, const SsspExpand &a, int n_v,
+                              const double *V, const double *q_rand, int from_start,
+                              int32_t *out_flag, int32_t *out_near, double *out_q);
 cudaError_t launch_nearest(const CtxView &cv, const LaunchCfg &lc, int n_v, const double *V,
                            const double *q, int reversed, int32_t *idx_out, double *dist_out);
 

@@ -131,6 +131,8 @@ _SIGS = {
     "mrmp_sample_free": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_int64, _dp, _lp]),
     "mrmp_state_dist": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
     "mrmp_mid_status": (C.c_int, [_vp, C.c_int64, _dp, _dp, _dp]),
+    "mrmp_rrt_extend": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double,
+                                  C.POINTER(C.c_int32), C.POINTER(C.c_int32), _dp]),
     "mrmp_nearest": (C.c_int, [_vp, C.c_int, _dp, _dp, C.c_int, _ip, _dp]),
     "mrmp_validate_solution": (C.c_int, [_vp, C.c_int64, _dp, C.POINTER(C.c_int32), _lp,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32),

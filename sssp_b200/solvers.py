@@ -141,21 +141,8 @@ def _rrt_connect_roadmap(ctx: Context, i: int, q_init, q_goal, smp: _AgentSample
     def conn1(q) -> bool:
         return bool(ctx.connect_points(ag, [q])[0])
 
-    def extend(q_rand, V, from_start):          # extend!, sssp.jl:404-440
-        q_near = V[ctx.nearest(np.stack(V), q_rand, reversed=not from_start)[0]]
-        flg, q_l, q_h = "reached", q_near, q_rand
-        blocked = (not conn2(q_near, q_h)) if from_start else \
-            (not (conn1(q_h) and conn2(q_h, q_near)))
-        if blocked:
-            flg = "trapped"
-            for _ in range(depth):
-                q = ctx.mid_status([q_l], [q_h])[0] if from_start else ctx.mid_status([q_h], [q_l])[0]
-                ok = conn2(q_near, q) if from_start else (conn1(q) and conn2(q, q_near))
-                if ok:
-                    flg, q_l = "advanced", q
-                else:
-                    q_h = q
-            q_h = q_l
+    def extend(q_rand, V, from_start):          # extend!, sssp.jl:404-440: one GPU call
+        flg, q_h, _ = ctx.rrt_extend(i, np.stack(V), q_rand, from_start, depth, epsilon)
         if flg != "trapped":
             V.append(q_h)
         return flg, q_h
