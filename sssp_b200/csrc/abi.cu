@@ -2,6 +2,8 @@
 // Host-side C++ only orchestrates; all arithmetic of the hot path runs in the kernels.
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "abi_internal.cuh"
 #include "arm_model.cuh"
 
@@ -1991,7 +1993,11 @@ extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm
     // stores: when the caller's buffer is pinned (mapped) host memory the kernel writes it in
     // place, the result travels while the kernel runs and no copy follows
     uint32_t *direct = nullptr;
-    if (group_size > 0 && c->model <= MRMP_MODEL_POINT3D) {
+    static const bool allow_direct = [] {   // MRMP_TABLE_DIRECT=0: always stage in device memory
+        const char *e = getenv("MRMP_TABLE_DIRECT");
+        return !(e && e[0] == '0');
+    }();
+    if (allow_direct && group_size > 0 && c->model <= MRMP_MODEL_POINT3D) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, out_bits) == cudaSuccess &&
             at.type == cudaMemoryTypeHost && at.devicePointer)

@@ -64,10 +64,23 @@ struct ColX {  // exact-stage record of a column (64 bytes in 2-D, 80 in 3-D)
     int key;            // col_key (0 without keys)
 };
 
+// Bounding box of the tile's midpoints and its largest reach as order-preserving integer keys of
+// floats rounded OUTWARD (a box that is 1e-7 too large only culls that much less): they can be
+// reduced with integer atomicMin / atomicMax by the threads that write the columns.
 template <int D>
-struct TileHdr {  // bounding box of the tile's midpoints and its largest reach
-    double lo[D], hi[D], hmax, pad;
+struct TileHdr {
+    int lo[D], hi[D];
+    int hmax;
+    int poison;  // a NaN midpoint / reach: the tile must never be culled by the box test
 };
+
+__device__ __forceinline__ int fkey(float f) {  // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float fkey_inv(int k) {
+    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
 
 // ---- Morton cell of an edge midpoint -------------------------------------------------------
 __device__ __forceinline__ unsigned spread2(unsigned x) {  // 6 bits -> every 2nd bit
@@ -278,11 +291,11 @@ __device__ __forceinline__ void tile_header(const ColPrep<D> &P, int64_t t, int 
         TileHdr<D> H;
 #pragma unroll
         for (int x = 0; x < D; ++x) {
-            H.lo[x] = poison ? -1e300 : lo[x];
-            H.hi[x] = poison ? 1e300 : hi[x];
+            H.lo[x] = fkey(__double2float_rd(lo[x]));
+            H.hi[x] = fkey(__double2float_ru(hi[x]));
         }
-        H.hmax = poison ? 1e300 : hmax;
-        H.pad = 0.0;
+        H.hmax = fkey(__double2float_ru(hmax));
+        H.poison = poison ? 1 : 0;
         P.hdrs[t] = H;
     }
 }
@@ -319,51 +332,44 @@ __global__ void __launch_bounds__(256) k_cross_prep_cols(ColPrep<D> P) {
         prep_tile<D>(P, t, lane);
 }
 
-// The whole column side in ONE launch for the usual case of a few thousand columns (a conflict
-// table has N x T of them): one CTA, every thread keeps its (up to 4) columns in registers,
-// counts the Morton cells in shared memory, scans, and writes the finished records straight to
-// their sorted position.  The tile headers (box of the midpoints, largest reach) are reduced with
-// shared-memory integer atomics on order-preserving float keys, rounded outward -- a box that is
-// 1e-7 too large only culls that much less.
+// The column side for the usual case of a few thousand columns (a conflict table has N x T of
+// them) in TWO launches instead of four: `place` -- one CTA -- counts the Morton cells in shared
+// memory, scans, and gives every column its sorted position (and resets the tile headers and the
+// work counter of the table kernel); `fill` -- a thread per column over many SMs -- builds the
+// records (a division and a square root each: too much for one SM) at their position and reduces
+// the tile headers with integer atomics.
 constexpr int kPrepSmallCpt = 4;
 constexpr int kPrepSmallMax = 1024 * kPrepSmallCpt;
-constexpr int kPrepSmallTiles = kPrepSmallMax / kCols;
-
-__device__ __forceinline__ int fkey(float f) {  // order-preserving float -> int
-    const int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float fkey_inv(int k) {
-    return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
-}
 
 template <int D>
-__global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
+__global__ void __launch_bounds__(1024)
+k_cross_cols_place(ColPrep<D> P, int32_t *__restrict__ place, unsigned int *__restrict__ work) {
     __shared__ int h[kSortCells];
-    __shared__ int part[1024];
-    __shared__ int t_lo[kPrepSmallTiles][D], t_hi[kPrepSmallTiles][D], t_h[kPrepSmallTiles];
-    __shared__ int t_poison[kPrepSmallTiles];
+    __shared__ int part[32];
     const int tid = threadIdx.x;
     for (int c = tid; c < kSortCells; c += 1024) h[c] = 0;
-    for (int t = tid; t < kPrepSmallTiles; t += 1024) {
+    for (int64_t t = tid; t < P.n_tiles; t += 1024) {
+        TileHdr<D> H;
 #pragma unroll
         for (int x = 0; x < D; ++x) {
-            t_lo[t][x] = fkey(INFINITY);
-            t_hi[t][x] = fkey(-INFINITY);
+            H.lo[x] = fkey(INFINITY);
+            H.hi[x] = fkey(-INFINITY);
         }
-        t_h[t] = fkey(0.0f);
-        t_poison[t] = 0;
+        H.hmax = fkey(0.0f);
+        H.poison = 0;
+        P.hdrs[t] = H;
     }
+    if (tid == 0 && work) *work = 0u;
     __syncthreads();
-    double a[kPrepSmallCpt][D], b[kPrepSmallCpt][D];
-    int ag[kPrepSmallCpt], cell[kPrepSmallCpt];
+    int cell[kPrepSmallCpt];
 #pragma unroll
     for (int i = 0; i < kPrepSmallCpt; ++i) {
         const int64_t k = tid + 1024 * i;
         cell[i] = -1;
         if (k < P.n_cols) {
-            ag[i] = P.el.get(k, a[i], b[i]);
-            cell[i] = morton_cell<D>(a[i], b[i]);
+            double a[D], b[D];
+            P.el.get(k, a, b);
+            cell[i] = morton_cell<D>(a, b);
             atomicAdd(&h[cell[i]], 1);
         }
     }
@@ -375,7 +381,6 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
         sum += v[k];
     }
     // exclusive scan of the 1024 partial sums: warp shuffles + one pass over the 32 warp totals
-    // (two barriers instead of twenty)
     const int lane = tid & 31, warp = tid >> 5;
     int incl = sum;
 #pragma unroll
@@ -404,47 +409,39 @@ __global__ void __launch_bounds__(1024) k_cross_prep_cols_small(ColPrep<D> P) {
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kPrepSmallCpt; ++i) {
-        if (cell[i] < 0) continue;
-        const int pos = atomicAdd(&h[cell[i]], 1);
-        ColB B;
-        ColX<D> X;
-        double m[D], hh;
-        make_col<D>(P, tid + 1024 * i, ag[i], a[i], b[i], B, X, m, hh);
-        P.cb[pos] = B;
-        P.cx[pos] = X;
-        const int t = pos / kCols;
-        bool bad = !(hh == hh);
-#pragma unroll
-        for (int x = 0; x < D; ++x) {
-            bad |= !(m[x] == m[x]);
-            atomicMin(&t_lo[t][x], fkey(__double2float_rd(m[x])));
-            atomicMax(&t_hi[t][x], fkey(__double2float_ru(m[x])));
-        }
-        atomicMax(&t_h[t], fkey(__double2float_ru(hh)));
-        if (bad) t_poison[t] = 1;  // a NaN midpoint / reach must never be culled by the box test
-    }
-    for (int64_t p = P.n_cols + tid; p < P.n_tiles * kCols; p += 1024) {
-        ColB B;
-        ColX<D> X;
+    for (int i = 0; i < kPrepSmallCpt; ++i)
+        if (cell[i] >= 0) place[tid + 1024 * i] = atomicAdd(&h[cell[i]], 1);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+k_cross_cols_fill(ColPrep<D> P, const int32_t *__restrict__ place) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= P.n_tiles * kCols) return;
+    ColB B;
+    ColX<D> X;
+    if (k >= P.n_cols) {  // the padding slots behind the last column
         make_pad<D>(B, X);
-        P.cb[p] = B;
-        P.cx[p] = X;
+        P.cb[k] = B;
+        P.cx[k] = X;
+        return;
     }
-    __syncthreads();
-    for (int t = tid; t < P.n_tiles; t += 1024) {
-        TileHdr<D> H;
-        const bool poison = t_poison[t] != 0;
+    double a[D], b[D], m[D], hh;
+    const int j = P.el.get(k, a, b);
+    make_col<D>(P, k, j, a, b, B, X, m, hh);
+    const int pos = place[k];
+    P.cb[pos] = B;
+    P.cx[pos] = X;
+    TileHdr<D> &H = P.hdrs[pos / kCols];
+    bool bad = !(hh == hh);
 #pragma unroll
-        for (int x = 0; x < D; ++x) {
-            H.lo[x] = poison ? -1e300 : (double)fkey_inv(t_lo[t][x]);
-            H.hi[x] = poison ? 1e300 : (double)fkey_inv(t_hi[t][x]);
-        }
-        const float hm = fkey_inv(t_h[t]);
-        H.hmax = (poison || !(hm < INFINITY)) ? 1e300 : (double)hm;
-        H.pad = 0.0;
-        P.hdrs[t] = H;
+    for (int x = 0; x < D; ++x) {
+        bad |= !(m[x] == m[x]);
+        atomicMin(&H.lo[x], fkey(__double2float_rd(m[x])));
+        atomicMax(&H.hi[x], fkey(__double2float_ru(m[x])));
     }
+    atomicMax(&H.hmax, fkey(__double2float_ru(hh)));
+    if (bad) H.poison = 1;
 }
 
 // ---- rows from the CSR of a roadmap set: edge e of row (agent a, vertex v) -----------------
@@ -599,6 +596,10 @@ struct CrossArgs {
 #ifndef MRMP_CROSS_MINB
 #define MRMP_CROSS_MINB 3
 #endif
+#ifndef MRMP_CROSS_UNROLL
+#define MRMP_CROSS_UNROLL 32   // broad-phase loop over the 32 columns of a tile
+#endif
+constexpr int kBroadUnroll = MRMP_CROSS_UNROLL;
 
 // The reference's own sequence of roundings for one pair (utils.jl:59-94): rare -- the filter
 // decides all but the pairs within 2^-20 of contact, near-parallel pairs and coordinates outside
@@ -747,11 +748,12 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                 double d2 = 0.0;
 #pragma unroll
                 for (int x = 0; x < D; ++x) {
-                    const double gap = fmax(fmax(H.lo[x] - hi[x], lo[x] - H.hi[x]), 0.0);
+                    const double hlo = (double)fkey_inv(H.lo[x]), hhi = (double)fkey_inv(H.hi[x]);
+                    const double gap = fmax(fmax(hlo - hi[x], lo[x] - hhi), 0.0);
                     d2 += gap * gap;
                 }
-                const double reach = Rmax + H.hmax;
-                near = poison || !(d2 > reach * reach);
+                const double reach = Rmax + (double)fkey_inv(H.hmax);  // +inf: never culled
+                near = poison || H.poison != 0 || !(d2 > reach * reach);
             }
             unsigned tmask = __ballot_sync(0xffffffffu, near);
             while (tmask) {
@@ -761,7 +763,7 @@ k_cross_collide(CtxView cv, CrossArgs<D> A) {
                 const ColX<D> *cxp = A.cx + (int64_t)t * kCols;
                 // ---- broad phase (FP32): this lane's row against the 32 columns of the tile
                 uint32_t mask = 0u;
-#pragma unroll
+#pragma unroll kBroadUnroll
                 for (int c = 0; c < kCols; ++c) {
                     const float4 q = __ldg(cbp + c);
                     bool keep = !bound32_far<D>(rb, q.x, q.y, FD ? 0.0f : q.z, q.w);
@@ -963,8 +965,10 @@ static cudaError_t prep_cols_t(const CtxView &cv, const LaunchCfg &lc, const Edg
     P.rads = cv.blob + cv.crads_off;
     P.n_agents = cv.n_agents;
     if (n_cols <= kPrepSmallMax) {
-        k_cross_prep_cols_small<D><<<1, 1024, 0, lc.stream>>>(P);
-        count_launch();
+        k_cross_cols_place<D><<<1, 1024, 0, lc.stream>>>(P, order, nullptr);
+        const int64_t slots = n_tiles * kCols;
+        k_cross_cols_fill<D><<<(int)((slots + 127) / 128), 128, 0, lc.stream>>>(P, order);
+        count_launch(2);
         return cudaGetLastError();
     }
     cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * kSortCells, lc.stream);

@@ -326,3 +326,44 @@ def test_validate_runs_collide_checks_on_the_collide_closure():
     near = S.gen_check_goal([q0, q1], goal_rad=0.1, ctx=connect.ctx)
     assert near(A(2 * math.pi - 0.05, 0.0), 0) is True     # wraps around: dist = 0.05 / pi
     assert near(A(1.0, 0.0), 0) is False
+
+
+@pytest.mark.parametrize("model", [O.POINT2D, O.POINT3D, O.ARM22])
+def test_rrt_extend_equals_the_per_call_sequence(model):
+    """mrmp_rrt_extend (one launch) == extend! of sssp.jl:404-440 spelled out with one oracle
+    closure call per step: nearest vertex, connection test, bisection, from both trees."""
+    path = [p for p in GOLD if {O.POINT2D: "point2d_many_n10", O.POINT3D: "point3d", O.ARM22: "arm22"}[model] in p][0]
+    fx, inst, orc, base = load(path)
+    ctx = S.Context(inst["model"], inst["rads"], np.array(inst["obstacles"]), base_pos=base,
+                    aux=inst.get("aux"))
+    N, d = len(inst["rads"]), ctx.d
+    rng = np.random.default_rng(12)
+    seen = set()
+    for trial in range(120):
+        i = int(rng.integers(0, N))
+        eps = [None, 0.2, 0.5][trial % 3]
+        depth = [0, 2, 4][trial % 3]
+        from_start = bool(trial % 2)
+        V = [orc.sample_free(i, 100 + trial, 1)[0][0] for _ in range(int(rng.integers(1, 12)))]
+        q_rand = orc.sample_state(7, i, trial)
+        conn2 = lambda a, b: (eps is None or orc.state_dist(a, b) <= eps) and orc.connect_edge(a, b, i)
+        conn1 = lambda q: orc.connect_point(q, i)
+        dists = [orc.state_dist(v, q_rand) if from_start else orc.state_dist(q_rand, v) for v in V]
+        near = int(np.argmin(dists))
+        q_near = V[near]
+        flg, q_l, q_h = "reached", q_near, q_rand
+        linked = (lambda x: conn2(q_near, x)) if from_start else (lambda x: conn1(x) and conn2(x, q_near))
+        if not linked(q_h):
+            flg = "trapped"
+            for _ in range(depth):
+                q = orc.mid_status(q_l, q_h) if from_start else orc.mid_status(q_h, q_l)
+                if linked(q):
+                    flg, q_l = "advanced", q
+                else:
+                    q_h = q
+            q_h = q_l
+        got_flg, got_q, got_near = ctx.rrt_extend(i, np.stack(V), q_rand, from_start, depth, eps)
+        assert (got_flg, got_near) == (flg, near), trial
+        assert np.array_equal(np.asarray(got_q).view(np.uint64), np.asarray(q_h, float).view(np.uint64)), trial
+        seen.add(flg)
+    assert len(seen) >= 2
