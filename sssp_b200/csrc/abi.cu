@@ -201,6 +201,13 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     c->s_k_owned = c->s_k;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    {
+        const char *ov = getenv("MRMP_TABLE_OVERLAP");
+        c->table_overlap = !(ov && ov[0] == '0');
+    }
     for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {
         e = cudaEventCreateWithFlags(&c->ev_in[s], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_k[s], cudaEventDisableTiming);
@@ -232,6 +239,9 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
     if (c->s_k_owned) cudaStreamDestroy(c->s_k_owned);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->blob) cudaFree(c->blob);
     if (c->stats_d) cudaFree(c->stats_d);
     delete c;
@@ -1596,7 +1606,10 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
                          int64_t n_cols, const int32_t *col_agent, const double *col_from,
                          const double *col_to, const int32_t *col_vf, const int32_t *col_vt,
                          const double *nodes, int agent0, int nv_stride, const CrossReq &rq,
-                         uint32_t *out, cudaStream_t s, const long long *n_rows_dev = nullptr) {
+                         uint32_t *out, cudaStream_t s, const long long *n_rows_dev = nullptr,
+                         bool cols_forked = false) {
+    // cols_forked: ev_fork was recorded on s before the caller queued its row sort there; the
+    // column tiles (which depend only on what precedes the fork) are prepared on s_aux meanwhile
     const int group_size = rq.group_size;
     const bool table = rq.mode == kCrossBits || rq.mode == kCrossOr;
     const int wpr = table ? cross_words(n_cols, group_size) : rq.n_groups;
@@ -1661,12 +1674,22 @@ static int cross_run_dev(mrmp_ctx *c, int64_t n_rows, const int32_t *row_agent,
         cc.col_group = rq.col_group ? rq.col_group + c0 : nullptr;
         cc.col_key = rq.col_key ? rq.col_key + c0 : nullptr;
         cc.orig_base = c0;
-        CU(launch_cross_prep_cols(c->cv, lc, nc, col_agent + c0,
+        const bool forked = cols_forked && nc == n_cols;  // one chunk only: the tiles are not reused
+        LaunchCfg lcp = lc;
+        if (forked) {
+            lcp.stream = c->s_aux;
+            CU(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+        }
+        CU(launch_cross_prep_cols(c->cv, lcp, nc, col_agent + c0,
                                   col_from ? col_from + c0 * d : nullptr,
                                   col_to ? col_to + c0 * d : nullptr, col_vf ? col_vf + c0 : nullptr,
                                   col_vt ? col_vt + c0 : nullptr, nodes, agent0, nv_stride, cc,
                                   (int32_t *)(b + o_cells), (int32_t *)(b + o_order), b + o_tiles,
                                   b + o_hdr));
+        if (forked) {
+            CU(cudaEventRecord(c->ev_join, c->s_aux));
+            CU(cudaStreamWaitEvent(s, c->ev_join, 0));
+        }
         const int64_t g0 = rq.mode == kCrossOr ? c0 / group_size : 0;
         CrossOut co;
         co.mode = rq.mode;
@@ -1930,12 +1953,15 @@ static int edge_conflicts_core(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_
     }
     if (n_cols == 0 || n_rows == 0) return MRMP_OK;
     CU(cudaSetDevice(c->device));
+    // the row sort (this stream) and the column tiles (s_aux) both read the finished roadmaps only
+    const bool fork = c->table_overlap && !rm->e_valid && c->model <= MRMP_MODEL_POINT3D;
+    if (fork) CU(cudaEventRecord(c->ev_fork, s));
     int rc = roadmaps_expand_edges(rm, s);
     if (rc) return rc;
     return cross_run_dev(c, n_rows, rm->e_agent, rm->e_from, rm->e_to, rm->e_rows, n_cols,
                          col_agent, nullptr, nullptr, col_vfrom, col_vto, rm_cols->nodes,
                          rm_cols->agent0, rm_cols->nv, table_req(group_size), out_bits, s,
-                         n_rows_dev);
+                         n_rows_dev, fork);
 }
 
 extern "C" int mrmp_roadmaps_edge_conflicts_dev(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,

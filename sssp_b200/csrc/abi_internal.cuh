@@ -75,6 +75,11 @@ struct mrmp_ctx {
     cudaStream_t s_k = nullptr, s_in = nullptr, s_out = nullptr;
     cudaStream_t s_k_owned = nullptr;  // s_k unless the caller installed its own stream
     cudaEvent_t ev_in[kSlots]{}, ev_k[kSlots]{}, ev_out[kSlots]{};
+    // conflict table of a roadmap set: the column tiles are prepared on s_aux while the rows are
+    // sorted on the caller's stream (edge_conflicts_core)
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool table_overlap = true;  // MRMP_TABLE_OVERLAP=0 keeps everything on one stream
     // chunk slots (device) and small-batch staging (pinned host + device)
     unsigned char *slot_buf[kSlots]{};
     size_t slot_bytes = 0;

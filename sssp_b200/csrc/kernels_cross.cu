@@ -43,7 +43,8 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kSortCells = 4096;  // Morton grid: 64 x 64 (2-D), 16^3 (3-D)
 
 template <int D>
-struct RowRec {  // one row edge, in Morton order
+struct alignas(16) RowRec {  // one row edge, in Morton order (16-byte aligned: the scatter of the
+                             // sort writes a record with 128-bit stores)
     double a[D], b[D];
     int agent, orig;  // orig = row index in the caller's order
 };
@@ -473,9 +474,12 @@ k_csr_expand_edges(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
 }
 
 // ---- CSR of a roadmap set -> Morton-sorted row records in two launches (point models) ------------
-// warp per CSR row (the source vertex is loaded once), lane per edge: count the cells, then -- with
-// the exclusive scan of the 4096 counts redone by every CTA in shared memory instead of a launch of
-// its own -- scatter the records.
+// kCsrLanes lanes per CSR row (a PRM vertex has about 8 neighbours at the BASELINE density; a full
+// warp per row left 3/4 of the lanes idle and the row loop serial), lane per edge: count the cells,
+// then -- with the exclusive scan of the 4096 counts redone by every CTA in shared memory instead
+// of a launch of its own -- scatter the records.
+constexpr int kCsrLanes = 8;
+
 template <int D>
 __global__ void __launch_bounds__(256)
 k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
@@ -484,17 +488,17 @@ k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
     __shared__ int h[kSortCells];
     for (int c = threadIdx.x; c < kSortCells; c += blockDim.x) h[c] = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows_csr;
-         row += n_warps) {
+    const int lane = threadIdx.x & (kCsrLanes - 1);
+    const int64_t n_sub = ((int64_t)gridDim.x * blockDim.x) / kCsrLanes;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kCsrLanes; row < n_rows_csr;
+         row += n_sub) {
         const int a = (int)(row / nv), v = (int)(row - (int64_t)a * nv);
         const double *tab = nodes + (int64_t)a * nv * D;
         double qv[D];
         load_state<D>(tab, v, qv);
         // (e_cap: capacity of col_idx / the row records; only an overflowing asynchronous build
         // ever reaches it, and that build is rejected by mrmp_roadmaps_finish)
-        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += 32) {
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += kCsrLanes) {
             double qk[D];
             load_state<D>(tab, col_idx[e], qk);
             atomicAdd(&h[morton_cell<D>(qv, qk)], 1);
@@ -540,16 +544,16 @@ k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
         }
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows_csr;
-         row += n_warps) {
+    const int lane = threadIdx.x & (kCsrLanes - 1);
+    const int64_t n_sub = ((int64_t)gridDim.x * blockDim.x) / kCsrLanes;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kCsrLanes; row < n_rows_csr;
+         row += n_sub) {
         const int a = (int)(row / nv), v = (int)(row - (int64_t)a * nv);
         const double *tab = nodes + (int64_t)a * nv * D;
         RowRec<D> r;
         load_state<D>(tab, v, r.a);
         r.agent = agent0 + a;
-        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += 32) {
+        for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += kCsrLanes) {
             load_state<D>(tab, col_idx[e], r.b);
             r.orig = e;
             const int cell = morton_cell<D>(r.a, r.b);
@@ -1009,7 +1013,7 @@ cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, i
     if (cv.model > 1) return cudaErrorNotSupported;
     cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * 2 * kSortCells, lc.stream);
     if (e != cudaSuccess) return e;
-    int64_t want = (n_rows_csr + 7) / 8;
+    int64_t want = (n_rows_csr * kCsrLanes + 255) / 256;
     const int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     if (cv.model == 0) {
