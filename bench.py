@@ -63,7 +63,7 @@ FLOPS_FILTER = 91              # FP64 verdict filter per surviving pair (2-D, FM
                                # point-segment distances 52, minimum 3, band compare 6
 FLOPS_EXACT = 170              # reference segment-segment test, SURVEY 8(d)
 FP64_UNFUSED_PEAK_TFLOPS = 18.58   # tools/fp64_peak.cu on this pool (profiles/r1_fp64_peak.json)
-NCU_DRAM_BYTES_PER_LAUNCH = 16.19e6   # profiles/r2_a_ncu_full_summary.md (read 16.19 MB, written 1 KB)
+NCU_DRAM_BYTES_PER_LAUNCH = 19.37e6   # profiles/r2_r_cross_ncu_summary.md (read 19.36 MB, written 9 KB: the table stays in L2)
 BYTES_CONNECT = 2 * 16 + 4 + 1
 BYTES_COLLIDE = 4 * 16 + 8 + 1
 
@@ -575,8 +575,8 @@ def run_b200(args):
         "achieved": achieved, "peak": FP64_UNFUSED_PEAK_TFLOPS, "unit": "TFLOP/s",
         "frac": achieved / FP64_UNFUSED_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` "
-                          "capture of this kernel on this workload (profiles/r2_a_ncu_full_summary.md); "
-                          "algorithmic bytes per launch: 17.0e6",
+                          "capture of this kernel on this workload (profiles/r2_r_cross_ncu_summary.md); "
+                          "algorithmic bytes per launch: 22.4e6 (396166 row records x 48 B + 3200 columns x 80 B + 8 B of table per row)",
         "peak_source": "un-fused DADD/DMUL issue peak measured with tools/fp64_peak.cu on this "
                        "pool (profiles/r1_fp64_peak.json); MEASURED_PEAKS.json has no FP64 figure "
                        "and bit parity forbids FMA in the reference arithmetic",

@@ -484,8 +484,11 @@ template <int D>
 __global__ void __launch_bounds__(256)
 k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
                 const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
-                int32_t *__restrict__ counts, int64_t e_cap) {
+                int32_t *__restrict__ counts, int32_t *__restrict__ cursor,
+                unsigned int *__restrict__ done, int64_t e_cap) {
     __shared__ int h[kSortCells];
+    __shared__ int part[8];
+    __shared__ bool s_last;
     for (int c = threadIdx.x; c < kSortCells; c += blockDim.x) h[c] = 0;
     __syncthreads();
     const int lane = threadIdx.x & (kCsrLanes - 1);
@@ -507,43 +510,44 @@ k_csr_cell_hist(int64_t n_rows_csr, int nv, const int32_t *__restrict__ row_ptr,
     __syncthreads();
     for (int c = threadIdx.x; c < kSortCells; c += blockDim.x)
         if (h[c]) atomicAdd(counts + c, h[c]);
+    // the CTA that finishes last turns the counts into the cursors of the scatter (exclusive
+    // scan, 16 cells per thread): no scan launch, and no scan in every CTA of the scatter
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int tid = threadIdx.x;
+    int v[16], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        v[k] = __ldcg(counts + 16 * tid + k);
+        sum += v[k];
+    }
+    const int ln = tid & 31, wp = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int tv = __shfl_up_sync(0xffffffffu, incl, o);
+        if (ln >= o) incl += tv;
+    }
+    if (ln == 31) part[wp] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int w = 0; w < wp; ++w) base += part[w];  // 8 warps
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        cursor[16 * tid + k] = base;
+        base += v[k];
+    }
 }
 
 template <int D>
 __global__ void __launch_bounds__(256)
 k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__restrict__ row_ptr,
                    const int32_t *__restrict__ col_idx, const double *__restrict__ nodes,
-                   const int32_t *__restrict__ counts, int32_t *__restrict__ cursor,
-                   RowRec<D> *__restrict__ rows, int64_t e_cap) {
-    __shared__ int off[kSortCells];
-    __shared__ int part[256];
-    {   // exclusive scan of the 4096 cell counts (16 per thread)
-        const int tid = threadIdx.x;
-        int v[16], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            v[k] = counts[16 * tid + k];
-            sum += v[k];
-        }
-        const int ln = tid & 31, wp = tid >> 5;
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int tv = __shfl_up_sync(0xffffffffu, incl, o);
-            if (ln >= o) incl += tv;
-        }
-        if (ln == 31) part[wp] = incl;
-        __syncthreads();
-        int wbase = 0;
-        for (int w = 0; w < wp; ++w) wbase += part[w];  // 8 warps
-        int base = wbase + incl - sum;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            off[16 * tid + k] = base;
-            base += v[k];
-        }
-        __syncthreads();
-    }
+                   int32_t *__restrict__ cursor, RowRec<D> *__restrict__ rows, int64_t e_cap) {
     const int lane = threadIdx.x & (kCsrLanes - 1);
     const int64_t n_sub = ((int64_t)gridDim.x * blockDim.x) / kCsrLanes;
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / kCsrLanes; row < n_rows_csr;
@@ -556,8 +560,7 @@ k_csr_rows_scatter(int64_t n_rows_csr, int nv, int agent0, const int32_t *__rest
         for (int e = row_ptr[row] + lane; e < row_ptr[row + 1] && e < e_cap; e += kCsrLanes) {
             load_state<D>(tab, col_idx[e], r.b);
             r.orig = e;
-            const int cell = morton_cell<D>(r.a, r.b);
-            rows[off[cell] + atomicAdd(cursor + cell, 1)] = r;
+            rows[atomicAdd(cursor + morton_cell<D>(r.a, r.b), 1)] = r;
         }
     }
 }
@@ -1004,30 +1007,32 @@ cudaError_t launch_cross_prep_cols(const CtxView &cv, const LaunchCfg &lc, int64
 }
 
 // CSR edges of a point-model roadmap set -> Morton-sorted RowRec array (row e <-> col_idx[e]);
-// cells = 2 * 4096 ints of device scratch (counts | cursors)
+// cells = 2 * 4096 + 1 ints of device scratch (counts | cursors | CTAs done)
 cudaError_t launch_cross_sort_csr_rows(const CtxView &cv, const LaunchCfg &lc, int64_t n_rows_csr,
                                        int nv, int agent0, const int32_t *row_ptr,
                                        const int32_t *col_idx, const double *nodes, int32_t *cells,
                                        void *rows_out, int64_t e_cap) {
     if (n_rows_csr <= 0) return cudaSuccess;
     if (cv.model > 1) return cudaErrorNotSupported;
-    cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * 2 * kSortCells, lc.stream);
+    cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int32_t) * (2 * kSortCells + 1), lc.stream);
     if (e != cudaSuccess) return e;
     int64_t want = (n_rows_csr * kCsrLanes + 255) / 256;
     const int64_t cap = (int64_t)lc.sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
+    int32_t *cursor = cells + kSortCells;
+    unsigned int *done = reinterpret_cast<unsigned int *>(cells + 2 * kSortCells);
     if (cv.model == 0) {
         k_csr_cell_hist<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells,
-                                                       e_cap);
+                                                       cursor, done, e_cap);
         k_csr_rows_scatter<2><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
-                                                          nodes, cells, cells + kSortCells,
-                                                          (RowRec<2> *)rows_out, e_cap);
+                                                          nodes, cursor, (RowRec<2> *)rows_out,
+                                                          e_cap);
     } else {
         k_csr_cell_hist<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, row_ptr, col_idx, nodes, cells,
-                                                       e_cap);
+                                                       cursor, done, e_cap);
         k_csr_rows_scatter<3><<<grid, 256, 0, lc.stream>>>(n_rows_csr, nv, agent0, row_ptr, col_idx,
-                                                          nodes, cells, cells + kSortCells,
-                                                          (RowRec<3> *)rows_out, e_cap);
+                                                          nodes, cursor, (RowRec<3> *)rows_out,
+                                                          e_cap);
     }
     count_launch(2);
     return cudaGetLastError();
