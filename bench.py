@@ -76,6 +76,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--separate-calls", action="store_true",
+                    help="multi-GPU strong step as one library call per stage (the form the stage "
+                         "timeline is taken with) instead of mrmp_roadmaps_strong_step")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="multi-GPU: strong = ONE scenario, roadmaps and table rows sharded by agent "
                          "(default); weak = one scenario per GPU on a sharded build")
@@ -347,7 +350,7 @@ def run_b200(args):
         nnz_all = torch.zeros(world, dtype=torch.int64, device=dev)
         nnz_all[rank] = nnz_sh
         dist.all_reduce(nnz_all)
-        mg = dict(ex=ex, p2p=p2p, round=0, cap_nnz=cap_nnz,
+        mg = dict(ex=ex, p2p=p2p, round=0, cap_nnz=cap_nnz, steps={},
                   tab_local=torch.zeros(tab_words, dtype=torch.int32, device=dev), tab_words=tab_words, slots=slots,
                   tab_slots=tab_slots, nnz_sh=[int(x) for x in nnz_all.tolist()],
                   exchange="nvlink peer stores from the producing kernels (CUDA IPC mappings) + flags"
@@ -389,6 +392,23 @@ def run_b200(args):
         edge count stays on the device).  The timed region ends when every rank holds all roadmaps
         and rank 0 the table.  marks: optional list that receives a CUDA event after every stage."""
         ex = mg["ex"]
+        if mg["p2p"] and marks is None and not args.separate_calls:
+            # the whole step of this rank is ONE call into the library (mrmp_roadmaps_strong_step:
+            # the same launches as below, adoption of the peers' shards on the ctx's second stream)
+            key = cols[0].data_ptr()
+            ss = mg["steps"].get(key)
+            if ss is None:
+                ss = mg["steps"][key] = P.StrongStep(
+                    ex, rm_all, rm_sh, nv, inst.seed, inst.q_init, inst.q_goal, radv, cap, mg["cap_nnz"],
+                    n_cols, cols[0].data_ptr(), cols[1].data_ptr(), cols[2].data_ptr(), N,
+                    mg["tab_local"].data_ptr(), wpr, tab_rows_cap, table_dst=0)
+            t_a = time.perf_counter()
+            ss.enqueue(advance=mg["round"] > 0)
+            mg["round"] += 1
+            t_b = time.perf_counter()
+            n = ss.finish()
+            mg["host_s"] = (t_b - t_a, time.perf_counter() - t_b)   # (enqueue, waits) of the last step
+            return n
 
         def mark():
             if marks is not None:
@@ -606,6 +626,7 @@ def run_b200(args):
     cols_up = [torch.empty_like(t) for t in cols_d]
 
     e2e_mode = {"direct": True}
+    e2e_trace = [] if os.environ.get("BENCH_E2E_TRACE") else None   # host seconds: (step, read-back)
 
     def step_e2e():
         if world == 1:
@@ -630,12 +651,15 @@ def run_b200(args):
             return
         # multi-GPU: path ids from pinned host memory on every rank, this rank's roadmaps back to
         # its host, the gathered table back to rank 0's host
+        tr = e2e_trace
+        t_a = time.perf_counter()
         for up, h in zip(cols_up, cols_h):
             up.copy_(h, non_blocking=True)
         if strong:
             step_strong(cols_up)
         else:
             step_weak()
+        t_b = time.perf_counter()
         nnz = C.c_int64(0)
         L.check(lib.mrmp_roadmaps_read_async(rm_sh._h, nodes_out_h.data_ptr(), rowptr_out_h.data_ptr(),
                                              colidx_out_h.data_ptr(), colidx_out_h.numel(), C.byref(nnz)))
@@ -646,6 +670,8 @@ def run_b200(args):
             bits_h.copy_(bits_d, non_blocking=True)
         L.check(lib.mrmp_roadmaps_read_wait(rm_sh._h))
         torch.cuda.current_stream().synchronize()
+        if tr is not None:
+            tr.append((t_b - t_a, time.perf_counter() - t_b) + tuple(mg.get("host_s", (0.0, 0.0))))
 
     for _ in range(2):
         step_e2e()
@@ -674,6 +700,11 @@ def run_b200(args):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    if e2e_trace:
+        tail = e2e_trace[-e2e_steps:]
+        mean = [1e6 * sum(t[k] for t in tail) / len(tail) for k in range(4)]
+        sys.stderr.write("e2e trace rank %d: step %.1f us (one-call form: enqueue %.1f, waits %.1f), "
+                         "read-back %.1f us (means of %d)\n" % (rank, mean[0], mean[2], mean[3], mean[1], len(tail)))
     h2d = 2 * N * d * 8 + 3 * n_cols * 4
     if world == 1:
         d2h = N * nv * d * 8 + (N * nv + 1) * 4 + nnz_total * 4 + nnz_total * wpr * 4
@@ -769,7 +800,11 @@ def run_b200(args):
                         if strong else "weak: one scenario per rank, sharded build",
                 "exchange": mg["exchange"], "csr_slot_bytes": 4 * (cap * nv + mg["cap_nnz"]),
                 "table_bytes_to_rank0": int(nnz_total * wpr * 4) if strong else 0,
-                "check": strong_check, "ms_per_step_each": per_step[:8], "timeline": timeline},
+                "check": strong_check, "ms_per_step_each": per_step[:8], "timeline": timeline,
+                "host_calls_per_step": ("one call per stage (--separate-calls)" if args.separate_calls or
+                                        not (strong and mg["p2p"]) else
+                                        "1 (mrmp_roadmaps_strong_step) + 2 finish; the stage timeline is "
+                                        "taken with one call per stage")},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu,
             "explicit_lists": lists, "sssp_expansion": sssp_x, "sssp_solve": sssp_solve, "arm22": arm, "point3d": p3d,

@@ -87,7 +87,10 @@ void mrmp_ctx_destroy(mrmp_ctx *ctx);
 int mrmp_ctx_state_dim(const mrmp_ctx *ctx);
 int mrmp_ctx_sync(mrmp_ctx *ctx);
 /* run the ctx's kernels and small copies on a caller-owned cudaStream_t (NULL restores the
- * ctx's own stream); lets a host framework order and time the work on its stream */
+ * ctx's own, non-blocking stream); lets a host framework order and time the work on its stream.
+ * A framework whose stream is the default stream (handle 0) passes cudaStreamLegacy
+ * ((cudaStream_t)0x1): otherwise the ctx's launches (own stream) and the `stream` arguments of
+ * the *_dev / *_async entry points (stream 0) would be two unordered streams. */
 int mrmp_ctx_set_stream(mrmp_ctx *ctx, void *stream);
 /* diagnostics since the last reset: out4[0] = point-model pairs that survived the cross
  * kernel's broad phase (ran the exact reference arithmetic); out4[1] = arm22 link pairs that ran
@@ -374,6 +377,21 @@ int mrmp_roadmaps_edge_conflicts_async(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols
                                        const int32_t *col_agent, const int32_t *col_vfrom,
                                        const int32_t *col_vto, int group_size, uint32_t *out_bits,
                                        int64_t out_cap_rows, void *stream);
+
+/* One step of the strong-scaled path (prm.jl:265-275 sharded by agent + pp.jl:179-189 sharded by
+ * row) on this rank in ONE call: [advance both channels] -> mrmp_roadmaps_sample(rm_all) ->
+ * mrmp_roadmaps_build_async(rm_shard) -> mrmp_roadmaps_push_csr_shard(channel 0) ->
+ * mrmp_roadmaps_edge_conflicts_async(rm_shard rows x rm_all columns -> tab_local) ->
+ * mrmp_roadmaps_push_table_rows(channel 1, rank table_dst) + flag -> [wait_table: wait for every
+ * rank's rows]; mrmp_roadmaps_adopt_csr_shards_async(rm_all) runs on the ctx's second stream.
+ * Everything is enqueued on the ctx's stream; finish rm_shard, then rm_all. */
+int mrmp_roadmaps_strong_step(mrmp_roadmaps *rm_all, mrmp_roadmaps *rm_shard, mrmp_exchange *x,
+                              int world, int advance, int nv, uint64_t seed, const double *q_init,
+                              const double *q_goal, const double *rad_shard, int cap_agents,
+                              int64_t cap_nnz, int64_t n_cols, const int32_t *col_agent,
+                              const int32_t *col_vfrom, const int32_t *col_vto, int group_size,
+                              uint32_t *tab_local, int words_per_row, int64_t tab_rows_cap,
+                              int table_dst, int wait_table);
 
 /* sampler: gen_uniform_sampling (point2d.jl:71-75, point3d.jl:82-86, arm22.jl:214-218)
  * restated on a counter-based generator; writes try t0..t0+n-1 of (seed, agent) */

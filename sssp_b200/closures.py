@@ -201,7 +201,13 @@ class Context:
         return out
 
     def set_stream(self, cuda_stream: int | None) -> None:
-        """Run this ctx's kernels on a caller-owned CUDA stream (e.g. torch's current)."""
+        """Run this ctx's kernels on a caller-owned CUDA stream (e.g. torch's current); None
+        restores the ctx's own stream.  The handle of the default stream is 0 (what
+        ``torch.cuda.current_stream().cuda_stream`` returns outside a stream context), which the
+        library would read as "own stream": it is passed on as cudaStreamLegacy (0x1), so that the
+        ctx's launches and the caller's work on stream 0 are ordered on ONE stream."""
+        if cuda_stream is not None and int(cuda_stream) == 0:
+            cuda_stream = 1   # cudaStreamLegacy
         L.check(self._lib.mrmp_ctx_set_stream(self._h, cuda_stream))
 
     # ---- batched host-buffer entry points (numpy in / numpy out) ---------------------

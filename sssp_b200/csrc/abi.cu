@@ -204,6 +204,8 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming);
     {
         const char *ov = getenv("MRMP_TABLE_OVERLAP");
         c->table_overlap = !(ov && ov[0] == '0');
@@ -242,6 +244,8 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
     if (c->s_aux) cudaStreamDestroy(c->s_aux);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     if (c->blob) cudaFree(c->blob);
     if (c->stats_d) cudaFree(c->stats_d);
     delete c;
@@ -1250,6 +1254,7 @@ extern "C" int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agent
                     (long long)cap_nnz);
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
+    CU(order_after_ctx(c, (cudaStream_t)stream));
     CU(launch_csr_pack_shard(lcfg(c, (cudaStream_t)stream), (int64_t)rm->n_agents * rm->nv,
                              (int64_t)cap_agents * rm->nv, rm->row_ptr, rm->col_idx, slot_dev));
     return MRMP_OK;
@@ -1257,6 +1262,18 @@ extern "C" int mrmp_roadmaps_pack_csr_shard_dev(mrmp_roadmaps *rm, int cap_agent
 
 static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int64_t cap_nnz,
                                const int32_t *slots_dev, void *stream, int64_t *nnz_out, bool async);
+
+// room for `need` column indices (contents are not kept: the caller rewrites the CSR)
+static int grow_col_idx(mrmp_roadmaps *rm, int64_t need, cudaStream_t s) {
+    if (need <= rm->col_cap) return MRMP_OK;
+    CU(cudaStreamSynchronize(s));
+    if (s != rm->ctx->s_k) CU(cudaStreamSynchronize(rm->ctx->s_k));
+    if (rm->col_idx) CU(cudaFree(rm->col_idx));
+    rm->col_idx = nullptr;
+    rm->col_cap = need + 64;
+    CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
+    return MRMP_OK;
+}
 
 extern "C" int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agents,
                                                 int64_t cap_nnz, const int32_t *slots_dev,
@@ -1275,18 +1292,14 @@ static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int
     const int64_t rows = (int64_t)rm->n_agents * rm->nv, rows_cap = (int64_t)cap_agents * rm->nv;
     const int64_t stride = rows_cap + cap_nnz;
     LaunchCfg lc = lcfg(c, s);
+    CU(order_after_ctx(c, s));  // earlier consumers of this set's CSR on the ctx's stream
     CU(launch_csr_shard_counts(lc, rows, rows_cap, stride, slots_dev, rm->row_cnt));
     rm->pending = false;
     rm->pend_slot_nnz = rm->pend_rows_cap = -1;
     CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
                            rm->chunk_ws, rm->chunk_ws_len, async ? rm->dev(rm->st_nnz()) : nullptr));
-    if ((int64_t)world * cap_nnz > rm->col_cap) {  // upper bound of the stitched size
-        CU(cudaStreamSynchronize(s));
-        if (rm->col_idx) CU(cudaFree(rm->col_idx));
-        rm->col_idx = nullptr;
-        rm->col_cap = (int64_t)world * cap_nnz + 64;
-        CU(cudaMalloc((void **)&rm->col_idx, sizeof(int32_t) * rm->col_cap));
-    }
+    int rc0 = grow_col_idx(rm, (int64_t)world * cap_nnz, s);  // upper bound of the stitched size
+    if (rc0) return rc0;
     CU(launch_csr_stitch(lc, rows, rows_cap, stride, slots_dev, rm->row_ptr, rm->col_idx,
                          rm->col_cap));
     if (async) {  // nnz stays on the device (and in the mapped mirror) until mrmp_roadmaps_finish
@@ -1326,6 +1339,7 @@ extern "C" int mrmp_roadmaps_push_csr_shard(mrmp_roadmaps *rm, mrmp_exchange *x,
          "exchange slot too small for the shard");
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
+    CU(order_after_ctx(c, (cudaStream_t)stream));
     LaunchCfg lc = lcfg(c, (cudaStream_t)stream);
     for (int d0 = 0; d0 < world; d0 += 8) {
         CsrPushDst dst;
@@ -1359,8 +1373,12 @@ extern "C" int mrmp_roadmaps_adopt_csr_shards_async(mrmp_roadmaps *rm, mrmp_exch
 
 static int adopt_impl(mrmp_roadmaps *rm, mrmp_exchange *x, int ch, int world, int cap_agents,
                       int64_t cap_nnz, void *stream, int64_t *nnz_out, bool async) {
-    NEED(rm && x && world >= 1 && world <= 32, "bad arguments");
-    int rc = mrmp_exchange_wait(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
+    NEED(rm && x && world >= 1 && world <= 32 && cap_nnz >= 0, "bad arguments");
+    // (a reallocation synchronises the stream: before the wait is queued, not behind it)
+    CU(cudaSetDevice(rm->ctx->device));
+    int rc = grow_col_idx(rm, (int64_t)world * cap_nnz, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = mrmp_exchange_wait(x, ch, world >= 32 ? 0xffffffffu : ((1u << world) - 1u), stream);
     if (rc) return rc;
     NEED(((int64_t)cap_agents * rm->nv + cap_nnz) % 4 == 0 &&
              mrmp_exchange_slot_bytes(x, ch) ==
@@ -1583,6 +1601,7 @@ extern "C" int mrmp_collide_edges_indexed_dev(mrmp_roadmaps *rm, int64_t n, cons
     if (n == 0) return MRMP_OK;
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
+    CU(order_after_ctx(c, (cudaStream_t)stream));
     CU(launch_collide_edges_indexed(c->cv, lcfg(c, (cudaStream_t)stream), n, i, j, vi_from, vi_to,
                                     vj_from, vj_to, rm->nodes, rm->agent0, rm->n_agents, rm->nv,
                                     out));
@@ -1953,6 +1972,7 @@ static int edge_conflicts_core(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols, int64_
     }
     if (n_cols == 0 || n_rows == 0) return MRMP_OK;
     CU(cudaSetDevice(c->device));
+    CU(order_after_ctx(c, s));  // the set (and rm_cols) were sampled / built on the ctx's stream
     // the row sort (this stream) and the column tiles (s_aux) both read the finished roadmaps only
     const bool fork = c->table_overlap && !rm->e_valid && c->model <= MRMP_MODEL_POINT3D;
     if (fork) CU(cudaEventRecord(c->ev_fork, s));
@@ -1984,6 +2004,60 @@ extern "C" int mrmp_roadmaps_edge_conflicts_async(mrmp_roadmaps *rm, mrmp_roadma
     NEED(out_cap_rows >= 0, "out_cap_rows must be >= 0");
     return edge_conflicts_core(rm, rm_cols, n_cols, col_agent, col_vfrom, col_vto, group_size,
                                out_bits, out_cap_rows, (cudaStream_t)stream);
+}
+
+/* One step of the strong-scaled path on this rank, enqueued by ONE host call (a rank's share of a
+ * small scenario is ~0.2 ms of GPU work: a dozen separate calls from an interpreted host cost as
+ * much).  Order: [next epoch] -> draw all vertices -> neighbour pass of this rank's agents ->
+ * shard into every rank's memory + flags -> table rows of this rank's agents -> rows into rank
+ * table_dst's memory + flag -> [destination: wait for every rank's rows]; the adoption of the
+ * peers' shards is queued on the ctx's second stream, so it does not sit between the table kernel
+ * and the row transfer.  Everything stays pending until mrmp_roadmaps_finish(rm_shard) and
+ * mrmp_roadmaps_finish(rm_all). */
+extern "C" int mrmp_roadmaps_strong_step(mrmp_roadmaps *rm_all, mrmp_roadmaps *rm_shard,
+                                         mrmp_exchange *x, int world, int advance, int nv,
+                                         uint64_t seed, const double *q_init, const double *q_goal,
+                                         const double *rad_shard, int cap_agents, int64_t cap_nnz,
+                                         int64_t n_cols, const int32_t *col_agent,
+                                         const int32_t *col_vfrom, const int32_t *col_vto,
+                                         int group_size, uint32_t *tab_local, int words_per_row,
+                                         int64_t tab_rows_cap, int table_dst, int wait_table) {
+    NEED(rm_all && rm_shard && x && rad_shard && tab_local, "bad arguments");
+    NEED(rm_all->ctx == rm_shard->ctx, "both sets must belong to one ctx");
+    NEED(world >= 1 && world <= 32 && table_dst >= 0 && table_dst < world, "bad world / table_dst");
+    mrmp_ctx *c = rm_all->ctx;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t s = c->s_k;
+    const unsigned all = world >= 32 ? 0xffffffffu : ((1u << world) - 1u);
+    int rc = MRMP_OK;
+    if (advance) {
+        rc = mrmp_exchange_advance(x, 0);
+        if (!rc) rc = mrmp_exchange_advance(x, 1);
+    }
+    if (!rc) rc = mrmp_roadmaps_sample(rm_all, nv, seed, q_init, q_goal, nullptr);
+    if (!rc) rc = mrmp_roadmaps_build_async(rm_shard, rad_shard);
+    if (!rc) rc = mrmp_roadmaps_push_csr_shard(rm_shard, x, 0, world, cap_agents, cap_nnz, s);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_aux, s));  // this rank's own slot and flag are on their way
+    rc = mrmp_roadmaps_edge_conflicts_async(rm_shard, rm_all, n_cols, col_agent, col_vfrom, col_vto,
+                                            group_size, tab_local, tab_rows_cap, s);
+    if (!rc)
+        rc = mrmp_roadmaps_push_table_rows(rm_shard, x, 1, table_dst, tab_local, words_per_row,
+                                           tab_rows_cap, s);
+    if (!rc) rc = mrmp_exchange_signal(x, 1, 1u << table_dst, s);
+    if (rc) return rc;
+    static const bool adopt_aux = [] {
+        const char *e = getenv("MRMP_STRONG_ADOPT_AUX");
+        return !(e && e[0] == '0');
+    }();
+    cudaStream_t s_adopt = s;
+    if (adopt_aux) {  // (queued after the column tiles of the table, which use the same stream)
+        CU(cudaStreamWaitEvent(c->s_aux, c->ev_aux, 0));
+        s_adopt = c->s_aux;
+    }
+    rc = mrmp_roadmaps_adopt_csr_shards_async(rm_all, x, 0, world, cap_agents, cap_nnz, s_adopt);
+    if (!rc && wait_table) rc = mrmp_exchange_wait(x, 1, all, s);
+    return rc;
 }
 
 extern "C" int mrmp_roadmaps_edge_conflicts(mrmp_roadmaps *rm, mrmp_roadmaps *rm_cols,

@@ -78,7 +78,7 @@ struct mrmp_ctx {
     // conflict table of a roadmap set: the column tiles are prepared on s_aux while the rows are
     // sorted on the caller's stream (edge_conflicts_core)
     cudaStream_t s_aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux = nullptr, ev_order = nullptr;
     bool table_overlap = true;  // MRMP_TABLE_OVERLAP=0 keeps everything on one stream
     // chunk slots (device) and small-batch staging (pinned host + device)
     unsigned char *slot_buf[kSlots]{};
@@ -124,6 +124,21 @@ inline int ensure_scratch(mrmp_ctx *c, int k, size_t bytes) {
     return MRMP_OK;
 }
 
+
+// A *_dev / *_async entry point that consumes a roadmap set on a stream other than the ctx's: the
+// set's sampling / build kernels run on the ctx's stream, so the consumer is ordered behind them.
+// (stream 0 and cudaStreamLegacy are the same stream)
+static inline bool same_stream(cudaStream_t a, cudaStream_t b) {
+    if (a == (cudaStream_t)0) a = cudaStreamLegacy;
+    if (b == (cudaStream_t)0) b = cudaStreamLegacy;
+    return a == b;
+}
+static inline cudaError_t order_after_ctx(mrmp_ctx *c, cudaStream_t s) {
+    if (same_stream(s, c->s_k) || s == c->s_aux) return cudaSuccess;  // (s_aux: ordered by its user)
+    cudaError_t e = cudaEventRecord(c->ev_order, c->s_k);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, c->ev_order, 0);
+    return e;
+}
 
 static inline LaunchCfg lcfg(const mrmp_ctx *c, cudaStream_t s) {
     return LaunchCfg{c->sm_count, s, c->stats_d};

@@ -104,6 +104,9 @@ _SIGS = {
                                                      _vp, C.c_int64, _vp]),
     "mrmp_roadmaps_adopt_csr_shards_async": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int64, _vp]),
     "mrmp_roadmaps_push_table_rows": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, C.c_int64, _vp]),
+    "mrmp_roadmaps_strong_step": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _dp, _dp, _dp,
+                                            C.c_int, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int, _vp,
+                                            C.c_int, C.c_int64, C.c_int, C.c_int]),
     "mrmp_exchange_push_counted": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "mrmp_roadmaps_set_csr_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp]),
     "mrmp_roadmaps_pack_csr_shard_dev": (C.c_int, [_vp, C.c_int, C.c_int64, _vp, _vp]),

@@ -143,6 +143,51 @@ class Exchange:
                                                         int(words_per_row), int(max_rows), stream))
 
 
+class StrongStep:
+    """One strong-scaled step of the roadmap + conflict-table path per foreign call
+    (mrmp_roadmaps_strong_step): the arguments are marshalled once, `enqueue()` is a single call
+    into the library, `finish()` the host waits of the step.  Channel 0 of `ex` carries the CSR
+    shards, channel 1 the table rows (to rank `table_dst`)."""
+
+    def __init__(self, ex: Exchange, rm_all, rm_shard, nv: int, seed: int, q_init, q_goal, rad_shard,
+                 cap_agents: int, cap_nnz: int, n_cols: int, col_agent_ptr: int, col_vfrom_ptr: int,
+                 col_vto_ptr: int, group_size: int, tab_local_ptr: int, words_per_row: int,
+                 tab_rows_cap: int, table_dst: int = 0):
+        d = rm_all.ctx.d
+        self.ex, self.rm_all, self.rm_shard = ex, rm_all, rm_shard
+        # host arrays the library reads during the call: kept alive here
+        self._qi = np.ascontiguousarray(np.asarray(q_init, np.float64).reshape(-1, d))
+        self._qg = np.ascontiguousarray(np.asarray(q_goal, np.float64).reshape(-1, d))
+        self._rad = np.broadcast_to(np.asarray(rad_shard, np.float64), (rm_shard.n,)).copy()
+        self._fn = ex._lib.mrmp_roadmaps_strong_step
+        self._head = (rm_all._h, rm_shard._h, ex._h, C.c_int(ex.world))
+        self._tail = (C.c_int(int(nv)), C.c_uint64(int(seed)), L.ptr(self._qi, L._dp),
+                      L.ptr(self._qg, L._dp), L.ptr(self._rad, L._dp), C.c_int(int(cap_agents)),
+                      C.c_int64(int(cap_nnz)), C.c_int64(int(n_cols)), C.c_void_p(int(col_agent_ptr)),
+                      C.c_void_p(int(col_vfrom_ptr)), C.c_void_p(int(col_vto_ptr)),
+                      C.c_int(int(group_size)), C.c_void_p(int(tab_local_ptr)),
+                      C.c_int(int(words_per_row)), C.c_int64(int(tab_rows_cap)),
+                      C.c_int(int(table_dst)), C.c_int(1 if ex.rank == int(table_dst) else 0))
+        self._adv = (C.c_int(0), C.c_int(1))
+        self.rounds = 0
+        rm_all.nv = int(nv)
+
+    def enqueue(self, advance=None) -> None:
+        """advance: move both channels to the next epoch first (default: every round but the
+        first one of this object)."""
+        adv = self.rounds > 0 if advance is None else bool(advance)
+        L.check(self._fn(*self._head, self._adv[1 if adv else 0], *self._tail))
+        self.rounds += 1
+
+    def finish(self) -> int:
+        """The host waits of the step; returns the edge count of the full set."""
+        self.rm_shard.finish()
+        n = self.rm_all.finish()
+        if self.ex.error():
+            raise L.MRMPError(L.ERR_CUDA, "exchange: rank %d never published" % (self.ex.error() - 1))
+        return n
+
+
 def csr_slot_words(cap_agents: int, nv: int, nnz_max: int) -> int:
     """cap_nnz for a shard slot: head room over the largest shard, and the slot
     (cap_agents*nv + cap_nnz words) a multiple of 16 bytes."""

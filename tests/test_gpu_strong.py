@@ -108,6 +108,63 @@ def test_row_sharded_table_equals_single_gpu_table(world, via):
             x.advance(1)
 
 
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_strong_step_in_one_call(world):
+    """mrmp_roadmaps_strong_step: the whole step of a rank enqueued by one call (own stream per
+    emulated rank, adoption on the ctx's second stream) gives the single-GPU roadmaps and table."""
+    import torch
+    N, nv, T = 10, 160, 17
+    inst = W.point2d_many(N=N, seed=4, nv=nv, rad=0.17)
+    ctx0 = S.Context(inst.model, inst.rads, inst.obstacles)
+    full = S.Roadmaps(ctx0, 0, N, nv)
+    full.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+    nnz = full.build(inst.rad)
+    rp_ref, col_ref = full.csr()
+    _, ca, vf, vt = W.random_walk_paths(inst, rp_ref, col_ref, T, seed=6)
+    bits_ref = full.edge_conflicts(ca, vf, vt, N)
+    wpr = bits_ref.shape[1]
+    cols_d = [torch.from_numpy(x).cuda() for x in (ca, vf, vt)]
+    torch.cuda.synchronize()
+    ranks, nnz_sh, streams = [], [], []
+    for r in range(world):
+        a0, n_local, cap = SH.agent_block(N, world, r)
+        assert n_local > 0
+        ctx = S.Context(inst.model, inst.rads, inst.obstacles)
+        streams.append(torch.cuda.Stream())
+        ctx.set_stream(streams[-1].cuda_stream)
+        allrm = S.Roadmaps(ctx, 0, N, nv)
+        allrm.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+        sh = S.Roadmaps(ctx, a0, n_local, nv)
+        sh.bind_nodes(nv, allrm.device_ptrs()["nodes"] + a0 * nv * 2 * 8)
+        nnz_sh.append(sh.build(inst.rad))
+        ranks.append((ctx, allrm, sh, a0, n_local, cap))
+    cap = ranks[0][5]
+    cap_nnz = P.csr_slot_words(cap, nv, max(nnz_sh))
+    tab_words = (max(nnz_sh) + 64) * wpr
+    tab_words += (-tab_words) % 4
+    xs = [P.Exchange(ranks[r][0], world, r, [4 * (cap * nv + cap_nnz), 4 * tab_words])
+          for r in range(world)]
+    P.Exchange.connect_local(xs)
+    local = [torch.full((tab_words,), -1, dtype=torch.int32, device="cuda") for _ in range(world)]
+    torch.cuda.synchronize()
+    steps = [P.StrongStep(xs[r], ranks[r][1], ranks[r][2], nv, inst.seed, inst.q_init, inst.q_goal,
+                          inst.rad, cap, cap_nnz, ca.size, cols_d[0].data_ptr(), cols_d[1].data_ptr(),
+                          cols_d[2].data_ptr(), N, local[r].data_ptr(), wpr, tab_words // wpr, table_dst=0)
+             for r in range(world)]
+    for round_ in range(3):
+        for r in range(world):
+            steps[r].enqueue()
+        for r in range(world):
+            assert steps[r].finish() == nnz
+            rp, col = ranks[r][1].csr()
+            assert np.array_equal(rp, rp_ref) and np.array_equal(col, col_ref)
+        torch.cuda.synchronize()
+        slots = torch.as_tensor(_CudaArray(xs[0].slots(1), (world, xs[0].slot_bytes(1) // 4), "<i4"),
+                                device="cuda").cpu().numpy().view(np.uint32)
+        got = np.concatenate([slots[r, : nnz_sh[r] * wpr].reshape(-1, wpr) for r in range(world)])
+        assert got.shape == bits_ref.shape and np.array_equal(got, bits_ref)
+
+
 class _CudaArray:
     def __init__(self, ptr, shape, typestr):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
@@ -160,3 +217,36 @@ def test_async_build_reports_capacity_overflow():
         rm.finish()
     assert e.value.code == L_ERR_CAPACITY
     assert (out[nnz // 2 + 32:].cpu().numpy() == -1).all()    # nothing written beyond the room given
+
+
+def test_consumers_on_another_stream_are_ordered_behind_the_build():
+    """The ctx runs on its own stream, the table is requested on the default stream: the library
+    orders the consumer behind the sampling / build kernels (inputs change every round, so a table
+    computed from the previous round's roadmaps would not match)."""
+    import torch
+    N, nv = 16, 300
+    inst = W.point2d_many(N=N, seed=2, nv=nv, rad=0.15)
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles)        # own (non-blocking) stream
+    ctx_ref = S.Context(inst.model, inst.rads, inst.obstacles)
+    rm, rm_ref = S.Roadmaps(ctx, 0, N, nv), S.Roadmaps(ctx_ref, 0, N, nv)
+    rng = np.random.default_rng(0)
+    n_cols = 12 * N
+    ca = np.repeat(np.arange(N, dtype=np.int32), 12)
+    vf = rng.integers(0, nv, n_cols).astype(np.int32)
+    vt = rng.integers(0, nv, n_cols).astype(np.int32)
+    cols_d = [torch.from_numpy(x).cuda() for x in (ca, vf, vt)]
+    cap = 200000
+    out = torch.empty((cap, 1), dtype=torch.int32, device="cuda")
+    for seed, rad in [(11, 0.15), (12, 0.2), (13, 0.11), (14, 0.18)]:
+        rm_ref.sample(nv, seed, inst.q_init, inst.q_goal)
+        nnz_ref = rm_ref.build(rad)
+        ref = rm_ref.edge_conflicts(ca, vf, vt, N)
+        assert nnz_ref <= cap
+        out.fill_(-1)
+        rm.sample(nv, seed, inst.q_init, inst.q_goal, tries=False)
+        rm.build_async(rad)
+        rm.edge_conflicts_async(n_cols, cols_d[0].data_ptr(), cols_d[1].data_ptr(), cols_d[2].data_ptr(),
+                                N, out.data_ptr(), cap, 0)
+        assert rm.finish() == nnz_ref
+        torch.cuda.synchronize()
+        assert np.array_equal(out[:nnz_ref].cpu().numpy().view(np.uint32), ref)
