@@ -623,38 +623,44 @@ def run_b200(args):
     nodes_out_h = torch.empty((n_ret, nv, d), dtype=torch.float64).pin_memory()
     rowptr_out_h = torch.empty(rows_sh + 1, dtype=torch.int32).pin_memory()
     colidx_out_h = torch.empty(max(nnz_total, 1), dtype=torch.int32).pin_memory()
-    cols_up = [torch.empty_like(t) for t in cols_d]
+    cols_h_all = torch.stack(cols_h).pin_memory()            # (agent, v_from, v_to) ids in one pinned block
+    cols_up_all = torch.empty_like(cols_h_all, device=dev)
+    cols_up = [cols_up_all[k] for k in range(3)]
 
-    e2e_mode = {"direct": True}
+    e2e_mode = {"direct": True, "early_read": not os.environ.get("BENCH_E2E_LATE_READ")}
     e2e_trace = [] if os.environ.get("BENCH_E2E_TRACE") else None   # host seconds: (step, read-back)
 
     def step_e2e():
         if world == 1:
             # host buffers in (init / goal states, path ids), host buffers out (roadmaps: nodes + CSR,
             # conflict table), through the asynchronous pipeline of the C ABI: one host wait
-            for up, h in zip(cols_up, cols_h):
-                up.copy_(h, non_blocking=True)                       # H2D: path ids
+            cols_up_all.copy_(cols_h_all, non_blocking=True)         # H2D: path ids (one copy)
             rm_all.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)   # host init / goal
             rm_all.build_async(radv_all)
+            nnz = C.c_int64(0)
+            if e2e_mode["early_read"]:   # D2H of the roadmaps beside the table kernel
+                L.check(lib.mrmp_roadmaps_read_async(rm_all._h, nodes_out_h.data_ptr(),
+                                                     rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
+                                                     colidx_out_h.numel(), C.byref(nnz)))
             out_ptr = bits_h.data_ptr() if e2e_mode["direct"] else bits_d.data_ptr()
             rm_all.edge_conflicts_async(n_cols, cols_up[0].data_ptr(), cols_up[1].data_ptr(),
                                         cols_up[2].data_ptr(), N, out_ptr, nnz_total, st)
-            rm_all.finish()
-            nnz = C.c_int64(0)
-            L.check(lib.mrmp_roadmaps_read_async(rm_all._h, nodes_out_h.data_ptr(),
-                                                 rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
-                                                 colidx_out_h.numel(), C.byref(nnz)))   # D2H: roadmaps
             if not e2e_mode["direct"]:
-                bits_h.copy_(bits_d, non_blocking=True)              # D2H: table
-                torch.cuda.current_stream().synchronize()
+                # D2H of the table queued behind the kernel on the same stream: the step's one host
+                # wait (finish) covers it, no second round trip
+                bits_h.copy_(bits_d, non_blocking=True)
+            rm_all.finish()
+            if not e2e_mode["early_read"]:
+                L.check(lib.mrmp_roadmaps_read_async(rm_all._h, nodes_out_h.data_ptr(),
+                                                     rowptr_out_h.data_ptr(), colidx_out_h.data_ptr(),
+                                                     colidx_out_h.numel(), C.byref(nnz)))   # D2H: roadmaps
             L.check(lib.mrmp_roadmaps_read_wait(rm_all._h))
             return
         # multi-GPU: path ids from pinned host memory on every rank, this rank's roadmaps back to
         # its host, the gathered table back to rank 0's host
         tr = e2e_trace
         t_a = time.perf_counter()
-        for up, h in zip(cols_up, cols_h):
-            up.copy_(h, non_blocking=True)
+        cols_up_all.copy_(cols_h_all, non_blocking=True)
         if strong:
             step_strong(cols_up)
         else:
@@ -700,6 +706,11 @@ def run_b200(args):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    if world == 1:   # what travelled to the host is the roadmap set the device holds
+        rp_chk, col_chk = rm_all.csr()
+        assert np.array_equal(rowptr_out_h.numpy(), rp_chk), "e2e: row_ptr read back differs"
+        assert np.array_equal(colidx_out_h.numpy()[: col_chk.size], col_chk), "e2e: col_idx read back differs"
+        assert np.array_equal(nodes_out_h.numpy(), rm_all.nodes()), "e2e: nodes read back differ"
     if e2e_trace:
         tail = e2e_trace[-e2e_steps:]
         mean = [1e6 * sum(t[k] for t in tail) / len(tail) for k in range(4)]
@@ -713,7 +724,8 @@ def run_b200(args):
     e2e = {"value": checks_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
            "note": "per rank; rank 0 also reads the gathered table" if world > 1 else
-                   "asynchronous pipeline, one host wait; " + json.dumps(e2e_variants)}
+                   "asynchronous pipeline, one host wait; roadmaps read back beside the table kernel; "
+                   + json.dumps(e2e_variants)}
 
     # ---- explicit-list kernels (HBM side of the path), SSSP expansion, arm22: rank 0 only
     lists = sssp_x = arm = sssp_solve = p3d = None

@@ -203,7 +203,11 @@ int mrmp_roadmaps_set_csr_shards_dev(mrmp_roadmaps *rm, int world, int cap_agent
 /* Asynchronous read-back of a built roadmap set (what PRMs returns, prm.jl:251-276) into PINNED
  * host buffers on the ctx's copy stream: returns at once, so the caller can launch the next
  * batch (e.g. the conflict table) while the roadmaps travel.  mrmp_roadmaps_read_wait() blocks
- * until they have arrived.  The set must not be rebuilt in between. */
+ * until they have arrived.  The set must not be rebuilt in between.
+ * Behind mrmp_roadmaps_build_async (call it before the table is launched): the copies wait for the
+ * build's kernels only and overlap the table kernel; the edge count is not known yet, so all
+ * col_cap entries are copied, *nnz_out is -1, and mrmp_roadmaps_finish reports the count (and
+ * MRMP_ERR_CAPACITY if it exceeded col_cap). */
 int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
                              int32_t *col_idx, int64_t col_cap, int64_t *nnz_out);
 int mrmp_roadmaps_read_wait(mrmp_roadmaps *rm);

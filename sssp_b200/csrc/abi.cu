@@ -206,6 +206,7 @@ extern "C" int mrmp_ctx_create(mrmp_ctx **out, int model, int n_agents, const do
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_read, cudaEventDisableTiming);
     {
         const char *ov = getenv("MRMP_TABLE_OVERLAP");
         c->table_overlap = !(ov && ov[0] == '0');
@@ -246,6 +247,7 @@ extern "C" void mrmp_ctx_destroy(mrmp_ctx *c) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_aux) cudaEventDestroy(c->ev_aux);
     if (c->ev_order) cudaEventDestroy(c->ev_order);
+    if (c->ev_read) cudaEventDestroy(c->ev_read);
     if (c->blob) cudaFree(c->blob);
     if (c->stats_d) cudaFree(c->stats_d);
     delete c;
@@ -812,6 +814,7 @@ struct mrmp_roadmaps {
     bool pending = false;
     int64_t pend_slot_nnz = -1;  // cap_nnz of a shard pushed while pending (-1: none)
     int64_t pend_rows_cap = -1;  // row capacity of a table computed while pending (-1: none)
+    int64_t pend_read_cap = -1;  // col_cap of a read-back queued while pending (-1: none)
     cudaStream_t pend_stream = nullptr;  // stream of an asynchronous adoption (finish waits on it)
     // CSR edges expanded to explicit (agent, from, to) rows for the cross kernels
     int32_t *e_agent = nullptr;
@@ -1067,7 +1070,7 @@ static int roadmaps_build_impl(mrmp_roadmaps *rm, const double *rad, bool async)
     NEED(rm && rad, "bad roadmaps / rad");
     NEED(rm->nv >= 1, "no nodes set");
     rm->pending = false;
-    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
+    rm->pend_slot_nnz = rm->pend_rows_cap = rm->pend_read_cap = -1;
     rm->pend_stream = nullptr;
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
@@ -1191,8 +1194,8 @@ extern "C" int mrmp_roadmaps_finish(mrmp_roadmaps *rm, int64_t *nnz_out) {
     }
     rm->nnz = *rm->st_nnz();
     if (nnz_out) *nnz_out = rm->nnz;
-    const int64_t slot = rm->pend_slot_nnz, rows_cap = rm->pend_rows_cap;
-    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
+    const int64_t slot = rm->pend_slot_nnz, rows_cap = rm->pend_rows_cap, read_cap = rm->pend_read_cap;
+    rm->pend_slot_nnz = rm->pend_rows_cap = rm->pend_read_cap = -1;
     if (rm->nnz >= ((int64_t)1 << 31)) return fail(MRMP_ERR_UNSUPPORTED, "nnz exceeds int32 CSR");
     if (rm->nnz > rm->col_cap) {
         CU(cudaFree(rm->col_idx));
@@ -1209,6 +1212,9 @@ extern "C" int mrmp_roadmaps_finish(mrmp_roadmaps *rm, int64_t *nnz_out) {
     if (rows_cap >= 0 && rm->nnz > rows_cap)
         return fail(MRMP_ERR_CAPACITY, "asynchronous build: table of %lld rows computed into room "
                     "for %lld", (long long)rm->nnz, (long long)rows_cap);
+    if (read_cap >= 0 && rm->nnz > read_cap)
+        return fail(MRMP_ERR_CAPACITY, "asynchronous build: %lld edges read back into col_cap %lld",
+                    (long long)rm->nnz, (long long)read_cap);
     return MRMP_OK;
 }
 
@@ -1295,7 +1301,7 @@ static int set_csr_shards_impl(mrmp_roadmaps *rm, int world, int cap_agents, int
     CU(order_after_ctx(c, s));  // earlier consumers of this set's CSR on the ctx's stream
     CU(launch_csr_shard_counts(lc, rows, rows_cap, stride, slots_dev, rm->row_cnt));
     rm->pending = false;
-    rm->pend_slot_nnz = rm->pend_rows_cap = -1;
+    rm->pend_slot_nnz = rm->pend_rows_cap = rm->pend_read_cap = -1;
     CU(launch_row_scan(lc, rows, rm->row_cnt, rm->row_ptr, rm->nnz_d,
                            rm->chunk_ws, rm->chunk_ws_len, async ? rm->dev(rm->st_nnz()) : nullptr));
     int rc0 = grow_col_idx(rm, (int64_t)world * cap_nnz, s);  // upper bound of the stitched size
@@ -1476,11 +1482,32 @@ extern "C" int mrmp_host_unregister(void *ptr) {
 
 extern "C" int mrmp_roadmaps_read_async(mrmp_roadmaps *rm, double *nodes_out, int32_t *row_ptr,
                                         int32_t *col_idx, int64_t col_cap, int64_t *nnz_out) {
-    NEED(rm && nodes_out && row_ptr && nnz_out, "bad arguments");
+    NEED(rm && nodes_out && row_ptr && nnz_out && col_cap >= 0, "bad arguments");
     NEED(rm->built, "roadmaps not built");
-    NEED(!rm->pending, "asynchronous build pending: call mrmp_roadmaps_finish first");
     mrmp_ctx *c = rm->ctx;
     CU(cudaSetDevice(c->device));
+    if (rm->pending) {
+        // Behind an asynchronous build (call it right after mrmp_roadmaps_build_async): the copies
+        // wait for what the ctx's stream holds now and then run beside whatever is launched next
+        // (the conflict table), instead of after the step's host wait.  The edge count is not on
+        // the host yet: all col_cap entries (bounded by the CSR buffer) are copied, *nnz_out is
+        // -1 and mrmp_roadmaps_finish reports MRMP_ERR_CAPACITY if nnz exceeded col_cap.
+        NEED(col_idx || col_cap == 0, "col_idx is NULL");
+        const int64_t rows = (int64_t)rm->n_agents * rm->nv;
+        const int64_t n_col = col_cap < rm->col_cap ? col_cap : rm->col_cap;
+        CU(cudaEventRecord(c->ev_read, c->s_k));
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_read, 0));
+        CU(cudaMemcpyAsync(nodes_out, rm->nodes, sizeof(double) * c->d * (size_t)rows,
+                           cudaMemcpyDeviceToHost, c->s_out));
+        CU(cudaMemcpyAsync(row_ptr, rm->row_ptr, sizeof(int32_t) * (rows + 1),
+                           cudaMemcpyDeviceToHost, c->s_out));
+        if (n_col > 0)
+            CU(cudaMemcpyAsync(col_idx, rm->col_idx, sizeof(int32_t) * n_col, cudaMemcpyDeviceToHost,
+                               c->s_out));
+        rm->pend_read_cap = col_cap;
+        *nnz_out = -1;
+        return MRMP_OK;
+    }
     *nnz_out = rm->nnz;
     if (col_cap < rm->nnz)
         return fail(MRMP_ERR_CAPACITY, "col_cap %lld < nnz %lld", (long long)col_cap,

@@ -78,7 +78,7 @@ struct mrmp_ctx {
     // conflict table of a roadmap set: the column tiles are prepared on s_aux while the rows are
     // sorted on the caller's stream (edge_conflicts_core)
     cudaStream_t s_aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux = nullptr, ev_order = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux = nullptr, ev_order = nullptr, ev_read = nullptr;
     bool table_overlap = true;  // MRMP_TABLE_OVERLAP=0 keeps everything on one stream
     // chunk slots (device) and small-batch staging (pinned host + device)
     unsigned char *slot_buf[kSlots]{};

@@ -250,3 +250,40 @@ def test_consumers_on_another_stream_are_ordered_behind_the_build():
         assert rm.finish() == nnz_ref
         torch.cuda.synchronize()
         assert np.array_equal(out[:nnz_ref].cpu().numpy().view(np.uint32), ref)
+
+
+def test_read_back_queued_behind_an_asynchronous_build():
+    """mrmp_roadmaps_read_async on a pending set: the copies are ordered behind the build only, the
+    count arrives with finish(), too little room is reported there."""
+    import ctypes as C
+    import torch
+    from sssp_b200 import lib as L
+    N, nv = 6, 150
+    inst = W.point2d_many(N=N, seed=5, nv=nv, rad=0.2)
+    ctx = S.Context(inst.model, inst.rads, inst.obstacles)
+    rm = S.Roadmaps(ctx, 0, N, nv)
+    rm.sample(nv, inst.seed, inst.q_init, inst.q_goal)
+    nnz = rm.build(inst.rad)
+    rp_ref, col_ref = rm.csr()
+    nodes_ref = rm.nodes()
+    lib = ctx._lib
+    nodes_h = torch.zeros((N, nv, 2), dtype=torch.float64).pin_memory()
+    rp_h = torch.zeros(N * nv + 1, dtype=torch.int32).pin_memory()
+    col_h = torch.full((nnz + 100,), -7, dtype=torch.int32).pin_memory()
+    out = C.c_int64(0)
+    for cap, ok in ((nnz + 100, True), (nnz, True), (nnz - 1, False)):
+        rm.sample(nv, inst.seed, inst.q_init, inst.q_goal, tries=False)
+        rm.build_async(inst.rad)
+        L.check(lib.mrmp_roadmaps_read_async(rm._h, nodes_h.data_ptr(), rp_h.data_ptr(), col_h.data_ptr(),
+                                             cap, C.byref(out)))
+        assert out.value == -1
+        if ok:
+            assert rm.finish() == nnz
+            L.check(lib.mrmp_roadmaps_read_wait(rm._h))
+            assert np.array_equal(rp_h.numpy(), rp_ref) and np.array_equal(col_h.numpy()[:nnz], col_ref)
+            assert np.array_equal(nodes_h.numpy(), nodes_ref)
+        else:
+            with pytest.raises(S.MRMPError) as e:
+                rm.finish()
+            assert e.value.code == L_ERR_CAPACITY
+            L.check(lib.mrmp_roadmaps_read_wait(rm._h))
