@@ -18,14 +18,18 @@ block-partitioned over the ranks (prm.jl:265-275: the roadmaps are independent).
 all vertices (counter-based sampler: nothing to communicate), builds the roadmaps of ITS agents,
 writes its CSR shard straight into every peer's memory over NVLink (peer mappings, one flag per
 peer -- sssp_b200/peer.py; NCCL all-gather only as a fallback or with --exchange nccl), computes
-the table rows of ITS agents' edges against all agents' path edges with the output pointer aimed
-at rank 0's memory, and adopts the peers' shards.  The step ends -- inside the CUDA-event region --
+the table rows of ITS agents' edges against all agents' path edges, copies them into rank 0's
+memory and adopts the peers' shards -- one call into the library per rank and step
+(mrmp_roadmaps_strong_step; --separate-calls issues one call per stage, which is how the stage
+timeline in `multi_gpu.timeline` is taken).  The step ends -- inside the CUDA-event region --
 when every rank holds all roadmaps and rank 0 the whole table; both are checked byte for byte
 against the 1-GPU result before timing.  checks/step are those of the one scenario; `value` =
 checks / max-over-ranks step time.  --scaling weak keeps the round-1 shape (one scenario per
 rank on a sharded build) as an extra.
 
-`value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream.
+`value`  = checks / step time, inputs resident in HBM, CUDA events on the launching stream (the
+           ctx is put on torch's current stream: Context.set_stream maps the default stream's
+           handle 0 to cudaStreamLegacy, so flush, events and every launch share ONE stream).
 `e2e`    = same through the host-buffer C ABI: host init/goal and path ids in, roadmaps
            (nodes + CSR) and the conflict table bits out, every step.
 `--impl reference` = the CPU oracle (C restatement of the reference, OpenMP on all host
