@@ -46,7 +46,12 @@ def allgather_nodes_inplace(gathered: torch.Tensor, cap: int, nv: int, d: int, g
 
 def allgather_csr(row_ptr_local: torch.Tensor, col_local: torch.Tensor, n_agents: int, nv: int,
                   world: int, rank: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather of per-shard CSR adjacency (two-phase: sizes, then padded payload).
+    """All-gather of per-shard CSR adjacency (two-phase: sizes, then padded payload) for a host
+    that holds its shard as plain tensors (any backend; tests/test_sharding_gloo.py runs it on
+    gloo).  The GPU paths do not come through here: the peer exchange (sssp_b200/peer.py) stores
+    fixed-size slots into the peers' memory, and its NCCL fallback all-gathers the same slots
+    (mrmp_roadmaps_pack_csr_shard_dev -> one all_gather_into_tensor ->
+    mrmp_roadmaps_set_csr_shards_dev), which needs one collective instead of three.
 
     row_ptr_local: int32 [n_local*nv + 1] with offsets into col_local (this rank's agents);
     returns the global packed CSR (row_ptr int64 [N*nv + 1], col int32 [nnz_total]) in agent
