@@ -197,7 +197,39 @@ def run_reference(args):
                                    % (CPU_ROW_STRIDE, n_rows, ca.size, cpu.threads)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    jl = julia_reference()
+    if jl is not None:
+        line["julia"] = jl
     print(json.dumps(line), flush=True)
+
+
+def julia_reference():
+    """when a `julia` binary and a checkout of the reference (MRMP_REFERENCE_DIR) are
+    present, run the REAL reference on the same workload (julia/ref_bench.jl over a fixture of
+    tools/export_ref_fixture.py): its timings and its agreement with the oracle ("oracle_pinned")
+    travel in the line under "julia".  Neither exists in this image or on the GPU box: None."""
+    import shutil
+    import tempfile
+    jl, ref = shutil.which("julia"), os.environ.get("MRMP_REFERENCE_DIR")
+    if not jl or not ref or not os.path.isdir(ref):
+        return None
+    try:
+        root = os.path.dirname(os.path.abspath(__file__))
+        sys.path.insert(0, os.path.join(root, "tools"))
+        import export_ref_fixture as E
+        fx = E.make(N_AGENTS, NV, RAD, T_STEPS, CPU_ROW_STRIDE, 2000, 0)
+        with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+            json.dump(fx, f)
+        p = subprocess.run([jl, "--project=" + ref, "--threads=auto",
+                            os.path.join(root, "julia", "ref_bench.jl"), f.name, "3"],
+                           capture_output=True, text=True, timeout=3600)
+        os.unlink(f.name)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"error": (p.stderr or p.stdout)[-400:]}
+    except Exception as e:   # never lets the optional leg break the arm
+        return {"error": str(e)[:400]}
 
 
 # ------------------------------------------------------------------------------------------
